@@ -1,0 +1,306 @@
+// abi_problem.cu — library state, problem definition and the batched operator entry points of the
+// C ABI (include/binest.h).  No CPU fallback: every compute call needs a CUDA device.
+#include <cstring>
+#include <functional>
+#include <memory>
+
+#include "problem.cuh"
+
+namespace binest {
+std::atomic<int64_t> g_launches{0};
+double g_logzero = -1.7976931348623157e308;
+thread_local std::string t_last_error;
+
+int guard(const std::function<void()> &f) {
+    try {
+        f();
+        return BINEST_OK;
+    } catch (const Error &e) {
+        t_last_error = e.what();
+        return e.code;
+    } catch (const std::bad_alloc &) {
+        t_last_error = "host allocation failed";
+        return BINEST_ERR_MEMORY;
+    } catch (const std::exception &e) {
+        t_last_error = e.what();
+        return BINEST_ERR_FUNCTION;
+    }
+}
+
+static double norm_cdf(double z) { return 0.5 * std::erfc(-z * 0.70710678118654752440084436210485); }
+
+static void fill_prior(PriorSpec &pr, int d, const int32_t *kind, const double *lo, const double *hi,
+                       const double *p0, const double *p1) {
+    pr.d = d;
+    for (int j = 0; j < d; ++j) {
+        pr.kind[j] = kind[j];
+        pr.lo[j] = lo[j];
+        pr.hi[j] = hi[j];
+        pr.p0[j] = p0 ? p0[j] : 0.0;
+        pr.p1[j] = p1 ? p1[j] : 1.0;
+        BN_REQUIRE(lo[j] < hi[j], BINEST_ERR_DIMENSION, "parameter box needs lo < hi");
+        switch (kind[j]) {
+        case BINEST_PRIOR_UNIFORM:  // BS:37-39
+            BN_REQUIRE(std::isfinite(lo[j]) && std::isfinite(hi[j]), BINEST_ERR_NUMERICAL,
+                       "LocationParameter prior needs a finite box");
+            pr.lognorm[j] = -std::log(hi[j] - lo[j]);
+            break;
+        case BINEST_PRIOR_SCALE:  // BS:42-48
+            BN_REQUIRE(lo[j] > 0.0 && std::isfinite(hi[j]), BINEST_ERR_NUMERICAL,
+                       "ScaleParameter prior needs 0 < lo < hi < inf");
+            pr.lognorm[j] = -std::log(std::log(hi[j] / lo[j]));
+            break;
+        case BINEST_PRIOR_NORMAL_TRUNC: {  // BS:51-59
+            BN_REQUIRE(pr.p1[j] > 0.0, BINEST_ERR_NUMERICAL, "truncated normal prior needs sd > 0");
+            const double mass = norm_cdf((hi[j] - pr.p0[j]) / pr.p1[j]) - norm_cdf((lo[j] - pr.p0[j]) / pr.p1[j]);
+            BN_REQUIRE(mass > 0.0, BINEST_ERR_NUMERICAL, "prior has no mass inside the parameter box");
+            pr.lognorm[j] = -std::log(pr.p1[j]) - kHalfLog2Pi - std::log(mass);
+            break;
+        }
+        default: throw Error(BINEST_ERR_TYPE, "unknown prior kind");
+        }
+    }
+}
+
+// row-major P x d host -> SoA [d][Ps] on the device (scratch of the problem)
+void upload_theta(binest_problem &p, const double *theta, int64_t P, int Ps) {
+    std::vector<double> soa((size_t)p.d * Ps, 1.0);
+    for (int64_t i = 0; i < P; ++i)
+        for (int j = 0; j < p.d; ++j) soa[(size_t)j * Ps + i] = theta[i * p.d + j];
+    if (p.s_theta.n < soa.size()) p.s_theta.alloc(soa.size());
+    if (p.s_out.n < (size_t)Ps) p.s_out.alloc(Ps);
+    BN_CUDA(cudaMemcpyAsync(p.s_theta.p, soa.data(), soa.size() * sizeof(double), cudaMemcpyHostToDevice, p.stream));
+    BN_CUDA(cudaStreamSynchronize(p.stream));  // soa is a stack-lifetime buffer
+}
+}  // namespace binest
+
+using namespace binest;
+
+extern "C" {
+
+int binest_version(void) { return BINEST_VERSION; }
+const char *binest_last_error(void) { return t_last_error.c_str(); }
+int64_t binest_launch_count(void) { return g_launches.load(); }
+
+int binest_device_count(int *count) {
+    return guard([&] { BN_CUDA(cudaGetDeviceCount(count)); });
+}
+
+int binest_init(double logzero, int device) {
+    return guard([&] {
+        BN_REQUIRE(logzero < 0.0 && std::isfinite(logzero), BINEST_ERR_NUMERICAL, "logzero must be finite and negative");
+        int n = 0;
+        BN_CUDA(cudaGetDeviceCount(&n));
+        BN_REQUIRE(n > 0, BINEST_ERR_CUDA, "no CUDA device: libbinest has no CPU fallback");
+        if (device >= 0) BN_CUDA(cudaSetDevice(device));
+        int dev = 0;
+        BN_CUDA(cudaGetDevice(&dev));
+        cudaDeviceProp prop;
+        BN_CUDA(cudaGetDeviceProperties(&prop, dev));
+        BN_REQUIRE(prop.major == 10, BINEST_ERR_CUDA,
+                   std::string("libbinest is built for sm_100a only; found ") + prop.name);
+        g_logzero = logzero;
+    });
+}
+
+void binest_default_options(binest_options *o) {
+    if (!o) return;
+    o->pool_size = 100;   // BS:839
+    o->batch_k = 1;
+    o->mc_steps = 200;    // BS:844
+    o->max_iter = 10000;  // BS:841
+    o->min_iter = 100;    // BS:842
+    o->term_frac = 0.01;  // BS:845
+    o->acc_min = 0.0;     // BS:848
+    o->acc_max = 1.0;
+    o->seed = 1;
+    o->first_run_id = 0;
+    o->n_runs = 1;
+}
+
+int binest_measure_fp64_peak(double *tflops, double *ms_out) {
+    return guard([&] {
+        int dev = 0, sms = 0;
+        BN_CUDA(cudaGetDevice(&dev));
+        BN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        DevBuf<double> out(1);
+        const int iters = 4096, blocks = sms * 8, threads = 256;
+        cudaEvent_t e0, e1;
+        BN_CUDA(cudaEventCreate(&e0));
+        BN_CUDA(cudaEventCreate(&e1));
+        float best = 1e30f;
+        for (int rep = 0; rep < 5; ++rep) {
+            BN_CUDA(cudaEventRecord(e0));
+            fp64_peak_kernel<<<blocks, threads>>>(out.p, iters, 1.0 + rep);
+            BN_LAUNCH_CHECK();
+            BN_CUDA(cudaEventRecord(e1));
+            BN_CUDA(cudaEventSynchronize(e1));
+            float ms = 0;
+            BN_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+            if (rep > 0 && ms < best) best = ms;
+        }
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        const double flops = 2.0 * 64.0 * (double)iters * (double)blocks * threads;
+        if (tflops) *tflops = flops / (best * 1e-3) / 1e12;
+        if (ms_out) *ms_out = best;
+    });
+}
+
+int binest_problem_create(int op_id, const int64_t *iparam, const double *inputs, int64_t n_rows, int64_t n_in,
+                          const double *outputs, int64_t n_out, int64_t d, const int32_t *prior_kind,
+                          const double *lo, const double *hi, const double *prior_p0, const double *prior_p1,
+                          binest_problem **out) {
+    return guard([&] {
+        BN_REQUIRE(out, BINEST_ERR_TYPE, "null output handle");
+        BN_REQUIRE(inputs && n_rows > 0 && n_in > 0, BINEST_ERR_DIMENSION, "empty data");
+        BN_REQUIRE(d > 0 && d <= BINEST_MAXD, BINEST_ERR_DIMENSION, "1 <= d <= 16 parameters supported");
+        BN_REQUIRE(prior_kind && lo && hi, BINEST_ERR_TYPE, "prior / parameter box missing");
+        int ndev = 0;
+        BN_CUDA(cudaGetDeviceCount(&ndev));
+        BN_REQUIRE(ndev > 0, BINEST_ERR_CUDA, "no CUDA device: libbinest has no CPU fallback");
+        std::unique_ptr<binest_problem> p(new binest_problem());
+        p->op = op_id;
+        for (int i = 0; i < 4; ++i) p->iparam[i] = iparam ? iparam[i] : 0;
+        p->d = (int)d;
+        BN_CUDA(cudaGetDevice(&p->device));
+        BN_CUDA(cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, p->device));
+        BN_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+        fill_prior(p->prior, (int)d, prior_kind, lo, hi, prior_p0, prior_p1);
+
+        std::vector<double> host;
+        auto need_out = [&] { BN_REQUIRE(outputs && n_out == 1, BINEST_ERR_DIMENSION, "operator needs one output column"); };
+        switch (op_id) {
+        case BINEST_OP_GAUSSIAN_IID:
+            BN_REQUIRE(n_in == 1 && d == 2, BINEST_ERR_DIMENSION, "Gaussian i.i.d.: 1 data column, theta = (mu, sigma)");
+            p->rows = n_rows; p->ncol = 1;
+            host.assign(inputs, inputs + n_rows);
+            break;
+        case BINEST_OP_POLYREG: {
+            need_out();
+            const int64_t deg = p->iparam[0];
+            BN_REQUIRE(n_in == 1 && deg >= 1 && deg <= 5 && d == deg + 2, BINEST_ERR_DIMENSION,
+                       "polynomial regression: 1 input column, degree 1..5, theta = (c_0..c_deg, sigma)");
+            p->rows = n_rows; p->ncol = 2;
+            host.resize((size_t)n_rows * 2);
+            for (int64_t i = 0; i < n_rows; ++i) { host[2 * i] = inputs[i]; host[2 * i + 1] = outputs[i]; }
+            break;
+        }
+        case BINEST_OP_LOGISTIC: {
+            need_out();
+            const int64_t K = p->iparam[1];
+            p->iparam[2] = n_in;
+            BN_REQUIRE(K >= 2 && d == (K - 1) * (n_in + 1), BINEST_ERR_DIMENSION,
+                       "logistic: theta = (K-1) blocks of (w_1..w_F, b)");
+            const int ncol = (int)((n_in + 2) & ~1LL);
+            p->rows = n_rows; p->ncol = ncol;
+            host.assign((size_t)n_rows * ncol, 0.0);
+            for (int64_t i = 0; i < n_rows; ++i) {
+                for (int64_t f = 0; f < n_in; ++f) host[i * ncol + f] = inputs[i * n_in + f];
+                const double lab = outputs[i];
+                BN_REQUIRE(lab >= 0 && lab < K && lab == std::floor(lab), BINEST_ERR_NUMERICAL,
+                           "logistic: class labels must be integers 0..K-1");
+                host[i * ncol + n_in] = lab;
+            }
+            break;
+        }
+        case BINEST_OP_GBM: {  // TemporalData adaptor BS:511-515: inputs = times, outputs = values
+            need_out();
+            BN_REQUIRE(n_in == 1 && d == 2 && n_rows >= 2, BINEST_ERR_DIMENSION,
+                       "GBM: times column, values column, theta = (mu, sigma)");
+            p->rows = n_rows - 1; p->ncol = 2;
+            host.resize((size_t)p->rows * 2);
+            long double cst = 0.0L;
+            for (int64_t i = 1; i < n_rows; ++i) {
+                const long double dt = (long double)inputs[i] - (long double)inputs[i - 1];
+                BN_REQUIRE(dt > 0 && outputs[i] > 0 && outputs[i - 1] > 0, BINEST_ERR_NUMERICAL,
+                           "GBM: times must increase and values must be positive");
+                const long double r = logl((long double)outputs[i] / (long double)outputs[i - 1]);
+                const long double sq = sqrtl(dt);
+                host[2 * (i - 1)] = (double)(r / sq);
+                host[2 * (i - 1) + 1] = (double)sq;
+                cst += -logl((long double)outputs[i]) - 0.5L * logl(dt);
+            }
+            cst -= (long double)p->rows * (long double)kHalfLog2Pi;
+            p->cst = (double)cst;
+            break;
+        }
+        case BINEST_OP_GP_SE: {
+            need_out();
+            BN_REQUIRE(d == 3, BINEST_ERR_DIMENSION, "GP (SE kernel): theta = (sigma_f, ell, sigma_n)");
+            p->gp_n = n_rows; p->gp_dim = n_in;
+            p->gp_x.alloc((size_t)n_rows * n_in);
+            p->gp_y.alloc((size_t)n_rows);
+            BN_CUDA(cudaMemcpy(p->gp_x.p, inputs, sizeof(double) * n_rows * n_in, cudaMemcpyHostToDevice));
+            BN_CUDA(cudaMemcpy(p->gp_y.p, outputs, sizeof(double) * n_rows, cudaMemcpyHostToDevice));
+            p->rows = n_rows; p->ncol = (int)n_in;
+            break;
+        }
+        default: throw Error(BINEST_ERR_FUNCTION, "unknown operator id");
+        }
+        if (!host.empty()) {
+            dispatch_op(*p, [](auto) {});  // reject shapes outside the fixed table before uploading
+            host.resize(host.size() + 4, 0.0);  // slack so 16-byte-rounded bulk copies stay in bounds
+            p->data.alloc(host.size());
+            BN_CUDA(cudaMemcpyAsync(p->data.p, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice,
+                                    p->stream));
+            BN_CUDA(cudaStreamSynchronize(p->stream));
+        }
+        *out = p.release();
+    });
+}
+
+int binest_problem_free(binest_problem *p) {
+    return guard([&] { delete p; });
+}
+
+int binest_problem_dim(const binest_problem *p, int64_t *d) {
+    return guard([&] {
+        BN_REQUIRE(p && d, BINEST_ERR_TYPE, "null argument");
+        *d = p->d;
+    });
+}
+
+int binest_loglike(binest_problem *p, const double *theta, int64_t P, double *out) {
+    return guard([&] {
+        BN_REQUIRE(p && theta && out, BINEST_ERR_TYPE, "null argument");
+        if (P <= 0) return;  // empty list in, empty list out (Listable)
+        BN_CUDA(cudaSetDevice(p->device));
+        const int Ps = (int)((P + 31) & ~31LL);
+        upload_theta(*p, theta, P, Ps);
+        loglike_device(*p, p->s_theta.p, (int)P, Ps, p->s_out.p);
+        BN_CUDA(cudaMemcpyAsync(out, p->s_out.p, sizeof(double) * P, cudaMemcpyDeviceToHost, p->stream));
+        BN_CUDA(cudaStreamSynchronize(p->stream));
+    });
+}
+
+int binest_logprior(binest_problem *p, const double *theta, int64_t P, double *out) {
+    return guard([&] {
+        BN_REQUIRE(p && theta && out, BINEST_ERR_TYPE, "null argument");
+        if (P <= 0) return;
+        BN_CUDA(cudaSetDevice(p->device));
+        const int Ps = (int)((P + 31) & ~31LL);
+        upload_theta(*p, theta, P, Ps);
+        logprior_kernel<<<(unsigned)((P + 127) / 128), 128, 0, p->stream>>>(p->s_theta.p, (int)P, Ps, p->prior,
+                                                                          g_logzero, p->s_out.p);
+        BN_LAUNCH_CHECK();
+        BN_CUDA(cudaMemcpyAsync(out, p->s_out.p, sizeof(double) * P, cudaMemcpyDeviceToHost, p->stream));
+        BN_CUDA(cudaStreamSynchronize(p->stream));
+    });
+}
+
+int binest_sample_prior(binest_problem *p, int64_t n, uint64_t seed, int64_t run_id, double *out) {
+    return guard([&] {
+        BN_REQUIRE(p && out, BINEST_ERR_TYPE, "null argument");
+        if (n <= 0) return;
+        BN_CUDA(cudaSetDevice(p->device));
+        DevBuf<double> buf((size_t)n * p->d);
+        sample_prior_kernel<<<(unsigned)((n + 127) / 128), 128, 0, p->stream>>>(p->prior, n, seed, (unsigned)run_id,
+                                                                               buf.p);
+        BN_LAUNCH_CHECK();
+        BN_CUDA(cudaMemcpyAsync(out, buf.p, sizeof(double) * n * p->d, cudaMemcpyDeviceToHost, p->stream));
+        BN_CUDA(cudaStreamSynchronize(p->stream));
+    });
+}
+
+}  // extern "C"

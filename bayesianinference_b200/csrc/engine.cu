@@ -1,0 +1,466 @@
+// engine.cu — host orchestration of nestedSamplingInternal (BS:859-1040) for a group of lock-step runs,
+// plus the evidence entry points (BS:812-831, 1158-1291).  One process drives one GPU; runs are sharded
+// across GPUs by the caller (first_run_id / n_runs) and merged on the host (combineRuns BS:1293-1315).
+#include <algorithm>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <vector>
+
+#include "evidence.cuh"
+#include "problem.cuh"
+#include "walk.cuh"
+
+namespace binest {
+int guard(const std::function<void()> &f);
+void upload_theta(binest_problem &p, const double *theta, int64_t P, int Ps);
+}  // namespace binest
+
+using namespace binest;
+
+struct binest_run {
+    binest_problem *prob = nullptr;
+    binest_options opt{};
+    RunParams prm{};
+    RunArrays A{};
+    int n_pad = 0;
+    StreamGeom geom{};
+    bool first = true;
+    bool finished = false;
+    int64_t evals = 0;
+    int64_t batches = 0;
+    int64_t dead_upper = 0;  // host-side upper bound of n_dead per run
+    cudaStream_t stream = nullptr;
+    cudaGraphExec_t walk_graph = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double walk_ms = 0.0;   // device time spent in walk graphs (CUDA events on the run's stream)
+    int64_t walk_graphs = 0;
+    RunState *h_state = nullptr;  // pinned mirror
+    int *h_unfrozen = nullptr;    // pinned
+    DevBuf<double> live_theta, live_logL, live_logPr, live_acc;
+    DevBuf<double> dead_theta, dead_logL, dead_logPr, dead_acc, dead_logX;
+    DevBuf<int> dead_pool, order, kill_slot, w_flags, w_nacc, w_steps, n_unfrozen;
+    DevBuf<RunState> state;
+    DevBuf<double> w_theta, w_logL, w_logPr, w_prop, w_prop_logPr, w_mean, w_cov, partials;
+
+    ~binest_run() {
+        if (walk_graph) cudaGraphExecDestroy(walk_graph);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (h_state) cudaFreeHost(h_state);
+        if (h_unfrozen) cudaFreeHost(h_unfrozen);
+    }
+};
+
+namespace {
+
+void bind_arrays(binest_run &r) {
+    RunArrays &A = r.A;
+    A.live_theta = r.live_theta.p; A.live_logL = r.live_logL.p; A.live_logPr = r.live_logPr.p; A.live_acc = r.live_acc.p;
+    A.dead_theta = r.dead_theta.p; A.dead_logL = r.dead_logL.p; A.dead_logPr = r.dead_logPr.p;
+    A.dead_acc = r.dead_acc.p; A.dead_logX = r.dead_logX.p; A.dead_pool = r.dead_pool.p;
+    A.order = r.order.p; A.kill_slot = r.kill_slot.p; A.state = r.state.p;
+    A.w_theta = r.w_theta.p; A.w_logL = r.w_logL.p; A.w_logPr = r.w_logPr.p; A.w_prop = r.w_prop.p;
+    A.w_prop_logPr = r.w_prop_logPr.p; A.w_mean = r.w_mean.p; A.w_cov = r.w_cov.p;
+    A.w_flags = r.w_flags.p; A.w_nacc = r.w_nacc.p; A.w_steps = r.w_steps.p; A.n_unfrozen = r.n_unfrozen.p;
+}
+
+template <class T>
+void grow(DevBuf<T> &buf, int R, int64_t old_cap, int64_t new_cap, int width, cudaStream_t s) {
+    DevBuf<T> nb((size_t)R * new_cap * width);
+    for (int r = 0; r < R; ++r)
+        BN_CUDA(cudaMemcpyAsync(nb.p + (size_t)r * new_cap * width, buf.p + (size_t)r * old_cap * width,
+                                sizeof(T) * old_cap * width, cudaMemcpyDeviceToDevice, s));
+    BN_CUDA(cudaStreamSynchronize(s));
+    buf = std::move(nb);
+}
+
+void ensure_dead_capacity(binest_run &r, int64_t need) {
+    if (need <= r.prm.cap) return;
+    int64_t cap = r.prm.cap;
+    while (cap < need) cap *= 2;
+    const int R = r.prm.R, d = r.prm.d;
+    grow(r.dead_theta, R, r.prm.cap, cap, d, r.stream);
+    grow(r.dead_logL, R, r.prm.cap, cap, 1, r.stream);
+    grow(r.dead_logPr, R, r.prm.cap, cap, 1, r.stream);
+    grow(r.dead_acc, R, r.prm.cap, cap, 1, r.stream);
+    grow(r.dead_logX, R, r.prm.cap, cap, 1, r.stream);
+    grow(r.dead_pool, R, r.prm.cap, cap, 1, r.stream);
+    r.prm.cap = cap;
+    bind_arrays(r);
+}
+
+// the S-step walk as one CUDA graph: [walk_step, loglike_stream] x S, then the final accept
+void build_walk_graph(binest_run &r) {
+    binest_problem &p = *r.prob;
+    const int P = r.prm.R * r.prm.K;
+    const int S = (int)r.prm.S;
+    const cudaStream_t s = r.stream;
+    dispatch_op(p, [&](auto op) {
+        using OP = decltype(op);
+        const dim3 sgrid((P + 127) / 128), sblock(128);
+        const dim3 lgrid(r.geom.G, r.geom.pgroups), lblock(r.geom.nwarps * 32);
+        BN_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        for (int step = 0; step <= S; ++step) {
+            walk_step_kernel<OP><<<sgrid, sblock, 0, s>>>(r.prm, r.A, p.prior, r.partials.p, r.geom.G, (double)p.rows,
+                                                         p.cst, step == S ? 1 : 0);
+            if (step < S)
+                loglike_stream_kernel<OP><<<lgrid, lblock, 0, s>>>(p.data.p, p.rows, r.geom.rows_per_cta, r.w_prop.p,
+                                                                  P, r.prm.Ps, r.partials.p);
+        }
+        cudaGraph_t g;
+        BN_CUDA(cudaStreamEndCapture(s, &g));
+        BN_CUDA(cudaGraphInstantiate(&r.walk_graph, g, 0));
+        cudaGraphDestroy(g);
+    });
+}
+
+void launch_update(binest_run &r, bool insert_only = false) {
+    BN_CUDA(cudaMemsetAsync(r.n_unfrozen.p, 0, sizeof(int), r.stream));
+    const size_t smem = (size_t)r.n_pad * (sizeof(double) + sizeof(int));
+    const int mode = insert_only ? 2 : (r.first ? 1 : 0);
+    run_update_kernel<<<r.prm.R, 1024, smem, r.stream>>>(r.prm, r.A, r.n_pad, mode);
+    BN_LAUNCH_CHECK();
+    if (!insert_only) r.first = false;
+}
+
+bool all_done(const binest_run &r) {
+    for (int i = 0; i < r.prm.R; ++i)
+        if (!r.h_state[i].done) return false;
+    return true;
+}
+
+void fetch_state(binest_run &r) {
+    BN_CUDA(cudaMemcpyAsync(r.h_state, r.state.p, sizeof(RunState) * r.prm.R, cudaMemcpyDeviceToHost, r.stream));
+    BN_CUDA(cudaMemcpyAsync(r.h_unfrozen, r.n_unfrozen.p, sizeof(int), cudaMemcpyDeviceToHost, r.stream));
+    BN_CUDA(cudaStreamSynchronize(r.stream));
+}
+
+}  // namespace
+
+extern "C" {
+
+int binest_run_create(binest_problem *p, const binest_options *o, const double *start_points, binest_run **out) {
+    return guard([&] {
+        BN_REQUIRE(p && o && out, BINEST_ERR_TYPE, "null argument");
+        BN_REQUIRE(o->pool_size >= 2 && o->pool_size <= 4096, BINEST_ERR_DIMENSION, "2 <= SamplePoolSize <= 4096");
+        BN_REQUIRE(o->batch_k >= 1 && o->batch_k < o->pool_size, BINEST_ERR_DIMENSION, "1 <= batch_k < SamplePoolSize");
+        BN_REQUIRE(o->mc_steps >= 1 && o->mc_steps <= 100000, BINEST_ERR_DIMENSION, "MonteCarloSteps out of range");
+        BN_REQUIRE(o->n_runs >= 1 && o->n_runs <= 4096, BINEST_ERR_DIMENSION, "n_runs out of range");
+        BN_REQUIRE(o->term_frac > 0.0, BINEST_ERR_NUMERICAL, "TerminationFraction must be positive");
+        BN_CUDA(cudaSetDevice(p->device));
+        std::unique_ptr<binest_run> r(new binest_run());
+        r->prob = p;
+        r->opt = *o;
+        r->stream = p->stream;
+        RunParams &q = r->prm;
+        q.d = p->d; q.n = (int)o->pool_size; q.K = (int)o->batch_k; q.R = (int)o->n_runs;
+        q.Ps = (q.R * q.K + 31) & ~31;
+        q.max_iter = std::max(o->max_iter, o->min_iter);  // BS:867-868
+        q.min_iter = std::min(o->max_iter, o->min_iter);
+        q.log_term_frac = std::log(o->term_frac);
+        q.acc_min = o->acc_min; q.acc_max = o->acc_max;
+        q.S = o->mc_steps; q.maxS = 5 * o->mc_steps;  // BS:872
+        q.seed = o->seed; q.first_run_id = (unsigned)o->first_run_id;
+        q.logzero = g_logzero;
+        q.cap = std::max<int64_t>(4096, 16 * (int64_t)q.n);
+        r->n_pad = 1;
+        while (r->n_pad < q.n) r->n_pad <<= 1;
+        const size_t Rn = (size_t)q.R * q.n, Ps = q.Ps, d = q.d;
+        r->live_theta.alloc(Rn * d); r->live_logL.alloc(Rn); r->live_logPr.alloc(Rn); r->live_acc.alloc(Rn);
+        r->dead_theta.alloc((size_t)q.R * q.cap * d); r->dead_logL.alloc((size_t)q.R * q.cap);
+        r->dead_logPr.alloc((size_t)q.R * q.cap); r->dead_acc.alloc((size_t)q.R * q.cap);
+        r->dead_logX.alloc((size_t)q.R * q.cap); r->dead_pool.alloc((size_t)q.R * q.cap);
+        r->order.alloc(Rn); r->kill_slot.alloc((size_t)q.R * q.K);
+        r->state.alloc(q.R); r->n_unfrozen.alloc(1);
+        r->w_theta.alloc(d * Ps); r->w_logL.alloc(Ps); r->w_logPr.alloc(Ps); r->w_prop.alloc(d * Ps);
+        r->w_prop_logPr.alloc(Ps); r->w_mean.alloc(d * Ps); r->w_cov.alloc(d * d * Ps);
+        r->w_flags.alloc(Ps); r->w_nacc.alloc(Ps); r->w_steps.alloc(Ps);
+        r->w_prop.zero(r->stream); r->w_theta.zero(r->stream); r->w_flags.zero(r->stream);
+        r->geom = stream_geom(*p, q.R * q.K);
+        r->partials.alloc((size_t)r->geom.G * Ps);
+        BN_CUDA(cudaMallocHost(&r->h_state, sizeof(RunState) * q.R));
+        BN_CUDA(cudaMallocHost(&r->h_unfrozen, sizeof(int)));
+        BN_CUDA(cudaEventCreate(&r->ev0));
+        BN_CUDA(cudaEventCreate(&r->ev1));
+        bind_arrays(*r);
+
+        // starting points: supplied, or i.i.d. prior draws per run (BS:1099-1114, 1320-1332)
+        if (start_points) {
+            BN_CUDA(cudaMemcpyAsync(r->live_theta.p, start_points, sizeof(double) * Rn * d, cudaMemcpyHostToDevice,
+                                    r->stream));
+        } else {
+            for (int i = 0; i < q.R; ++i) {
+                sample_prior_kernel<<<(q.n + 127) / 128, 128, 0, r->stream>>>(p->prior, q.n, q.seed, q.first_run_id + i,
+                                                                             r->live_theta.p + (size_t)i * q.n * d);
+                BN_LAUNCH_CHECK();
+            }
+        }
+        // initial logL / log prior of all start points (BS:902-916): transpose to SoA, evaluate as one batch
+        {
+            std::vector<double> h(Rn * d);
+            BN_CUDA(cudaMemcpyAsync(h.data(), r->live_theta.p, sizeof(double) * Rn * d, cudaMemcpyDeviceToHost, r->stream));
+            BN_CUDA(cudaStreamSynchronize(r->stream));
+            const int P = (int)Rn, Pst = (P + 31) & ~31;
+            upload_theta(*p, h.data(), P, Pst);
+            loglike_device(*p, p->s_theta.p, P, Pst, r->live_logL.p);
+            logprior_kernel<<<(P + 127) / 128, 128, 0, r->stream>>>(p->s_theta.p, P, Pst, p->prior, g_logzero,
+                                                                   r->live_logPr.p);
+            BN_LAUNCH_CHECK();
+            std::vector<double> hl(Rn), nan(Rn, std::nan(""));
+            BN_CUDA(cudaMemcpyAsync(hl.data(), r->live_logL.p, sizeof(double) * Rn, cudaMemcpyDeviceToHost, r->stream));
+            BN_CUDA(cudaMemcpyAsync(r->live_acc.p, nan.data(), sizeof(double) * Rn, cudaMemcpyHostToDevice, r->stream));
+            BN_CUDA(cudaStreamSynchronize(r->stream));
+            for (double v : hl)  // BS:917-921
+                BN_REQUIRE(std::isfinite(v), BINEST_ERR_BAD_LIKELIHOOD, "Bad likelihood function");
+            r->evals += (int64_t)Rn;
+        }
+        std::vector<RunState> init(q.R);
+        for (auto &s : init) {
+            std::memset(&s, 0, sizeof(RunState));
+            s.dead.m = -INFINITY;
+            s.iteration = 1;
+            s.logZ = g_logzero;
+        }
+        BN_CUDA(cudaMemcpyAsync(r->state.p, init.data(), sizeof(RunState) * q.R, cudaMemcpyHostToDevice, r->stream));
+        BN_CUDA(cudaStreamSynchronize(r->stream));
+        BN_CUDA(cudaFuncSetAttribute(run_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        build_walk_graph(*r);
+        *out = r.release();
+    });
+}
+
+int binest_run_advance(binest_run *r, int64_t max_batches, int32_t *finished) {
+    return guard([&] {
+        BN_REQUIRE(r, BINEST_ERR_TYPE, "null run");
+        BN_CUDA(cudaSetDevice(r->prob->device));
+        const RunParams &q = r->prm;
+        const bool acc_loop = q.acc_min > 0.0 || q.acc_max < 1.0;
+        int64_t done_batches = 0;
+        while (!r->finished && (max_batches <= 0 || done_batches < max_batches)) {
+            ensure_dead_capacity(*r, r->dead_upper + q.K + 1);
+            launch_update(*r);
+            fetch_state(*r);
+            if (all_done(*r)) { r->finished = true; break; }
+            int64_t active = 0;
+            for (int i = 0; i < q.R; ++i) active += r->h_state[i].done ? 0 : r->h_state[i].Kb;
+            r->dead_upper += q.K;
+            // S steps; then extra S-step blocks while some walker's acceptance is out of range (BS:730-736)
+            int blocks = 0;
+            do {
+                BN_CUDA(cudaEventRecord(r->ev0, r->stream));
+                BN_CUDA(cudaGraphLaunch(r->walk_graph, r->stream));
+                count_launch(2 * (int)q.S + 1);
+                BN_CUDA(cudaEventRecord(r->ev1, r->stream));
+                BN_CUDA(cudaEventSynchronize(r->ev1));
+                float ms = 0;
+                BN_CUDA(cudaEventElapsedTime(&ms, r->ev0, r->ev1));
+                r->walk_ms += ms;
+                r->walk_graphs += 1;
+                r->evals += (int64_t)q.S * (int64_t)(blocks == 0 ? active : *r->h_unfrozen);
+                ++blocks;
+                if (!acc_loop) break;
+                BN_CUDA(cudaMemcpyAsync(r->h_unfrozen, r->n_unfrozen.p, sizeof(int), cudaMemcpyDeviceToHost, r->stream));
+                BN_CUDA(cudaStreamSynchronize(r->stream));
+            } while (*r->h_unfrozen > 0 && blocks < 5);
+            ++done_batches;
+            ++r->batches;
+        }
+        if (finished) *finished = r->finished ? 1 : 0;
+    });
+}
+
+int binest_run_sizes(binest_run *r, int64_t run, int64_t *M, int64_t *n_deleted, int64_t *iterations, int64_t *evals) {
+    return guard([&] {
+        BN_REQUIRE(r && run >= 0 && run < r->prm.R, BINEST_ERR_DIMENSION, "run index out of range");
+        BN_CUDA(cudaSetDevice(r->prob->device));
+        fetch_state(*r);
+        const RunState &s = r->h_state[run];
+        if (M) *M = s.n_dead + r->prm.n;
+        if (n_deleted) *n_deleted = s.n_dead;
+        if (iterations) *iterations = s.iteration - 1;
+        if (evals) *evals = r->evals;
+    });
+}
+
+// Assemble the sorted sample list of one run: deleted points in order of removal + the live set sorted
+// by {logL, point}.  If the run has not terminated, the batch in flight is first inserted (one update).
+int binest_run_fetch(binest_run *r, int64_t run, double *points, double *logL, double *logPrior, double *acc,
+                     int64_t *pool, double *logX, double *crude_logw, double *summary) {
+    return guard([&] {
+        BN_REQUIRE(r && run >= 0 && run < r->prm.R, BINEST_ERR_DIMENSION, "run index out of range");
+        BN_CUDA(cudaSetDevice(r->prob->device));
+        BN_REQUIRE(!r->first, BINEST_ERR_FUNCTION, "binest_run_fetch: advance the run first");
+        if (!r->finished) launch_update(*r, true);  // insert the batch in flight and re-sort; no new kill
+        fetch_state(*r);
+        const RunParams &q = r->prm;
+        const RunState &s = r->h_state[run];
+        const int64_t D = s.n_dead, n = q.n, M = D + n;
+        const int d = q.d;
+        std::vector<double> h_pts((size_t)M * d), h_L(M), h_Pr(M), h_acc(M);
+        std::vector<int> h_pool(M), h_order(n);
+        std::vector<double> l_th((size_t)n * d), l_L(n), l_Pr(n), l_acc(n);
+        cudaStream_t st = r->stream;
+        const size_t db = (size_t)run * q.cap, lb = (size_t)run * n;
+        auto d2h = [&](void *dst, const void *src, size_t bytes) {
+            if (bytes) BN_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
+        };
+        d2h(h_pts.data(), r->dead_theta.p + db * d, sizeof(double) * D * d);
+        d2h(h_L.data(), r->dead_logL.p + db, sizeof(double) * D);
+        d2h(h_Pr.data(), r->dead_logPr.p + db, sizeof(double) * D);
+        d2h(h_acc.data(), r->dead_acc.p + db, sizeof(double) * D);
+        d2h(h_pool.data(), r->dead_pool.p + db, sizeof(int) * D);
+        d2h(h_order.data(), r->order.p + lb, sizeof(int) * n);
+        d2h(l_th.data(), r->live_theta.p + lb * d, sizeof(double) * n * d);
+        d2h(l_L.data(), r->live_logL.p + lb, sizeof(double) * n);
+        d2h(l_Pr.data(), r->live_logPr.p + lb, sizeof(double) * n);
+        d2h(l_acc.data(), r->live_acc.p + lb, sizeof(double) * n);
+        BN_CUDA(cudaStreamSynchronize(st));
+        for (int64_t j = 0; j < n; ++j) {
+            const int src = h_order[j];
+            std::memcpy(&h_pts[(size_t)(D + j) * d], &l_th[(size_t)src * d], sizeof(double) * d);
+            h_L[D + j] = l_L[src]; h_Pr[D + j] = l_Pr[src]; h_acc[D + j] = l_acc[src];
+            h_pool[D + j] = (int)(n - j);
+        }
+        if (points) std::memcpy(points, h_pts.data(), sizeof(double) * M * d);
+        if (logL) std::memcpy(logL, h_L.data(), sizeof(double) * M);
+        if (logPrior) std::memcpy(logPrior, h_Pr.data(), sizeof(double) * M);
+        if (acc) std::memcpy(acc, h_acc.data(), sizeof(double) * M);
+        if (pool) for (int64_t k = 0; k < M; ++k) pool[k] = h_pool[k];
+        if (logX || crude_logw || summary) {
+            DevBuf<double> dL(M), dX(M), dW(M), dS(4);
+            DevBuf<int> dP(M);
+            BN_CUDA(cudaMemcpyAsync(dL.p, h_L.data(), sizeof(double) * M, cudaMemcpyHostToDevice, st));
+            BN_CUDA(cudaMemcpyAsync(dP.p, h_pool.data(), sizeof(int) * M, cudaMemcpyHostToDevice, st));
+            crude_weights_kernel<<<1, 1024, 0, st>>>(M, n, dL.p, dP.p, nullptr, dX.p, dW.p, dS.p);
+            BN_LAUNCH_CHECK();
+            if (logX) d2h(logX, dX.p, sizeof(double) * M);
+            if (crude_logw) d2h(crude_logw, dW.p, sizeof(double) * M);
+            if (summary) d2h(summary, dS.p, sizeof(double) * 4);
+            BN_CUDA(cudaStreamSynchronize(st));
+        }
+    });
+}
+
+int binest_run_estimates(binest_run *r, int64_t run, double *mean, double *cov) {
+    return guard([&] {
+        BN_REQUIRE(r && run >= 0 && run < r->prm.R, BINEST_ERR_DIMENSION, "run index out of range");
+        BN_CUDA(cudaSetDevice(r->prob->device));
+        fetch_state(*r);
+        const RunState &s = r->h_state[run];
+        const int d = r->prm.d;
+        if (mean) std::memcpy(mean, s.meanEst, sizeof(double) * d);
+        if (cov) std::memcpy(cov, s.covEst, sizeof(double) * d * d);
+    });
+}
+
+// device time of the walk graphs so far (CUDA events on the run's stream), number of graphs, kernel launches/graph
+int binest_run_timing(binest_run *r, double *walk_ms, int64_t *walk_graphs, int64_t *batches) {
+    return guard([&] {
+        BN_REQUIRE(r, BINEST_ERR_TYPE, "null run");
+        if (walk_ms) *walk_ms = r->walk_ms;
+        if (walk_graphs) *walk_graphs = r->walk_graphs;
+        if (batches) *batches = r->batches;
+    });
+}
+
+int binest_run_free(binest_run *r) {
+    return guard([&] {
+        if (r) { cudaSetDevice(r->prob->device); cudaStreamSynchronize(r->stream); }
+        delete r;
+    });
+}
+
+int binest_crude_weights(int64_t M, const double *logL, const int64_t *pool, int64_t n_live, double *logX,
+                         double *crude_logw, double *summary) {
+    return guard([&] {
+        BN_REQUIRE(logL && pool && M >= 2 && n_live >= 1 && n_live <= M, BINEST_ERR_DIMENSION, "bad sample list");
+        DevBuf<double> dL(M), dX(M), dW(M), dS(4);
+        DevBuf<long long> dP(M);
+        BN_CUDA(cudaMemcpy(dL.p, logL, sizeof(double) * M, cudaMemcpyHostToDevice));
+        BN_CUDA(cudaMemcpy(dP.p, pool, sizeof(int64_t) * M, cudaMemcpyHostToDevice));
+        crude_weights_kernel<<<1, 1024>>>(M, n_live, dL.p, nullptr, dP.p, dX.p, dW.p, dS.p);
+        BN_LAUNCH_CHECK();
+        if (logX) BN_CUDA(cudaMemcpy(logX, dX.p, sizeof(double) * M, cudaMemcpyDeviceToHost));
+        if (crude_logw) BN_CUDA(cudaMemcpy(crude_logw, dW.p, sizeof(double) * M, cudaMemcpyDeviceToHost));
+        if (summary) BN_CUDA(cudaMemcpy(summary, dS.p, sizeof(double) * 4, cudaMemcpyDeviceToHost));
+    });
+}
+
+int binest_evidence_sampling(int64_t M, int64_t d, const double *points, const double *logL, const int64_t *pool,
+                             int64_t n_live, int64_t post_runs, uint64_t seed, double *z, double *logw_mean,
+                             double *logw_sd, double *slx_mean, double *slx_sd, double *pmean, double *H) {
+    return guard([&] {
+        BN_REQUIRE(points && logL && pool && M >= 2 && n_live >= 1 && n_live <= M && d >= 1, BINEST_ERR_DIMENSION,
+                   "bad sample list");
+        BN_REQUIRE(post_runs >= 2 && post_runs <= 65535, BINEST_ERR_DIMENSION, "2 <= PostProcessSamplingRuns <= 65535");
+        const int R = (int)post_runs;
+        DevBuf<double> dPts((size_t)M * d), dL(M), dSlx((size_t)R * M), dLw((size_t)R * M), dZ(R), dPm((size_t)R * d), dH(R);
+        DevBuf<long long> dP(M);
+        DevBuf<double> o1(M), o2(M), o3(M), o4(M);
+        BN_CUDA(cudaMemcpy(dPts.p, points, sizeof(double) * M * d, cudaMemcpyHostToDevice));
+        BN_CUDA(cudaMemcpy(dL.p, logL, sizeof(double) * M, cudaMemcpyHostToDevice));
+        BN_CUDA(cudaMemcpy(dP.p, pool, sizeof(int64_t) * M, cudaMemcpyHostToDevice));
+        evidence_sampling_kernel<<<R, 1024>>>(M, (int)d, n_live, dPts.p, dL.p, dP.p, seed, dSlx.p, dLw.p, dZ.p, dPm.p, dH.p);
+        BN_LAUNCH_CHECK();
+        evidence_moments_kernel<<<(unsigned)((M + 255) / 256), 256>>>(M, R, dSlx.p, dLw.p, dZ.p, o1.p, o2.p, o3.p, o4.p);
+        BN_LAUNCH_CHECK();
+        auto back = [&](double *dst, const double *src, size_t cnt) {
+            if (dst) BN_CUDA(cudaMemcpy(dst, src, sizeof(double) * cnt, cudaMemcpyDeviceToHost));
+        };
+        back(z, dZ.p, R); back(logw_mean, o1.p, M); back(logw_sd, o2.p, M); back(slx_mean, o3.p, M);
+        back(slx_sd, o4.p, M); back(pmean, dPm.p, (size_t)R * d); back(H, dH.p, R);
+    });
+}
+
+// ---- measurement helpers for bench.py: inputs resident in HBM, CUDA events on the launching stream ----
+// Evaluate the likelihood of P prior draws `reps` times (after `warmup`), optionally flushing L2 between
+// repetitions; ms_kernel = average duration of loglike_stream_kernel alone, ms_total incl. the finalize kernel.
+int binest_bench_loglike(binest_problem *p, int64_t P, int64_t reps, int64_t warmup, int flush_l2, double *ms_kernel,
+                         double *ms_total) {
+    return guard([&] {
+        BN_REQUIRE(p && P > 0 && reps > 0, BINEST_ERR_DIMENSION, "bad arguments");
+        BN_REQUIRE(p->op != BINEST_OP_GP_SE, BINEST_ERR_FUNCTION, "use binest_bench_gp for the GP operator");
+        BN_CUDA(cudaSetDevice(p->device));
+        const int Ps = (int)((P + 31) & ~31LL);
+        DevBuf<double> rows((size_t)P * p->d), soa((size_t)p->d * Ps), out(Ps), flush;
+        sample_prior_kernel<<<(unsigned)((P + 127) / 128), 128, 0, p->stream>>>(p->prior, P, 900, 0, rows.p);
+        BN_LAUNCH_CHECK();
+        std::vector<double> h((size_t)P * p->d), hs((size_t)p->d * Ps, 1.0);
+        BN_CUDA(cudaMemcpyAsync(h.data(), rows.p, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, p->stream));
+        BN_CUDA(cudaStreamSynchronize(p->stream));
+        for (int64_t i = 0; i < P; ++i)
+            for (int j = 0; j < p->d; ++j) hs[(size_t)j * Ps + i] = h[i * p->d + j];
+        BN_CUDA(cudaMemcpyAsync(soa.p, hs.data(), sizeof(double) * hs.size(), cudaMemcpyHostToDevice, p->stream));
+        const size_t flush_n = (size_t)256 << 20;  // 256 MiB > 126 MB L2
+        if (flush_l2) flush.alloc(flush_n / sizeof(double));
+        const StreamGeom g = stream_geom(*p, (int)P);
+        DevBuf<double> partials((size_t)g.G * Ps);
+        cudaEvent_t e0, e1, e2;
+        BN_CUDA(cudaEventCreate(&e0)); BN_CUDA(cudaEventCreate(&e1)); BN_CUDA(cudaEventCreate(&e2));
+        double tk = 0.0, tt = 0.0;
+        dispatch_op(*p, [&](auto op) {
+            using OP = decltype(op);
+            for (int64_t it = 0; it < warmup + reps; ++it) {
+                if (flush_l2) BN_CUDA(cudaMemsetAsync(flush.p, it & 0xff, flush_n, p->stream));
+                BN_CUDA(cudaEventRecord(e0, p->stream));
+                launch_loglike<OP>(*p, soa.p, (int)P, Ps, partials.p, g);
+                BN_CUDA(cudaEventRecord(e1, p->stream));
+                loglike_finalize_kernel<OP><<<(unsigned)((P + 127) / 128), 128, 0, p->stream>>>(
+                    soa.p, (int)P, Ps, partials.p, g.G, (double)p->rows, p->cst, p->prior, g_logzero, out.p);
+                BN_LAUNCH_CHECK();
+                BN_CUDA(cudaEventRecord(e2, p->stream));
+                BN_CUDA(cudaEventSynchronize(e2));
+                float a = 0, b = 0;
+                BN_CUDA(cudaEventElapsedTime(&a, e0, e1));
+                BN_CUDA(cudaEventElapsedTime(&b, e0, e2));
+                if (it >= warmup) { tk += a; tt += b; }
+            }
+        });
+        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+        if (ms_kernel) *ms_kernel = tk / (double)reps;
+        if (ms_total) *ms_total = tt / (double)reps;
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,161 @@
+// operators.cuh — the fixed likelihood-operator table (per-datum device functions).
+//
+// Each operator replaces one symbolic builder of the reference:
+//   OpGaussian / OpPolyReg / OpLogistic / OpGbm  <- logLikelihoodFunction BS:429-505 and
+//   regressionLogLikelihoodFunction BS:517-595 (Sum over the data of the per-datum log-density,
+//   guarded by the parameter constraints; failure -> logzero).
+// Per-datum formulas: SURVEY.md §8a (WL LogLikelihood closed forms).  The parameter-independent
+// additive constants are kept, because LogEvidence and the 1e-12 logL parity depend on them.
+//
+// Interface (lane = walker: every thread owns one parameter vector, rows are broadcast from smem):
+//   D      number of parameters             NCOL  fp64 columns per device row
+//   Coef   per-theta derived coefficients   prepare(th, ok) -> Coef   (ok = operator constraints)
+//   row(coef, r, acc)   accumulate one datum      finish(coef, acc, rows, cst) -> logL
+#pragma once
+#include "common.cuh"
+
+namespace binest {
+
+// ------------------------------------------------------------------ NormalDistribution[mu, sigma], i.i.d. data
+struct OpGaussian {
+    static constexpr int D = 2, NCOL = 1;
+    struct Coef { double mu, h, lognorm; };
+    __device__ static Coef prepare(const double (&th)[D], bool &ok) {
+        ok = th[1] > 0.0;  // DistributionParameterAssumptions, BS:439
+        return Coef{th[0], 1.0 / (2.0 * th[1] * th[1]), -log(th[1]) - kHalfLog2Pi};
+    }
+    __device__ __forceinline__ static void row(const Coef &c, const double *__restrict__ r, double &acc) {
+        const double e = r[0] - c.mu;
+        acc = fma(e, e, acc);
+    }
+    __device__ static double finish(const Coef &c, double acc, double rows, double) {
+        return rows * c.lognorm - c.h * acc;
+    }
+};
+
+// ------------------------------------------------------------------ NormalDistribution[Sum_j c_j x^j, sigma]
+template <int DEG>
+struct OpPolyReg {
+    static constexpr int D = DEG + 2, NCOL = 2;
+    struct Coef { double c[DEG + 1]; double h, lognorm; };
+    __device__ static Coef prepare(const double (&th)[D], bool &ok) {
+        Coef c;
+#pragma unroll
+        for (int j = 0; j <= DEG; ++j) c.c[j] = th[j];
+        const double sg = th[DEG + 1];
+        ok = sg > 0.0;  // BS:523
+        c.h = 1.0 / (2.0 * sg * sg);
+        c.lognorm = -log(sg) - kHalfLog2Pi;
+        return c;
+    }
+    // 9 flop per datum at DEG = 3: 3 Horner FMA, 1 subtract, 1 FMA-accumulate
+    __device__ __forceinline__ static void row(const Coef &c, const double *__restrict__ r, double &acc) {
+        const double x = r[0];
+        double t = c.c[DEG];
+#pragma unroll
+        for (int j = DEG - 1; j >= 0; --j) t = fma(t, x, c.c[j]);
+        const double e = r[1] - t;
+        acc = fma(e, e, acc);
+    }
+    __device__ static double finish(const Coef &c, double acc, double rows, double) {
+        return rows * c.lognorm - c.h * acc;
+    }
+};
+
+// ------------------------------------------------------------------ softmax classification, reference class K
+// theta = K-1 blocks of (w_1..w_F, b); device row = (x_1..x_F, label, pad...) with NCOL even
+template <int F, int K>
+struct OpLogistic {
+    static constexpr int D = (K - 1) * (F + 1), NCOL = (F + 2) & ~1;
+    struct Coef { double w[K - 1][F + 1]; };
+    __device__ static Coef prepare(const double (&th)[D], bool &ok) {
+        Coef c;
+        ok = true;
+#pragma unroll
+        for (int k = 0; k < K - 1; ++k)
+#pragma unroll
+            for (int f = 0; f <= F; ++f) c.w[k][f] = th[k * (F + 1) + f];
+        return c;
+    }
+    __device__ __forceinline__ static void row(const Coef &c, const double *__restrict__ r, double &acc) {
+        double z[K - 1];
+        double mx = 0.0;  // z_K = 0
+        const int lab = (int)r[F];
+        double zy = 0.0;
+#pragma unroll
+        for (int k = 0; k < K - 1; ++k) {
+            double a = c.w[k][F];
+#pragma unroll
+            for (int f = 0; f < F; ++f) a = fma(c.w[k][f], r[f], a);
+            z[k] = a;
+            mx = fmax(mx, a);
+            zy = (lab == k) ? a : zy;
+        }
+        double s = exp(-mx);
+#pragma unroll
+        for (int k = 0; k < K - 1; ++k) s += exp(z[k] - mx);
+        acc += (zy - mx) - log(s);
+    }
+    __device__ static double finish(const Coef &, double acc, double, double) { return acc; }
+};
+
+// ------------------------------------------------------------------ GeometricBrownianMotionProcess[mu, sigma, x0]
+// device row i = (a_i, b_i) = (r_i / sqrt(dt_i), sqrt(dt_i)), r_i = log(x_i / x_{i-1});
+// cst = Sum_i(-log x_i - 1/2 log dt_i) - rows * 1/2 log 2pi  (parameter independent, fixed at upload)
+struct OpGbm {
+    static constexpr int D = 2, NCOL = 2;
+    struct Coef { double m, h, lognorm; };
+    __device__ static Coef prepare(const double (&th)[D], bool &ok) {
+        ok = th[1] > 0.0;
+        return Coef{th[0] - 0.5 * th[1] * th[1], 1.0 / (2.0 * th[1] * th[1]), -log(th[1])};
+    }
+    __device__ __forceinline__ static void row(const Coef &c, const double *__restrict__ r, double &acc) {
+        const double e = fma(-c.m, r[1], r[0]);
+        acc = fma(e, e, acc);
+    }
+    __device__ static double finish(const Coef &c, double acc, double rows, double cst) {
+        return rows * c.lognorm + cst - c.h * acc;
+    }
+};
+
+// ------------------------------------------------------------------ priors (BS:25-64, BS:365-427)
+struct PriorSpec {
+    int d;
+    int kind[BINEST_MAXD];
+    double lo[BINEST_MAXD], hi[BINEST_MAXD];
+    double p0[BINEST_MAXD], p1[BINEST_MAXD];
+    double lognorm[BINEST_MAXD];  // per-dimension additive constant, fixed at problem creation
+};
+
+// open box lo < theta < hi (BS:327-336)
+template <int D>
+__device__ __forceinline__ bool in_box(const PriorSpec &pr, const double (&th)[D]) {
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < D; ++j) ok = ok && (th[j] > pr.lo[j]) && (th[j] < pr.hi[j]);
+    return ok;
+}
+__device__ __forceinline__ bool in_box_dyn(const PriorSpec &pr, const double *th) {
+    bool ok = true;
+    for (int j = 0; j < pr.d; ++j) ok = ok && (th[j] > pr.lo[j]) && (th[j] < pr.hi[j]);
+    return ok;
+}
+// log prior density inside the box (caller has checked the box)
+__device__ __forceinline__ double logprior_dim(const PriorSpec &pr, int j, double t) {
+    switch (pr.kind[j]) {
+    case BINEST_PRIOR_UNIFORM: return pr.lognorm[j];             // -log(hi - lo)
+    case BINEST_PRIOR_SCALE: return -log(t) + pr.lognorm[j];     // -log t - log log(hi/lo)
+    default: {                                                   // truncated normal
+        const double z = (t - pr.p0[j]) / pr.p1[j];
+        return -0.5 * z * z + pr.lognorm[j];                     // - log s - 1/2 log 2pi - log mass
+    }
+    }
+}
+__device__ __forceinline__ double logprior_dyn(const PriorSpec &pr, const double *th, double logzero) {
+    if (!in_box_dyn(pr, th)) return logzero;
+    double s = 0.0;
+    for (int j = 0; j < pr.d; ++j) s += logprior_dim(pr, j, th[j]);
+    return isfinite(s) ? s : logzero;
+}
+
+}  // namespace binest

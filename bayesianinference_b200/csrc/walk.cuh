@@ -1,0 +1,424 @@
+// walk.cuh — device side of nestedSamplingInternal (BS:859-1040):
+//   run_update_kernel   one CTA per run: insert the walkers' points, sort the live set by {logL, point}
+//                       (BS:814, 902), crude evidence / entropy / termination test in the log domain
+//                       (BS:967-978, 1006-1020), kill the Kb worst (pool sizes n, n-1, ...), covariance blend
+//                       (BS:989), proposal Cholesky, RandomChoice of the walkers' starting points (BS:993)
+//   walk_step_kernel    one thread per walker: accept/reject the proposal just scored (nsDensity BS:602-617,
+//                       Metropolis rule of the "Log" chain BS:720-727), Haario recursion on the chain state,
+//                       next proposal x' = x + L z from Philox normals
+// The likelihood of all proposals of a step is scored by loglike_stream_kernel (loglike.cuh) in between.
+#pragma once
+#include "loglike.cuh"
+
+namespace binest {
+
+struct RunState {
+    double Lstar;       // likelihood threshold of the current batch (BS:981)
+    double logZ;        // crude log evidence (BS:1019)
+    double entropy;     // BS:1020
+    double logLmax;
+    double logXlast;    // logX of the last deleted point
+    double logXmin;     // logX of the best live point (BS:929, 935)
+    LseAcc dead;        // finalised trapezoid terms of deleted points 1..n_dead-1
+    long long iteration;   // 1-based, counts replacements (BS:885, 1021)
+    long long n_dead;
+    long long walk_base;   // walks started before this batch (Philox counter word 2)
+    int done;
+    int Kb;             // points replaced by the batch in flight
+    int chol_ok;
+    int pad_;
+    double meanEst[BINEST_MAXD];
+    double covEst[BINEST_MAXD * BINEST_MAXD];
+    double cholL[BINEST_MAXD * BINEST_MAXD];
+};
+
+struct RunParams {
+    int d, n, K, R, Ps;
+    long long cap;         // dead capacity per run
+    long long max_iter, min_iter;
+    double log_term_frac;
+    double acc_min, acc_max;
+    long long S, maxS;
+    unsigned long long seed;
+    unsigned first_run_id;
+    double logzero;
+};
+
+struct RunArrays {
+    // live set, row-major per run
+    double *live_theta;   // [R][n][d]
+    double *live_logL, *live_logPr, *live_acc;  // [R][n]
+    // dead list
+    double *dead_theta;   // [R][cap][d]
+    double *dead_logL, *dead_logPr, *dead_acc, *dead_logX;  // [R][cap]
+    int *dead_pool;       // [R][cap]
+    int *order;           // [R][n] live slots sorted ascending by {logL, point}
+    int *kill_slot;       // [R][K] live slots freed by the batch in flight
+    RunState *state;      // [R]
+    // walkers, SoA with stride Ps; walker w = run * K + j
+    double *w_theta;      // [d][Ps] current chain position
+    double *w_logL, *w_logPr;
+    double *w_prop;       // [d][Ps] proposal being scored
+    double *w_prop_logPr;
+    double *w_mean;       // [d][Ps]   Haario running mean
+    double *w_cov;        // [d*d][Ps] Haario running covariance
+    int *w_flags;         // bit0: proposal passes box + prior ratio; bit1: a proposal is in flight; bit2: frozen
+    int *w_nacc, *w_steps;
+    int *n_unfrozen;      // walkers still stepping (acceptance-range loop, BS:730-736)
+};
+
+enum : int { WF_PRE = 1, WF_HASPROP = 2, WF_FROZEN = 4 };
+
+// ---------------------------------------------------------------------------------------------------
+// ordering {logL, point, slot}
+__device__ __forceinline__ bool sample_less(double la, int ia, double lb, int ib, const double *__restrict__ theta,
+                                            int d) {
+    if (la < lb) return true;
+    if (la > lb) return false;
+    if (ia < 0 || ib < 0) return ib < 0 && ia >= 0;  // padding sorts last
+    for (int j = 0; j < d; ++j) {
+        const double a = theta[(size_t)ia * d + j], b = theta[(size_t)ib * d + j];
+        if (a < b) return true;
+        if (a > b) return false;
+    }
+    return ia < ib;
+}
+
+// proposal factor chol(s_d (C + eps I)), s_d = 2.4^2/d (Haario et al. 2001); row-major lower triangle
+__device__ inline int proposal_chol(const double *cov, int d, double *L) {
+    double tr = 0.0;
+    for (int a = 0; a < d; ++a) tr += cov[a * d + a];
+    const double eps = 1e-10 * (tr / d) + 1e-300;
+    const double sd = 2.4 * 2.4 / (double)d;
+    for (int a = 0; a < d * d; ++a) L[a] = 0.0;
+    for (int j = 0; j < d; ++j) {
+        double s = sd * (cov[j * d + j] + eps);
+        for (int k = 0; k < j; ++k) s -= L[j * d + k] * L[j * d + k];
+        if (!(s > 0.0)) return 0;
+        const double l = sqrt(s);
+        L[j * d + j] = l;
+        for (int i = j + 1; i < d; ++i) {
+            double t = sd * 0.5 * (cov[i * d + j] + cov[j * d + i]);  // symmetrizeMatrix BS:705, 716
+            for (int k = 0; k < j; ++k) t -= L[i * d + k] * L[j * d + k];
+            L[i * d + j] = t / l;
+        }
+    }
+    return 1;
+}
+
+// one CTA (1024 threads) per run.  Dynamic smem: n_pad doubles + n_pad ints.
+__global__ void __launch_bounds__(1024) run_update_kernel(const __grid_constant__ RunParams prm, RunArrays A, int n_pad,
+                                                          int mode /* 0 normal, 1 first call, 2 insert only */) {
+    const int first_call = (mode == 1);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *s_key = reinterpret_cast<double *>(smem_raw);
+    int *s_idx = reinterpret_cast<int *>(s_key + n_pad);
+    __shared__ double scratch[100];
+    __shared__ double s_mean[BINEST_MAXD];
+    __shared__ double s_cov[BINEST_MAXD * BINEST_MAXD];
+
+    const int r = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    const int d = prm.d, n = prm.n, K = prm.K, Ps = prm.Ps;
+    RunState &st = A.state[r];
+    if (st.done) return;
+    double *lth = A.live_theta + (size_t)r * n * d;
+    double *lL = A.live_logL + (size_t)r * n, *lPr = A.live_logPr + (size_t)r * n, *lAcc = A.live_acc + (size_t)r * n;
+    int *order = A.order + (size_t)r * n;
+    int *kill = A.kill_slot + (size_t)r * K;
+    const size_t dbase = (size_t)r * prm.cap;
+
+    // ---- 1. insert the points the walkers produced (BS:1006-1016) and adopt their chain estimates (BS:999)
+    const int Kprev = first_call ? 0 : st.Kb;
+    if (Kprev > 0) {
+        for (int j = tid; j < Kprev; j += nt) {
+            const int w = r * K + j, slot = kill[j];
+            for (int a = 0; a < d; ++a) lth[(size_t)slot * d + a] = A.w_theta[(size_t)a * Ps + w];
+            lL[slot] = A.w_logL[w];
+            lPr[slot] = A.w_logPr[w];
+            lAcc[slot] = (double)A.w_nacc[w] / (double)max(A.w_steps[w], 1);
+        }
+        for (int a = 0; a < d; ++a) {
+            double v = 0.0;
+            for (int j = tid; j < Kprev; j += nt) v += A.w_mean[(size_t)a * Ps + r * K + j];
+            v = block_sum(v, scratch);
+            if (tid == 0) st.meanEst[a] = v / (double)Kprev;
+        }
+        for (int a = 0; a < d; ++a)
+            for (int b = 0; b <= a; ++b) {
+                double v = 0.0;
+                for (int j = tid; j < Kprev; j += nt)
+                    v += 0.5 * (A.w_cov[(size_t)(a * d + b) * Ps + r * K + j] + A.w_cov[(size_t)(b * d + a) * Ps + r * K + j]);
+                v = block_sum(v, scratch);
+                if (tid == 0) st.covEst[a * d + b] = st.covEst[b * d + a] = v / (double)Kprev;
+            }
+        if (tid == 0) st.walk_base += Kprev;
+    }
+    __syncthreads();
+
+    // ---- 2. sort the live set ascending by {logL, point} (bitonic network in shared memory)
+    for (int i = tid; i < n_pad; i += nt) {
+        s_key[i] = (i < n) ? lL[i] : CUDART_INF;
+        s_idx[i] = (i < n) ? i : -1;
+    }
+    __syncthreads();
+    for (int k = 2; k <= n_pad; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < n_pad; i += nt) {
+                const int p = i ^ j;
+                if (p > i) {
+                    const bool up = ((i & k) == 0);
+                    const double ka = s_key[i], kb = s_key[p];
+                    const int ia = s_idx[i], ib = s_idx[p];
+                    const bool lt = sample_less(kb, ib, ka, ia, lth, d);  // partner < me
+                    if (lt == up) { s_key[i] = kb; s_key[p] = ka; s_idx[i] = ib; s_idx[p] = ia; }
+                }
+            }
+            __syncthreads();
+        }
+    for (int i = tid; i < n; i += nt) order[i] = s_idx[i];
+    const double logLmax = s_key[n - 1];
+    __syncthreads();
+
+    // ---- 3. crude evidence with the current dead list + sorted live set (calculateWeightsCrude BS:812-831)
+    const long long D = st.n_dead;
+    const double lxD = st.logXlast;  // 0 when D == 0
+    const long long M = D + n;
+    const double log_half = log(0.5), log_np1 = log((double)n + 1.0);
+    LseAcc acc = lse_empty();
+    for (int j = tid; j < n; j += nt) {
+        const long long k = D + j + 1;  // 1-based index in the full list
+        const double lx = (log((double)(n - j)) - log_np1) + lxD;
+        double left;
+        if (k == 1) left = log_subtract(log(2.0), lx);
+        else left = (j == 0) ? lxD : (log((double)(n - j + 1)) - log_np1) + lxD;
+        double lw;
+        if (k < M) lw = log_half + log_subtract(left, (log((double)(n - j - 1)) - log_np1) + lxD);
+        else lw = log_half + log_add(left, lx);
+        acc = lse_merge(acc, lse_term(lw + s_key[j], s_key[j]));
+    }
+    if (tid == 0 && D >= 1) {  // the last deleted point: right neighbour is the worst live point
+        const double left = (D == 1) ? log_subtract(log(2.0), lxD) : A.dead_logX[dbase + D - 2];
+        const double right = (log((double)n) - log_np1) + lxD;
+        const double L = A.dead_logL[dbase + D - 1];
+        acc = lse_merge(acc, lse_term(log_half + log_subtract(left, right) + L, L));
+    }
+    acc = block_lse(acc, scratch);
+    const LseAcc tot = lse_merge(st.dead, acc);
+    const double logZ = tot.m + log(tot.s0);
+    const double entropy = tot.s1 / tot.s0 - logZ;  // BS:801-810
+    const double logXmin = lxD - log_np1;
+    __syncthreads();
+
+    // ---- 4. termination test (BS:967-978) in the log domain: X_min L_max <= Z frac
+    const long long it = st.iteration;
+    const bool go = it <= prm.max_iter &&
+                    (it == 1 || it <= prm.min_iter || !(logXmin + logLmax <= logZ + prm.log_term_frac));
+    if (tid == 0) {
+        st.logZ = logZ; st.entropy = entropy; st.logLmax = logLmax; st.logXmin = logXmin;
+    }
+    if (mode == 2) {  // flush for binest_run_fetch on an unfinished run: no kill, no new batch
+        if (tid == 0) st.Kb = 0;
+        return;
+    }
+    if (!go) {
+        if (tid == 0) { st.done = 1; st.Kb = 0; }
+        return;
+    }
+    long long Kb_ll = K;
+    if (Kb_ll > prm.max_iter - it + 1) Kb_ll = prm.max_iter - it + 1;
+    if (Kb_ll > n - 1) Kb_ll = n - 1;
+    const int Kb = (int)Kb_ll;
+
+    // ---- 5. covariance of the live set, blend with the running estimate (BS:989), proposal factor
+    for (int a = 0; a < d; ++a) {
+        double v = 0.0;
+        for (int i = tid; i < n; i += nt) v += lth[(size_t)i * d + a];
+        v = block_sum(v, scratch);
+        if (tid == 0) s_mean[a] = v / (double)n;
+    }
+    __syncthreads();
+    for (int a = 0; a < d; ++a)
+        for (int b = 0; b <= a; ++b) {
+            double v = 0.0;
+            const double ma = s_mean[a], mb = s_mean[b];
+            for (int i = tid; i < n; i += nt) v += (lth[(size_t)i * d + a] - ma) * (lth[(size_t)i * d + b] - mb);
+            v = block_sum(v, scratch);
+            if (tid == 0) s_cov[a * d + b] = s_cov[b * d + a] = v / (double)(n - 1);
+        }
+    __syncthreads();
+    if (tid == 0) {
+        if (first_call) {  // BS:922-923
+            for (int a = 0; a < d; ++a) st.meanEst[a] = s_mean[a];
+            for (int a = 0; a < d * d; ++a) st.covEst[a] = s_cov[a];
+        }
+        for (int a = 0; a < d * d; ++a) st.covEst[a] = (st.covEst[a] + s_cov[a]) / 2.0;  // BS:989
+        st.chol_ok = proposal_chol(st.covEst, d, st.cholL);
+        st.Lstar = s_key[Kb - 1];  // BS:981 (K = 1: Min)
+        st.Kb = Kb;
+    }
+
+    // ---- 6. kill the Kb worst in order; the j-th removed sees pool size n - j
+    for (int j = tid; j < Kb; j += nt) {
+        const int slot = s_idx[j];
+        const size_t k = dbase + D + j;
+        for (int a = 0; a < d; ++a) A.dead_theta[k * d + a] = lth[(size_t)slot * d + a];
+        A.dead_logL[k] = lL[slot];
+        A.dead_logPr[k] = lPr[slot];
+        A.dead_acc[k] = lAcc[slot];
+        A.dead_pool[k] = n - j;
+        kill[j] = slot;
+    }
+    if (tid == 0) {  // logX_k = logX_{k-1} - 1/pool_k, sequential like the oracle
+        double c = lxD;
+        for (int j = 0; j < Kb; ++j) { c -= 1.0 / (double)(n - j); A.dead_logX[dbase + D + j] = c; }
+        st.logXlast = c;
+    }
+    __syncthreads();
+    // newly finalised trapezoid terms: 1-based k = max(1, D) .. D + Kb - 1
+    LseAcc fin = lse_empty();
+    for (int j = tid; j < Kb; j += nt) {
+        const long long k = D + j;
+        if (k >= 1 && k <= D + Kb - 1) {
+            const double left = (k == 1) ? log_subtract(log(2.0), A.dead_logX[dbase]) : A.dead_logX[dbase + k - 2];
+            const double right = A.dead_logX[dbase + k];
+            const double L = A.dead_logL[dbase + k - 1];
+            fin = lse_merge(fin, lse_term(log_half + log_subtract(left, right) + L, L));
+        }
+    }
+    fin = block_lse(fin, scratch);
+    if (tid == 0) {
+        st.dead = lse_merge(st.dead, fin);
+        st.n_dead = D + Kb;
+        st.iteration = it + Kb;
+    }
+
+    // ---- 7. start the walkers at random survivors (RandomChoice BS:993)
+    for (int j = tid; j < K; j += nt) {
+        const int w = r * K + j;
+        if (j < Kb) {
+            double u0, u1;
+            rng_uniform2(prm.seed, 0u, 0u, (uint32_t)(st.walk_base + j), TAG_START, prm.first_run_id + r, u0, u1);
+            int pick = Kb + (int)(u0 * (double)(n - Kb));
+            if (pick > n - 1) pick = n - 1;
+            const int src = s_idx[pick];
+            for (int a = 0; a < d; ++a) A.w_theta[(size_t)a * Ps + w] = lth[(size_t)src * d + a];
+            A.w_logL[w] = lL[src];
+            A.w_logPr[w] = lPr[src];
+            A.w_flags[w] = 0;
+        } else {
+            A.w_flags[w] = WF_FROZEN;
+        }
+        A.w_nacc[w] = 0;
+        A.w_steps[w] = 0;
+    }
+    __syncthreads();  // st.meanEst / covEst written by thread 0 above
+    for (int j = tid; j < Kb; j += nt) {
+        const int w = r * K + j;
+        for (int a = 0; a < d; ++a) A.w_mean[(size_t)a * Ps + w] = st.meanEst[a];
+        for (int a = 0; a < d * d; ++a) A.w_cov[(size_t)a * Ps + w] = st.covEst[a];
+    }
+    if (tid == 0) atomicAdd(A.n_unfrozen, Kb);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// accept phase of the proposal scored by the preceding loglike_stream_kernel, then the next proposal.
+// final_step: accept only.
+template <class OP>
+__global__ void walk_step_kernel(const __grid_constant__ RunParams prm, RunArrays A, const __grid_constant__ PriorSpec prior,
+                                 const double *__restrict__ partials, int G, double rows, double cst, int final_step) {
+    constexpr int D = OP::D;
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    const int K = prm.K, Ps = prm.Ps;
+    if (w >= prm.R * K) return;
+    const int r = w / K, j = w - r * K;
+    const RunState &st = A.state[r];
+    if (st.done || j >= st.Kb) return;
+    int flags = A.w_flags[w];
+    if (flags & WF_FROZEN) return;
+
+    double x[D];
+#pragma unroll
+    for (int a = 0; a < D; ++a) x[a] = A.w_theta[(size_t)a * Ps + w];
+    double xPr = A.w_logPr[w];
+    int steps = A.w_steps[w];
+
+    if (flags & WF_HASPROP) {
+        double xn[D];
+#pragma unroll
+        for (int a = 0; a < D; ++a) xn[a] = A.w_prop[(size_t)a * Ps + w];
+        bool acc = false;
+        if (flags & WF_PRE) {
+            const double nL = loglike_combine<OP>(xn, partials, G, Ps, w, rows, cst, prm.logzero);
+            if (nL > st.Lstar) {  // nsDensity: logL > threshold, strict (BS:605)
+                acc = true;
+                A.w_logL[w] = nL;
+            }
+        }
+        if (acc) {
+#pragma unroll
+            for (int a = 0; a < D; ++a) { x[a] = xn[a]; A.w_theta[(size_t)a * Ps + w] = xn[a]; }
+            xPr = A.w_prop_logPr[w];
+            A.w_logPr[w] = xPr;
+            A.w_nacc[w] += 1;
+        }
+        // Haario recursion on the chain state, started at t = 10 (BS:715-727)
+        const double t = 10.0 + (double)steps;
+        double mo[D], mn[D];
+#pragma unroll
+        for (int a = 0; a < D; ++a) {
+            mo[a] = A.w_mean[(size_t)a * Ps + w];
+            mn[a] = mo[a] + (x[a] - mo[a]) / (t + 1.0);
+            A.w_mean[(size_t)a * Ps + w] = mn[a];
+        }
+#pragma unroll
+        for (int a = 0; a < D; ++a)
+#pragma unroll
+            for (int b = 0; b < D; ++b) {
+                const size_t o = (size_t)(a * D + b) * Ps + w;
+                A.w_cov[o] = (t - 1.0) / t * A.w_cov[o] + (x[a] - mo[a]) * (x[b] - mn[b]) / t;
+            }
+        ++steps;
+        A.w_steps[w] = steps;
+        flags &= ~(WF_HASPROP | WF_PRE);
+        if (steps % prm.S == 0) {  // BS:730-736: extra S-step blocks until the rate is in range or 5S steps
+            const double rate = (double)A.w_nacc[w] / (double)steps;
+            if ((rate >= prm.acc_min && rate <= prm.acc_max) || steps >= prm.maxS) {
+                flags |= WF_FROZEN;
+                atomicSub(A.n_unfrozen, 1);
+            }
+        }
+    }
+    if (!final_step && !(flags & WF_FROZEN)) {
+        const uint32_t walk_id = (uint32_t)(st.walk_base + j), run_id = prm.first_run_id + r;
+        double z[D + 1];
+#pragma unroll
+        for (int b = 0; b < (D + 1) / 2; ++b)
+            rng_normal2(prm.seed, (uint32_t)b, (uint32_t)steps, walk_id, TAG_NORMAL, run_id, z[2 * b], z[2 * b + 1]);
+        double xn[D];
+#pragma unroll
+        for (int a = 0; a < D; ++a) {
+            double s = x[a];
+            if (st.chol_ok) {
+#pragma unroll
+                for (int b = 0; b <= a; ++b) s += st.cholL[a * D + b] * z[b];
+            }
+            xn[a] = s;
+            A.w_prop[(size_t)a * Ps + w] = s;
+        }
+        double u0, u1;
+        rng_uniform2(prm.seed, 0u, (uint32_t)steps, walk_id, TAG_ACCEPT, run_id, u0, u1);
+        int pre = 0;
+        if (in_box<D>(prior, xn)) {
+            double nPr = 0.0;
+#pragma unroll
+            for (int a = 0; a < D; ++a) nPr += logprior_dim(prior, a, xn[a]);
+            if (!isfinite(nPr)) nPr = prm.logzero;
+            A.w_prop_logPr[w] = nPr;
+            pre = (nPr - xPr > log(u0)) ? WF_PRE : 0;  // Metropolis rule on the log density
+        }
+        flags |= WF_HASPROP | pre;
+    }
+    A.w_flags[w] = flags;
+}
+
+}  // namespace binest

@@ -1,0 +1,208 @@
+"""Thin object layer over the C ABI (include/binest.h): Problem = operator + resident data + prior,
+RunGroup = one or more lock-step nested-sampling runs.  No numerics live here."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import LOGZERO, Options, check, dptr, iptr
+
+_initialised = False
+
+
+def init(logzero: float = LOGZERO, device: int = -1):
+    """binest_init: fails loudly without a B200 (no CPU fallback)."""
+    global _initialised
+    check(_lib.load().binest_init(logzero, device))
+    _initialised = True
+
+
+def _ensure_init():
+    if not _initialised:
+        init()
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def default_options(**kw) -> Options:
+    o = Options()
+    _lib.load().binest_default_options(C.byref(o))
+    for k, v in kw.items():
+        if not hasattr(o, k):
+            raise TypeError(f"unknown option {k}")
+        setattr(o, k, v)
+    return o
+
+
+class Problem:
+    """Device-resident inference problem (the data-carrying half of defineInferenceProblem, BS:167-307)."""
+
+    def __init__(self, op, inputs, outputs, iparam, kinds, lo, hi, p0=None, p1=None):
+        _ensure_init()
+        L = _lib.load()
+        self.op = int(op)
+        inputs = _f64(inputs)
+        if inputs.ndim == 1:
+            inputs = inputs.reshape(-1, 1)
+        n = inputs.shape[0]
+        outputs = None if outputs is None else _f64(outputs).reshape(n, -1)
+        self.d = len(kinds)
+        ip = np.ascontiguousarray(list(iparam) + [0] * (4 - len(iparam)), dtype=np.int64)
+        kinds = np.ascontiguousarray(kinds, dtype=np.int32)
+        lo, hi = _f64(lo), _f64(hi)
+        p0 = None if p0 is None or len(p0) == 0 else _f64(p0)
+        p1 = None if p1 is None or len(p1) == 0 else _f64(p1)
+        h = C.c_void_p()
+        check(L.binest_problem_create(self.op, iptr(ip), dptr(inputs), n, inputs.shape[1], dptr(outputs),
+                                      0 if outputs is None else outputs.shape[1], self.d,
+                                      kinds.ctypes.data_as(C.POINTER(C.c_int32)), dptr(lo), dptr(hi), dptr(p0),
+                                      dptr(p1), C.byref(h)))
+        self.h = h
+        self.n_rows = n
+
+    @classmethod
+    def from_config(cls, cfg):
+        return cls(cfg.op, cfg.inputs, cfg.outputs, cfg.iparam, cfg.kinds, cfg.lo, cfg.hi, cfg.p0, cfg.p1)
+
+    def loglike(self, theta):
+        """"LogLikelihoodFunction" (Listable): theta (P, d) -> (P,)."""
+        theta = _f64(np.atleast_2d(theta))
+        if theta.shape[1] != self.d:
+            raise ValueError(f"theta must have {self.d} columns")
+        out = np.empty(theta.shape[0])
+        check(_lib.load().binest_loglike(self.h, dptr(theta), theta.shape[0], dptr(out)))
+        return out
+
+    def logprior(self, theta):
+        """"LogPriorPDFFunction"."""
+        theta = _f64(np.atleast_2d(theta))
+        out = np.empty(theta.shape[0])
+        check(_lib.load().binest_logprior(self.h, dptr(theta), theta.shape[0], dptr(out)))
+        return out
+
+    def sample_prior(self, n, seed=1, run_id=0):
+        """generateStartingPoints (BS:1055-1068)."""
+        out = np.empty((n, self.d))
+        check(_lib.load().binest_sample_prior(self.h, n, seed, run_id, dptr(out)))
+        return out
+
+    def bench_loglike(self, P, reps=20, warmup=3, flush_l2=True):
+        a, b = C.c_double(), C.c_double()
+        check(_lib.load().binest_bench_loglike(self.h, P, reps, warmup, 1 if flush_l2 else 0, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def close(self):
+        if getattr(self, "h", None):
+            _lib.load().binest_problem_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class RunGroup:
+    """n_runs lock-step runs of nestedSamplingInternal (BS:859-1040) on the current device."""
+
+    def __init__(self, problem: Problem, options: Options, start_points=None):
+        self.problem = problem
+        self.options = options
+        sp = None
+        if start_points is not None:
+            sp = _f64(start_points).reshape(options.n_runs, options.pool_size, problem.d)
+        h = C.c_void_p()
+        check(_lib.load().binest_run_create(problem.h, C.byref(options), dptr(sp), C.byref(h)))
+        self.h = h
+        self.n_runs = int(options.n_runs)
+
+    def advance(self, max_batches=0) -> bool:
+        fin = C.c_int32()
+        check(_lib.load().binest_run_advance(self.h, max_batches, C.byref(fin)))
+        return bool(fin.value)
+
+    def sizes(self, run=0):
+        M, nd, it, ev = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+        check(_lib.load().binest_run_sizes(self.h, run, C.byref(M), C.byref(nd), C.byref(it), C.byref(ev)))
+        return dict(M=M.value, n_deleted=nd.value, iterations=it.value, evals=ev.value)
+
+    def timing(self):
+        ms, g, b = C.c_double(), C.c_int64(), C.c_int64()
+        check(_lib.load().binest_run_timing(self.h, C.byref(ms), C.byref(g), C.byref(b)))
+        return dict(walk_ms=ms.value, walk_graphs=g.value, batches=b.value)
+
+    def fetch(self, run=0):
+        """Sorted sample list of one run + calculateWeightsCrude columns (BS:812-831)."""
+        L = _lib.load()
+        # an unfinished run is flushed by the fetch itself, so sizes are read after a first NULL fetch
+        check(L.binest_run_fetch(self.h, run, None, None, None, None, None, None, None, None))
+        s = self.sizes(run)
+        M, d = s["M"], self.problem.d
+        pts = np.empty((M, d))
+        logL, logPr, acc, logX, lw = (np.empty(M) for _ in range(5))
+        pool = np.empty(M, dtype=np.int64)
+        summ = np.empty(4)
+        check(L.binest_run_fetch(self.h, run, dptr(pts), dptr(logL), dptr(logPr), dptr(acc), iptr(pool), dptr(logX),
+                                 dptr(lw), dptr(summ)))
+        return dict(points=pts, logL=logL, logPrior=logPr, acc=acc, pool=pool, logX=logX, crude_logw=lw,
+                    crude_logZ=float(summ[0]), entropy=float(summ[1]), logLmax=float(summ[2]),
+                    log_missing=float(summ[3]), n=int(self.options.pool_size), **s)
+
+    def estimates(self, run=0):
+        d = self.problem.d
+        m, c = np.empty(d), np.empty((d, d))
+        check(_lib.load().binest_run_estimates(self.h, run, dptr(m), dptr(c)))
+        return m, c
+
+    def close(self):
+        if getattr(self, "h", None):
+            _lib.load().binest_run_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def evidence_sampling(points, logL, pool, n_live, post_runs=100, seed=1):
+    """evidenceSampling (BS:1158-1291) on a sorted sample list; raw per-draw outputs."""
+    _ensure_init()
+    points, logL = _f64(points), _f64(logL)
+    pool = np.ascontiguousarray(pool, dtype=np.int64)
+    M, d = points.shape
+    z, H = np.empty(post_runs), np.empty(post_runs)
+    lwm, lws, sxm, sxs = (np.empty(M) for _ in range(4))
+    pm = np.empty((post_runs, d))
+    check(_lib.load().binest_evidence_sampling(M, d, dptr(points), dptr(logL), iptr(pool), n_live, post_runs, seed,
+                                               dptr(z), dptr(lwm), dptr(lws), dptr(sxm), dptr(sxs), dptr(pm), dptr(H)))
+    return dict(z=z, H=H, logw_mean=lwm, logw_sd=lws, slx_mean=sxm, slx_sd=sxs, pmean=pm)
+
+
+def crude_weights(logL, pool, n_live):
+    """calculateWeightsCrude + logSumExp + calculateEntropy on a sorted list (BS:812-831, BU:318-335)."""
+    _ensure_init()
+    logL = _f64(logL)
+    pool = np.ascontiguousarray(pool, dtype=np.int64)
+    M = logL.size
+    lx, lw, s = np.empty(M), np.empty(M), np.empty(4)
+    check(_lib.load().binest_crude_weights(M, dptr(logL), iptr(pool), n_live, dptr(lx), dptr(lw), dptr(s)))
+    return dict(logX=lx, crude_logw=lw, crude_logZ=float(s[0]), entropy=float(s[1]), logLmax=float(s[2]),
+                log_missing=float(s[3]))
+
+
+def fp64_peak():
+    _ensure_init()
+    t, ms = C.c_double(), C.c_double()
+    check(_lib.load().binest_measure_fp64_peak(C.byref(t), C.byref(ms)))
+    return t.value
+
+
+def launch_count():
+    return int(_lib.load().binest_launch_count())

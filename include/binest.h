@@ -1,0 +1,160 @@
+/*
+ * binest.h — C ABI of the B200-native nested-sampling engine (libbinest.so).
+ *
+ * This is the drop-in boundary for the hot path of ssmit1986/BayesianInference: the library
+ * replaces the *body* of nestedSamplingInternal (BayesianStatistics.wl:859-1040) and the
+ * operators it calls, and is reached from the Wolfram Language host package only through the
+ * LibraryLink shim (bayesianinference_b200/wl/librarylink_shim.c).  Plain pointers and sizes
+ * only: row-major fp64 arrays, 64-bit integer counts, opaque handles, int status codes.
+ * All array arguments are HOST pointers unless a name ends in _dev.
+ *
+ * Citations: BS = BayesianInference/Kernel/BayesianStatistics.wl, BU = BayesianUtilities.wl,
+ * GP = BayesianGaussianProcess.wl (reference checkout).
+ *
+ * Error convention (BS:422-425, BU:47): operators never fail — a numerically impossible
+ * parameter vector evaluates to `logzero`.  API misuse / CUDA failures return a non-zero
+ * status; binest_last_error() gives the message (thread-local).  There is NO CPU fallback:
+ * every compute entry point fails with BINEST_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef BINEST_H
+#define BINEST_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BINEST_VERSION 100
+
+/* status codes; 1..6 coincide with LibraryLink's LIBRARY_*_ERROR so the shim passes them through */
+enum {
+    BINEST_OK = 0,
+    BINEST_ERR_TYPE = 1,
+    BINEST_ERR_RANK = 2,
+    BINEST_ERR_DIMENSION = 3,
+    BINEST_ERR_NUMERICAL = 4,
+    BINEST_ERR_MEMORY = 5,
+    BINEST_ERR_FUNCTION = 6,
+    BINEST_ERR_CUDA = 7,
+    BINEST_ERR_BAD_LIKELIHOOD = 8 /* "Bad likelihood function", BS:917-921 */
+};
+
+/* Fixed operator table.  Replaces the symbolic builders logLikelihoodFunction (BS:429-505),
+ * regressionLogLikelihoodFunction (BS:517-595) and the GP wiring (GP:161-199, 296-307). */
+enum {
+    BINEST_OP_GAUSSIAN_IID = 1, /* NormalDistribution[mu, sigma]; theta = (mu, sigma)                  */
+    BINEST_OP_POLYREG = 2,      /* NormalDistribution[Sum_j c_j x^j, sigma]; theta = (c_0..c_deg, sigma)
+                                   iparam[0] = degree (1..5)                                          */
+    BINEST_OP_LOGISTIC = 3,     /* softmax, reference class K (z_K = 0); theta = K-1 blocks (w_1..w_F, b)
+                                   iparam[1] = K (2..3); outputs = class index 0..K-1 as fp64          */
+    BINEST_OP_GBM = 4,          /* GeometricBrownianMotionProcess[mu, sigma, x0] on (t_i, x_i); theta = (mu, sigma);
+                                   TemporalData adaptor BS:511-515: inputs = times, outputs = values   */
+    BINEST_OP_GP_SE = 5         /* GP marginal likelihood, squared-exponential kernel + nugget;
+                                   theta = (sigma_f, ell, sigma_n)                                     */
+};
+
+/* Prior kinds per parameter: ignorancePrior BS:25-64 / logPDFFunction BS:365-427. */
+enum {
+    BINEST_PRIOR_UNIFORM = 1,     /* "LocationParameter": UniformDistribution[{lo, hi}]      BS:37-39 */
+    BINEST_PRIOR_SCALE = 2,       /* "ScaleParameter": 1/x normalised on [lo, hi]            BS:42-48 */
+    BINEST_PRIOR_NORMAL_TRUNC = 3 /* NormalDistribution[p0, p1] truncated to the box         BS:51-59 */
+};
+
+typedef struct binest_problem binest_problem;
+typedef struct binest_run binest_run;
+
+/* Options of nestedSampling (BS:837-851) + evidenceSampling (BS:833-836), flattened. */
+typedef struct binest_options {
+    int64_t pool_size;   /* "SamplePoolSize"        default 100    BS:839 */
+    int64_t batch_k;     /* live points replaced per iteration; 1 = the reference scheme BS:980-1018 */
+    int64_t mc_steps;    /* "MonteCarloSteps"       default 200    BS:844 ({S, S, 5S} BS:872) */
+    int64_t max_iter;    /* "MaxIterations"         default 10000  BS:841 */
+    int64_t min_iter;    /* "MinIterations"         default 100    BS:842 */
+    double term_frac;    /* "TerminationFraction"   default 0.01   BS:845 */
+    double acc_min;      /* "MinMaxAcceptanceRate"  default {0,1}  BS:848 */
+    double acc_max;
+    uint64_t seed;       /* Philox key; results depend on (seed, run id) only, not on the GPU count */
+    int64_t first_run_id;/* id of the first run of this group (run-sharding across ranks/GPUs) */
+    int64_t n_runs;      /* independent runs advanced in lock-step on this device ("ParallelRuns" BS:1369) */
+} binest_options;
+
+/* ---- library ----------------------------------------------------------------------------- */
+int binest_version(void);
+const char *binest_last_error(void);
+/* logzero = $MachineLogZero of the host (BU:47); device < 0 keeps the current CUDA device. */
+int binest_init(double logzero, int device);
+int binest_device_count(int *count);
+void binest_default_options(binest_options *opts);
+/* Measured fp64 FMA throughput of the current device (register-resident DFMA loop on all SMs),
+ * in TFLOP/s; the roofline denominator SURVEY.md §8d asks the build to measure. */
+int binest_measure_fp64_peak(double *tflops, double *ms);
+/* Number of kernels this library has launched since load (bench.py's gpu_launches). */
+int64_t binest_launch_count(void);
+
+/* ---- problem definition: the data-carrying half of defineInferenceProblem (BS:167-307) ---- */
+/* inputs: n_rows x n_in (i.i.d. data: the data matrix itself, BS:492); outputs: n_rows x n_out or NULL.
+ * Data are uploaded once and stay device-resident (the reference bakes them into the compiled
+ * function, BS:488-504).  lo/hi: open parameter box (BS:327-336); prior_p0/p1 may be NULL. */
+int binest_problem_create(int op_id, const int64_t *iparam /*[4]*/, const double *inputs, int64_t n_rows,
+                          int64_t n_in, const double *outputs, int64_t n_out, int64_t d,
+                          const int32_t *prior_kind, const double *lo, const double *hi,
+                          const double *prior_p0, const double *prior_p1, binest_problem **out);
+int binest_problem_free(binest_problem *p);
+int binest_problem_dim(const binest_problem *p, int64_t *d);
+
+/* "LogLikelihoodFunction" (Listable, BS:499): theta P x d -> out[P].  Box / operator constraints
+ * violated -> logzero (BS:491-494, 580-583). */
+int binest_loglike(binest_problem *p, const double *theta, int64_t P, double *out);
+/* "LogPriorPDFFunction" (BS:410-426). */
+int binest_logprior(binest_problem *p, const double *theta, int64_t P, double *out);
+/* generateStartingPoints (BS:1055-1068): n i.i.d. prior draws, out n x d. */
+int binest_sample_prior(binest_problem *p, int64_t n, uint64_t seed, int64_t run_id, double *out);
+
+/* ---- the engine: nestedSamplingInternal (BS:859-1040) for n_runs lock-step runs ----------- */
+/* start_points: n_runs x pool_size x d, or NULL to draw them from the prior (each run its own,
+ * BS:1320-1332).  Returns BINEST_ERR_BAD_LIKELIHOOD when an initial logL is not finite (BS:917-921). */
+int binest_run_create(binest_problem *p, const binest_options *opts, const double *start_points,
+                      binest_run **out);
+/* Advance by at most max_batches iterations (each replaces batch_k points per run); <= 0: to
+ * termination (BS:967-978).  *finished = 1 when every run has terminated. */
+int binest_run_advance(binest_run *r, int64_t max_batches, int32_t *finished);
+/* per run: total samples M (dead + live), deleted count, iterations (= replacements), and the
+ * number of likelihood evaluations spent so far (whole group). */
+int binest_run_sizes(binest_run *r, int64_t run, int64_t *M, int64_t *n_deleted, int64_t *iterations,
+                     int64_t *evals);
+/* Sorted sample list of one run (SortBy {logL, point}, BS:814): any output may be NULL.
+ * points M x d; acc = NaN for initial samples (Missing["InitialSample"], BS:911); pool = pool size
+ * at each sample's removal; logX, crude_logw = calculateWeightsCrude (BS:812-831);
+ * summary[4] = {CrudeLogEvidence, CrudeRelativeEntropy, LogLikelihoodMaximum, LogEstimatedMissingEvidence}
+ * (BS:1183-1194). */
+int binest_run_fetch(binest_run *r, int64_t run, double *points, double *logL, double *logPrior,
+                     double *acc, int64_t *pool, double *logX, double *crude_logw, double *summary);
+/* walker-level chain estimates of the last iteration: MeanEstimate d, CovarianceEstimate d x d (BS:999) */
+int binest_run_estimates(binest_run *r, int64_t run, double *mean, double *cov);
+/* device time spent in the walk graphs so far (CUDA events on the run's stream), graphs launched, batches */
+int binest_run_timing(binest_run *r, double *walk_ms, int64_t *walk_graphs, int64_t *batches);
+int binest_run_free(binest_run *r);
+
+/* ---- evidenceSampling (BS:1158-1291) on a sorted sample list ------------------------------ */
+/* pool: per-sample pool sizes (first M - n_live entries used); outputs may be NULL:
+ *  z[post_runs]; logw_mean/sd[M] (LogPosteriorWeight); slx_mean/sd[M] (SampledLogX);
+ *  pmean[post_runs x d] (parameter means per draw); H[post_runs] (relative entropy per draw). */
+int binest_evidence_sampling(int64_t M, int64_t d, const double *points, const double *logL,
+                             const int64_t *pool, int64_t n_live, int64_t post_runs, uint64_t seed,
+                             double *z, double *logw_mean, double *logw_sd, double *slx_mean,
+                             double *slx_sd, double *pmean, double *H);
+/* calculateWeightsCrude + logSumExp + calculateEntropy (BS:812-831, BU:318-335, BS:801-810). */
+int binest_crude_weights(int64_t M, const double *logL, const int64_t *pool, int64_t n_live,
+                         double *logX, double *crude_logw, double *summary /*[4]*/);
+
+/* ---- measurement helper (bench.py): inputs resident in HBM, CUDA events on the launching stream ---- */
+/* Scores P prior draws `reps` times after `warmup`; flush_l2 != 0 writes 256 MiB between repetitions.
+ * ms_kernel: mean duration of the streaming likelihood kernel; ms_total: including the finalize kernel. */
+int binest_bench_loglike(binest_problem *p, int64_t P, int64_t reps, int64_t warmup, int flush_l2,
+                         double *ms_kernel, double *ms_total);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BINEST_H */

@@ -818,7 +818,7 @@ static int cmp_double(const void *a, const void *b) {
 }
 ORC_API void orc_evidence_sampling(int64_t M, int d, const double *points, const double *logL,
                                    const int64_t *pool, int64_t n, int64_t nruns, uint64_t seed,
-                                   double *z, double *logw_mean, double *logw_sd, double *slx_mean,
+                                   int sorted_draws, double *z, double *logw_mean, double *logw_sd, double *slx_mean,
                                    double *slx_sd, double *pmean, double *H) {
     const int64_t nd = M - n;
     double *lx = (double *)malloc(sizeof(double) * M);
@@ -830,15 +830,25 @@ ORC_API void orc_evidence_sampling(int64_t M, int d, const double *points, const
         double acc = 0.0, u[2];
         for (int64_t k = 0; k < nd; ++k) {
             orc_uniform2(seed, 0, (uint32_t)r, (uint32_t)k, TAG_EV_DEAD, 0, u);
-            acc -= -log(u[0]) / (double)pool[k];
+            acc += log(u[0]) / (double)pool[k];
             lx[k] = acc;
         }
-        for (int64_t j = 0; j < n; ++j) {
-            orc_uniform2(seed, 0, (uint32_t)r, (uint32_t)j, TAG_EV_LIVE, 0, u);
-            e[j] = -log(u[0]);
+        if (sorted_draws) { /* literal BS:1209-1215: Sort of n i.i.d. Exp(1) draws */
+            for (int64_t j = 0; j < n; ++j) {
+                orc_uniform2(seed, 0, (uint32_t)r, (uint32_t)j, TAG_EV_LIVE, 0, u);
+                e[j] = -log(u[0]);
+            }
+            qsort(e, n, sizeof(double), cmp_double);
+            for (int64_t j = 0; j < n; ++j) lx[nd + j] = acc - e[j];
+        } else { /* same law without the sort (Renyi representation of exponential order
+                    statistics): e_(j) = Sum_{i<=j} E_i/(n-i); this is what the CUDA kernel draws */
+            double c = 0.0;
+            for (int64_t j = 0; j < n; ++j) {
+                orc_uniform2(seed, 0, (uint32_t)r, (uint32_t)j, TAG_EV_LIVE, 0, u);
+                c += log(u[0]) / (double)(n - j);
+                lx[nd + j] = acc + c;
+            }
         }
-        qsort(e, n, sizeof(double), cmp_double);
-        for (int64_t j = 0; j < n; ++j) lx[nd + j] = acc - e[j];
         orc_trapezoid_log(lx, M, lw);
         for (int64_t k = 0; k < M; ++k) lw[k] += logL[k];
         const double zr = orc_logsumexp(lw, M);

@@ -73,7 +73,7 @@ def lib():
         L.orc_run_fetch.argtypes = [C.c_void_p, dp, dp, dp, dp, ip, dp, dp, dp]
         L.orc_run_free.argtypes = [C.c_void_p]
         L.orc_evidence_sampling.argtypes = [C.c_int64, C.c_int, dp, dp, ip, C.c_int64, C.c_int64,
-                                            C.c_uint64, dp, dp, dp, dp, dp, dp, dp]
+                                            C.c_uint64, C.c_int, dp, dp, dp, dp, dp, dp, dp]
         L.orc_bench_walks.restype = C.c_int64
         L.orc_bench_walks.argtypes = [C.c_void_p, C.c_void_p, dp, C.c_int64, C.c_double, C.c_int64,
                                       C.c_int64, C.c_uint64, C.c_int, dp]
@@ -264,7 +264,7 @@ def nested_sampling(problem: Problem, prior: Prior, pool_size=100, batch_k=1, mc
                      pool_size, nd.value, it.value, ev.value)
 
 
-def evidence_sampling(points, logL, pool, n, nruns=100, seed=1):
+def evidence_sampling(points, logL, pool, n, nruns=100, seed=1, sorted_draws=False):
     """BS:1158-1291 on a sorted sample list.  Returns a dict mirroring the reference keys."""
     points, logL = _f64(points), _f64(logL)
     pool = np.ascontiguousarray(pool, dtype=np.int64)
@@ -272,7 +272,7 @@ def evidence_sampling(points, logL, pool, n, nruns=100, seed=1):
     z, H = np.empty(nruns), np.empty(nruns)
     lwm, lws, sxm, sxs = (np.empty(M) for _ in range(4))
     pm = np.empty((nruns, d))
-    lib().orc_evidence_sampling(M, d, _dp(points), _dp(logL), _ip(pool), n, nruns, seed, _dp(z), _dp(lwm),
+    lib().orc_evidence_sampling(M, d, _dp(points), _dp(logL), _ip(pool), n, nruns, seed, int(sorted_draws), _dp(z), _dp(lwm),
                                 _dp(lws), _dp(sxm), _dp(sxs), _dp(pm), _dp(H))
     return {
         "zSamples": z,

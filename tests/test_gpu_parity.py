@@ -1,0 +1,210 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+
+Tolerances: per-parameter log-likelihoods 1e-12 relative against the __float128 oracle (BASELINE.json
+north_star); integer/index outputs exact; RNG-driven trajectories 1e-9 (libm vs libdevice differ in the
+last ulp of log/sincos)."""
+import numpy as np
+import pytest
+
+from bayesianinference_b200 import configs as cfg
+
+pytestmark = pytest.mark.gpu
+
+RTOL_LOGL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from bayesianinference_b200 import engine
+    engine.init()
+    return engine
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import oracle
+    return oracle
+
+
+def _pair(eng, O, c):
+    gp = eng.Problem.from_config(c)
+    op = O.Problem(c.op, c.d, c.inputs, c.outputs, c.iparam)
+    pr = O.Prior(c.kinds, c.lo, c.hi, c.p0 or None, c.p1 or None)
+    return gp, op, pr
+
+
+def _thetas(O, pr, c, P, seed=900):
+    th = pr.sample(P, seed)
+    # a few rows outside the box / violating the operator constraints -> logzero on both sides
+    if P >= 8:
+        th[1, -1] = -0.3
+        th[3, 0] = c.hi[0] + 1.0
+        th[5, 0] = c.lo[0]
+    return th
+
+
+CASES = {
+    "C1": lambda: cfg.c1_gaussian(),
+    "C1-odd": lambda: cfg.c1_gaussian(N=777, seed=7),
+    "C2-20k": lambda: cfg.c2_polyreg(N=20_000),
+    "C2-deg1": lambda: cfg.c2_polyreg(N=5_001, degree=1),
+    "C2-deg5": lambda: cfg.c2_polyreg(N=4_097, degree=5),
+    "C3-20k": lambda: cfg.c3_logistic(N=20_000),
+    "C3-binary": lambda: cfg.c3_logistic(N=3_000, F=2, K=2),
+    "C4": lambda: cfg.c4_gbm(),
+    "C4-short": lambda: cfg.c4_gbm(T=37),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("P", [1, 33, 300])
+def test_loglike_matches_oracle(eng, O, name, P):
+    c = CASES[name]()
+    gp, op, pr = _pair(eng, O, c)
+    th = _thetas(O, pr, c, P)
+    got = gp.loglike(th)
+    ref64 = op.loglike(th, pr)
+    hi, lo = op.loglike_quad(th)
+    ok = ref64 > 0.5 * O.LOGZERO
+    assert np.array_equal(got[~ok], ref64[~ok]), "constraint violations must give logzero exactly"
+    rel = np.abs((got[ok] - hi[ok]) - lo[ok]) / np.abs(hi[ok])
+    assert rel.max() <= RTOL_LOGL, f"{name}: max rel err vs float128 oracle {rel.max():.3e}"
+    # the fp64 sequential restatement itself sits within the same band of the quad value
+    rel64 = np.abs((ref64[ok] - hi[ok]) - lo[ok]) / np.abs(hi[ok])
+    assert rel64.max() <= 1e-10
+
+
+def test_loglike_empty_and_tiny(eng, O):
+    c = cfg.c1_gaussian(N=1, seed=3)
+    gp, op, pr = _pair(eng, O, c)
+    assert gp.loglike(np.empty((0, 2))).shape == (0,)
+    th = pr.sample(5, 1)
+    np.testing.assert_allclose(gp.loglike(th), op.loglike(th, pr), rtol=1e-13)
+    for N in (2, 3, 65, 129):
+        c = cfg.c2_polyreg(N=N)
+        gp, op, pr = _pair(eng, O, c)
+        th = pr.sample(40, 2)
+        np.testing.assert_allclose(gp.loglike(th), op.loglike(th, pr), rtol=1e-12)
+
+
+def test_loglike_full_size_pins_and_additivity(eng, O):
+    """BASELINE size (N = 1e6): known-answer pin from SURVEY Appendix A and the size-independent
+    property logL(data) = logL(first half) + logL(second half)."""
+    c = cfg.c2_polyreg()
+    gp = eng.Problem.from_config(c)
+    x, y = c.inputs[:, 0], c.outputs[:, 0]
+    X = np.vander(x, 4, increasing=True)
+    coef, *_ = np.linalg.lstsq(X, y, rcond=None)
+    s = np.sqrt(((y - X @ coef) ** 2).sum() / x.size)
+    th = np.concatenate([coef, [s]])[None, :]
+    got = gp.loglike(th)[0]
+    assert abs(got - (-31470.229840)) < 2e-6
+    h = x.size // 2 + 1
+    ca = cfg.Config(c.name, c.op, c.inputs[:h], c.outputs[:h], c.iparam, c.names, c.kinds, c.lo, c.hi)
+    cb = cfg.Config(c.name, c.op, c.inputs[h:], c.outputs[h:], c.iparam, c.names, c.kinds, c.lo, c.hi)
+    pr = O.Prior(c.kinds, c.lo, c.hi)
+    ths = pr.sample(64, 5)
+    full = gp.loglike(ths)
+    parts = eng.Problem.from_config(ca).loglike(ths) + eng.Problem.from_config(cb).loglike(ths)
+    np.testing.assert_allclose(full, parts, rtol=1e-12)
+    # GBM pin
+    c4 = cfg.c4_gbm()
+    g4 = eng.Problem.from_config(c4)
+    assert abs(g4.loglike([[0.08, 0.25]])[0] - (-72297.49504288615)) < 1e-7
+
+
+def test_prior_and_philox(eng, O):
+    for c in (cfg.c1_gaussian(), cfg.c3_logistic(N=100)):
+        gp, op, pr = _pair(eng, O, c)
+        a = gp.sample_prior(257, seed=11, run_id=3)
+        b = pr.sample(257, 11, 3)
+        np.testing.assert_allclose(a, b, rtol=1e-13, atol=1e-13)  # same Philox words, libm vs libdevice exp/log
+        th = np.vstack([b, b * 1.7])
+        np.testing.assert_allclose(gp.logprior(th), pr.logpdf(th), rtol=1e-13)
+
+
+def test_crude_weights_and_evidence_sampling(eng, O):
+    rng = np.random.default_rng(5)
+    n, nd, d = 100, 900, 2
+    M = n + nd
+    logL = np.sort(rng.normal(-120, 8, M))
+    pts = rng.normal(size=(M, d))
+    pool = np.concatenate([np.full(nd, n), np.arange(n, 0, -1)]).astype(np.int64)
+    g = eng.crude_weights(logL, pool, n)
+    lx = O.xvalues_log(n, nd, pool)
+    lw = O.trapezoid_log(lx) + logL
+    np.testing.assert_allclose(g["logX"], lx, rtol=1e-13)
+    np.testing.assert_allclose(g["crude_logw"], lw, rtol=1e-12)
+    z = O.logsumexp(lw)
+    assert abs(g["crude_logZ"] - z) < 1e-11
+    assert abs(g["entropy"] - O.entropy(lw, logL, z)) < 1e-10
+    # reference X sequence BS:785-799 (constant pool): K3 pin of SURVEY 8c
+    np.testing.assert_allclose(g["logX"], O.xvalues_log(n, nd), rtol=1e-12)
+    # Monte-Carlo error estimate: same Philox draws on both sides
+    pool_b = pool.copy()
+    pool_b[:nd] = n - (np.arange(nd) % 8)  # batched replacement pool sizes
+    ev = eng.evidence_sampling(pts, logL, pool_b, n, 50, seed=9)
+    ref = O.evidence_sampling(pts, logL, pool_b, n, 50, seed=9)
+    np.testing.assert_allclose(ev["z"], ref["zSamples"], rtol=1e-11)
+    np.testing.assert_allclose(ev["pmean"], ref["parameterSamples"], rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(ev["slx_mean"], ref["SampledLogX"]["Mean"], rtol=1e-10)
+    np.testing.assert_allclose(ev["logw_mean"], ref["LogPosteriorWeight"]["Mean"], rtol=1e-9)
+    np.testing.assert_allclose(ev["logw_sd"], ref["LogPosteriorWeight"]["StandardError"], rtol=1e-6, atol=1e-9)
+
+
+@pytest.mark.parametrize("K", [1, 8])
+def test_engine_trajectory_matches_oracle(eng, O, K):
+    """Same seed, same Philox addressing, proposal factor frozen per iteration on both sides: the whole
+    nested-sampling trajectory (dead list, live set, crude evidence) must coincide."""
+    c = cfg.c1_gaussian()
+    gp, op, pr = _pair(eng, O, c)
+    start = pr.sample(100, 21, 0)
+    opts = eng.default_options(pool_size=100, batch_k=K, mc_steps=40, max_iter=400, min_iter=100, seed=21)
+    run = eng.RunGroup(gp, opts, start)
+    assert run.advance(0)
+    got = run.fetch(0)
+    ref = O.nested_sampling(op, pr, pool_size=100, batch_k=K, mc_steps=40, max_iter=400, min_iter=100, seed=21,
+                            adapt_in_walk=False, start_points=start)
+    assert got["M"] == ref.logL.size and got["n_deleted"] == ref.n_deleted and got["iterations"] == ref.iterations
+    assert np.array_equal(got["pool"], ref.pool)
+    np.testing.assert_allclose(got["logL"], ref.logL, rtol=1e-9)
+    np.testing.assert_allclose(got["points"], ref.points, rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(got["acc"][~np.isnan(ref.acc)], ref.acc[~np.isnan(ref.acc)], rtol=1e-12)
+    assert np.array_equal(np.isnan(got["acc"]), np.isnan(ref.acc))
+    np.testing.assert_allclose(got["logX"], ref.logX, rtol=1e-12)
+    assert abs(got["crude_logZ"] - ref.crude_logZ) < 1e-8
+    assert abs(got["entropy"] - ref.entropy) < 1e-7
+
+
+def test_engine_logz_c1(eng, O):
+    """LogEvidence within 3 sigma of the quadrature value (K4 pin, SURVEY Appendix A: -114.641064)."""
+    c = cfg.c1_gaussian()
+    gp = eng.Problem.from_config(c)
+    pulls = []
+    for seed in (1, 2, 3, 4):
+        opts = eng.default_options(pool_size=100, batch_k=8, mc_steps=200, max_iter=100000, seed=seed)
+        run = eng.RunGroup(gp, opts)
+        assert run.advance(0)
+        s = run.fetch(0)
+        ev = eng.evidence_sampling(s["points"], s["logL"], s["pool"], 100, 100, seed)
+        mu, sd = ev["z"].mean(), ev["z"].std(ddof=1)
+        assert 0.15 < sd < 0.45
+        pulls.append((mu - c.truth["logZ"]) / sd)
+    assert max(abs(p) for p in pulls) < 3.0, pulls
+    assert abs(np.mean(pulls)) < 1.5, pulls
+
+
+def test_multi_run_group_is_shard_invariant(eng):
+    """Run r of a group equals the same run executed alone (results depend on (seed, run id) only)."""
+    c = cfg.c4_gbm(T=512)
+    gp = eng.Problem.from_config(c)
+    o4 = eng.default_options(pool_size=64, batch_k=8, mc_steps=30, max_iter=300, seed=5, n_runs=4, first_run_id=0)
+    g = eng.RunGroup(gp, o4)
+    assert g.advance(0)
+    o1 = eng.default_options(pool_size=64, batch_k=8, mc_steps=30, max_iter=300, seed=5, n_runs=1, first_run_id=2)
+    s = eng.RunGroup(gp, o1)
+    assert s.advance(0)
+    a, b = g.fetch(2), s.fetch(0)
+    assert a["M"] == b["M"]
+    np.testing.assert_allclose(a["points"], b["points"], rtol=1e-12)
+    np.testing.assert_allclose(a["logL"], b["logL"], rtol=1e-12)
