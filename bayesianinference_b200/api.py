@@ -1,0 +1,491 @@
+"""Host-side mirror of the reference's Wolfram Language API for the nested-sampling path.
+
+Same function names, option names, result keys and error behaviour as the package:
+  defineInferenceProblem   BS:148-308      generateStartingPoints  BS:1042-1097
+  nestedSampling           BS:1099-1136    parallelNestedSampling  BS:1317-1371
+  evidenceSampling         BS:1158-1291    combineRuns             BS:1293-1315
+  inferenceObject          BU:107-138      defineGaussianProcess   GP:201-330
+All numerics run in libbinest.so (CUDA); this file only marshals arguments and assembles associations.
+The Wolfram Language host package (wl/BayesianInferenceB200.wl) is the same layer in the reference's own
+language; it cannot be executed in this image (no Wolfram Engine), so tests drive this mirror.
+
+A symbolic "GeneratingDistribution" is replaced by a descriptor from the fixed operator table
+(SURVEY.md Appendix A mapping); anything else fails like the reference does when LogLikelihood does not
+evaluate: message + inferenceObject[$Failed] (BS:456-459, 308).  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import warnings
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import configs as _cfg
+
+FAILED = "$Failed"
+
+
+# ----------------------------------------------------------------------------------------------------
+# inferenceObject (BU:107-138): an association wrapper with obj["Key"] access
+class inferenceObject:
+    def __init__(self, assoc):
+        self._assoc = assoc
+
+    def __getitem__(self, key):
+        if self.failed:
+            raise KeyError(key)
+        v = self._assoc.get(key, None)
+        if v is None and key not in self._assoc:
+            return Missing("KeyAbsent", key)
+        return v
+
+    def get(self, key, default=None):
+        return default if self.failed else self._assoc.get(key, default)
+
+    def keys(self):
+        return [] if self.failed else [k for k in self._assoc if not k.startswith("_")]
+
+    def Normal(self):  # BU:125
+        return dict(self._assoc) if not self.failed else FAILED
+
+    @property
+    def failed(self):
+        return not isinstance(self._assoc, dict)
+
+    def __contains__(self, key):
+        return (not self.failed) and key in self._assoc
+
+    def __repr__(self):
+        if self.failed:
+            return "inferenceObject[$Failed]"
+        return f"inferenceObject[<|{', '.join(self.keys())}|>]"
+
+
+@dataclass(frozen=True)
+class Missing:
+    reason: str
+    key: str = ""
+
+    def __bool__(self):
+        return False
+
+
+def inferenceObjectQ(x):
+    return isinstance(x, inferenceObject) and not x.failed
+
+
+# ----------------------------------------------------------------------------------------------------
+# distribution descriptors: the fixed operator table
+@dataclass(frozen=True)
+class Polynomial:
+    """Sum_j coefficients[j] * variable^j"""
+    variable: str
+    coefficients: tuple
+
+
+@dataclass(frozen=True)
+class NormalDistribution:
+    mean: object  # parameter name, number (priors) or Polynomial
+    sd: object
+
+
+@dataclass(frozen=True)
+class UniformDistribution:
+    lo: float
+    hi: float
+
+
+@dataclass(frozen=True)
+class CategoricalSoftmax:
+    """Softmax classification with reference class K: logits z_k = b_k + w_k . x (k < K), z_K = 0.
+    params: K-1 blocks (w_1..w_F, b) of parameter names."""
+    params: tuple
+    n_classes: int = 3
+
+
+@dataclass(frozen=True)
+class GeometricBrownianMotionProcess:
+    mu: str
+    sigma: str
+    x0: float = None
+
+
+@dataclass(frozen=True)
+class SquaredExponentialGP:
+    sigma_f: str
+    ell: str
+    sigma_n: str
+
+
+class DefinitionError(ValueError):
+    pass
+
+
+_PARAM_MSG = "defineInferenceProblem::parameters"
+
+
+def _param_normal_form(params):
+    """paramNormalForm BS:133-145: {sym, lo, hi} triples."""
+    out = []
+    for p in params:
+        if isinstance(p, str):
+            out.append((p, -np.inf, np.inf))
+        else:
+            name, lo, hi = p
+            out.append((str(name), float(lo), float(hi)))
+    return out
+
+
+def _prior_spec(prior, params):
+    """ignorancePrior BS:25-64: list entries "LocationParameter" | "ScaleParameter" | distribution."""
+    kinds, p0, p1 = [], [], []
+    if not isinstance(prior, (list, tuple)) or len(prior) != len(params):
+        raise DefinitionError("PriorDistribution must be a list with one entry per parameter")
+    for spec, (_, lo, hi) in zip(prior, params):
+        if spec == "LocationParameter" or isinstance(spec, UniformDistribution):
+            kinds.append(_cfg.PRIOR_UNIFORM); p0.append(0.0); p1.append(1.0)
+        elif spec == "ScaleParameter":
+            kinds.append(_cfg.PRIOR_SCALE); p0.append(0.0); p1.append(1.0)
+        elif isinstance(spec, NormalDistribution) and np.isscalar(spec.mean) and np.isscalar(spec.sd):
+            kinds.append(_cfg.PRIOR_NORMAL_TRUNC); p0.append(float(spec.mean)); p1.append(float(spec.sd))
+        else:
+            raise DefinitionError(f"defineInferenceProblem::prior: unsupported prior {spec!r}")
+    return kinds, p0, p1
+
+
+def _operator_from_distribution(dist, data, names, indep):
+    """Map a "GeneratingDistribution" pattern to (op id, iparam, inputs, outputs) — SURVEY Appendix A."""
+    if isinstance(dist, NormalDistribution) and isinstance(dist.mean, str) and isinstance(dist.sd, str):
+        x = np.asarray(data, dtype=np.float64)
+        if isinstance(data, tuple) or x.ndim > 2 or (x.ndim == 2 and x.shape[1] != 1):
+            raise DefinitionError("NormalDistribution[mu, sigma] needs vector data")
+        if names != [dist.mean, dist.sd]:
+            raise DefinitionError("Parameters must be ordered {mu, sigma}")
+        return _cfg.OP_GAUSSIAN_IID, (0, 0, 0, 0), x.reshape(-1, 1), None
+    if isinstance(dist, NormalDistribution) and isinstance(dist.mean, Polynomial):
+        if not (isinstance(data, tuple) and len(data) == 2):
+            raise DefinitionError("regression data must be (inputs, outputs)")
+        poly = dist.mean
+        if indep is None or list(indep) != [poly.variable]:
+            raise DefinitionError("IndependentVariables must name the polynomial's variable")
+        deg = len(poly.coefficients) - 1
+        if names != list(poly.coefficients) + [dist.sd]:
+            raise DefinitionError("Parameters must be ordered {c_0..c_deg, sigma}")
+        return _cfg.OP_POLYREG, (deg, 0, 0, 0), np.asarray(data[0], float).reshape(-1, 1), np.asarray(data[1], float).reshape(-1, 1)
+    if isinstance(dist, CategoricalSoftmax):
+        x, y = data
+        x = np.asarray(x, float)
+        x = x.reshape(-1, 1) if x.ndim == 1 else x
+        if names != list(dist.params):
+            raise DefinitionError("Parameters must be ordered as the softmax blocks (w_1..w_F, b)")
+        return _cfg.OP_LOGISTIC, (0, dist.n_classes, 0, 0), x, np.asarray(y, float).reshape(-1, 1)
+    if isinstance(dist, GeometricBrownianMotionProcess):
+        t, v = data  # TemporalData adaptor BS:511-515
+        if names != [dist.mu, dist.sigma]:
+            raise DefinitionError("Parameters must be ordered {mu, sigma}")
+        return _cfg.OP_GBM, (0, 0, 0, 0), np.asarray(t, float).reshape(-1, 1), np.asarray(v, float).reshape(-1, 1)
+    if isinstance(dist, SquaredExponentialGP):
+        x, y = data
+        x = np.asarray(x, float)
+        x = x.reshape(-1, 1) if x.ndim == 1 else x
+        return _cfg.OP_GP_SE, (0, 0, x.shape[1], 0), x, np.asarray(y, float).reshape(-1, 1)
+    # the reference would try LogLikelihood[dist, ...] symbolically (BS:452-459); only the table runs on the GPU
+    raise DefinitionError(f"defineInferenceProblem::logLike: {dist!r} is not in the GPU operator table")
+
+
+def _backend(backend):
+    if backend is not None:
+        return backend
+    from . import engine
+    return engine
+
+
+def defineInferenceProblem(rules=None, _backend_override=None, **kw):
+    """BS:148-308.  Keys: "Data", "Parameters", "PriorDistribution", "GeneratingDistribution",
+    "IndependentVariables".  Returns inferenceObject[...] or inferenceObject[$Failed] (+ a warning carrying the
+    reference's message tag)."""
+    a = dict(rules or {})
+    a.update(kw)
+    try:
+        for k in ("Data", "Parameters", "GeneratingDistribution", "PriorDistribution"):
+            if k not in a:
+                raise DefinitionError(f"defineInferenceProblem::insuffInfo: missing {k}")  # BS:148-152
+        params = _param_normal_form(a["Parameters"])
+        names = [p[0] for p in params]
+        kinds, p0, p1 = _prior_spec(a["PriorDistribution"], params)
+        op, iparam, inputs, outputs = _operator_from_distribution(a["GeneratingDistribution"], a["Data"], names,
+                                                                   a.get("IndependentVariables"))
+        be = _backend(_backend_override)
+        prob = be.Problem(op, inputs, outputs, iparam, kinds, [p[1] for p in params], [p[2] for p in params], p0, p1)
+        # BS:276-298: both functions must return real machine numbers on random points of the box
+        test = prob.sample_prior(100, seed=20260, run_id=0)
+        ll, lp = prob.loglike(test), prob.logprior(test)
+        if not (np.all(np.isfinite(ll)) and np.all(np.isfinite(lp))):
+            raise DefinitionError("defineInferenceProblem::failed: functions are not numeric on the parameter box")
+    except DefinitionError as e:
+        warnings.warn(str(e))
+        return inferenceObject(FAILED)
+    a.update({
+        "Parameters": params, "ParameterSymbols": names,
+        "LogLikelihoodFunction": prob.loglike,   # Listable, BS:499
+        "LogPriorPDFFunction": prob.logprior,    # BS:410-426
+        "_problem": prob, "_backend": be,
+    })
+    return inferenceObject(a)
+
+
+def defineGaussianProcess(data, kernel: SquaredExponentialGP, parameters, prior, **rest):
+    """GP:201-330 for the squared-exponential kernel + nugget (the operator of BASELINE config C5)."""
+    return defineInferenceProblem(Data=data, GeneratingDistribution=kernel, Parameters=parameters,
+                                  PriorDistribution=prior, **rest)
+
+
+def generateStartingPoints(obj, n, seed=1):
+    """BS:1046-1068: n i.i.d. draws from the prior, stored under "StartingPoints"."""
+    if not inferenceObjectQ(obj):
+        return inferenceObject(FAILED)
+    a = obj.Normal()
+    a["StartingPoints"] = a["_problem"].sample_prior(int(n), seed=seed, run_id=0)
+    return inferenceObject(a)
+
+
+# ----------------------------------------------------------------------------------------------------
+NS_DEFAULTS = {  # Options[nestedSampling] BS:837-851 (+ engine knobs)
+    "SamplePoolSize": 100, "StartingPoints": "Automatic", "MaxIterations": 10000, "MinIterations": 100,
+    "MonteCarloMethod": "Automatic", "MonteCarloSteps": 200, "TerminationFraction": 0.01, "Monitor": True,
+    "LogLikelihoodMaximum": "Automatic", "MinMaxAcceptanceRate": (0, 1),
+    "PostProcessSamplingRuns": 100, "EmpiricalPosteriorDistributionType": "Simple",
+    "BatchSize": 1, "Seed": 1,
+}
+
+
+def _ns_options(opts, allowed):
+    bad = [k for k in opts if k not in allowed]
+    if bad:
+        raise TypeError(f"Unknown option(s) {bad}")  # OptionValue::nodef
+    o = dict(NS_DEFAULTS)
+    o.update(opts)
+    steps = o["MonteCarloSteps"]
+    if not isinstance(steps, (int, np.integer)):  # BS:869-878
+        warnings.warn(f"nestedSampling::MCSteps: cannot use value {steps!r}; defaulting to 200")
+        o["MonteCarloSteps"] = 200
+    return o
+
+
+def _engine_options(be, o, n_runs=1, first_run_id=0):
+    lo, hi = o["MinMaxAcceptanceRate"]
+    return be.default_options(pool_size=int(o["SamplePoolSize"]), batch_k=int(o["BatchSize"]),
+                              mc_steps=int(o["MonteCarloSteps"]), max_iter=int(o["MaxIterations"]),
+                              min_iter=int(o["MinIterations"]), term_frac=float(o["TerminationFraction"]),
+                              acc_min=float(lo), acc_max=float(hi), seed=int(o["Seed"]),
+                              first_run_id=int(first_run_id), n_runs=int(n_runs))
+
+
+def _samples_table(s):
+    """Columnar form of the per-sample records (BS:907-912, 1009-1015, 825-828)."""
+    return {
+        "Point": s["points"], "LogLikelihood": s["logL"], "LogPriorPDF": s["logPrior"],
+        "AcceptanceRate": s["acc"],  # NaN = Missing["InitialSample"] (BS:911)
+        "PoolSize": s["pool"], "LogX": s["logX"], "X": np.exp(s["logX"]),
+        "CrudeLogPosteriorWeight": s["crude_logw"],
+    }
+
+
+def _result_assoc(s, n):
+    M = s["logL"].size
+    pts = s["points"]
+    return {  # BS:1026-1032
+        "Samples": _samples_table(s), "SamplePoolSize": int(n), "GeneratedNestedSamples": int(M - n),
+        "TotalSamples": int(M), "ParameterRanges": np.stack([pts.min(0), pts.max(0)], 1),
+    }
+
+
+def nestedSampling(obj, _backend_override=None, **opts):
+    """BS:1099-1136.  Options as in the reference, plus "BatchSize" (points replaced per iteration; 1 is the
+    reference scheme) and "Seed"."""
+    if not inferenceObjectQ(obj):
+        return inferenceObject(FAILED)
+    o = _ns_options(opts, NS_DEFAULTS)
+    a = obj.Normal()
+    be = _backend(_backend_override or a.get("_backend"))
+    start = o["StartingPoints"]
+    if isinstance(start, str):
+        start = a.get("StartingPoints")
+    if start is not None:
+        start = np.asarray(start, dtype=np.float64)
+        if start.ndim != 2 or start.shape[1] != len(a["Parameters"]):
+            return inferenceObject(FAILED)
+        o["SamplePoolSize"] = start.shape[0]
+    run = be.RunGroup(a["_problem"], _engine_options(be, o), start)  # "Bad likelihood function" raises (BS:920)
+    run.advance(0)
+    s = run.fetch(0)
+    run.close()
+    a.update(_result_assoc(s, o["SamplePoolSize"]))
+    if start is not None:
+        a["StartingPoints"] = start
+    ev = evidenceSampling(a, a["ParameterSymbols"], _backend_override=be,
+                          PostProcessSamplingRuns=o["PostProcessSamplingRuns"],
+                          EmpiricalPosteriorDistributionType=o["EmpiricalPosteriorDistributionType"], Seed=o["Seed"])
+    return inferenceObject(ev)
+
+
+def _mean_and_error(x, axis=0):  # meanAndError BS:1138-1156: Mean and (n-1) StandardDeviation
+    x = np.asarray(x)
+    return {"Mean": x.mean(axis), "StandardError": x.std(axis, ddof=1)}
+
+
+def evidenceSampling(obj_or_assoc, paramNames=None, _backend_override=None, **opts):
+    """BS:1158-1291.  Accepts an inferenceObject (returns one) or an association (returns one)."""
+    wrap = isinstance(obj_or_assoc, inferenceObject)
+    if wrap and not inferenceObjectQ(obj_or_assoc):
+        return inferenceObject(FAILED)
+    a = obj_or_assoc.Normal() if wrap else dict(obj_or_assoc)
+    o = {"PostProcessSamplingRuns": 100, "EmpiricalPosteriorDistributionType": "Simple", "Seed": 1}
+    bad = [k for k in opts if k not in o]
+    if bad:
+        raise TypeError(f"Unknown option(s) {bad}")
+    o.update(opts)
+    be = _backend(_backend_override or a.get("_backend"))
+    names = paramNames if paramNames is not None else a.get("ParameterSymbols", [])
+    S = a["Samples"]
+    n = int(a["SamplePoolSize"])
+    # calculateWeightsCrude: samples must be sorted by {logL, point} (BS:814) — restore that order first
+    order = np.lexsort(tuple(S["Point"][:, j] for j in range(S["Point"].shape[1] - 1, -1, -1)) + (S["LogLikelihood"],))
+    S = {k: v[order] for k, v in S.items()}
+    pool = S.get("PoolSize")
+    M = S["LogLikelihood"].size
+    if pool is None:
+        pool = np.concatenate([np.full(M - n, n), np.arange(n, 0, -1)]).astype(np.int64)
+    cw = be.crude_weights(S["LogLikelihood"], pool, n)
+    S["LogX"], S["X"], S["CrudeLogPosteriorWeight"] = cw["logX"], np.exp(cw["logX"]), cw["crude_logw"]
+    out = dict(a)
+    out.update({  # BS:1183-1194
+        "CrudeLogEvidence": cw["crude_logZ"], "LogLikelihoodMaximum": cw["logLmax"],
+        "LogEstimatedMissingEvidence": cw["log_missing"], "CrudeRelativeEntropy": cw["entropy"],
+    })
+    nruns = o["PostProcessSamplingRuns"]
+    if not (isinstance(nruns, (int, np.integer)) and nruns > 0):  # BS:1195-1197
+        out["Samples"] = S
+        return inferenceObject(out) if wrap else out
+    ev = be.evidence_sampling(S["Point"], S["LogLikelihood"], pool, n, int(max(nruns, 2)), int(o["Seed"]))
+    S["CrudeLogPosteriorWeight"] = S["CrudeLogPosteriorWeight"] - cw["crude_logZ"]          # BS:1236
+    S["CrudePosteriorWeight"] = np.exp(S["CrudeLogPosteriorWeight"])                         # BS:1237
+    S["SampledLogX"] = {"Mean": ev["slx_mean"], "StandardError": ev["slx_sd"]}                # BS:1244
+    S["LogPosteriorWeight"] = {"Mean": ev["logw_mean"], "StandardError": ev["logw_sd"]}       # BS:1245-1250
+    srt = np.argsort(-S["CrudeLogPosteriorWeight"], kind="stable")                            # BS:1241
+    S = {k: ({kk: vv[srt] for kk, vv in v.items()} if isinstance(v, dict) else v[srt]) for k, v in S.items()}
+    pme = _mean_and_error(ev["pmean"], 0)
+    out.update({
+        "Samples": S,
+        "LogEvidence": {"Mean": float(ev["z"].mean()), "StandardError": float(ev["z"].std(ddof=1))},  # BS:1254
+        "ParameterExpectedValues": (  # BS:1255-1262
+            {nm: {"Mean": float(pme["Mean"][i]), "StandardError": float(pme["StandardError"][i])}
+             for i, nm in enumerate(names)} if len(names) == ev["pmean"].shape[1] else pme),
+        "RelativeEntropy": {"Mean": float(ev["H"].mean()), "StandardError": float(ev["H"].std(ddof=1))},  # BS:1263
+        "EmpiricalPosteriorDistribution": {"Type": o["EmpiricalPosteriorDistributionType"],  # BS:1269-1288
+                                           "Weights": S["CrudePosteriorWeight"], "Points": S["Point"]},
+    })
+    return inferenceObject(out) if wrap else out
+
+
+def _merge_samples(tables, pool_sizes):
+    """combineRuns BS:1293-1297: Join, DeleteDuplicatesBy Point (first kept), SortBy {logL, Point};
+    per-sample pool size = sum over runs of that run's pool size at the sample's likelihood level."""
+    pts = np.concatenate([t["Point"] for t in tables])
+    cols = {k: np.concatenate([t[k] for t in tables]) for k in ("LogLikelihood", "LogPriorPDF", "AcceptanceRate")}
+    rid = np.concatenate([np.full(t["LogLikelihood"].size, i) for i, t in enumerate(tables)])
+    _, first = np.unique(pts, axis=0, return_index=True)
+    keep = np.sort(first)
+    pts, rid = pts[keep], rid[keep]
+    cols = {k: v[keep] for k, v in cols.items()}
+    order = np.lexsort(tuple(pts[:, j] for j in range(pts.shape[1] - 1, -1, -1)) + (cols["LogLikelihood"],))
+    pts, rid = pts[order], rid[order]
+    cols = {k: v[order] for k, v in cols.items()}
+    pool = np.zeros(pts.shape[0], dtype=np.int64)
+    for t, n in zip(tables, pool_sizes):
+        o = np.lexsort(tuple(t["Point"][:, j] for j in range(t["Point"].shape[1] - 1, -1, -1)) + (t["LogLikelihood"],))
+        tl = t["LogLikelihood"][o]
+        tp = t.get("PoolSize")
+        tp = tp[o] if tp is not None else np.concatenate([np.full(tl.size - n, n), np.arange(n, 0, -1)])
+        idx = np.searchsorted(tl, cols["LogLikelihood"], side="left")
+        pool += np.where(idx < tl.size, tp[np.minimum(idx, tl.size - 1)], 0)
+    out = {"Point": pts, "PoolSize": pool, "RunIndex": rid}
+    out.update(cols)
+    return out
+
+
+def combineRuns(*results, _backend_override=None, **opts):
+    """BS:1293-1315."""
+    if len(results) < 1 or not all(inferenceObjectQ(r) for r in results):
+        return inferenceObject(FAILED)
+    assocs = [r.Normal() for r in results]
+    pools = [int(a["SamplePoolSize"]) for a in assocs]
+    merged = _merge_samples([a["Samples"] for a in assocs], pools)
+    n_tot = int(sum(pools))
+    M = merged["LogLikelihood"].size
+    a = dict(assocs[0])
+    a.update({
+        "Samples": merged,
+        "LogLikelihoodMaximum": max(float(np.max(x["Samples"]["LogLikelihood"])) for x in assocs),  # BS:1306
+        "SamplePoolSize": n_tot, "GeneratedNestedSamples": M - n_tot, "TotalSamples": M,          # BS:1307-1309
+    })
+    # the last n_tot samples play the role of the live set; their pool sizes follow BS:791-797
+    a["Samples"]["PoolSize"][M - n_tot:] = np.arange(n_tot, 0, -1)
+    return inferenceObject(evidenceSampling(a, a.get("ParameterSymbols"), _backend_override=_backend_override, **opts))
+
+
+def _shard(n_runs, rank, world):
+    """contiguous block of run ids for this rank"""
+    base, rem = divmod(n_runs, world)
+    lo = rank * base + min(rank, rem)
+    return lo, base + (1 if rank < rem else 0)
+
+
+def parallelNestedSampling(obj, _backend_override=None, **opts):
+    """BS:1317-1371.  "ParallelRuns" independent runs, each drawing its own starting points, advanced in lock
+    step on the GPU (one library call instead of ParallelTable over subkernels) and merged with combineRuns.
+    Under torch.distributed (one process per GPU) the runs are sharded across ranks with no data-path
+    collective; the per-run sample lists are gathered and every rank returns the merged object."""
+    if not inferenceObjectQ(obj):
+        return inferenceObject(FAILED)
+    allowed = dict(NS_DEFAULTS)
+    allowed["ParallelRuns"] = 4  # BS:1369
+    o = _ns_options(opts, allowed)
+    R = int(o.get("ParallelRuns", 4))
+    a = obj.Normal()
+    if a.get("StartingPoints") is not None:  # BS:1320-1332
+        n0 = len(a["StartingPoints"])
+        warnings.warn("parallelNestedSampling::startingPts: pre-specified starting points are ignored; "
+                      f'continuing with "SamplePoolSize" -> {n0}')
+        o["SamplePoolSize"] = n0
+        a.pop("StartingPoints")
+    be = _backend(_backend_override or a.get("_backend"))
+    rank, world = 0, 1
+    dist = None
+    try:
+        import torch.distributed as dist_mod
+        if dist_mod.is_available() and dist_mod.is_initialized():
+            dist = dist_mod
+            rank, world = dist.get_rank(), dist.get_world_size()
+    except ImportError:
+        pass
+    first, count = _shard(R, rank, world)
+    local = []
+    if count > 0:
+        grp = be.RunGroup(a["_problem"], _engine_options(be, o, n_runs=count, first_run_id=first), None)
+        grp.advance(0)
+        local = [(first + i, grp.fetch(i)) for i in range(count)]
+        grp.close()
+    if dist is not None and world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, local)  # host merge only: no collective on the data path
+        local = [x for part in gathered for x in part]
+    local.sort(key=lambda t: t[0])
+    n = int(o["SamplePoolSize"])
+    runs = []
+    for _, s in local:
+        ra = dict(a)
+        ra.update(_result_assoc(s, n))
+        runs.append(inferenceObject(ra))
+    return combineRuns(*runs, _backend_override=be, PostProcessSamplingRuns=o["PostProcessSamplingRuns"],
+                       EmpiricalPosteriorDistributionType=o["EmpiricalPosteriorDistributionType"], Seed=o["Seed"])

@@ -98,15 +98,14 @@ void build_walk_graph(binest_run &r) {
     const cudaStream_t s = r.stream;
     dispatch_op(p, [&](auto op) {
         using OP = decltype(op);
-        const dim3 sgrid((P + 127) / 128), sblock(128);
-        const dim3 lgrid(r.geom.G, r.geom.pgroups), lblock(r.geom.nwarps * 32);
+        r.geom = stream_geom<OP>(p, P);
+        r.partials.alloc((size_t)r.geom.Gs * r.prm.Ps);
+        const dim3 sgrid((P * 32 + 255) / 256), sblock(256);  // one warp per walker
         BN_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
         for (int step = 0; step <= S; ++step) {
-            walk_step_kernel<OP><<<sgrid, sblock, 0, s>>>(r.prm, r.A, p.prior, r.partials.p, r.geom.G, (double)p.rows,
-                                                         p.cst, step == S ? 1 : 0);
-            if (step < S)
-                loglike_stream_kernel<OP><<<lgrid, lblock, 0, s>>>(p.data.p, p.rows, r.geom.rows_per_cta, r.w_prop.p,
-                                                                  P, r.prm.Ps, r.partials.p);
+            walk_step_kernel<OP><<<sgrid, sblock, 0, s>>>(r.prm, r.A, p.prior, r.partials.p, r.geom.G, r.geom.Gs,
+                                                         (double)p.rows, p.cst, step == S ? 1 : 0);
+            if (step < S) launch_loglike<OP>(p, r.w_prop.p, P, r.prm.Ps, r.partials.p, r.geom, s, false);
         }
         cudaGraph_t g;
         BN_CUDA(cudaStreamEndCapture(s, &g));
@@ -177,8 +176,6 @@ int binest_run_create(binest_problem *p, const binest_options *o, const double *
         r->w_prop_logPr.alloc(Ps); r->w_mean.alloc(d * Ps); r->w_cov.alloc(d * d * Ps);
         r->w_flags.alloc(Ps); r->w_nacc.alloc(Ps); r->w_steps.alloc(Ps);
         r->w_prop.zero(r->stream); r->w_theta.zero(r->stream); r->w_flags.zero(r->stream);
-        r->geom = stream_geom(*p, q.R * q.K);
-        r->partials.alloc((size_t)r->geom.G * Ps);
         BN_CUDA(cudaMallocHost(&r->h_state, sizeof(RunState) * q.R));
         BN_CUDA(cudaMallocHost(&r->h_unfrozen, sizeof(int)));
         BN_CUDA(cudaEventCreate(&r->ev0));
@@ -434,20 +431,20 @@ int binest_bench_loglike(binest_problem *p, int64_t P, int64_t reps, int64_t war
         BN_CUDA(cudaMemcpyAsync(soa.p, hs.data(), sizeof(double) * hs.size(), cudaMemcpyHostToDevice, p->stream));
         const size_t flush_n = (size_t)256 << 20;  // 256 MiB > 126 MB L2
         if (flush_l2) flush.alloc(flush_n / sizeof(double));
-        const StreamGeom g = stream_geom(*p, (int)P);
-        DevBuf<double> partials((size_t)g.G * Ps);
         cudaEvent_t e0, e1, e2;
         BN_CUDA(cudaEventCreate(&e0)); BN_CUDA(cudaEventCreate(&e1)); BN_CUDA(cudaEventCreate(&e2));
         double tk = 0.0, tt = 0.0;
         dispatch_op(*p, [&](auto op) {
             using OP = decltype(op);
+            const StreamGeom g = stream_geom<OP>(*p, (int)P);
+            DevBuf<double> partials((size_t)g.Gs * Ps);
             for (int64_t it = 0; it < warmup + reps; ++it) {
                 if (flush_l2) BN_CUDA(cudaMemsetAsync(flush.p, it & 0xff, flush_n, p->stream));
                 BN_CUDA(cudaEventRecord(e0, p->stream));
-                launch_loglike<OP>(*p, soa.p, (int)P, Ps, partials.p, g);
+                launch_loglike<OP>(*p, soa.p, (int)P, Ps, partials.p, g, p->stream);
                 BN_CUDA(cudaEventRecord(e1, p->stream));
-                loglike_finalize_kernel<OP><<<(unsigned)((P + 127) / 128), 128, 0, p->stream>>>(
-                    soa.p, (int)P, Ps, partials.p, g.G, (double)p->rows, p->cst, p->prior, g_logzero, out.p);
+                loglike_finalize_kernel<OP><<<(unsigned)((P * 32 + 255) / 256), 256, 0, p->stream>>>(
+                    soa.p, (int)P, Ps, partials.p, g.G, g.Gs, (double)p->rows, p->cst, p->prior, g_logzero, out.p);
                 BN_LAUNCH_CHECK();
                 BN_CUDA(cudaEventRecord(e2, p->stream));
                 BN_CUDA(cudaEventSynchronize(e2));

@@ -1,13 +1,16 @@
 // loglike.cuh — the batched log-likelihood reduction  logL(theta_w) = Sum_i logpdf(theta_w; row_i)
 // for P parameter vectors over N data rows (BS:492 / BS:581 evaluated for a whole batch of walkers).
 //
-// Mapping (B200): lane = walker.  A CTA of up to 8 warps owns up to 256 parameter vectors (their
-// derived coefficients live in registers) and a contiguous slice of the data.  The slice is streamed
-// through shared memory in 16 KiB tiles by the TMA engine (cp.async.bulk -> SASS UBLKCP, completion on
-// an mbarrier, double buffered); every warp reads each row with one broadcast LDS and spends the
-// operator's DFMA sequence on it, so the fp64 pipe — not HBM/L2 — is the bound.
-// Partial sums go to partials[cta][walker] and are combined in a fixed order by the consumer
-// (finalize kernel or the walk's accept kernel), so results are reproducible run to run.
+// Mapping (B200).  A CTA owns 32*TW walkers and a contiguous slice of the data rows:
+//   * lane l holds the derived coefficients of TW walkers in registers (walkers l, l+32, ...);
+//   * the slice is streamed through shared memory in 16 KiB tiles by the TMA engine
+//     (cp.async.bulk -> SASS UBLKCP, completion on an mbarrier, double buffered);
+//   * the 8 warps split the rows of each tile; a row is read with one broadcast LDS.128 and
+//     feeds TW DFMA sequences, so the shared-memory return path (128 B/clk/SM = one LDS.128 per
+//     4 clk per warp) stays below the fp64 pipe (first version, TW = 1, was LDS-bound at 65 %);
+//   * per-warp sums are combined across warps in shared memory in a fixed order and written to
+//     partials[walker][cta]; the consumer (finalize kernel / walk step) sums them in a fixed order.
+// The fp64 pipe — not HBM/L2 — is the bound when P >= ~11 walkers share a tile.
 #pragma once
 #include "operators.cuh"
 
@@ -15,29 +18,25 @@ namespace binest {
 
 constexpr int kTileBytes = 16384;
 constexpr int kStages = 2;
-constexpr int kMaxWarps = 8;
+constexpr int kWarps = 8;
 
 template <class OP>
 __host__ __device__ constexpr int tile_rows() {
     return (kTileBytes / (8 * OP::NCOL)) & ~1;
 }
 
-template <class OP>
-__global__ void __launch_bounds__(kMaxWarps * 32)
+template <class OP, int TW>
+__global__ void __launch_bounds__(kWarps * 32)
 loglike_stream_kernel(const double *__restrict__ data, long long rows, long long rows_per_cta,
                       const double *__restrict__ theta /* SoA [D][Ps] */, int P, int Ps,
-                      double *__restrict__ partials /* [gridDim.x][Ps] */) {
+                      double *__restrict__ partials /* [Ps][Gs] */, int Gs) {
     constexpr int TR = tile_rows<OP>();
     constexpr int NCOL = OP::NCOL;
     __shared__ __align__(128) double tiles[kStages][TR * NCOL];
     __shared__ uint64_t full[kStages];
 
-    const int w = blockIdx.y * blockDim.x + threadIdx.x;
-    double th[OP::D];
-#pragma unroll
-    for (int j = 0; j < OP::D; ++j) th[j] = (w < P) ? theta[(size_t)j * Ps + w] : 1.0;
-    bool ok;
-    const typename OP::Coef c = OP::prepare(th, ok);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int wbase = blockIdx.y * (32 * TW);
 
     const long long r0 = (long long)blockIdx.x * rows_per_cta;
     const long long r1 = (r0 + rows_per_cta < rows) ? r0 + rows_per_cta : rows;
@@ -61,56 +60,93 @@ loglike_stream_kernel(const double *__restrict__ data, long long rows, long long
     if (threadIdx.x == 0)
         for (int t = 0; t < kStages && t < ntiles; ++t) issue(t);
 
-    double acc0 = 0.0, acc1 = 0.0;
+    // per-datum coefficients of the lane's TW walkers (loaded while the first tiles are in flight)
+    typename OP::Row c[TW];
+#pragma unroll
+    for (int t = 0; t < TW; ++t) {
+        const int w = wbase + lane + 32 * t;
+        double th[OP::D];
+#pragma unroll
+        for (int j = 0; j < OP::D; ++j) th[j] = (w < P) ? theta[(size_t)j * Ps + w] : 1.0;
+        c[t] = OP::make_row(th);
+    }
+
+    double acc[TW];
+#pragma unroll
+    for (int t = 0; t < TW; ++t) acc[t] = 0.0;
+
     for (int t = 0; t < ntiles; ++t) {
         const int s = t % kStages;
         mbar_wait(&full[s], (uint32_t)((t / kStages) & 1));
         const double *__restrict__ tile = &tiles[s][0];
         const long long a = r0 + (long long)t * TR;
         const int nr = (int)((r1 - a < TR) ? (r1 - a) : TR);
-        int i = 0;
-#pragma unroll 4
-        for (; i + 1 < nr; i += 2) {
-            OP::row(c, tile + (size_t)i * NCOL, acc0);
-            OP::row(c, tile + (size_t)(i + 1) * NCOL, acc1);
-        }
-        if (i < nr) OP::row(c, tile + (size_t)i * NCOL, acc0);
+        // one row at a time for all TW walkers of the lane: the row operands are shared by TW consecutive
+        // DFMAs (register-reuse cache), which keeps each DFMA at two distinct register reads — three
+        // distinct 64-bit sources issue at 2/3 rate on sm_100 (scripts/dfma_patterns.cu)
+#pragma unroll 2
+        for (int i = wid; i < nr; i += kWarps) OP::template rows<TW>(c, tile + (size_t)i * NCOL, acc);
         __syncthreads();  // everyone is done with stage s before the TMA engine refills it
         if (threadIdx.x == 0 && t + kStages < ntiles) issue(t + kStages);
     }
-    if (w < Ps) partials[(size_t)blockIdx.x * Ps + w] = acc0 + acc1;
+
+    // fixed-order cross-warp combine (reuses the tile buffer), then one partial per (walker, CTA)
+    static_assert(kStages * TR * NCOL >= kWarps * 32 * TW, "tile buffer too small for the cross-warp combine");
+    double *red = &tiles[0][0];  // [kWarps][32*TW]
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < TW; ++u) red[wid * (32 * TW) + lane + 32 * u] = acc[u];
+    __syncthreads();
+    for (int k = threadIdx.x; k < 32 * TW; k += blockDim.x) {
+        double sum = 0.0;
+#pragma unroll
+        for (int q = 0; q < kWarps; ++q) sum += red[q * (32 * TW) + k];
+        const int w = wbase + k;
+        if (w < Ps) partials[(size_t)w * Gs + blockIdx.x] = sum;
+    }
 }
 
-// fixed-order combine of the per-CTA partials + operator epilogue + constraint guards
+// fixed-order combine of the per-CTA partials of one walker by one warp (all lanes get the sum)
+__device__ __forceinline__ double combine_partials_warp(const double *__restrict__ partials, int G, int Gs, int w,
+                                                        int lane) {
+    double s = 0.0;
+    for (int g = lane; g < G; g += 32) s += partials[(size_t)w * Gs + g];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    return s;
+}
+
+// operator epilogue + operator constraints (RuntimeErrorHandler -> logzero, BS:500-503)
 template <class OP>
-__device__ __forceinline__ double loglike_combine(const double (&th)[OP::D], const double *__restrict__ partials,
-                                                  int G, int Ps, int w, double rows, double cst, double logzero) {
+__device__ __forceinline__ double loglike_finish(const double (&th)[OP::D], double sum, double rows, double cst,
+                                                 double logzero) {
     bool ok;
     const typename OP::Coef c = OP::prepare(th, ok);
-    double s = 0.0;
-    for (int g = 0; g < G; ++g) s += partials[(size_t)g * Ps + w];
-    const double v = OP::finish(c, s, rows, cst);
-    return (ok && isfinite(v)) ? v : logzero;  // RuntimeErrorHandler -> logzero, BS:500-503
+    const double v = OP::finish(c, sum, rows, cst);
+    return (ok && isfinite(v)) ? v : logzero;
 }
 
+// one warp per walker
 template <class OP>
 __global__ void loglike_finalize_kernel(const double *__restrict__ theta, int P, int Ps,
-                                        const double *__restrict__ partials, int G, double rows, double cst,
+                                        const double *__restrict__ partials, int G, int Gs, double rows, double cst,
                                         const __grid_constant__ PriorSpec prior, double logzero,
                                         double *__restrict__ out) {
-    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (w >= P) return;
+    const double s = combine_partials_warp(partials, G, Gs, w, lane);
     double th[OP::D];
 #pragma unroll
     for (int j = 0; j < OP::D; ++j) th[j] = theta[(size_t)j * Ps + w];
-    double v = loglike_combine<OP>(th, partials, G, Ps, w, rows, cst, logzero);
+    double v = loglike_finish<OP>(th, s, rows, cst, logzero);
     if (!in_box<OP::D>(prior, th)) v = logzero;  // If[constraints[theta], Sum[...], logzero] BS:491-494
-    out[w] = v;
+    if (lane == 0) out[w] = v;
 }
 
 // log prior density for a batch (BS:410-426); theta SoA [d][Ps]
-static __global__ void logprior_kernel(const double *__restrict__ theta, int P, int Ps, const __grid_constant__ PriorSpec prior,
-                                double logzero, double *__restrict__ out) {
+static __global__ void logprior_kernel(const double *__restrict__ theta, int P, int Ps,
+                                       const __grid_constant__ PriorSpec prior, double logzero,
+                                       double *__restrict__ out) {
     const int w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= P) return;
     double th[BINEST_MAXD];
@@ -120,8 +156,8 @@ static __global__ void logprior_kernel(const double *__restrict__ theta, int P, 
 
 // generateStartingPoints (BS:1055-1068): i.i.d. prior draws by inverse CDF (rejection from the parent
 // normal for the truncated case); out row-major [n][d].  Same Philox addressing as the oracle.
-static __global__ void sample_prior_kernel(const __grid_constant__ PriorSpec prior, long long n, unsigned long long seed,
-                                    unsigned run_id, double *__restrict__ out) {
+static __global__ void sample_prior_kernel(const __grid_constant__ PriorSpec prior, long long n,
+                                           unsigned long long seed, unsigned run_id, double *__restrict__ out) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     for (int j = 0; j < prior.d; ++j) {

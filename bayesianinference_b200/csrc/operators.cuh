@@ -7,10 +7,16 @@
 // Per-datum formulas: SURVEY.md §8a (WL LogLikelihood closed forms).  The parameter-independent
 // additive constants are kept, because LogEvidence and the 1e-12 logL parity depend on them.
 //
-// Interface (lane = walker: every thread owns one parameter vector, rows are broadcast from smem):
+// Interface (lane = walker: every lane owns TW parameter vectors, rows are broadcast from smem):
 //   D      number of parameters             NCOL  fp64 columns per device row
-//   Coef   per-theta derived coefficients   prepare(th, ok) -> Coef   (ok = operator constraints)
-//   row(coef, r, acc)   accumulate one datum      finish(coef, acc, rows, cst) -> logL
+//   TW_MAX walkers register-tiled per lane
+//   Row    per-theta coefficients used per datum (make_row); Coef = those of the epilogue only
+//          prepare(th, ok) -> Coef   (ok = operator constraints)
+//   rows<TW>(coef[TW], r, acc[TW])   accumulate one datum for TW walkers.  Written step-major (the same
+//       Horner step for all TW walkers back to back) so that consecutive DFMAs share the row operand:
+//       on sm_100 a DFMA with three distinct 64-bit register sources issues at 2/3 rate, with a shared
+//       operand in the reuse cache at full rate (measured: scripts/dfma_patterns.cu).
+//   finish(coef, acc, rows, cst) -> logL
 #pragma once
 #include "common.cuh"
 
@@ -18,15 +24,22 @@ namespace binest {
 
 // ------------------------------------------------------------------ NormalDistribution[mu, sigma], i.i.d. data
 struct OpGaussian {
-    static constexpr int D = 2, NCOL = 1;
+    static constexpr int D = 2, NCOL = 1, TW_MAX = 8;
     struct Coef { double mu, h, lognorm; };
+    struct Row { double mu; };
+    __device__ __forceinline__ static Row make_row(const double (&th)[D]) { return Row{th[0]}; }
     __device__ static Coef prepare(const double (&th)[D], bool &ok) {
         ok = th[1] > 0.0;  // DistributionParameterAssumptions, BS:439
         return Coef{th[0], 1.0 / (2.0 * th[1] * th[1]), -log(th[1]) - kHalfLog2Pi};
     }
-    __device__ __forceinline__ static void row(const Coef &c, const double *__restrict__ r, double &acc) {
-        const double e = r[0] - c.mu;
-        acc = fma(e, e, acc);
+    template <int TW>
+    __device__ __forceinline__ static void rows(const Row (&c)[TW], const double *__restrict__ r, double (&acc)[TW]) {
+        const double x = r[0];
+        double e[TW];
+#pragma unroll
+        for (int u = 0; u < TW; ++u) e[u] = x - c[u].mu;
+#pragma unroll
+        for (int u = 0; u < TW; ++u) acc[u] = fma(e[u], e[u], acc[u]);
     }
     __device__ static double finish(const Coef &c, double acc, double rows, double) {
         return rows * c.lognorm - c.h * acc;
@@ -36,26 +49,38 @@ struct OpGaussian {
 // ------------------------------------------------------------------ NormalDistribution[Sum_j c_j x^j, sigma]
 template <int DEG>
 struct OpPolyReg {
-    static constexpr int D = DEG + 2, NCOL = 2;
-    struct Coef { double c[DEG + 1]; double h, lognorm; };
-    __device__ static Coef prepare(const double (&th)[D], bool &ok) {
-        Coef c;
+    static constexpr int D = DEG + 2, NCOL = 2, TW_MAX = 8;
+    struct Coef { double h, lognorm; };
+    struct Row { double c[DEG + 1]; };
+    __device__ __forceinline__ static Row make_row(const double (&th)[D]) {
+        Row c;
 #pragma unroll
         for (int j = 0; j <= DEG; ++j) c.c[j] = th[j];
+        return c;
+    }
+    __device__ static Coef prepare(const double (&th)[D], bool &ok) {
+        Coef c;
         const double sg = th[DEG + 1];
         ok = sg > 0.0;  // BS:523
         c.h = 1.0 / (2.0 * sg * sg);
         c.lognorm = -log(sg) - kHalfLog2Pi;
         return c;
     }
-    // 9 flop per datum at DEG = 3: 3 Horner FMA, 1 subtract, 1 FMA-accumulate
-    __device__ __forceinline__ static void row(const Coef &c, const double *__restrict__ r, double &acc) {
-        const double x = r[0];
-        double t = c.c[DEG];
+    // 9 flop per datum-walker at DEG = 3: 3 Horner FMA, 1 subtract, 1 FMA-accumulate
+    template <int TW>
+    __device__ __forceinline__ static void rows(const Row (&c)[TW], const double *__restrict__ r, double (&acc)[TW]) {
+        const double x = r[0], y = r[1];
+        double t[TW];
 #pragma unroll
-        for (int j = DEG - 1; j >= 0; --j) t = fma(t, x, c.c[j]);
-        const double e = r[1] - t;
-        acc = fma(e, e, acc);
+        for (int u = 0; u < TW; ++u) t[u] = fma(c[u].c[DEG], x, c[u].c[DEG - 1]);
+#pragma unroll
+        for (int j = DEG - 2; j >= 0; --j)
+#pragma unroll
+            for (int u = 0; u < TW; ++u) t[u] = fma(t[u], x, c[u].c[j]);
+#pragma unroll
+        for (int u = 0; u < TW; ++u) t[u] = y - t[u];
+#pragma unroll
+        for (int u = 0; u < TW; ++u) acc[u] = fma(t[u], t[u], acc[u]);
     }
     __device__ static double finish(const Coef &c, double acc, double rows, double) {
         return rows * c.lognorm - c.h * acc;
@@ -66,35 +91,50 @@ struct OpPolyReg {
 // theta = K-1 blocks of (w_1..w_F, b); device row = (x_1..x_F, label, pad...) with NCOL even
 template <int F, int K>
 struct OpLogistic {
-    static constexpr int D = (K - 1) * (F + 1), NCOL = (F + 2) & ~1;
-    struct Coef { double w[K - 1][F + 1]; };
-    __device__ static Coef prepare(const double (&th)[D], bool &ok) {
-        Coef c;
-        ok = true;
+    static constexpr int D = (K - 1) * (F + 1), NCOL = (F + 2) & ~1, TW_MAX = 2;
+    struct Coef { int unused; };
+    struct Row { double w[K - 1][F + 1]; };
+    __device__ __forceinline__ static Row make_row(const double (&th)[D]) {
+        Row c;
 #pragma unroll
         for (int k = 0; k < K - 1; ++k)
 #pragma unroll
             for (int f = 0; f <= F; ++f) c.w[k][f] = th[k * (F + 1) + f];
         return c;
     }
-    __device__ __forceinline__ static void row(const Coef &c, const double *__restrict__ r, double &acc) {
-        double z[K - 1];
-        double mx = 0.0;  // z_K = 0
+    __device__ static Coef prepare(const double (&)[D], bool &ok) {
+        ok = true;
+        return Coef{0};
+    }
+    template <int TW>
+    __device__ __forceinline__ static void rows(const Row (&c)[TW], const double *__restrict__ r, double (&acc)[TW]) {
+        double z[TW][K - 1];
         const int lab = (int)r[F];
-        double zy = 0.0;
 #pragma unroll
-        for (int k = 0; k < K - 1; ++k) {
-            double a = c.w[k][F];
+        for (int k = 0; k < K - 1; ++k)
 #pragma unroll
-            for (int f = 0; f < F; ++f) a = fma(c.w[k][f], r[f], a);
-            z[k] = a;
-            mx = fmax(mx, a);
-            zy = (lab == k) ? a : zy;
+            for (int u = 0; u < TW; ++u) z[u][k] = c[u].w[k][F];
+#pragma unroll
+        for (int f = 0; f < F; ++f) {
+            const double x = r[f];
+#pragma unroll
+            for (int k = 0; k < K - 1; ++k)
+#pragma unroll
+                for (int u = 0; u < TW; ++u) z[u][k] = fma(c[u].w[k][f], x, z[u][k]);
         }
-        double s = exp(-mx);
 #pragma unroll
-        for (int k = 0; k < K - 1; ++k) s += exp(z[k] - mx);
-        acc += (zy - mx) - log(s);
+        for (int u = 0; u < TW; ++u) {
+            double mx = 0.0, zy = 0.0;  // z_K = 0
+#pragma unroll
+            for (int k = 0; k < K - 1; ++k) {
+                mx = fmax(mx, z[u][k]);
+                zy = (lab == k) ? z[u][k] : zy;
+            }
+            double s = exp(-mx);
+#pragma unroll
+            for (int k = 0; k < K - 1; ++k) s += exp(z[u][k] - mx);
+            acc[u] += (zy - mx) - log(s);
+        }
     }
     __device__ static double finish(const Coef &, double acc, double, double) { return acc; }
 };
@@ -103,15 +143,22 @@ struct OpLogistic {
 // device row i = (a_i, b_i) = (r_i / sqrt(dt_i), sqrt(dt_i)), r_i = log(x_i / x_{i-1});
 // cst = Sum_i(-log x_i - 1/2 log dt_i) - rows * 1/2 log 2pi  (parameter independent, fixed at upload)
 struct OpGbm {
-    static constexpr int D = 2, NCOL = 2;
-    struct Coef { double m, h, lognorm; };
+    static constexpr int D = 2, NCOL = 2, TW_MAX = 8;
+    struct Coef { double h, lognorm; };
+    struct Row { double negm; };
+    __device__ __forceinline__ static Row make_row(const double (&th)[D]) { return Row{-(th[0] - 0.5 * th[1] * th[1])}; }
     __device__ static Coef prepare(const double (&th)[D], bool &ok) {
         ok = th[1] > 0.0;
-        return Coef{th[0] - 0.5 * th[1] * th[1], 1.0 / (2.0 * th[1] * th[1]), -log(th[1])};
+        return Coef{1.0 / (2.0 * th[1] * th[1]), -log(th[1])};
     }
-    __device__ __forceinline__ static void row(const Coef &c, const double *__restrict__ r, double &acc) {
-        const double e = fma(-c.m, r[1], r[0]);
-        acc = fma(e, e, acc);
+    template <int TW>
+    __device__ __forceinline__ static void rows(const Row (&c)[TW], const double *__restrict__ r, double (&acc)[TW]) {
+        const double a = r[0], b = r[1];
+        double e[TW];
+#pragma unroll
+        for (int u = 0; u < TW; ++u) e[u] = fma(c[u].negm, b, a);
+#pragma unroll
+        for (int u = 0; u < TW; ++u) acc[u] = fma(e[u], e[u], acc[u]);
     }
     __device__ static double finish(const Coef &c, double acc, double rows, double cst) {
         return rows * c.lognorm + cst - c.h * acc;

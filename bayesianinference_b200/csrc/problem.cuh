@@ -2,7 +2,9 @@
 // This is the data-carrying half of defineInferenceProblem (BS:167-307): where the reference bakes
 // the data matrix into a compiled function (BS:488-504, 576-593), the data are uploaded once here.
 #pragma once
+#include <algorithm>
 #include <cmath>
+#include <type_traits>
 #include <vector>
 
 #include "loglike.cuh"
@@ -32,22 +34,38 @@ struct binest_problem {
 
 namespace binest {
 
-// choose the data split of the streaming kernel: G CTAs in x, each a contiguous even-sized row slice
+// launch geometry of the streaming kernel: TW walkers per lane, G data slices (CTAs in x), pgroups walker
+// groups (CTAs in y); every slice is a contiguous, even-sized row range
 struct StreamGeom {
-    int nwarps, pgroups, G;
+    int tw, pgroups, G, Gs;
     long long rows_per_cta;
 };
+
+template <class OP, class F>
+inline void dispatch_tw(int tw, F &&f);
+
+template <class OP>
 inline StreamGeom stream_geom(const binest_problem &p, int P) {
     StreamGeom g;
-    g.nwarps = std::min(kMaxWarps, std::max(1, (P + 31) / 32));
-    g.pgroups = (P + g.nwarps * 32 - 1) / (g.nwarps * 32);
-    const int ctas_per_sm = 4;
-    long long gmax = std::max(1, (p.num_sms * ctas_per_sm) / g.pgroups);
+    const int lanesets = (P + 31) / 32;
+    g.tw = 1;
+    while (g.tw < OP::TW_MAX && g.tw < lanesets) g.tw <<= 1;
+    g.pgroups = (P + 32 * g.tw - 1) / (32 * g.tw);
+    // exactly one wave: grid = SMs x resident CTAs of this instantiation, all slices the same size
+    // (a 592-CTA grid at 3 resident CTAs/SM ran 1.33 waves and left the fp64 pipe 22 % idle in the tail)
+    int ctas_per_sm = 1;
+    dispatch_tw<OP>(g.tw, [&](auto twc) {
+        constexpr int TW = decltype(twc)::value;
+        BN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, loglike_stream_kernel<OP, TW>, kWarps * 32, 0));
+    });
+    ctas_per_sm = std::max(1, ctas_per_sm);
+    const long long gmax = std::max(1, (p.num_sms * ctas_per_sm) / g.pgroups);
     long long rpc = (p.rows + gmax - 1) / gmax;
-    rpc = std::max<long long>(rpc, 64);
+    rpc = std::max<long long>(rpc, 8 * kWarps);
     rpc = (rpc + 1) & ~1LL;
     g.rows_per_cta = rpc;
     g.G = (int)std::max<long long>(1, (p.rows + rpc - 1) / rpc);
+    g.Gs = (g.G + 3) & ~3;
     return g;
 }
 
@@ -79,14 +97,27 @@ inline void dispatch_op(const binest_problem &p, F &&f) {
     throw Error(BINEST_ERR_FUNCTION, "operator/shape not in the fixed operator table");
 }
 
-// theta SoA [d][Ps] on the device -> out_dev[P]; runs on p.stream
+// invoke f(integral_constant<int, TW>) for tw in {1, 2, 4, 8} and tw <= OP::TW_MAX
+template <class OP, class F>
+inline void dispatch_tw(int tw, F &&f) {
+    if (tw == 1) { f(std::integral_constant<int, 1>{}); return; }
+    if constexpr (OP::TW_MAX >= 2) if (tw == 2) { f(std::integral_constant<int, 2>{}); return; }
+    if constexpr (OP::TW_MAX >= 4) if (tw == 4) { f(std::integral_constant<int, 4>{}); return; }
+    if constexpr (OP::TW_MAX >= 8) if (tw == 8) { f(std::integral_constant<int, 8>{}); return; }
+    throw Error(BINEST_ERR_FUNCTION, "bad walker tiling");
+}
+
+// theta SoA [d][Ps] on the device -> partials[Ps][Gs]; runs on stream s (also used under graph capture)
 template <class OP>
 inline void launch_loglike(binest_problem &p, const double *theta_dev, int P, int Ps, double *partials_dev,
-                           const StreamGeom &g) {
-    dim3 grid(g.G, g.pgroups), block(g.nwarps * 32);
-    loglike_stream_kernel<OP><<<grid, block, 0, p.stream>>>(p.data.p, p.rows, g.rows_per_cta, theta_dev, P, Ps,
-                                                           partials_dev);
-    BN_LAUNCH_CHECK();
+                           const StreamGeom &g, cudaStream_t s, bool check = true) {
+    dim3 grid(g.G, g.pgroups), block(kWarps * 32);
+    dispatch_tw<OP>(g.tw, [&](auto twc) {
+        constexpr int TW = decltype(twc)::value;
+        loglike_stream_kernel<OP, TW><<<grid, block, 0, s>>>(p.data.p, p.rows, g.rows_per_cta, theta_dev, P, Ps,
+                                                            partials_dev, g.Gs);
+    });
+    if (check) BN_LAUNCH_CHECK();
 }
 
 void gp_loglike_device(binest_problem &p, const double *theta_dev, int P, int Ps, double *out_dev, bool check_box);
@@ -97,14 +128,14 @@ inline void loglike_device(binest_problem &p, const double *theta_dev, int P, in
         gp_loglike_device(p, theta_dev, P, Ps, out_dev, true);
         return;
     }
-    const StreamGeom g = stream_geom(p, P);
-    const size_t need = (size_t)g.G * Ps;
-    if (p.s_partials.n < need) p.s_partials.alloc(need);
     dispatch_op(p, [&](auto op) {
         using OP = decltype(op);
-        launch_loglike<OP>(p, theta_dev, P, Ps, p.s_partials.p, g);
-        loglike_finalize_kernel<OP><<<(P + 127) / 128, 128, 0, p.stream>>>(
-            theta_dev, P, Ps, p.s_partials.p, g.G, (double)p.rows, p.cst, p.prior, g_logzero, out_dev);
+        const StreamGeom g = stream_geom<OP>(p, P);
+        const size_t need = (size_t)g.Gs * Ps;
+        if (p.s_partials.n < need) p.s_partials.alloc(need);
+        launch_loglike<OP>(p, theta_dev, P, Ps, p.s_partials.p, g, p.stream);
+        loglike_finalize_kernel<OP><<<(P * 32 + 255) / 256, 256, 0, p.stream>>>(
+            theta_dev, P, Ps, p.s_partials.p, g.G, g.Gs, (double)p.rows, p.cst, p.prior, g_logzero, out_dev);
         BN_LAUNCH_CHECK();
     });
 }

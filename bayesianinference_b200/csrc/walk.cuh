@@ -132,14 +132,14 @@ __global__ void __launch_bounds__(1024) run_update_kernel(const __grid_constant_
     if (Kprev > 0) {
         for (int j = tid; j < Kprev; j += nt) {
             const int w = r * K + j, slot = kill[j];
-            for (int a = 0; a < d; ++a) lth[(size_t)slot * d + a] = A.w_theta[(size_t)a * Ps + w];
+            for (int a = 0; a < d; ++a) lth[(size_t)slot * d + a] = A.w_theta[(size_t)w * d + a];
             lL[slot] = A.w_logL[w];
             lPr[slot] = A.w_logPr[w];
             lAcc[slot] = (double)A.w_nacc[w] / (double)max(A.w_steps[w], 1);
         }
         for (int a = 0; a < d; ++a) {
             double v = 0.0;
-            for (int j = tid; j < Kprev; j += nt) v += A.w_mean[(size_t)a * Ps + r * K + j];
+            for (int j = tid; j < Kprev; j += nt) v += A.w_mean[(size_t)(r * K + j) * d + a];
             v = block_sum(v, scratch);
             if (tid == 0) st.meanEst[a] = v / (double)Kprev;
         }
@@ -147,7 +147,8 @@ __global__ void __launch_bounds__(1024) run_update_kernel(const __grid_constant_
             for (int b = 0; b <= a; ++b) {
                 double v = 0.0;
                 for (int j = tid; j < Kprev; j += nt)
-                    v += 0.5 * (A.w_cov[(size_t)(a * d + b) * Ps + r * K + j] + A.w_cov[(size_t)(b * d + a) * Ps + r * K + j]);
+                    v += 0.5 * (A.w_cov[(size_t)(r * K + j) * d * d + a * d + b] +
+                                A.w_cov[(size_t)(r * K + j) * d * d + b * d + a]);
                 v = block_sum(v, scratch);
                 if (tid == 0) st.covEst[a * d + b] = st.covEst[b * d + a] = v / (double)Kprev;
             }
@@ -301,7 +302,7 @@ __global__ void __launch_bounds__(1024) run_update_kernel(const __grid_constant_
             int pick = Kb + (int)(u0 * (double)(n - Kb));
             if (pick > n - 1) pick = n - 1;
             const int src = s_idx[pick];
-            for (int a = 0; a < d; ++a) A.w_theta[(size_t)a * Ps + w] = lth[(size_t)src * d + a];
+            for (int a = 0; a < d; ++a) A.w_theta[(size_t)w * d + a] = lth[(size_t)src * d + a];
             A.w_logL[w] = lL[src];
             A.w_logPr[w] = lPr[src];
             A.w_flags[w] = 0;
@@ -314,20 +315,23 @@ __global__ void __launch_bounds__(1024) run_update_kernel(const __grid_constant_
     __syncthreads();  // st.meanEst / covEst written by thread 0 above
     for (int j = tid; j < Kb; j += nt) {
         const int w = r * K + j;
-        for (int a = 0; a < d; ++a) A.w_mean[(size_t)a * Ps + w] = st.meanEst[a];
-        for (int a = 0; a < d * d; ++a) A.w_cov[(size_t)a * Ps + w] = st.covEst[a];
+        for (int a = 0; a < d; ++a) A.w_mean[(size_t)w * d + a] = st.meanEst[a];
+        for (int a = 0; a < d * d; ++a) A.w_cov[(size_t)w * d * d + a] = st.covEst[a];
     }
     if (tid == 0) atomicAdd(A.n_unfrozen, Kb);
 }
 
 // ---------------------------------------------------------------------------------------------------
-// accept phase of the proposal scored by the preceding loglike_stream_kernel, then the next proposal.
+// One warp per walker.  Accept phase of the proposal scored by the preceding loglike_stream_kernel (all 32
+// lanes sum the per-CTA partials of their walker in a fixed order), then the next proposal.  The scalar
+// chain logic is executed redundantly by every lane (same values); only lane 0 stores.
 // final_step: accept only.
 template <class OP>
-__global__ void walk_step_kernel(const __grid_constant__ RunParams prm, RunArrays A, const __grid_constant__ PriorSpec prior,
-                                 const double *__restrict__ partials, int G, double rows, double cst, int final_step) {
+__global__ void __launch_bounds__(256)
+walk_step_kernel(const __grid_constant__ RunParams prm, RunArrays A, const __grid_constant__ PriorSpec prior,
+                 const double *__restrict__ partials, int G, int Gs, double rows, double cst, int final_step) {
     constexpr int D = OP::D;
-    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const int K = prm.K, Ps = prm.Ps;
     if (w >= prm.R * K) return;
     const int r = w / K, j = w - r * K;
@@ -335,12 +339,14 @@ __global__ void walk_step_kernel(const __grid_constant__ RunParams prm, RunArray
     if (st.done || j >= st.Kb) return;
     int flags = A.w_flags[w];
     if (flags & WF_FROZEN) return;
+    const bool lead = lane == 0;
 
     double x[D];
 #pragma unroll
-    for (int a = 0; a < D; ++a) x[a] = A.w_theta[(size_t)a * Ps + w];
+    for (int a = 0; a < D; ++a) x[a] = A.w_theta[(size_t)w * D + a];
     double xPr = A.w_logPr[w];
     int steps = A.w_steps[w];
+    int nacc = A.w_nacc[w];
 
     if (flags & WF_HASPROP) {
         double xn[D];
@@ -348,43 +354,51 @@ __global__ void walk_step_kernel(const __grid_constant__ RunParams prm, RunArray
         for (int a = 0; a < D; ++a) xn[a] = A.w_prop[(size_t)a * Ps + w];
         bool acc = false;
         if (flags & WF_PRE) {
-            const double nL = loglike_combine<OP>(xn, partials, G, Ps, w, rows, cst, prm.logzero);
+            const double sum = combine_partials_warp(partials, G, Gs, w, lane);
+            const double nL = loglike_finish<OP>(xn, sum, rows, cst, prm.logzero);
             if (nL > st.Lstar) {  // nsDensity: logL > threshold, strict (BS:605)
                 acc = true;
-                A.w_logL[w] = nL;
+                if (lead) A.w_logL[w] = nL;
             }
         }
         if (acc) {
 #pragma unroll
-            for (int a = 0; a < D; ++a) { x[a] = xn[a]; A.w_theta[(size_t)a * Ps + w] = xn[a]; }
+            for (int a = 0; a < D; ++a) {
+                x[a] = xn[a];
+                if (lead) A.w_theta[(size_t)w * D + a] = xn[a];
+            }
             xPr = A.w_prop_logPr[w];
-            A.w_logPr[w] = xPr;
-            A.w_nacc[w] += 1;
+            ++nacc;
+            if (lead) { A.w_logPr[w] = xPr; A.w_nacc[w] = nacc; }
         }
-        // Haario recursion on the chain state, started at t = 10 (BS:715-727)
+        // Haario recursion on the chain state, started at t = 10 (BS:715-727); entries spread over the lanes
         const double t = 10.0 + (double)steps;
-        double mo[D], mn[D];
+        double dm_o[D], dm_n[D];  // x - mean_old, x - mean_new
 #pragma unroll
         for (int a = 0; a < D; ++a) {
-            mo[a] = A.w_mean[(size_t)a * Ps + w];
-            mn[a] = mo[a] + (x[a] - mo[a]) / (t + 1.0);
-            A.w_mean[(size_t)a * Ps + w] = mn[a];
+            const double mo = A.w_mean[(size_t)w * D + a];
+            const double mn = mo + (x[a] - mo) / (t + 1.0);
+            dm_o[a] = x[a] - mo;
+            dm_n[a] = x[a] - mn;
+            if (lead) A.w_mean[(size_t)w * D + a] = mn;
         }
+        {
+            double *cov = A.w_cov + (size_t)w * D * D;
+            const double f = (t - 1.0) / t;
 #pragma unroll
-        for (int a = 0; a < D; ++a)
+            for (int a = 0; a < D; ++a)
 #pragma unroll
-            for (int b = 0; b < D; ++b) {
-                const size_t o = (size_t)(a * D + b) * Ps + w;
-                A.w_cov[o] = (t - 1.0) / t * A.w_cov[o] + (x[a] - mo[a]) * (x[b] - mn[b]) / t;
-            }
+                for (int b = 0; b < D; ++b)
+                    if (((a * D + b) & 31) == lane) cov[a * D + b] = f * cov[a * D + b] + dm_o[a] * dm_n[b] / t;
+        }
         ++steps;
-        A.w_steps[w] = steps;
+        if (lead) A.w_steps[w] = steps;
         flags &= ~(WF_HASPROP | WF_PRE);
         if (steps % prm.S == 0) {  // BS:730-736: extra S-step blocks until the rate is in range or 5S steps
-            const double rate = (double)A.w_nacc[w] / (double)steps;
+            const double rate = (double)nacc / (double)steps;
             if ((rate >= prm.acc_min && rate <= prm.acc_max) || steps >= prm.maxS) {
                 flags |= WF_FROZEN;
-                atomicSub(A.n_unfrozen, 1);
+                if (lead) atomicSub(A.n_unfrozen, 1);
             }
         }
     }
@@ -403,7 +417,7 @@ __global__ void walk_step_kernel(const __grid_constant__ RunParams prm, RunArray
                 for (int b = 0; b <= a; ++b) s += st.cholL[a * D + b] * z[b];
             }
             xn[a] = s;
-            A.w_prop[(size_t)a * Ps + w] = s;
+            if (lead) A.w_prop[(size_t)a * Ps + w] = s;
         }
         double u0, u1;
         rng_uniform2(prm.seed, 0u, (uint32_t)steps, walk_id, TAG_ACCEPT, run_id, u0, u1);
@@ -413,12 +427,12 @@ __global__ void walk_step_kernel(const __grid_constant__ RunParams prm, RunArray
 #pragma unroll
             for (int a = 0; a < D; ++a) nPr += logprior_dim(prior, a, xn[a]);
             if (!isfinite(nPr)) nPr = prm.logzero;
-            A.w_prop_logPr[w] = nPr;
+            if (lead) A.w_prop_logPr[w] = nPr;
             pre = (nPr - xPr > log(u0)) ? WF_PRE : 0;  // Metropolis rule on the log density
         }
         flags |= WF_HASPROP | pre;
     }
-    A.w_flags[w] = flags;
+    if (lead) A.w_flags[w] = flags;
 }
 
 }  // namespace binest
