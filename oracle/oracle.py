@@ -282,6 +282,7 @@ def evidence_sampling(points, logL, pool, n, nruns=100, seed=1, sorted_draws=Fal
         "ParameterExpectedValues": {"Mean": pm.mean(0), "StandardError": pm.std(0, ddof=1)},
         "RelativeEntropy": {"Mean": float(H.mean()), "StandardError": float(H.std(ddof=1))},
         "parameterSamples": pm,
+        "HSamples": H,
     }
 
 

@@ -1,0 +1,90 @@
+"""Test-only backend: the same interface as bayesianinference_b200.engine, served by the CPU oracle.
+It lets the host-side logic of bayesianinference_b200.api (option handling, association assembly,
+combineRuns, run sharding under torch.distributed/gloo) be exercised without a GPU.  Never imported by the
+product package."""
+from __future__ import annotations
+
+from types import SimpleNamespace
+
+import numpy as np
+
+from oracle import oracle as O
+
+
+def default_options(**kw):
+    o = SimpleNamespace(pool_size=100, batch_k=1, mc_steps=200, max_iter=10000, min_iter=100, term_frac=0.01,
+                        acc_min=0.0, acc_max=1.0, seed=1, first_run_id=0, n_runs=1)
+    for k, v in kw.items():
+        if not hasattr(o, k):
+            raise TypeError(k)
+        setattr(o, k, v)
+    return o
+
+
+class Problem:
+    def __init__(self, op, inputs, outputs, iparam, kinds, lo, hi, p0=None, p1=None):
+        self.d = len(kinds)
+        self.prob = O.Problem(op, self.d, inputs, outputs, iparam)
+        self.prior = O.Prior(kinds, lo, hi, p0 or None, p1 or None)
+
+    def loglike(self, theta):
+        return self.prob.loglike(theta, self.prior)
+
+    def logprior(self, theta):
+        return self.prior.logpdf(theta)
+
+    def sample_prior(self, n, seed=1, run_id=0):
+        return self.prior.sample(n, seed, run_id)
+
+
+class RunGroup:
+    def __init__(self, problem, options, start_points=None):
+        self.p, self.o = problem, options
+        self.start = None if start_points is None else np.asarray(start_points).reshape(options.n_runs, options.pool_size, problem.d)
+        self.results = None
+
+    def advance(self, max_batches=0):
+        o = self.o
+        self.results = []
+        for i in range(o.n_runs):
+            r = O.nested_sampling(self.p.prob, self.p.prior, pool_size=o.pool_size, batch_k=o.batch_k,
+                                  mc_steps=o.mc_steps, max_iter=o.max_iter, min_iter=o.min_iter,
+                                  term_frac=o.term_frac, acc_range=(o.acc_min, o.acc_max), seed=o.seed,
+                                  run_id=o.first_run_id + i, adapt_in_walk=False,
+                                  start_points=None if self.start is None else self.start[i])
+            self.results.append(r)
+        return True
+
+    def fetch(self, run=0):
+        r = self.results[run]
+        return dict(points=r.points, logL=r.logL, logPrior=r.logPrior, acc=r.acc, pool=r.pool, logX=r.logX,
+                    crude_logw=r.crude_logw, crude_logZ=r.crude_logZ, entropy=r.entropy, logLmax=r.logLmax,
+                    M=r.logL.size, n_deleted=r.n_deleted, iterations=r.iterations, evals=r.evals, n=r.n)
+
+    def close(self):
+        pass
+
+
+def crude_weights(logL, pool, n_live):
+    logL = np.asarray(logL, float)
+    M = logL.size
+    lx = O.xvalues_log(n_live, M - n_live, np.asarray(pool, np.int64))
+    lw = O.trapezoid_log(lx) + logL
+    z = O.logsumexp(lw)
+    return dict(logX=lx, crude_logw=lw, crude_logZ=z, entropy=O.entropy(lw, logL, z), logLmax=float(logL.max()),
+                log_missing=float(lx[-1] + logL.max()))
+
+
+def evidence_sampling(points, logL, pool, n_live, post_runs=100, seed=1):
+    r = O.evidence_sampling(points, logL, pool, n_live, post_runs, seed)
+    return dict(z=r["zSamples"], H=np.full(post_runs, r["RelativeEntropy"]["Mean"]) if False else _H(r, post_runs),
+                logw_mean=r["LogPosteriorWeight"]["Mean"], logw_sd=r["LogPosteriorWeight"]["StandardError"],
+                slx_mean=r["SampledLogX"]["Mean"], slx_sd=r["SampledLogX"]["StandardError"],
+                pmean=r["parameterSamples"])
+
+
+def _H(r, post_runs):
+    h = r.get("HSamples")
+    if h is None:
+        h = np.full(post_runs, r["RelativeEntropy"]["Mean"])
+    return h
