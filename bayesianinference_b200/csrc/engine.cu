@@ -14,6 +14,8 @@
 namespace binest {
 int guard(const std::function<void()> &f);
 void upload_theta(binest_problem &p, const double *theta, int64_t P, int Ps);
+void gp_loglike_device_strided(binest_problem &p, const double *theta_dev, int P, int Ps, double *out_dev,
+                               int out_stride, bool check_box);
 }  // namespace binest
 
 using namespace binest;
@@ -96,6 +98,11 @@ void build_walk_graph(binest_run &r) {
     const int P = r.prm.R * r.prm.K;
     const int S = (int)r.prm.S;
     const cudaStream_t s = r.stream;
+    if (p.op == BINEST_OP_GP_SE) {  // a GP step is hundreds of launches: stepped directly, see walk_block()
+        r.geom = StreamGeom{1, 1, 1, 4, 0};
+        r.partials.alloc((size_t)r.geom.Gs * r.prm.Ps);
+        return;
+    }
     dispatch_op(p, [&](auto op) {
         using OP = decltype(op);
         r.geom = stream_geom<OP>(p, P);
@@ -112,6 +119,25 @@ void build_walk_graph(binest_run &r) {
         BN_CUDA(cudaGraphInstantiate(&r.walk_graph, g, 0));
         cudaGraphDestroy(g);
     });
+}
+
+// one block of S walk steps for every active walker
+void walk_block(binest_run &r) {
+    binest_problem &p = *r.prob;
+    const RunParams &q = r.prm;
+    if (p.op != BINEST_OP_GP_SE) {
+        BN_CUDA(cudaGraphLaunch(r.walk_graph, r.stream));
+        count_launch(2 * (int)q.S + 1);
+        return;
+    }
+    const int P = q.R * q.K;
+    const dim3 sgrid((P * 32 + 255) / 256), sblock(256);
+    for (int step = 0; step <= q.S; ++step) {
+        walk_step_kernel<OpGpSe><<<sgrid, sblock, 0, r.stream>>>(q, r.A, p.prior, r.partials.p, r.geom.G, r.geom.Gs,
+                                                                 (double)p.rows, p.cst, step == q.S ? 1 : 0);
+        BN_LAUNCH_CHECK();
+        if (step < q.S) gp_loglike_device_strided(p, r.w_prop.p, P, q.Ps, r.partials.p, r.geom.Gs, false);
+    }
 }
 
 void launch_update(binest_run &r, bool insert_only = false) {
@@ -246,8 +272,7 @@ int binest_run_advance(binest_run *r, int64_t max_batches, int32_t *finished) {
             int blocks = 0;
             do {
                 BN_CUDA(cudaEventRecord(r->ev0, r->stream));
-                BN_CUDA(cudaGraphLaunch(r->walk_graph, r->stream));
-                count_launch(2 * (int)q.S + 1);
+                walk_block(*r);
                 BN_CUDA(cudaEventRecord(r->ev1, r->stream));
                 BN_CUDA(cudaEventSynchronize(r->ev1));
                 float ms = 0;

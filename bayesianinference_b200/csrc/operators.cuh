@@ -165,6 +165,19 @@ struct OpGbm {
     }
 };
 
+// ------------------------------------------------------------------ GP marginal likelihood (gp.cu)
+// Not a streaming reduction: gp.cu writes the finished logL where the walk expects the (single) partial sum,
+// so only the epilogue interface is needed here.
+struct OpGpSe {
+    static constexpr int D = 3;
+    struct Coef { int unused; };
+    __device__ static Coef prepare(const double (&th)[D], bool &ok) {
+        ok = th[0] > 0.0 && th[1] > 0.0 && th[2] > 0.0;
+        return Coef{0};
+    }
+    __device__ static double finish(const Coef &, double acc, double, double) { return acc; }
+};
+
 // ------------------------------------------------------------------ priors (BS:25-64, BS:365-427)
 struct PriorSpec {
     int d;

@@ -208,3 +208,40 @@ def test_multi_run_group_is_shard_invariant(eng):
     assert a["M"] == b["M"]
     np.testing.assert_allclose(a["points"], b["points"], rtol=1e-12)
     np.testing.assert_allclose(a["logL"], b["logL"], rtol=1e-12)
+
+
+@pytest.mark.parametrize("N", [200, 512])
+def test_gp_marginal_likelihood_matches_oracle(eng, O, N):
+    """C5 operator (K7 pin): batched covariance fill + blocked Cholesky (DMMA trailing update) against the
+    oracle's LU path (GP:130-141) and its long-double Cholesky.  kappa(K) <~ 1e4 here; tolerance 1e-10 rel."""
+    c = cfg.c5_gp(N=N)
+    gp, op, pr = _pair(eng, O, c)
+    th = pr.sample(12, 31)
+    th[0] = [1.0, 0.8, 0.3]
+    got = gp.loglike(th)
+    ref = op.loglike(th, pr)
+    hi, lo = op.loglike_quad(th)
+    np.testing.assert_allclose(got, hi, rtol=1e-10)
+    np.testing.assert_allclose(ref, hi, rtol=1e-9)
+    bad = th.copy()
+    bad[2, 1] = -1.0   # outside the box -> logzero
+    bad[3, 2] = 0.0
+    out = gp.loglike(bad)
+    assert out[2] == O.LOGZERO and out[3] == O.LOGZERO
+    np.testing.assert_allclose(out[[0, 1, 4]], got[[0, 1, 4]], rtol=1e-13)
+
+
+def test_gp_nested_sampling_small(eng, O):
+    """A short GP run end to end: engine trajectory equals the oracle's (same seed, frozen proposals)."""
+    c = cfg.c5_gp(N=96)
+    gp, op, pr = _pair(eng, O, c)
+    start = pr.sample(24, 8, 0)
+    opts = eng.default_options(pool_size=24, batch_k=6, mc_steps=8, max_iter=36, min_iter=36, seed=8)
+    run = eng.RunGroup(gp, opts, start)
+    assert run.advance(0)
+    got = run.fetch(0)
+    ref = O.nested_sampling(op, pr, pool_size=24, batch_k=6, mc_steps=8, max_iter=36, min_iter=36, seed=8,
+                            adapt_in_walk=False, start_points=start)
+    assert got["M"] == ref.logL.size
+    np.testing.assert_allclose(got["logL"], ref.logL, rtol=1e-8)
+    np.testing.assert_allclose(got["points"], ref.points, rtol=1e-7, atol=1e-9)
