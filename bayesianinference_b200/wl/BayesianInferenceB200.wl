@@ -1,0 +1,244 @@
+(* ::Package:: *)
+
+(* BayesianInferenceB200` — Wolfram Language host for the B200-native nested-sampling engine.
+
+   Drop-in for the nested-sampling path of ssmit1986/BayesianInference: the same public symbols with the same
+   options and result keys; everything numerical happens in libbinest.so (hand-written sm_100a CUDA), reached only
+   through the LibraryLink shim librarylink_shim.c.  This file is the reference's own host language; it cannot be
+   executed in the build image (no Wolfram Engine), so all logic that can live behind the C ABI does, and the Python
+   mirror bayesianinference_b200/api.py (same structure, tested) documents the intended behaviour line by line.
+
+   Reference locations (BayesianInference/Kernel/):
+     defineInferenceProblem   BayesianStatistics.wl:148-308     nestedSampling          :1099-1136
+     nestedSamplingInternal   BayesianStatistics.wl:859-1040    parallelNestedSampling  :1317-1371
+     evidenceSampling         BayesianStatistics.wl:1158-1291   combineRuns             :1293-1315
+     generateStartingPoints   BayesianStatistics.wl:1042-1097   inferenceObject         BayesianUtilities.wl:107-138
+*)
+
+BeginPackage["BayesianInferenceB200`"];
+
+defineInferenceProblem::usage = "defineInferenceProblem[rules...] — as in BayesianInference`; \"GeneratingDistribution\" must match the GPU operator table.";
+nestedSampling::usage = "nestedSampling[inferenceObject, opts] runs nested sampling on the GPU.";
+parallelNestedSampling::usage = "parallelNestedSampling[inferenceObject, opts] runs \"ParallelRuns\" independent runs in one library call and merges them.";
+evidenceSampling::usage = "evidenceSampling[inferenceObject, opts] estimates the evidence error by Monte-Carlo draws of the X sequence.";
+combineRuns::usage = "combineRuns[obj1, obj2, ...] merges nested-sampling runs.";
+generateStartingPoints::usage = "generateStartingPoints[inferenceObject, n] draws n points from the prior.";
+inferenceObject::usage = "inferenceObject[assoc] wraps the results; obj[\"Key\"] extracts a property.";
+inferenceObjectQ::usage = "inferenceObjectQ[obj]";
+$binestLibrary::usage = "Path of the compiled LibraryLink shim (binestLink).";
+categoricalSoftmax::usage = "categoricalSoftmax[{{w11,..,w1F,b1},...}, {x1,..,xF}] — softmax classification with reference class K.";
+
+Begin["`Private`"];
+
+$MachineLogZero = -$MaxMachineNumber; (* BU:47: -Statistics`Library`MachineInfinity *)
+
+(* ------------------------------------------------------------------ LibraryLink bindings: no logic *)
+$binestLibrary = FindLibrary["binestLink"];
+ll[name_, args_, res_] := ll[name, args, res] = LibraryFunctionLoad[$binestLibrary, name, args, res];
+check[rc_Integer] /; rc =!= 0 := (Message[inferenceObject::binest, ll["binestLastError", {}, "UTF8String"][]]; $Failed);
+check[other_] := other;
+inferenceObject::binest = "libbinest: `1`";
+
+binestInit := ll["binestInit", {Real, Integer}, Integer];
+binestProblemCreate := ll["binestProblemCreate", {Integer, {Integer, 1}, {Real, 2, "Constant"}, {Real, 2, "Constant"},
+    {Integer, 1}, {Real, 1}, {Real, 1}, {Real, 1}, {Real, 1}}, Integer];
+binestLogLike := ll["binestLogLike", {Integer, {Real, 2, "Constant"}}, {Real, 1}];
+binestLogPrior := ll["binestLogPrior", {Integer, {Real, 2, "Constant"}}, {Real, 1}];
+binestSamplePrior := ll["binestSamplePrior", {Integer, Integer, Integer, Integer}, {Real, 2}];
+binestRunCreate := ll["binestRunCreate", {Integer, {Integer, 1}, {Real, 1}, {Real, _, "Constant"}}, Integer];
+binestRunAdvance := ll["binestRunAdvance", {Integer, Integer}, Integer];
+binestRunFetch := ll["binestRunFetch", {Integer, Integer, Integer}, {Real, 2}];
+binestRunFree := ll["binestRunFree", {Integer}, Integer];
+binestEvidenceSampling := ll["binestEvidenceSampling", {{Real, 2, "Constant"}, {Real, 1, "Constant"}, {Integer, 1, "Constant"}, Integer, Integer, Integer}, {Real, 1}];
+binestCrudeWeights := ll["binestCrudeWeights", {{Real, 1, "Constant"}, {Integer, 1, "Constant"}, Integer}, {Real, 1}];
+
+initialised = False;
+ensureInit[] := If[!initialised, check @ binestInit[$MachineLogZero, -1]; initialised = True];
+
+(* ------------------------------------------------------------------ inferenceObject (BU:107-138) *)
+inferenceObject[assoc_?AssociationQ][prop_] := assoc[prop];
+inferenceObject /: Normal[inferenceObject[assoc_]] := assoc;
+inferenceObjectQ[inferenceObject[_?AssociationQ]] := True;
+inferenceObjectQ[___] := False;
+
+paramSpecPattern = {_Symbol, _?NumericQ | DirectedInfinity[-1], _?NumericQ | DirectedInfinity[1]};
+
+(* ------------------------------------------------------------------ operator table (SURVEY.md Appendix A) *)
+(* returns {opId, iparam, inputs, outputs} or $Failed *)
+operatorFromDistribution[NormalDistribution[mu_Symbol, sigma_Symbol], data_?VectorQ, {mu_, sigma_}, _] :=
+    {1, {0, 0, 0, 0}, List /@ N[data], {{}}};
+operatorFromDistribution[NormalDistribution[poly_, sigma_Symbol], Rule[in_, out_], params_List, {x_Symbol}] /;
+        PolynomialQ[poly, x] && Most[params] === CoefficientList[poly, x] && Last[params] === sigma :=
+    {2, {Exponent[poly, x], 0, 0, 0}, ArrayReshape[N[in], {Length[in], 1}], ArrayReshape[N[out], {Length[out], 1}]};
+operatorFromDistribution[categoricalSoftmax[blocks_?MatrixQ, vars_List], Rule[in_?MatrixQ, labels_], params_List, vars_List] /;
+        Flatten[blocks] === params :=
+    {3, {0, Length[blocks] + 1, 0, 0}, N[in], ArrayReshape[N[labels], {Length[labels], 1}]};
+operatorFromDistribution[GeometricBrownianMotionProcess[mu_Symbol, sigma_Symbol, _], ts_TemporalData, {mu_, sigma_}, _] :=
+    {4, {0, 0, 0, 0}, List /@ N[ts["Times"]], List /@ N[ts["Values"]]}; (* TemporalData adaptor BS:511-515 *)
+operatorFromDistribution[dist_, ___] := (Message[defineInferenceProblem::logLike, dist]; $Failed);
+defineInferenceProblem::logLike = "`1` is not in the GPU operator table; there is no CPU fallback."; (* cf. BS:456-459 *)
+defineInferenceProblem::insuffInfo = "Not enough information was provided to define the problem"; (* BS:148-152 *)
+
+priorKinds[prior_List, params_] := MapThread[
+    Function[{spec, par},
+        Switch[spec,
+            "LocationParameter" | _UniformDistribution, {1, 0., 1.},   (* BS:37-39 *)
+            "ScaleParameter", {2, 0., 1.},                              (* BS:42-48 *)
+            NormalDistribution[_?NumericQ, _?NumericQ], {3, N[spec[[1]]], N[spec[[2]]]}, (* BS:51-59 *)
+            _, Throw[$Failed, "problemDef"]]],
+    {prior, params}];
+
+defineInferenceProblem[rules__Rule] := defineInferenceProblem[Association[rules]];
+defineInferenceProblem[assoc_?AssociationQ] := Catch[
+    Module[{params, names, kinds, op, handle, test},
+        If[!AllTrue[{"Data", "Parameters", "GeneratingDistribution", "PriorDistribution"}, KeyExistsQ[assoc, #] &],
+            Message[defineInferenceProblem::insuffInfo]; Throw[$Failed, "problemDef"]];
+        ensureInit[];
+        params = Replace[assoc["Parameters"], s_Symbol :> {s, -Infinity, Infinity}, {1}]; (* paramNormalForm BS:133-145 *)
+        names = params[[All, 1]];
+        kinds = priorKinds[assoc["PriorDistribution"], params];
+        op = operatorFromDistribution[assoc["GeneratingDistribution"], assoc["Data"], names,
+            Lookup[assoc, "IndependentVariables", {}]];
+        If[op === $Failed, Throw[$Failed, "problemDef"]];
+        handle = check @ binestProblemCreate[op[[1]], op[[2]], op[[3]], op[[4]], kinds[[All, 1]],
+            N[params[[All, 2]]], N[params[[All, 3]]], kinds[[All, 2]], kinds[[All, 3]]];
+        If[handle === $Failed, Throw[$Failed, "problemDef"]];
+        (* BS:276-298: both functions must be numeric on random points of the box *)
+        test = binestSamplePrior[handle, 100, 20260, 0];
+        If[!VectorQ[binestLogLike[handle, test], NumericQ] || !VectorQ[binestLogPrior[handle, test], NumericQ],
+            Throw[$Failed, "problemDef"]];
+        inferenceObject @ Join[assoc, <|
+            "Parameters" -> params, "ParameterSymbols" -> names,
+            "LogLikelihoodFunction" -> Function[pts, binestLogLike[handle, If[VectorQ[pts], {pts}, pts]]],  (* Listable, BS:499 *)
+            "LogPriorPDFFunction" -> Function[pts, binestLogPrior[handle, If[VectorQ[pts], {pts}, pts]]],
+            "binestHandle" -> handle|>]
+    ],
+    "problemDef", Function[inferenceObject[$Failed]] (* BS:308 *)
+];
+
+generateStartingPoints[inferenceObject[assoc_?AssociationQ], n_Integer, seed_Integer : 1] :=
+    inferenceObject[Append[assoc, "StartingPoints" -> binestSamplePrior[assoc["binestHandle"], n, seed, 0]]]; (* BS:1046-1068 *)
+
+(* ------------------------------------------------------------------ options: BS:833-851, 1366-1371 *)
+Options[evidenceSampling] = {"PostProcessSamplingRuns" -> 100, "EmpiricalPosteriorDistributionType" -> "Simple", "Seed" -> 1};
+Options[nestedSampling] = Join[{
+    "SamplePoolSize" -> 100, "StartingPoints" -> Automatic, "MaxIterations" -> 10000, "MinIterations" -> 100,
+    "MonteCarloMethod" -> Automatic, "MonteCarloSteps" -> 200, "TerminationFraction" -> 0.01, "Monitor" -> True,
+    "LogLikelihoodMaximum" -> Automatic, "MinMaxAcceptanceRate" -> {0, 1},
+    "BatchSize" -> 1 (* live points replaced per iteration; 1 = the reference scheme BS:980-1018 *)},
+    Options[evidenceSampling]];
+Options[parallelNestedSampling] = Join[DeleteCases[Options[nestedSampling], "StartingPoints" -> _], {"ParallelRuns" :> 4}];
+Options[combineRuns] = Options[evidenceSampling];
+
+runGroup[handle_, d_, opts_, nRuns_, firstRun_, start_] := Module[{run, fin, tables},
+    run = check @ binestRunCreate[handle,
+        {opts["SamplePoolSize"], opts["BatchSize"], opts["MonteCarloSteps"], opts["MaxIterations"], opts["MinIterations"],
+            opts["Seed"], firstRun, nRuns},
+        N @ {opts["TerminationFraction"], opts["MinMaxAcceptanceRate"][[1]], opts["MinMaxAcceptanceRate"][[2]]},
+        start];
+    If[run === $Failed, Return[$Failed, Module]];
+    fin = binestRunAdvance[run, 0];
+    tables = Table[binestRunFetch[run, i, d], {i, 0, nRuns - 1}];
+    binestRunFree[run];
+    tables
+];
+
+(* fetch matrix -> association of the reference's result keys (BS:1026-1032) *)
+resultAssociation[table_, d_, n_] := With[{rows = Most[table]},
+    <|
+        "Samples" -> <|
+            "Point" -> rows[[All, ;; d]], "LogLikelihood" -> rows[[All, d + 1]], "LogPriorPDF" -> rows[[All, d + 2]],
+            "AcceptanceRate" -> Replace[rows[[All, d + 3]], x_ /; !NumericQ[x] || x != x :> Missing["InitialSample"], {1}], (* BS:911 *)
+            "PoolSize" -> Round @ rows[[All, d + 4]], "LogX" -> rows[[All, d + 5]], "X" -> Exp[rows[[All, d + 5]]],
+            "CrudeLogPosteriorWeight" -> rows[[All, d + 6]]|>,
+        "SamplePoolSize" -> n, "GeneratedNestedSamples" -> Length[rows] - n, "TotalSamples" -> Length[rows],
+        "ParameterRanges" -> CoordinateBounds[rows[[All, ;; d]]]
+    |>
+];
+
+nestedSampling[inferenceObject[assoc_?AssociationQ], opts : OptionsPattern[]] := Module[{
+    o = Association[Options[nestedSampling], opts], start, d = Length[assoc["Parameters"]], tables},
+    start = Replace[o["StartingPoints"], Automatic :> Lookup[assoc, "StartingPoints", {}]];
+    If[MatrixQ[start, NumericQ], o["SamplePoolSize"] = Length[start]; start = {N[start]}, start = {}]; (* BS:1116-1131 *)
+    tables = runGroup[assoc["binestHandle"], d, o, 1, 0, start];
+    If[tables === $Failed, Return["Bad likelihood function", Module]]; (* BS:920 *)
+    evidenceSampling[
+        inferenceObject[Join[assoc, resultAssociation[First[tables], d, o["SamplePoolSize"]]]],
+        Sequence @@ FilterRules[Normal[o], Options[evidenceSampling]]]
+];
+
+meanAndError[v_?VectorQ] := <|"Mean" -> Mean[v], "StandardError" -> StandardDeviation[v]|>; (* BS:1138-1149 *)
+
+evidenceSampling[inferenceObject[assoc_?AssociationQ], opts : OptionsPattern[]] := Module[{
+    o = Association[Options[evidenceSampling], opts], s = assoc["Samples"], n = assoc["SamplePoolSize"], m, d, ord, cw, ev, r, pool, out},
+    ord = Ordering[Transpose[{s["LogLikelihood"], s["Point"]}]]; (* SortBy {logL, point}, BS:814 *)
+    s = Map[#[[ord]] &, s];
+    m = Length[ord]; d = Length[First[s["Point"]]];
+    pool = Lookup[s, "PoolSize", Join[ConstantArray[n, m - n], Range[n, 1, -1]]];
+    cw = binestCrudeWeights[s["LogLikelihood"], pool, n];
+    s["LogX"] = cw[[;; m]]; s["X"] = Exp[s["LogX"]]; s["CrudeLogPosteriorWeight"] = cw[[m + 1 ;; 2 m]];
+    out = Join[assoc, <|"CrudeLogEvidence" -> cw[[2 m + 1]], "CrudeRelativeEntropy" -> cw[[2 m + 2]],
+        "LogLikelihoodMaximum" -> cw[[2 m + 3]], "LogEstimatedMissingEvidence" -> cw[[2 m + 4]]|>]; (* BS:1183-1194 *)
+    r = o["PostProcessSamplingRuns"];
+    If[!TrueQ[IntegerQ[r] && r > 0], Return[inferenceObject[Append[out, "Samples" -> s]], Module]]; (* BS:1195-1197 *)
+    ev = binestEvidenceSampling[s["Point"], s["LogLikelihood"], pool, n, r, o["Seed"]];
+    s["CrudeLogPosteriorWeight"] -= out["CrudeLogEvidence"];                                   (* BS:1236 *)
+    s["CrudePosteriorWeight"] = Exp[s["CrudeLogPosteriorWeight"]];                             (* BS:1237 *)
+    With[{off = 2 r + r d},
+        s["LogPosteriorWeight"] = <|"Mean" -> ev[[off + 1 ;; off + m]], "StandardError" -> ev[[off + m + 1 ;; off + 2 m]]|>;
+        s["SampledLogX"] = <|"Mean" -> ev[[off + 2 m + 1 ;; off + 3 m]], "StandardError" -> ev[[off + 3 m + 1 ;; off + 4 m]]|>];
+    ord = Ordering[-s["CrudeLogPosteriorWeight"]];                                            (* BS:1241 *)
+    s = Map[If[AssociationQ[#], Map[Function[v, v[[ord]]], #], #[[ord]]] &, s];
+    inferenceObject @ Join[out, <|
+        "Samples" -> s,
+        "LogEvidence" -> meanAndError[ev[[;; r]]],                                            (* BS:1254 *)
+        "RelativeEntropy" -> meanAndError[ev[[r + 1 ;; 2 r]]],                                 (* BS:1263 *)
+        "ParameterExpectedValues" -> AssociationThread[
+            Lookup[assoc, "ParameterSymbols", Range[d]],
+            meanAndError /@ Transpose[Partition[ev[[2 r + 1 ;; 2 r + r d]], d]]],               (* BS:1255-1262 *)
+        "EmpiricalPosteriorDistribution" -> EmpiricalDistribution[s["CrudePosteriorWeight"] -> s["Point"]] (* BS:1272-1277 *)
+    |>]
+];
+
+combineRuns[results : inferenceObject[_?AssociationQ] .., opts : OptionsPattern[]] := Module[{
+    assocs = {results}[[All, 1]], joined, keep, pools, nTot, merged},
+    joined = Join @@@ Transpose[Values /@ KeyTake[#["Samples"], {"Point", "LogLikelihood", "LogPriorPDF", "AcceptanceRate"}] & /@ assocs];
+    keep = Values[PositionIndex[joined[[1]]][[All, 1]]];                                        (* DeleteDuplicatesBy Point, BS:1294-1297 *)
+    joined = joined[[All, keep]];
+    pools = #["SamplePoolSize"] & /@ assocs; nTot = Total[pools];
+    merged = AssociationThread[{"Point", "LogLikelihood", "LogPriorPDF", "AcceptanceRate"}, joined];
+    (* per-sample pool sizes: sum over runs of the run's pool size at the sample's likelihood level;
+       with constant pools this is the reference's Total of SamplePoolSize (BS:1307) *)
+    merged["PoolSize"] = Total @ Map[
+        Function[a, With[{sl = Sort[a["Samples"]["LogLikelihood"]], sp = Lookup[a["Samples"], "PoolSize", None]},
+            Map[Function[l, With[{i = LengthWhile[sl, # < l &] + 1}, If[i > Length[sl], 0, If[sp === None, a["SamplePoolSize"], sp[[Ordering[a["Samples"]["LogLikelihood"]]]][[i]]]]]], merged["LogLikelihood"]]]],
+        assocs];
+    evidenceSampling[
+        inferenceObject @ Join[First[assocs], <|
+            "Samples" -> merged,
+            "LogLikelihoodMaximum" -> Max[#["LogLikelihoodMaximum"] & /@ assocs],             (* BS:1306 *)
+            "SamplePoolSize" -> nTot, "GeneratedNestedSamples" -> Length[keep] - nTot, "TotalSamples" -> Length[keep]|>], (* BS:1307-1309 *)
+        opts]
+];
+
+parallelNestedSampling::startingPts = "Cannot use pre-specified starting points for parallel sampling because each parallel process should generate starting points independently.
+Continuing with option \"SamplePoolSize\" -> `1`"; (* BS:1317-1318 *)
+
+parallelNestedSampling[inferenceObject[assoc_?AssociationQ], opts : OptionsPattern[]] /; MatrixQ[assoc["StartingPoints"], NumericQ] := (
+    Message[parallelNestedSampling::startingPts, Length[assoc["StartingPoints"]]];
+    parallelNestedSampling[inferenceObject[KeyDrop[assoc, "StartingPoints"]], "SamplePoolSize" -> Length[assoc["StartingPoints"]], opts]
+); (* BS:1320-1332 *)
+
+(* One library call advances all runs in lock step on the GPU (instead of ParallelTable over subkernels, BS:1349-1357:
+   eight subkernels would mean eight CUDA contexts fighting for the device). *)
+parallelNestedSampling[inferenceObject[assoc_?AssociationQ], opts : OptionsPattern[]] := Module[{
+    o = Association[Options[parallelNestedSampling], opts], d = Length[assoc["Parameters"]], tables},
+    tables = runGroup[assoc["binestHandle"], d, o, o["ParallelRuns"], 0, {}];
+    If[tables === $Failed, Return["Bad likelihood function", Module]];
+    combineRuns[
+        Sequence @@ (inferenceObject[Join[assoc, resultAssociation[#, d, o["SamplePoolSize"]]]] & /@ tables),
+        Sequence @@ FilterRules[Normal[o], Options[combineRuns]]]
+];
+
+End[];
+EndPackage[];

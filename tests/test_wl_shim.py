@@ -1,0 +1,33 @@
+"""The LibraryLink shim cannot run here (no Wolfram Engine), but it must at least compile and link against
+libbinest.so, export the entry points the WL package loads, and contain no arithmetic of its own."""
+import os
+import re
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SHIM = os.path.join(ROOT, "bayesianinference_b200", "wl", "librarylink_shim.c")
+WL = os.path.join(ROOT, "bayesianinference_b200", "wl", "BayesianInferenceB200.wl")
+
+
+def test_shim_compiles_links_and_exports(tmp_path):
+    out = tmp_path / "binestLink.so"
+    cmd = ["/usr/bin/gcc", "-shared", "-fPIC", "-Wall", "-Werror=implicit-function-declaration",
+           "-I", os.path.join(ROOT, "tests", "wl_stub"), "-I", os.path.join(ROOT, "include"), SHIM, "-o", str(out),
+           "-L", os.path.join(ROOT, "bayesianinference_b200"), "-lbinest"]
+    subprocess.check_call(cmd)
+    syms = subprocess.check_output(["nm", "-D", "--defined-only", str(out)], text=True)
+    loaded = set(re.findall(r'll\["(binest[A-Za-z]+)"', open(WL).read()))
+    assert len(loaded) >= 12
+    for name in loaded | {"WolframLibrary_getVersion", "WolframLibrary_initialize", "WolframLibrary_uninitialize"}:
+        assert re.search(rf"\b{name}\b", syms), f"{name} loaded by the WL package but not exported by the shim"
+
+
+def test_wl_package_keeps_the_reference_api_surface():
+    src = open(WL).read()
+    for sym in ("defineInferenceProblem", "nestedSampling", "parallelNestedSampling", "evidenceSampling", "combineRuns",
+                "generateStartingPoints", "inferenceObject"):
+        assert re.search(rf"^{sym}::usage", src, flags=re.M), sym
+    for opt in ('"SamplePoolSize" -> 100', '"MaxIterations" -> 10000', '"MinIterations" -> 100', '"MonteCarloSteps" -> 200',
+                '"TerminationFraction" -> 0.01', '"MinMaxAcceptanceRate" -> {0, 1}', '"PostProcessSamplingRuns" -> 100',
+                '"ParallelRuns" :> 4'):
+        assert opt in src, opt  # Options of BS:833-851, 1366-1371
