@@ -227,6 +227,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// programmatic dependent launch (PDL): the next kernel of the walk graph may start its prologue while this one
+// drains; it must call pdl_wait() before touching anything its predecessor wrote.  Both are no-ops for kernels
+// launched without the programmatic-stream-serialization attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // global -> shared::cta bulk async copy, completion signalled on an mbarrier (bytes multiple of 16, 16B aligned)
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(

@@ -2,6 +2,7 @@
 // plus the evidence entry points (BS:812-831, 1158-1291).  One process drives one GPU; runs are sharded
 // across GPUs by the caller (first_run_id / n_runs) and merged on the host (combineRuns BS:1293-1315).
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <memory>
@@ -109,10 +110,17 @@ void build_walk_graph(binest_run &r) {
         r.partials.alloc((size_t)r.geom.Gs * r.prm.Ps);
         const dim3 sgrid((P * 32 + 255) / 256), sblock(256);  // one warp per walker
         BN_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        // every node after the first is a programmatic dependent of its predecessor (PDL): the likelihood
+        // kernel prefetches its first data tiles while walk_step runs, walk_step is resident when the
+        // likelihood kernel drains
+        const bool pdl = std::getenv("BINEST_NO_PDL") == nullptr;
         for (int step = 0; step <= S; ++step) {
-            walk_step_kernel<OP><<<sgrid, sblock, 0, s>>>(r.prm, r.A, p.prior, r.partials.p, r.geom.G, r.geom.Gs,
-                                                         (double)p.rows, p.cst, step == S ? 1 : 0);
-            if (step < S) launch_loglike<OP>(p, r.w_prop.p, P, r.prm.Ps, r.partials.p, r.geom, s, false);
+            PdlConfig lc(sgrid, sblock, s, pdl && step > 0);
+            const double *partials = r.partials.p;
+            int G = r.geom.G, Gs = r.geom.Gs, fin = step == S ? 1 : 0;
+            double rows = (double)p.rows, cst = p.cst;
+            BN_CUDA(cudaLaunchKernelEx(&lc.cfg, walk_step_kernel<OP>, r.prm, r.A, p.prior, partials, G, Gs, rows, cst, fin));
+            if (step < S) launch_loglike<OP>(p, r.w_prop.p, P, r.prm.Ps, r.partials.p, r.geom, s, false, pdl);
         }
         cudaGraph_t g;
         BN_CUDA(cudaStreamEndCapture(s, &g));

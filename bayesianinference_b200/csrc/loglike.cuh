@@ -60,6 +60,11 @@ loglike_stream_kernel(const double *__restrict__ data, long long rows, long long
     if (threadIdx.x == 0)
         for (int t = 0; t < kStages && t < ntiles; ++t) issue(t);
 
+    // PDL: everything above only reads the immutable data set, so it overlaps the predecessor (walk_step);
+    // theta and the partials buffer belong to the predecessor / successor and are touched after the wait.
+    pdl_launch_dependents();
+    pdl_wait();
+
     // per-datum coefficients of the lane's TW walkers (loaded while the first tiles are in flight)
     typename OP::Row c[TW];
 #pragma unroll

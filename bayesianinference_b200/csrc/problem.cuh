@@ -108,14 +108,34 @@ inline void dispatch_tw(int tw, F &&f) {
 }
 
 // theta SoA [d][Ps] on the device -> partials[Ps][Gs]; runs on stream s (also used under graph capture)
+// launch configuration with the programmatic-dependent-launch attribute (see pdl_wait in common.cuh)
+struct PdlConfig {
+    cudaLaunchConfig_t cfg{};
+    cudaLaunchAttribute attr[1];
+    PdlConfig(dim3 grid, dim3 block, cudaStream_t s, bool pdl) {
+        cfg.gridDim = grid;
+        cfg.blockDim = block;
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = s;
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = pdl ? 1 : 0;
+    }
+};
+
 template <class OP>
 inline void launch_loglike(binest_problem &p, const double *theta_dev, int P, int Ps, double *partials_dev,
-                           const StreamGeom &g, cudaStream_t s, bool check = true) {
+                           const StreamGeom &g, cudaStream_t s, bool check = true, bool pdl = false) {
     dim3 grid(g.G, g.pgroups), block(kWarps * 32);
     dispatch_tw<OP>(g.tw, [&](auto twc) {
         constexpr int TW = decltype(twc)::value;
-        loglike_stream_kernel<OP, TW><<<grid, block, 0, s>>>(p.data.p, p.rows, g.rows_per_cta, theta_dev, P, Ps,
-                                                            partials_dev, g.Gs);
+        PdlConfig lc(grid, block, s, pdl);
+        const double *data = p.data.p;
+        long long rows = p.rows, rpc = g.rows_per_cta;
+        int Gs = g.Gs;
+        BN_CUDA(cudaLaunchKernelEx(&lc.cfg, loglike_stream_kernel<OP, TW>, data, rows, rpc, theta_dev, P, Ps,
+                                   partials_dev, Gs));
     });
     if (check) BN_LAUNCH_CHECK();
 }

@@ -331,6 +331,8 @@ __global__ void __launch_bounds__(256)
 walk_step_kernel(const __grid_constant__ RunParams prm, RunArrays A, const __grid_constant__ PriorSpec prior,
                  const double *__restrict__ partials, int G, int Gs, double rows, double cst, int final_step) {
     constexpr int D = OP::D;
+    pdl_wait();               // partials / walker state of the predecessors are complete and visible
+    pdl_launch_dependents();  // let the next likelihood kernel start prefetching its data tiles
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const int K = prm.K, Ps = prm.Ps;
     if (w >= prm.R * K) return;
