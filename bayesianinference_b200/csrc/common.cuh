@@ -227,6 +227,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// distributed shared memory: address of the same smem offset in CTA `rank` of the cluster, and a remote 8-byte store
+// that signals the remote CTA's mbarrier with complete_tx (sm_90+)
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_async_f64(uint32_t remote_addr, double v, uint32_t remote_mbar) {
+    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(remote_addr),
+                 "l"(__double_as_longlong(v)), "r"(remote_mbar)
+                 : "memory");
+}
+
 // programmatic dependent launch (PDL): the next kernel of the walk graph may start its prologue while this one
 // drains; it must call pdl_wait() before touching anything its predecessor wrote.  Both are no-ops for kernels
 // launched without the programmatic-stream-serialization attribute.

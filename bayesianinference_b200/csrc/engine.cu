@@ -11,6 +11,7 @@
 #include "evidence.cuh"
 #include "problem.cuh"
 #include "walk.cuh"
+#include "walk_resident.cuh"
 
 namespace binest {
 int guard(const std::function<void()> &f);
@@ -28,6 +29,10 @@ struct binest_run {
     RunArrays A{};
     int n_pad = 0;
     StreamGeom geom{};
+    bool resident = false;      // whole walk in one launch, data in (distributed) shared memory
+    int res_cs = 1;             // cluster size of the resident kernel
+    long long res_rpc = 0;      // data rows per CTA of the cluster
+    size_t res_smem = 0;
     bool first = true;
     bool finished = false;
     int64_t evals = 0;
@@ -108,6 +113,27 @@ void build_walk_graph(binest_run &r) {
         using OP = decltype(op);
         r.geom = stream_geom<OP>(p, P);
         r.partials.alloc((size_t)r.geom.Gs * r.prm.Ps);
+        // small data: the resident cluster kernel replaces the per-step graph (walk_resident.cuh)
+        if (std::getenv("BINEST_NO_RESIDENT") == nullptr) {
+            const size_t budget = 200 * 1024;
+            int cs = 1;
+            auto fits = [&](int c) {
+                long long rpc = ((p.rows + c - 1) / c + 1) & ~1LL;
+                return resident_smem_doubles<OP>(rpc, c) * sizeof(double) <= budget;
+            };
+            while (cs < 8 && !fits(cs)) cs <<= 1;
+            if (fits(cs)) {
+                const int groups = (P + 31) / 32;
+                while (cs < 8 && groups * cs * 2 <= p.num_sms && p.rows / (cs * 2) >= 8 * kResWarps) cs <<= 1;
+                r.resident = true;
+                r.res_cs = cs;
+                r.res_rpc = ((p.rows + cs - 1) / cs + 1) & ~1LL;
+                r.res_smem = resident_smem_doubles<OP>(r.res_rpc, cs) * sizeof(double);
+                BN_CUDA(cudaFuncSetAttribute(walk_resident_kernel<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)r.res_smem));
+                return;
+            }
+        }
         const dim3 sgrid((P * 32 + 255) / 256), sblock(256);  // one warp per walker
         BN_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
         // every node after the first is a programmatic dependent of its predecessor (PDL): the likelihood
@@ -133,6 +159,31 @@ void build_walk_graph(binest_run &r) {
 void walk_block(binest_run &r) {
     binest_problem &p = *r.prob;
     const RunParams &q = r.prm;
+    if (r.resident) {
+        dispatch_op(p, [&](auto op) {
+            using OP = decltype(op);
+            const int groups = (q.R * q.K + 31) / 32;
+            cudaLaunchConfig_t cfg{};
+            cudaLaunchAttribute attr[1];
+            cfg.gridDim = dim3(groups * r.res_cs);
+            cfg.blockDim = dim3(kResWarps * 32);
+            cfg.dynamicSmemBytes = r.res_smem;
+            cfg.stream = r.stream;
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = r.res_cs;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = r.res_cs > 1 ? 1 : 0;
+            const double *data = p.data.p;
+            long long rows = p.rows, rpc = r.res_rpc;
+            double cst = p.cst;
+            int cs = r.res_cs;
+            BN_CUDA(cudaLaunchKernelEx(&cfg, walk_resident_kernel<OP>, q, r.A, p.prior, data, rows, rpc, cst, cs));
+            BN_LAUNCH_CHECK();
+        });
+        return;
+    }
     if (p.op != BINEST_OP_GP_SE) {
         BN_CUDA(cudaGraphLaunch(r.walk_graph, r.stream));
         count_launch(2 * (int)q.S + 1);

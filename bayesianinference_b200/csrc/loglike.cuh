@@ -76,9 +76,9 @@ loglike_stream_kernel(const double *__restrict__ data, long long rows, long long
         c[t] = OP::make_row(th);
     }
 
-    double acc[TW];
+    typename OP::Acc acc[TW];
 #pragma unroll
-    for (int t = 0; t < TW; ++t) acc[t] = 0.0;
+    for (int t = 0; t < TW; ++t) acc[t] = OP::acc_init();
 
     for (int t = 0; t < ntiles; ++t) {
         const int s = t % kStages;
@@ -100,7 +100,7 @@ loglike_stream_kernel(const double *__restrict__ data, long long rows, long long
     double *red = &tiles[0][0];  // [kWarps][32*TW]
     __syncthreads();
 #pragma unroll
-    for (int u = 0; u < TW; ++u) red[wid * (32 * TW) + lane + 32 * u] = acc[u];
+    for (int u = 0; u < TW; ++u) red[wid * (32 * TW) + lane + 32 * u] = OP::acc_value(acc[u]);
     __syncthreads();
     for (int k = threadIdx.x; k < 32 * TW; k += blockDim.x) {
         double sum = 0.0;

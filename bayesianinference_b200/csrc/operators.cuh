@@ -27,6 +27,9 @@ struct OpGaussian {
     static constexpr int D = 2, NCOL = 1, TW_MAX = 8;
     struct Coef { double mu, h, lognorm; };
     struct Row { double mu; };
+    using Acc = double;
+    __device__ __forceinline__ static Acc acc_init() { return 0.0; }
+    __device__ __forceinline__ static double acc_value(const Acc &a) { return a; }
     __device__ __forceinline__ static Row make_row(const double (&th)[D]) { return Row{th[0]}; }
     __device__ static Coef prepare(const double (&th)[D], bool &ok) {
         ok = th[1] > 0.0;  // DistributionParameterAssumptions, BS:439
@@ -52,6 +55,9 @@ struct OpPolyReg {
     static constexpr int D = DEG + 2, NCOL = 2, TW_MAX = 8;
     struct Coef { double h, lognorm; };
     struct Row { double c[DEG + 1]; };
+    using Acc = double;
+    __device__ __forceinline__ static Acc acc_init() { return 0.0; }
+    __device__ __forceinline__ static double acc_value(const Acc &a) { return a; }
     __device__ __forceinline__ static Row make_row(const double (&th)[D]) {
         Row c;
 #pragma unroll
@@ -106,8 +112,16 @@ struct OpLogistic {
         ok = true;
         return Coef{0};
     }
+    // log Sum_k exp z_k with z_K = 0, K <= 3, costs two exps and 1/32 of a log per datum:
+    //   * after sorting, one of the K shifted terms is exactly exp(0) = 1:  s = 1 + exp(a) + exp(b), a, b <= 0;
+    //   * Sum_i log s_i = log Prod_i s_i: s in (1, 3], so 32 factors (<= 3^32 = 1.9e15) are multiplied before one
+    //     log is taken (relative rounding 32 * 1.1e-16 on the product, i.e. ~4e-15 absolute on a sum of ~32 terms).
+    struct Acc { double lin, prod; int cnt; };
+    __device__ __forceinline__ static Acc acc_init() { return Acc{0.0, 1.0, 0}; }
+    __device__ __forceinline__ static double acc_value(const Acc &a) { return a.lin - log(a.prod); }
     template <int TW>
-    __device__ __forceinline__ static void rows(const Row (&c)[TW], const double *__restrict__ r, double (&acc)[TW]) {
+    __device__ __forceinline__ static void rows(const Row (&c)[TW], const double *__restrict__ r, Acc (&acc)[TW]) {
+        static_assert(K == 2 || K == 3, "softmax operator is specialised for 2 or 3 classes");
         double z[TW][K - 1];
         const int lab = (int)r[F];
 #pragma unroll
@@ -124,16 +138,28 @@ struct OpLogistic {
         }
 #pragma unroll
         for (int u = 0; u < TW; ++u) {
-            double mx = 0.0, zy = 0.0;  // z_K = 0
+            double zy = 0.0;  // z_K = 0
 #pragma unroll
-            for (int k = 0; k < K - 1; ++k) {
-                mx = fmax(mx, z[u][k]);
-                zy = (lab == k) ? z[u][k] : zy;
+            for (int k = 0; k < K - 1; ++k) zy = (lab == k) ? z[u][k] : zy;
+            double mx, s;
+            if (K == 2) {
+                mx = fmax(z[u][0], 0.0);
+                s = 1.0 + exp(-fabs(z[u][0]));
+            } else {
+                const double hi = fmax(z[u][0], z[u][K - 2]), lo = fmin(z[u][0], z[u][K - 2]);
+                mx = fmax(hi, 0.0);
+                s = (1.0 + exp(-fabs(hi))) + exp(lo - mx);
             }
-            double s = exp(-mx);
+            acc[u].lin += zy - mx;
+            acc[u].prod *= s;
+        }
+        if (++acc[0].cnt == 32) {
 #pragma unroll
-            for (int k = 0; k < K - 1; ++k) s += exp(z[u][k] - mx);
-            acc[u] += (zy - mx) - log(s);
+            for (int u = 0; u < TW; ++u) {
+                acc[u].lin -= log(acc[u].prod);
+                acc[u].prod = 1.0;
+            }
+            acc[0].cnt = 0;
         }
     }
     __device__ static double finish(const Coef &, double acc, double, double) { return acc; }
@@ -146,6 +172,9 @@ struct OpGbm {
     static constexpr int D = 2, NCOL = 2, TW_MAX = 8;
     struct Coef { double h, lognorm; };
     struct Row { double negm; };
+    using Acc = double;
+    __device__ __forceinline__ static Acc acc_init() { return 0.0; }
+    __device__ __forceinline__ static double acc_value(const Acc &a) { return a; }
     __device__ __forceinline__ static Row make_row(const double (&th)[D]) { return Row{-(th[0] - 0.5 * th[1] * th[1])}; }
     __device__ static Coef prepare(const double (&th)[D], bool &ok) {
         ok = th[1] > 0.0;
