@@ -501,7 +501,6 @@ int binest_bench_loglike(binest_problem *p, int64_t P, int64_t reps, int64_t war
                          double *ms_total) {
     return guard([&] {
         BN_REQUIRE(p && P > 0 && reps > 0, BINEST_ERR_DIMENSION, "bad arguments");
-        BN_REQUIRE(p->op != BINEST_OP_GP_SE, BINEST_ERR_FUNCTION, "use binest_bench_gp for the GP operator");
         BN_CUDA(cudaSetDevice(p->device));
         const int Ps = (int)((P + 31) & ~31LL);
         DevBuf<double> rows((size_t)P * p->d), soa((size_t)p->d * Ps), out(Ps), flush;
@@ -518,6 +517,18 @@ int binest_bench_loglike(binest_problem *p, int64_t P, int64_t reps, int64_t war
         cudaEvent_t e0, e1, e2;
         BN_CUDA(cudaEventCreate(&e0)); BN_CUDA(cudaEventCreate(&e1)); BN_CUDA(cudaEventCreate(&e2));
         double tk = 0.0, tt = 0.0;
+        if (p->op == BINEST_OP_GP_SE) {  // whole fill + Cholesky pipeline per repetition (ms_kernel == ms_total)
+            for (int64_t it = 0; it < warmup + reps; ++it) {
+                if (flush_l2) BN_CUDA(cudaMemsetAsync(flush.p, it & 0xff, flush_n, p->stream));
+                BN_CUDA(cudaEventRecord(e0, p->stream));
+                gp_loglike_device_strided(*p, soa.p, (int)P, Ps, out.p, 1, true);
+                BN_CUDA(cudaEventRecord(e2, p->stream));
+                BN_CUDA(cudaEventSynchronize(e2));
+                float b = 0;
+                BN_CUDA(cudaEventElapsedTime(&b, e0, e2));
+                if (it >= warmup) { tk += b; tt += b; }
+            }
+        } else
         dispatch_op(*p, [&](auto op) {
             using OP = decltype(op);
             const StreamGeom g = stream_geom<OP>(*p, (int)P);

@@ -110,22 +110,34 @@ __global__ void __launch_bounds__(256) gp_potf2_kernel(GpBatch g, int k0) {
     }
     if (tid == 0) s_fail = 0;
     __syncthreads();
-    for (int j = 0; j < NB; ++j) {
-        const double piv = s[j * LD + j];
-        if (!(piv > 0.0) || !isfinite(piv)) {  // not positive definite -> logzero (GP:131-135)
-            if (tid == 0) s_fail = 1;
-            break;
+    // left-looking (Crout) column sweep: two threads per row split the dot product L[i][0:j] . L[j][0:j] by the
+    // parity of k and keep two accumulators each; one barrier pair per column, no index arithmetic in the loop
+    {
+        const int i = tid >> 1, half = tid & 1;
+        for (int j = 0; j < NB; ++j) {
+            double v = 0.0;
+            if (i >= j) {
+                double a0 = 0.0, a1 = 0.0;
+                const double *ri = s + i * LD, *rj = s + j * LD;
+                int k = half;
+                for (; k + 2 < j; k += 4) {
+                    a0 = fma(ri[k], rj[k], a0);
+                    a1 = fma(ri[k + 2], rj[k + 2], a1);
+                }
+                if (k < j) a0 = fma(ri[k], rj[k], a0);
+                v = a0 + a1;
+            }
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v = s[i * LD + j] - v;  // only meaningful for i >= j
+            if (i == j && half == 0) {
+                if (!(v > 0.0) || !isfinite(v)) s_fail = 1;  // not positive definite -> logzero (GP:131-135)
+                s[j * LD + j] = sqrt(v);
+            }
+            __syncthreads();
+            if (s_fail) break;
+            if (i > j && half == 0) s[i * LD + j] = v / s[j * LD + j];
+            __syncthreads();
         }
-        const double l = sqrt(piv), inv = 1.0 / l;
-        __syncthreads();
-        for (int i = j + tid; i < NB; i += blockDim.x) s[i * LD + j] = (i == j) ? l : s[i * LD + j] * inv;
-        __syncthreads();
-        const int rem = NB - 1 - j;
-        for (int e = tid; e < rem * rem; e += blockDim.x) {
-            const int c = j + 1 + e / rem, i = j + 1 + e % rem;
-            if (i >= c) s[i * LD + c] = fma(-s[i * LD + j], s[c * LD + j], s[i * LD + c]);
-        }
-        __syncthreads();
     }
     __syncthreads();
     if (s_fail) {
@@ -146,9 +158,17 @@ __global__ void __launch_bounds__(256) gp_potf2_kernel(GpBatch g, int k0) {
         const int c = tid;
         const double xcc = 1.0 / s[c * LD + c];
         for (int i = c + 1; i < NB; ++i) {
-            double acc = s[i * LD + c] * xcc;
-            for (int k = c + 1; k < i; ++k) acc = fma(s[i * LD + k], s[c * LD + k], acc);
-            s[c * LD + i] = -acc / s[i * LD + i];
+            double a0 = s[i * LD + c] * xcc, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            const double *ri = s + i * LD, *rc = s + c * LD;
+            int k = c + 1;
+            for (; k + 3 < i; k += 4) {
+                a0 = fma(ri[k], rc[k], a0);
+                a1 = fma(ri[k + 1], rc[k + 1], a1);
+                a2 = fma(ri[k + 2], rc[k + 2], a2);
+                a3 = fma(ri[k + 3], rc[k + 3], a3);
+            }
+            for (; k < i; ++k) a0 = fma(ri[k], rc[k], a0);
+            s[c * LD + i] = -((a0 + a1) + (a2 + a3)) / ri[i];
         }
     }
     __syncthreads();
@@ -178,6 +198,7 @@ __global__ void __launch_bounds__(256) gp_potf2_kernel(GpBatch g, int k0) {
 // shared GEMM core: acc[4][4][2] (32x32 per warp, 16 warps -> 128x128) += sign * A(128 x KC) B(128 x KC)^T
 // sA, sB: [KC][LDS_] (k-major).  Fragment maps of mma.m8n8k4.f64: a[row = lane/4][k = lane%4],
 // b[k = lane%4][col = lane/4], c[row = lane/4][col = 2*(lane%4) + {0,1}].
+template <int LDB>
 __device__ __forceinline__ void gemm_chunk(const double *__restrict__ sA, const double *__restrict__ sB, int wm, int wn,
                                            int lane, double (&acc)[4][4][2], bool negate) {
     const int r = lane >> 2, q = lane & 3;
@@ -190,7 +211,7 @@ __device__ __forceinline__ void gemm_chunk(const double *__restrict__ sA, const 
             a[i] = negate ? -v : v;
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) bb[j] = sB[(kk + q) * LDS_ + wn * 32 + j * 8 + r];
+        for (int j = 0; j < 4; ++j) bb[j] = sB[(kk + q) * LDB + wn * 32 + j * 8 + r];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -198,37 +219,41 @@ __device__ __forceinline__ void gemm_chunk(const double *__restrict__ sA, const 
     }
 }
 
-// load a 128 x KC column-major panel chunk (columns contiguous in global) into smem [KC][LDS_] with cp.async
+// load a ROWS x KC column-major panel chunk (columns contiguous in global) into smem [KC][LDD] with cp.async
+template <int ROWS = NB, int LDD = LDS_>
 __device__ __forceinline__ void load_chunk_async(double *sdst, const double *__restrict__ gsrc, size_t ld) {
-    // KC columns x 128 rows = KC*64 16-byte pieces; 512 threads
-    for (int e = threadIdx.x; e < KC * (NB / 2); e += blockDim.x) {
-        const int k = e / (NB / 2), m2 = e - k * (NB / 2);
-        cp_async16(sdst + k * LDS_ + 2 * m2, gsrc + (size_t)k * ld + 2 * m2);
+    for (int e = threadIdx.x; e < KC * (ROWS / 2); e += blockDim.x) {
+        const int k = e / (ROWS / 2), m2 = e - k * (ROWS / 2);
+        cp_async16(sdst + k * LDD + 2 * m2, gsrc + (size_t)k * ld + 2 * m2);
     }
 }
 
-// trailing update: C(I,J) -= P_I P_J^T for the lower tiles of the trailing matrix (starts at k0 + NB)
-__global__ void __launch_bounds__(512) gp_syrk_kernel(GpBatch g, int k0) {
-    extern __shared__ __align__(16) double sm[];  // 2 stages x (A chunk + B chunk)
+// trailing update: C(I,J) -= P_I P_J^T on 128 x 64 tiles (I: 128-row blocks, J: 64-column blocks) that touch the
+// lower triangle of the trailing matrix (starts at k0 + NB).  8 warps (4 x 2), 32 x 32 per warp; two CTAs per SM so
+// that one CTA's C-tile load/store overlaps the other's DMMA stream (a single 128 x 128 CTA per SM left the tensor
+// pipe idle 38 % of the time while C moved).
+constexpr int NBH = NB / 2;
+constexpr int LDSH_ = NBH + 4;
+__global__ void __launch_bounds__(256, 2) gp_syrk_kernel(GpBatch g, int k0) {
+    extern __shared__ __align__(16) double sm[];  // 2 stages x (A chunk [KC][LDS_] + B chunk [KC][LDSH_])
     const int b = blockIdx.y;
     if (g.fail[b]) return;
     int t = blockIdx.x, ti = 0;
-    while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
-    const int tj = t - ti * (ti + 1) / 2;
+    while ((ti + 1) * (ti + 2) <= t) ++ti;
+    const int tj = t - ti * (ti + 1);  // 0 .. 2*ti + 1
     const int base = k0 + NB;
-    const int i0 = base + ti * NB, j0 = base + tj * NB;
+    const int i0 = base + ti * NB, j0 = base + tj * NBH;
     double *A = g.A + (size_t)b * g.Np * g.Np;
     const size_t ld = g.Np;
     const double *PA = A + (size_t)k0 * ld + i0, *PB = A + (size_t)k0 * ld + j0;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wm = warp >> 2, wn = warp & 3;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wm = warp >> 1, wn = warp & 1;
     const int r = lane >> 2, q = lane & 3;
-
-    double *sA[2] = {sm, sm + 2 * KC * LDS_}, *sB[2] = {sm + KC * LDS_, sm + 3 * KC * LDS_};
-    load_chunk_async(sA[0], PA, ld);
-    load_chunk_async(sB[0], PB, ld);
+    constexpr int STAGE = KC * LDS_ + KC * LDSH_;
+    double *sA[2] = {sm, sm + STAGE}, *sB[2] = {sm + KC * LDS_, sm + STAGE + KC * LDS_};
+    load_chunk_async<NB, LDS_>(sA[0], PA, ld);
+    load_chunk_async<NBH, LDSH_>(sB[0], PB, ld);
     cp_async_commit();
 
-    // C fragments straight from global (column-major: 8 consecutive rows per column = 64 B segments)
     double acc[4][4][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -243,15 +268,15 @@ __global__ void __launch_bounds__(512) gp_syrk_kernel(GpBatch g, int k0) {
 #pragma unroll 1
     for (int c = 0; c < NCH; ++c) {
         if (c + 1 < NCH) {
-            load_chunk_async(sA[(c + 1) & 1], PA + (size_t)(c + 1) * KC * ld, ld);
-            load_chunk_async(sB[(c + 1) & 1], PB + (size_t)(c + 1) * KC * ld, ld);
+            load_chunk_async<NB, LDS_>(sA[(c + 1) & 1], PA + (size_t)(c + 1) * KC * ld, ld);
+            load_chunk_async<NBH, LDSH_>(sB[(c + 1) & 1], PB + (size_t)(c + 1) * KC * ld, ld);
             cp_async_commit();
             cp_async_wait<1>();
         } else {
             cp_async_wait<0>();
         }
         __syncthreads();
-        gemm_chunk(sA[c & 1], sB[c & 1], wm, wn, lane, acc, true);
+        gemm_chunk<LDSH_>(sA[c & 1], sB[c & 1], wm, wn, lane, acc, true);
         __syncthreads();
     }
 #pragma unroll
@@ -300,7 +325,7 @@ __global__ void __launch_bounds__(512) gp_trsm_kernel(GpBatch g, int k0) {
             cp_async_wait<0>();
         }
         __syncthreads();
-        gemm_chunk(sAfull + c * KC * LDS_, sB[c & 1], wm, wn, lane, acc, false);
+        gemm_chunk<LDS_>(sAfull + c * KC * LDS_, sB[c & 1], wm, wn, lane, acc, false);
         __syncthreads();
     }
     // results: write L21 in place and keep a copy in smem ([n][m] over the A tile buffer) for the y update
@@ -365,7 +390,7 @@ void gp_loglike_device_strided(binest_problem &p, const double *theta_dev, int P
         ws_cap = fit; ws_np = Np;
     }
     const size_t smem_potf2 = (size_t)NB * (NB + 1) * sizeof(double);
-    const size_t smem_syrk = (size_t)4 * KC * LDS_ * sizeof(double);
+    const size_t smem_syrk = (size_t)2 * (KC * LDS_ + KC * LDSH_) * sizeof(double);
     const size_t smem_trsm = ((size_t)NB * LDS_ + 2 * KC * LDS_ + NB) * sizeof(double);
     BN_CUDA(cudaFuncSetAttribute(gp_potf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_potf2));
     BN_CUDA(cudaFuncSetAttribute(gp_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_syrk));
@@ -384,7 +409,7 @@ void gp_loglike_device_strided(binest_problem &p, const double *theta_dev, int P
             if (rest > 0) {
                 gp_trsm_kernel<<<dim3(rest, B), 512, smem_trsm, s>>>(g, k0);
                 BN_LAUNCH_CHECK();
-                gp_syrk_kernel<<<dim3(rest * (rest + 1) / 2, B), 512, smem_syrk, s>>>(g, k0);
+                gp_syrk_kernel<<<dim3(rest * (rest + 1), B), 256, smem_syrk, s>>>(g, k0);
                 BN_LAUNCH_CHECK();
             }
         }
