@@ -39,6 +39,15 @@ WORKLOADS = {
 }
 
 
+def _workload_config(c, K, n_runs, world):
+    N = c.inputs.shape[0]
+    return {"workload": f"{c.name}: N={N} rows, d={c.d}, {c.pool_size} live points, {n_runs} run(s)/GPU x K={K} replaced per "
+                        f"iteration, {MC_STEPS} walk steps each",
+            "l2": "256 MiB written between timed iterations (inside the timed region); the data set (<= 48 MB) is "
+                  "L2-resident across the 200 walk steps of an iteration by design",
+            "parallelism": f"run-sharded x{world}, no collective"}
+
+
 def _dist_env():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
 
@@ -105,7 +114,7 @@ def run_reference(args):
     from oracle import oracle as O
     factory, K, flop, byts = WORKLOADS[args.config]
     c = factory()
-    threads = O.max_threads()
+    threads = len(os.sched_getaffinity(0))  # all host cores, even when torchrun pins OMP_NUM_THREADS=1
     for _ in range(max(args.warmup, 0) and 1):  # one short warm-up pass is enough for a CPU loop
         _cpu_leg(c, threads, 1)
     tot_e, tot_t = 0, 0.0
@@ -119,7 +128,7 @@ def run_reference(args):
         "impl": "reference", "metric": "loglikelihood evals/s", "value": v, "unit": "evals/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{c.name}: N={c.inputs.shape[0]} rows, d={c.d}, walk of {MC_STEPS} steps per replacement"},
+        "config": _workload_config(c, K, args.runs_per_gpu, max(args.gpus, 1)),
         "replacements_per_s": v / MC_STEPS,
         "cpu_baseline": {"value": v, "unit": "evals/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -195,13 +204,21 @@ def run_ours(args):
                                         seed=11, first_run_id=rank * n_runs, n_runs=n_runs)
 
         def e2e_step():
+            t = [time.perf_counter()]
             p2 = engine.Problem(c.op, inp, out, c.iparam, c.kinds, c.lo, c.hi, c.p0, c.p1)
+            t.append(time.perf_counter())
             r2 = engine.RunGroup(p2, e_opts, sp)
+            t.append(time.perf_counter())
             r2.advance(1)
+            t.append(time.perf_counter())
             res = r2.fetch(0)
+            t.append(time.perf_counter())
             nbytes = sum(v.nbytes for v in res.values() if isinstance(v, np.ndarray))
             r2.close()
             p2.close()
+            t.append(time.perf_counter())
+            if os.environ.get("BINEST_E2E_DEBUG"):
+                print("e2e phases ms:", [round(1e3 * (b - a), 2) for a, b in zip(t, t[1:])], file=sys.stderr)
             return nbytes
 
         for _ in range(min(args.warmup, 3)):
@@ -252,7 +269,7 @@ def run_ours(args):
                 "why": "P walkers share every data tile, intensity = flop*P/bytes >> fp64 ridge (~6 flop/B): fp64-FMA bound"}
         # ---- CPU baseline beside it: oracle port, bounded sample
         from oracle import oracle as O
-        threads = O.max_threads()
+        threads = len(os.sched_getaffinity(0))  # all host cores, even when torchrun pins OMP_NUM_THREADS=1
         e, t = _cpu_leg(c, threads, 1 if N >= 100_000 else 200)
         cpu = {"value": e / t, "unit": "evals/s", "cores": threads, "kind": "port",
                "sample": f"{e} evals ({threads} threads x {e // max(threads, 1) // MC_STEPS} replacements x {MC_STEPS} steps) "
@@ -261,11 +278,7 @@ def run_ours(args):
             "metric": "loglikelihood evals/s", "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{c.name}: N={N} rows, d={d}, {n} live points, {n_runs} run(s)/GPU x K={K} replaced per "
-                                   f"iteration, {MC_STEPS} walk steps each",
-                       "l2": "256 MiB written between timed iterations (inside the timed region); the 16 MB data set is "
-                             "L2-resident across the 200 walk steps of an iteration by design",
-                       "parallelism": f"run-sharded x{world}, no collective"},
+            "config": _workload_config(c, K, n_runs, world),
             "replacements_per_s": value / MC_STEPS,
             "device_walk_ms_per_step": walk_ms / max(graphs, 1),
             "gpu_launches": int(launches),
