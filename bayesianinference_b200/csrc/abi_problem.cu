@@ -1,5 +1,6 @@
 // abi_problem.cu — library state, problem definition and the batched operator entry points of the
 // C ABI (include/binest.h).  No CPU fallback: every compute call needs a CUDA device.
+#include <algorithm>
 #include <cstring>
 #include <functional>
 #include <memory>
@@ -24,6 +25,26 @@ int guard(const std::function<void()> &f) {
     } catch (const std::exception &e) {
         t_last_error = e.what();
         return BINEST_ERR_FUNCTION;
+    }
+}
+
+// device row layout from the caller's column blocks: row i = (inputs[i][0..n_in), outputs[i], 0-padding to ncol).
+// The raw blocks are copied host->device as they are (one DMA each, straight from the caller's — possibly pinned —
+// buffers) and interleaved here, instead of being repacked on the host into a pageable staging vector.
+// n_classes > 0: outputs are class labels, anything but an integer in [0, n_classes) raises *bad.
+__global__ void pack_rows_kernel(const double *__restrict__ in, int n_in, const double *__restrict__ out, long long rows,
+                                 int ncol, int n_classes, double *__restrict__ data, int *__restrict__ bad) {
+    const long long total = rows * ncol;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long i = e / ncol;
+        const int c = (int)(e - i * ncol);
+        double v = 0.0;
+        if (c < n_in) v = in[i * n_in + c];
+        else if (c == n_in && out) {
+            v = out[i];
+            if (n_classes > 0 && !(v >= 0.0 && v < (double)n_classes && v == floor(v))) atomicOr(bad, 1);
+        }
+        data[e] = v;
     }
 }
 
@@ -99,6 +120,7 @@ int binest_init(double logzero, int device) {
         BN_CUDA(cudaGetDeviceProperties(&prop, dev));
         BN_REQUIRE(prop.major == 10, BINEST_ERR_CUDA,
                    std::string("libbinest is built for sm_100a only; found ") + prop.name);
+        dev_pool_configure(dev);
         g_logzero = logzero;
     });
 }
@@ -168,13 +190,15 @@ int binest_problem_create(int op_id, const int64_t *iparam, const double *inputs
         BN_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
         fill_prior(p->prior, (int)d, prior_kind, lo, hi, prior_p0, prior_p1);
 
-        std::vector<double> host;
+        std::vector<double> host;  // only the GBM adaptor pre-processes on the host (long double increments)
         auto need_out = [&] { BN_REQUIRE(outputs && n_out == 1, BINEST_ERR_DIMENSION, "operator needs one output column"); };
+        int n_classes = 0;
+        bool pack = false;
         switch (op_id) {
         case BINEST_OP_GAUSSIAN_IID:
             BN_REQUIRE(n_in == 1 && d == 2, BINEST_ERR_DIMENSION, "Gaussian i.i.d.: 1 data column, theta = (mu, sigma)");
             p->rows = n_rows; p->ncol = 1;
-            host.assign(inputs, inputs + n_rows);
+            pack = true;
             break;
         case BINEST_OP_POLYREG: {
             need_out();
@@ -182,8 +206,7 @@ int binest_problem_create(int op_id, const int64_t *iparam, const double *inputs
             BN_REQUIRE(n_in == 1 && deg >= 1 && deg <= 5 && d == deg + 2, BINEST_ERR_DIMENSION,
                        "polynomial regression: 1 input column, degree 1..5, theta = (c_0..c_deg, sigma)");
             p->rows = n_rows; p->ncol = 2;
-            host.resize((size_t)n_rows * 2);
-            for (int64_t i = 0; i < n_rows; ++i) { host[2 * i] = inputs[i]; host[2 * i + 1] = outputs[i]; }
+            pack = true;
             break;
         }
         case BINEST_OP_LOGISTIC: {
@@ -192,16 +215,9 @@ int binest_problem_create(int op_id, const int64_t *iparam, const double *inputs
             p->iparam[2] = n_in;
             BN_REQUIRE(K >= 2 && d == (K - 1) * (n_in + 1), BINEST_ERR_DIMENSION,
                        "logistic: theta = (K-1) blocks of (w_1..w_F, b)");
-            const int ncol = (int)((n_in + 2) & ~1LL);
-            p->rows = n_rows; p->ncol = ncol;
-            host.assign((size_t)n_rows * ncol, 0.0);
-            for (int64_t i = 0; i < n_rows; ++i) {
-                for (int64_t f = 0; f < n_in; ++f) host[i * ncol + f] = inputs[i * n_in + f];
-                const double lab = outputs[i];
-                BN_REQUIRE(lab >= 0 && lab < K && lab == std::floor(lab), BINEST_ERR_NUMERICAL,
-                           "logistic: class labels must be integers 0..K-1");
-                host[i * ncol + n_in] = lab;
-            }
+            p->rows = n_rows; p->ncol = (int)((n_in + 2) & ~1LL);
+            n_classes = (int)K;
+            pack = true;
             break;
         }
         case BINEST_OP_GBM: {  // TemporalData adaptor BS:511-515: inputs = times, outputs = values
@@ -238,13 +254,33 @@ int binest_problem_create(int op_id, const int64_t *iparam, const double *inputs
         }
         default: throw Error(BINEST_ERR_FUNCTION, "unknown operator id");
         }
-        if (!host.empty()) {
+        if (pack || !host.empty()) {
             dispatch_op(*p, [](auto) {});  // reject shapes outside the fixed table before uploading
-            host.resize(host.size() + 4, 0.0);  // slack so 16-byte-rounded bulk copies stay in bounds
-            p->data.alloc(host.size());
-            BN_CUDA(cudaMemcpyAsync(p->data.p, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice,
-                                    p->stream));
-            BN_CUDA(cudaStreamSynchronize(p->stream));
+            const size_t cells = (size_t)p->rows * p->ncol;
+            p->data.alloc(cells + 4);  // slack so 16-byte-rounded bulk copies stay in bounds
+            BN_CUDA(cudaMemsetAsync(p->data.p + cells, 0, 4 * sizeof(double), p->stream));
+            if (!host.empty()) {
+                BN_CUDA(cudaMemcpyAsync(p->data.p, host.data(), cells * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+                BN_CUDA(cudaStreamSynchronize(p->stream));
+            } else if (p->ncol == n_in && !outputs) {  // rows are already in device layout
+                BN_CUDA(cudaMemcpyAsync(p->data.p, inputs, cells * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+                BN_CUDA(cudaStreamSynchronize(p->stream));
+            } else {
+                DevBuf<double> raw_in((size_t)n_rows * n_in), raw_out(outputs ? (size_t)n_rows : 0);
+                DevBuf<int> bad(1);
+                bad.zero(p->stream);
+                BN_CUDA(cudaMemcpyAsync(raw_in.p, inputs, raw_in.n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+                if (outputs)
+                    BN_CUDA(cudaMemcpyAsync(raw_out.p, outputs, raw_out.n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+                const unsigned grid = (unsigned)std::min<size_t>((cells + 255) / 256, (size_t)p->num_sms * 16);
+                pack_rows_kernel<<<grid, 256, 0, p->stream>>>(raw_in.p, (int)n_in, raw_out.p, p->rows, p->ncol, n_classes,
+                                                            p->data.p, bad.p);
+                BN_LAUNCH_CHECK();
+                int h_bad = 0;
+                BN_CUDA(cudaMemcpyAsync(&h_bad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+                BN_CUDA(cudaStreamSynchronize(p->stream));
+                BN_REQUIRE(!h_bad, BINEST_ERR_NUMERICAL, "logistic: class labels must be integers 0..K-1");
+            }
         }
         *out = p.release();
     });

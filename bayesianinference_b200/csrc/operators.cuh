@@ -95,6 +95,61 @@ struct OpPolyReg {
 
 // ------------------------------------------------------------------ softmax classification, reference class K
 // theta = K-1 blocks of (w_1..w_F, b); device row = (x_1..x_F, label, pad...) with NCOL even
+//
+// In-kernel exp.  libdevice exp() rebuilt its constants with ~50 integer instructions per call and carried
+// slow-path branches; with two exps per datum the kernel was issue-bound at 0.47 of the fp64 pipe.  exp_bounded is
+// branch-free, 14 fp64-pipe instructions: Cody-Waite reduction r = x - k ln2 (magic-number rounding, two FMAs),
+// degree-10 polynomial (scripts/gen_exp_poly.py: max relative error 3.4e-16 on |r| <= ln2/2) whose coefficients
+// sit in the constant bank (DFMA takes a c[][] operand: two register sources, full issue rate), then k is added to
+// the exponent field.  Valid for |x| < 700 (result normal); callers route anything else through the slow path.
+__constant__ double kExpPoly[11] = {
+    1.0,
+    1.0000000000000067,      // 0x3ff000000000001e
+    0.5000000000000006,      // 0x3fe0000000000005
+    0.16666666666554314,     // 0x3fc555555554b736
+    0.041666666666573066,    // 0x3fa55555555520a4
+    0.008333333385699212,    // 0x3f81111112ddae8b
+    0.001388888893251478,    // 0x3f56c16c17f46982
+    0.00019841170230570286,  // 0x3f2a01978b8b3d18
+    2.480150431378554e-05,   // 0x3efa019a6611cad5
+    2.764019739169484e-06,   // 0x3ec72fafebdaf273
+    2.7626371065696354e-07,  // 0x3e928a2ca617b969
+};
+__constant__ double kExpRed[4] = {
+    1.4426950408889634,         // log2(e)
+    6755399441055744.0,         // 1.5 * 2^52: adding it leaves rint(x log2 e) in the low word
+    -6.93147180369123816490e-01,  // -ln2, high part (trailing zeros)
+    -1.90821492927058770002e-10,  // -ln2, low part
+};
+__device__ __forceinline__ bool exp_arg_bounded(double x) {  // |x| < 700, false for NaN/Inf
+    return (__double2hiint(x) & 0x7fffffff) < 0x4085E000;
+}
+// the N independent exps of one datum, step-major so that consecutive DFMAs come from different chains
+template <int N>
+__device__ __forceinline__ void exp_bounded(const double (&x)[N], double (&out)[N]) {
+    double t[N], r[N], p[N];
+    int k[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) t[i] = fma(x[i], kExpRed[0], kExpRed[1]);
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        k[i] = __double2loint(t[i]);
+        t[i] -= kExpRed[1];
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) r[i] = fma(t[i], kExpRed[2], x[i]);
+#pragma unroll
+    for (int i = 0; i < N; ++i) r[i] = fma(t[i], kExpRed[3], r[i]);
+#pragma unroll
+    for (int i = 0; i < N; ++i) p[i] = fma(r[i], kExpPoly[10], kExpPoly[9]);
+#pragma unroll
+    for (int j = 8; j >= 0; --j)
+#pragma unroll
+        for (int i = 0; i < N; ++i) p[i] = fma(p[i], r[i], kExpPoly[j]);
+#pragma unroll
+    for (int i = 0; i < N; ++i) out[i] = __hiloint2double(__double2hiint(p[i]) + (k[i] << 20), __double2loint(p[i]));
+}
+
 template <int F, int K>
 struct OpLogistic {
     static constexpr int D = (K - 1) * (F + 1), NCOL = (F + 2) & ~1, TW_MAX = 2;
@@ -112,54 +167,70 @@ struct OpLogistic {
         ok = true;
         return Coef{0};
     }
-    // log Sum_k exp z_k with z_K = 0, K <= 3, costs two exps and 1/32 of a log per datum:
-    //   * after sorting, one of the K shifted terms is exactly exp(0) = 1:  s = 1 + exp(a) + exp(b), a, b <= 0;
-    //   * Sum_i log s_i = log Prod_i s_i: s in (1, 3], so 32 factors (<= 3^32 = 1.9e15) are multiplied before one
-    //     log is taken (relative rounding 32 * 1.1e-16 on the product, i.e. ~4e-15 absolute on a sum of ~32 terms).
-    struct Acc { double lin, prod; int cnt; };
+    // Per datum, with the label's own logit z_y as the shift:  log p_y = -log(1 + Sum_{k != y} exp(z_k - z_y)).
+    // Every term has the same sign (no cancellation against a separate Sum z_y), K-1 exps, no max/sort.
+    // Sum_i log s_i = log Prod_i s_i: the running product is renormalised to [1, 2) after every factor by moving
+    // its exponent field into an integer (4 ALU instructions instead of a log per datum); one log at the end.
+    // |z_k - z_y| >= 700 (overflow / subnormal territory, NaN) takes the slow path: max-shifted libdevice exp/log.
+    struct Acc { double lin, prod; long long e2; };
     __device__ __forceinline__ static Acc acc_init() { return Acc{0.0, 1.0, 0}; }
-    __device__ __forceinline__ static double acc_value(const Acc &a) { return a.lin - log(a.prod); }
+    __device__ __forceinline__ static double acc_value(const Acc &a) {
+        return a.lin - fma((double)a.e2, 0.693147180559945309417232, log(a.prod));
+    }
     template <int TW>
     __device__ __forceinline__ static void rows(const Row (&c)[TW], const double *__restrict__ r, Acc (&acc)[TW]) {
         static_assert(K == 2 || K == 3, "softmax operator is specialised for 2 or 3 classes");
-        double z[TW][K - 1];
+        constexpr int E = K - 1;  // exps per datum
+        double z[TW][E];
         const int lab = (int)r[F];
 #pragma unroll
-        for (int k = 0; k < K - 1; ++k)
+        for (int k = 0; k < E; ++k)
 #pragma unroll
             for (int u = 0; u < TW; ++u) z[u][k] = c[u].w[k][F];
 #pragma unroll
         for (int f = 0; f < F; ++f) {
             const double x = r[f];
 #pragma unroll
-            for (int k = 0; k < K - 1; ++k)
+            for (int k = 0; k < E; ++k)
 #pragma unroll
                 for (int u = 0; u < TW; ++u) z[u][k] = fma(c[u].w[k][f], x, z[u][k]);
         }
+        double dz[TW * E], ex[TW * E];
+        bool fast = true;
 #pragma unroll
         for (int u = 0; u < TW; ++u) {
-            double zy = 0.0;  // z_K = 0
-#pragma unroll
-            for (int k = 0; k < K - 1; ++k) zy = (lab == k) ? z[u][k] : zy;
-            double mx, s;
             if (K == 2) {
-                mx = fmax(z[u][0], 0.0);
-                s = 1.0 + exp(-fabs(z[u][0]));
+                dz[u] = (lab == 0) ? -z[u][0] : z[u][0];  // label 1 is the reference class (z = 0)
             } else {
-                const double hi = fmax(z[u][0], z[u][K - 2]), lo = fmin(z[u][0], z[u][K - 2]);
-                mx = fmax(hi, 0.0);
-                s = (1.0 + exp(-fabs(hi))) + exp(lo - mx);
+                const double zy = (lab == 0) ? z[u][0] : ((lab == 1) ? z[u][1] : 0.0);
+                const double za = (lab == 0) ? z[u][1] : z[u][0];
+                const double zb = (lab == 2) ? z[u][1] : 0.0;
+                dz[u * E] = za - zy;
+                dz[u * E + 1] = zb - zy;
             }
-            acc[u].lin += zy - mx;
-            acc[u].prod *= s;
+#pragma unroll
+            for (int k = 0; k < E; ++k) fast = fast && exp_arg_bounded(dz[u * E + k]);
         }
-        if (++acc[0].cnt == 32) {
+        if (__builtin_expect(fast, 1)) {
+            exp_bounded<TW * E>(dz, ex);
 #pragma unroll
             for (int u = 0; u < TW; ++u) {
-                acc[u].lin -= log(acc[u].prod);
-                acc[u].prod = 1.0;
+                double s = 1.0 + ex[u * E];
+                if (K == 3) s += ex[u * E + 1];
+                const double p = acc[u].prod * s;  // < 2 * 3 e^700: finite
+                const int hi = __double2hiint(p), e = (hi >> 20) - 1023;
+                acc[u].e2 += e;
+                acc[u].prod = __hiloint2double(hi - (e << 20), __double2loint(p));
             }
-            acc[0].cnt = 0;
+        } else {
+#pragma unroll
+            for (int u = 0; u < TW; ++u) {
+                double mx = fmax(dz[u * E], 0.0);
+                if (K == 3) mx = fmax(mx, dz[u * E + 1]);
+                double s = exp(-mx) + exp(dz[u * E] - mx);
+                if (K == 3) s += exp(dz[u * E + 1] - mx);
+                acc[u].lin -= mx + log(s);
+            }
         }
     }
     __device__ static double finish(const Coef &, double acc, double, double) { return acc; }
