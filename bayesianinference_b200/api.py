@@ -203,7 +203,11 @@ def _backend(backend):
 def defineInferenceProblem(rules=None, _backend_override=None, **kw):
     """BS:148-308.  Keys: "Data", "Parameters", "PriorDistribution", "GeneratingDistribution",
     "IndependentVariables".  Returns inferenceObject[...] or inferenceObject[$Failed] (+ a warning carrying the
-    reference's message tag)."""
+    reference's message tag).
+
+    Extra key "DataSharding" (no reference counterpart; SURVEY §8e "very large N"): None (default), a backend Comm,
+    or "Automatic" = one shard per torch.distributed rank.  Every rank passes the full "Data"; only its row block
+    is uploaded, and "LogLikelihoodFunction" / nestedSampling become collectives that all ranks must call alike."""
     a = dict(rules or {})
     a.update(kw)
     try:
@@ -216,7 +220,20 @@ def defineInferenceProblem(rules=None, _backend_override=None, **kw):
         op, iparam, inputs, outputs = _operator_from_distribution(a["GeneratingDistribution"], a["Data"], names,
                                                                    a.get("IndependentVariables"))
         be = _backend(_backend_override)
-        prob = be.Problem(op, inputs, outputs, iparam, kinds, [p[1] for p in params], [p[2] for p in params], p0, p1)
+        comm = a.get("DataSharding")
+        if isinstance(comm, str):
+            if comm != "Automatic":
+                raise DefinitionError(f"defineInferenceProblem::insuffInfo: bad DataSharding value {comm!r}")
+            import torch.distributed as dist
+            comm = None
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                comm = be.Comm(dist.get_rank(), dist.get_world_size())
+        extra = {} if comm is None else {"comm": comm}
+        if comm is not None and op == _cfg.OP_GP_SE:
+            raise DefinitionError("defineInferenceProblem::logLike: the GP operator does not shard by rows")
+        prob = be.Problem(op, inputs, outputs, iparam, kinds, [p[1] for p in params], [p[2] for p in params], p0, p1,
+                          **extra)
+        a["DataSharding"] = comm
         # BS:276-298: both functions must return real machine numbers on random points of the box
         test = prob.sample_prior(100, seed=20260, run_id=0)
         ll, lp = prob.loglike(test), prob.logprior(test)

@@ -113,6 +113,8 @@ void build_walk_graph(binest_run &r) {
         using OP = decltype(op);
         r.geom = stream_geom<OP>(p, P);
         r.partials.alloc((size_t)r.geom.Gs * r.prm.Ps);
+        // data-sharded: stepped directly (the per-step all-gather is a NCCL call), see walk_block()
+        if (p.comm) return;
         // small data: the resident cluster kernel replaces the per-step graph (walk_resident.cuh)
         if (std::getenv("BINEST_NO_RESIDENT") == nullptr) {
             const size_t budget = 200 * 1024;
@@ -142,10 +144,10 @@ void build_walk_graph(binest_run &r) {
         const bool pdl = std::getenv("BINEST_NO_PDL") == nullptr;
         for (int step = 0; step <= S; ++step) {
             PdlConfig lc(sgrid, sblock, s, pdl && step > 0);
-            const double *partials = r.partials.p;
-            int G = r.geom.G, Gs = r.geom.Gs, fin = step == S ? 1 : 0;
+            const PartialView pv{r.partials.p, r.geom.G, r.geom.Gs, 1};
+            int fin = step == S ? 1 : 0;
             double rows = (double)p.rows, cst = p.cst;
-            BN_CUDA(cudaLaunchKernelEx(&lc.cfg, walk_step_kernel<OP>, r.prm, r.A, p.prior, partials, G, Gs, rows, cst, fin));
+            BN_CUDA(cudaLaunchKernelEx(&lc.cfg, walk_step_kernel<OP>, r.prm, r.A, p.prior, pv, rows, cst, fin));
             if (step < S) launch_loglike<OP>(p, r.w_prop.p, P, r.prm.Ps, r.partials.p, r.geom, s, false, pdl);
         }
         cudaGraph_t g;
@@ -184,15 +186,33 @@ void walk_block(binest_run &r) {
         });
         return;
     }
+    const int P = q.R * q.K;
+    const dim3 sgrid((P * 32 + 255) / 256), sblock(256);
+    if (p.comm) {
+        // data-sharded: every rank walks the same chains (same Philox counters) on its own rows; after each
+        // likelihood launch the per-rank sums are all-gathered and combined in rank order (shard_exchange)
+        dispatch_op(p, [&](auto op) {
+            using OP = decltype(op);
+            PartialView pv{p.sh_recv.p, p.comm->world, 1, q.Ps};
+            for (int step = 0; step <= q.S; ++step) {
+                walk_step_kernel<OP><<<sgrid, sblock, 0, r.stream>>>(q, r.A, p.prior, pv, p.rows_eff(), p.cst_eff(),
+                                                                    step == q.S ? 1 : 0);
+                BN_LAUNCH_CHECK();
+                if (step < q.S) {
+                    launch_loglike<OP>(p, r.w_prop.p, P, q.Ps, r.partials.p, r.geom, r.stream);
+                    pv = shard_exchange(p, r.partials.p, q.Ps, r.geom, r.stream);
+                }
+            }
+        });
+        return;
+    }
     if (p.op != BINEST_OP_GP_SE) {
         BN_CUDA(cudaGraphLaunch(r.walk_graph, r.stream));
         count_launch(2 * (int)q.S + 1);
         return;
     }
-    const int P = q.R * q.K;
-    const dim3 sgrid((P * 32 + 255) / 256), sblock(256);
     for (int step = 0; step <= q.S; ++step) {
-        walk_step_kernel<OpGpSe><<<sgrid, sblock, 0, r.stream>>>(q, r.A, p.prior, r.partials.p, r.geom.G, r.geom.Gs,
+        walk_step_kernel<OpGpSe><<<sgrid, sblock, 0, r.stream>>>(q, r.A, p.prior, PartialView{r.partials.p, r.geom.G, r.geom.Gs, 1},
                                                                  (double)p.rows, p.cst, step == q.S ? 1 : 0);
         BN_LAUNCH_CHECK();
         if (step < q.S) gp_loglike_device_strided(p, r.w_prop.p, P, q.Ps, r.partials.p, r.geom.Gs, false);
@@ -539,7 +559,7 @@ int binest_bench_loglike(binest_problem *p, int64_t P, int64_t reps, int64_t war
                 launch_loglike<OP>(*p, soa.p, (int)P, Ps, partials.p, g, p->stream);
                 BN_CUDA(cudaEventRecord(e1, p->stream));
                 loglike_finalize_kernel<OP><<<(unsigned)((P * 32 + 255) / 256), 256, 0, p->stream>>>(
-                    soa.p, (int)P, Ps, partials.p, g.G, g.Gs, (double)p->rows, p->cst, p->prior, g_logzero, out.p);
+                    soa.p, (int)P, Ps, PartialView{partials.p, g.G, g.Gs, 1}, (double)p->rows, p->cst, p->prior, g_logzero, out.p);
                 BN_LAUNCH_CHECK();
                 BN_CUDA(cudaEventRecord(e2, p->stream));
                 BN_CUDA(cudaEventSynchronize(e2));

@@ -111,11 +111,19 @@ loglike_stream_kernel(const double *__restrict__ data, long long rows, long long
     }
 }
 
-// fixed-order combine of the per-CTA partials of one walker by one warp (all lanes get the sum)
-__device__ __forceinline__ double combine_partials_warp(const double *__restrict__ partials, int G, int Gs, int w,
-                                                        int lane) {
+// where the G partial sums of walker w live: partial (w, g) at p[w * sw + g * sg].
+//   single GPU:   the per-CTA partials of loglike_stream_kernel, [Ps][Gs]            -> sw = Gs, sg = 1
+//   data-sharded: the per-rank sums after the all-gather (comm.cu), [world][Ps]      -> sw = 1,  sg = Ps
+struct PartialView {
+    const double *p;
+    int G;
+    long long sw, sg;
+};
+
+// fixed-order combine of the partials of one walker by one warp (all lanes get the sum)
+__device__ __forceinline__ double combine_partials_warp(const PartialView &pv, int w, int lane) {
     double s = 0.0;
-    for (int g = lane; g < G; g += 32) s += partials[(size_t)w * Gs + g];
+    for (int g = lane; g < pv.G; g += 32) s += pv.p[(size_t)w * pv.sw + (size_t)g * pv.sg];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     return s;
@@ -134,18 +142,26 @@ __device__ __forceinline__ double loglike_finish(const double (&th)[OP::D], doub
 // one warp per walker
 template <class OP>
 __global__ void loglike_finalize_kernel(const double *__restrict__ theta, int P, int Ps,
-                                        const double *__restrict__ partials, int G, int Gs, double rows, double cst,
+                                        const PartialView pv, double rows, double cst,
                                         const __grid_constant__ PriorSpec prior, double logzero,
                                         double *__restrict__ out) {
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (w >= P) return;
-    const double s = combine_partials_warp(partials, G, Gs, w, lane);
+    const double s = combine_partials_warp(pv, w, lane);
     double th[OP::D];
 #pragma unroll
     for (int j = 0; j < OP::D; ++j) th[j] = theta[(size_t)j * Ps + w];
     double v = loglike_finish<OP>(th, s, rows, cst, logzero);
     if (!in_box<OP::D>(prior, th)) v = logzero;  // If[constraints[theta], Sum[...], logzero] BS:491-494
     if (lane == 0) out[w] = v;
+}
+
+// data-sharded mode: this rank's sum over its own slices, one value per walker (the all-gather payload)
+static __global__ void shard_reduce_kernel(const PartialView pv, int Ps, double *__restrict__ send) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= Ps) return;
+    const double s = combine_partials_warp(pv, w, lane);
+    if (lane == 0) send[w] = s;
 }
 
 // log prior density for a batch (BS:410-426); theta SoA [d][Ps]

@@ -9,6 +9,12 @@
 
 #include "loglike.cuh"
 
+// data-sharded mode: one communicator per process, created by binest_comm_create (comm.cu)
+struct binest_comm {
+    void *nccl = nullptr;  // ncclComm_t
+    int rank = 0, world = 1, device = 0;
+};
+
 struct binest_problem {
     int op = 0;
     int64_t iparam[4] = {0, 0, 0, 0};
@@ -26,6 +32,12 @@ struct binest_problem {
     binest::DevBuf<double> gp_x, gp_y;
     // scratch reused by the batched entry points
     binest::DevBuf<double> s_theta, s_partials, s_out;
+    // data-sharded mode: this problem holds rows [shard of the data]; logL = Sum over ranks of the shard sums
+    binest_comm *comm = nullptr;
+    double rows_total = 0.0, cst_total = 0.0;   // over all shards (operator epilogues need the global values)
+    binest::DevBuf<double> sh_send, sh_recv;    // [Ps], [world][Ps]
+    double rows_eff() const { return comm ? rows_total : (double)rows; }
+    double cst_eff() const { return comm ? cst_total : cst; }
 
     ~binest_problem() {
         if (stream) cudaStreamDestroy(stream);
@@ -142,6 +154,22 @@ inline void launch_loglike(binest_problem &p, const double *theta_dev, int P, in
 
 void gp_loglike_device(binest_problem &p, const double *theta_dev, int P, int Ps, double *out_dev, bool check_box);
 
+// comm.cu: all-gather of `count` doubles per rank on stream s (NCCL over NVLink)
+void comm_allgather_f64(binest_comm &c, const double *send, double *recv, size_t count, cudaStream_t s);
+
+// Data-sharded exchange after a likelihood launch: reduce this rank's per-CTA partials to one sum per walker in a
+// fixed order, all-gather the P sums of every rank, and hand the consumer a view over [world][Ps].  Every rank then
+// adds the same `world` numbers in the same (rank) order, so accept/reject decisions are bit-identical everywhere —
+// which an all-reduce would not guarantee across algorithms.  Traffic: 8 P bytes per rank per step.
+inline PartialView shard_exchange(binest_problem &p, const double *partials, int Ps, const StreamGeom &g, cudaStream_t s) {
+    if (p.sh_send.n < (size_t)Ps) p.sh_send.alloc(Ps);
+    if (p.sh_recv.n < (size_t)Ps * p.comm->world) p.sh_recv.alloc((size_t)Ps * p.comm->world);
+    shard_reduce_kernel<<<(Ps * 32 + 255) / 256, 256, 0, s>>>(PartialView{partials, g.G, g.Gs, 1}, Ps, p.sh_send.p);
+    BN_LAUNCH_CHECK();
+    comm_allgather_f64(*p.comm, p.sh_send.p, p.sh_recv.p, (size_t)Ps, s);
+    return PartialView{p.sh_recv.p, p.comm->world, 1, Ps};
+}
+
 // full batched evaluation: theta_dev SoA [d][Ps] -> out_dev[P]
 inline void loglike_device(binest_problem &p, const double *theta_dev, int P, int Ps, double *out_dev) {
     if (p.op == BINEST_OP_GP_SE) {
@@ -154,8 +182,10 @@ inline void loglike_device(binest_problem &p, const double *theta_dev, int P, in
         const size_t need = (size_t)g.Gs * Ps;
         if (p.s_partials.n < need) p.s_partials.alloc(need);
         launch_loglike<OP>(p, theta_dev, P, Ps, p.s_partials.p, g, p.stream);
+        PartialView pv{p.s_partials.p, g.G, g.Gs, 1};
+        if (p.comm) pv = shard_exchange(p, p.s_partials.p, Ps, g, p.stream);
         loglike_finalize_kernel<OP><<<(P * 32 + 255) / 256, 256, 0, p.stream>>>(
-            theta_dev, P, Ps, p.s_partials.p, g.G, g.Gs, (double)p.rows, p.cst, p.prior, g_logzero, out_dev);
+            theta_dev, P, Ps, pv, p.rows_eff(), p.cst_eff(), p.prior, g_logzero, out_dev);
         BN_LAUNCH_CHECK();
     });
 }

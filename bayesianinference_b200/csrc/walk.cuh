@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(1024) run_update_kernel(const __grid_constant_
 template <class OP>
 __global__ void __launch_bounds__(256)
 walk_step_kernel(const __grid_constant__ RunParams prm, RunArrays A, const __grid_constant__ PriorSpec prior,
-                 const double *__restrict__ partials, int G, int Gs, double rows, double cst, int final_step) {
+                 const PartialView pv, double rows, double cst, int final_step) {
     constexpr int D = OP::D;
     pdl_wait();               // partials / walker state of the predecessors are complete and visible
     pdl_launch_dependents();  // let the next likelihood kernel start prefetching its data tiles
@@ -356,7 +356,7 @@ walk_step_kernel(const __grid_constant__ RunParams prm, RunArrays A, const __gri
         for (int a = 0; a < D; ++a) xn[a] = A.w_prop[(size_t)a * Ps + w];
         bool acc = false;
         if (flags & WF_PRE) {
-            const double sum = combine_partials_warp(partials, G, Gs, w, lane);
+            const double sum = combine_partials_warp(pv, w, lane);
             const double nL = loglike_finish<OP>(xn, sum, rows, cst, prm.logzero);
             if (nL > st.Lstar) {  // nsDensity: logL > threshold, strict (BS:605)
                 acc = true;

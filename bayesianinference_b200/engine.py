@@ -38,10 +38,60 @@ def default_options(**kw) -> Options:
     return o
 
 
-class Problem:
-    """Device-resident inference problem (the data-carrying half of defineInferenceProblem, BS:167-307)."""
+def shard_rows(n_rows: int, rank: int, world: int, overlap: int = 0):
+    """Row range [lo, hi) of `rank` in the data-sharded mode: `world` contiguous blocks whose sizes differ by at
+    most one.  overlap = 1 for point series whose rows are increments (GBM): shard r > 0 starts one point early, so
+    the increment across the cut belongs to the later shard and every increment is counted exactly once."""
+    if not (0 <= rank < world):
+        raise ValueError("0 <= rank < world")
+    units = n_rows - overlap  # rows (or increments) to distribute
+    if units < world:
+        raise ValueError(f"cannot split {units} rows over {world} ranks")
+    base, extra = divmod(units, world)
+    lo = rank * base + min(rank, extra)
+    hi = lo + base + (1 if rank < extra else 0)
+    return lo, hi + overlap
 
-    def __init__(self, op, inputs, outputs, iparam, kinds, lo, hi, p0=None, p1=None):
+
+class Comm:
+    """Communicator of the data-sharded mode (binest_comm_*): one per process, NCCL underneath.
+
+    `exchange(obj_or_None)` must hand rank 0's bytes to every rank; with torch.distributed initialised the default
+    uses broadcast_object_list (any backend)."""
+
+    def __init__(self, rank: int, world: int, exchange=None):
+        _ensure_init()
+        L = _lib.load()
+        ident = (C.c_uint8 * _lib.COMM_ID_BYTES)()
+        if rank == 0:
+            check(L.binest_comm_unique_id(ident))
+        payload = bytes(ident) if rank == 0 else None
+        if exchange is None:
+            import torch.distributed as dist
+
+            def exchange(b):
+                box = [b]
+                dist.broadcast_object_list(box, src=0)
+                return box[0]
+        payload = exchange(payload)
+        ident = (C.c_uint8 * _lib.COMM_ID_BYTES).from_buffer_copy(payload)
+        h = C.c_void_p()
+        check(L.binest_comm_create(rank, world, ident, C.byref(h)))
+        self.h, self.rank, self.world = h, rank, world
+
+    def close(self):
+        if getattr(self, "h", None):
+            _lib.load().binest_comm_free(self.h)
+            self.h = None
+
+
+class Problem:
+    """Device-resident inference problem (the data-carrying half of defineInferenceProblem, BS:167-307).
+
+    comm: data-sharded mode — `inputs`/`outputs` are the FULL data on every rank; only this rank's row block
+    (shard_rows) is uploaded and the problem is declared a shard (binest_problem_shard, collective)."""
+
+    def __init__(self, op, inputs, outputs, iparam, kinds, lo, hi, p0=None, p1=None, comm=None):
         _ensure_init()
         L = _lib.load()
         self.op = int(op)
@@ -50,6 +100,13 @@ class Problem:
             inputs = inputs.reshape(-1, 1)
         n = inputs.shape[0]
         outputs = None if outputs is None else _f64(outputs).reshape(n, -1)
+        if comm is not None:
+            from .configs import OP_GBM
+            r0, r1 = shard_rows(n, comm.rank, comm.world, overlap=1 if self.op == OP_GBM else 0)
+            inputs = np.ascontiguousarray(inputs[r0:r1])
+            outputs = None if outputs is None else np.ascontiguousarray(outputs[r0:r1])
+            n = r1 - r0
+        self.comm = comm
         self.d = len(kinds)
         ip = np.ascontiguousarray(list(iparam) + [0] * (4 - len(iparam)), dtype=np.int64)
         kinds = np.ascontiguousarray(kinds, dtype=np.int32)
@@ -63,10 +120,12 @@ class Problem:
                                       dptr(p1), C.byref(h)))
         self.h = h
         self.n_rows = n
+        if comm is not None:
+            check(L.binest_problem_shard(self.h, comm.h))
 
     @classmethod
-    def from_config(cls, cfg):
-        return cls(cfg.op, cfg.inputs, cfg.outputs, cfg.iparam, cfg.kinds, cfg.lo, cfg.hi, cfg.p0, cfg.p1)
+    def from_config(cls, cfg, comm=None):
+        return cls(cfg.op, cfg.inputs, cfg.outputs, cfg.iparam, cfg.kinds, cfg.lo, cfg.hi, cfg.p0, cfg.p1, comm=comm)
 
     def loglike(self, theta):
         """"LogLikelihoodFunction" (Listable): theta (P, d) -> (P,)."""

@@ -148,6 +148,24 @@ int binest_evidence_sampling(int64_t M, int64_t d, const double *points, const d
 int binest_crude_weights(int64_t M, const double *logL, const int64_t *pool, int64_t n_live,
                          double *logX, double *crude_logw, double *summary /*[4]*/);
 
+/* ---- data-sharded mode ("very large N"): rows split across the GPUs of one box ------------
+ * One process per GPU.  Rank 0 makes an id, the host passes it to every rank (any channel), every rank creates
+ * its communicator (collective), defines its problem from ITS rows only (GBM: shards overlap by one point, the
+ * increment between them belongs to the later shard) and declares it a shard (collective).  From then on
+ * binest_loglike / binest_run_* are collectives: all ranks must make the same calls with the same theta / options /
+ * seed / first_run_id.  Every rank walks the same chains (same Philox counters); after each likelihood launch the
+ * per-walker shard sums are all-gathered (NCCL, 8 P bytes per rank) and added in rank order, so every rank takes
+ * bit-identical accept/reject decisions and returns the same samples.  The reference has no such mode (its only
+ * parallelism is independent runs, BS:1349-1357); logL values equal the unsharded ones up to summation order.
+ * Not available for BINEST_OP_GP_SE (replicas only). */
+#define BINEST_COMM_ID_BYTES 128
+typedef struct binest_comm binest_comm;
+int binest_comm_unique_id(uint8_t *id /*[BINEST_COMM_ID_BYTES]*/);
+int binest_comm_create(int rank, int world, const uint8_t *id, binest_comm **out);
+int binest_comm_info(const binest_comm *c, int *rank, int *world);
+int binest_comm_free(binest_comm *c);
+int binest_problem_shard(binest_problem *p, binest_comm *c);
+
 /* ---- measurement helper (bench.py): inputs resident in HBM, CUDA events on the launching stream ---- */
 /* Scores P prior draws `reps` times after `warmup`; flush_l2 != 0 writes 256 MiB between repetitions.
  * ms_kernel: mean duration of the streaming likelihood kernel; ms_total: including the finalize kernel. */

@@ -21,14 +21,45 @@ def default_options(**kw):
     return o
 
 
+class Comm:
+    """Data-sharded mode on CPU: the per-rank sums travel over torch.distributed (gloo) instead of NCCL."""
+
+    def __init__(self, rank, world):
+        self.rank, self.world = rank, world
+
+    def allgather(self, x):
+        import torch
+        import torch.distributed as dist
+        out = [torch.empty(x.shape, dtype=torch.float64) for _ in range(self.world)]
+        dist.all_gather(out, torch.from_numpy(np.ascontiguousarray(x)))
+        return np.stack([t.numpy() for t in out])
+
+
 class Problem:
-    def __init__(self, op, inputs, outputs, iparam, kinds, lo, hi, p0=None, p1=None):
+    def __init__(self, op, inputs, outputs, iparam, kinds, lo, hi, p0=None, p1=None, comm=None):
         self.d = len(kinds)
+        self.comm = comm
+        if comm is not None:
+            from bayesianinference_b200 import configs as _cfg
+            from bayesianinference_b200.engine import shard_rows
+            inputs = np.asarray(inputs, float)
+            inputs = inputs.reshape(-1, 1) if inputs.ndim == 1 else inputs
+            r0, r1 = shard_rows(inputs.shape[0], comm.rank, comm.world, overlap=1 if op == _cfg.OP_GBM else 0)
+            inputs = inputs[r0:r1]
+            outputs = None if outputs is None else np.asarray(outputs, float).reshape(-1, 1)[r0:r1]
         self.prob = O.Problem(op, self.d, inputs, outputs, iparam)
         self.prior = O.Prior(kinds, lo, hi, p0 or None, p1 or None)
 
     def loglike(self, theta):
-        return self.prob.loglike(theta, self.prior)
+        v = self.prob.loglike(theta, self.prior)
+        if self.comm is None:
+            return v
+        parts = self.comm.allgather(v)  # [world][P], summed in rank order like shard_exchange (problem.cuh)
+        bad = (parts <= O.LOGZERO).any(0)
+        tot = np.zeros(parts.shape[1])
+        for r in range(self.comm.world):
+            tot = tot + parts[r]
+        return np.where(bad, O.LOGZERO, tot)
 
     def logprior(self, theta):
         return self.prior.logpdf(theta)

@@ -140,3 +140,73 @@ def test_shard_plan():
         parts = [api._shard(R, r, W) for r in range(W)]
         assert sum(c for _, c in parts) == R
         assert parts[0][0] == 0 and all(parts[i][0] + parts[i][1] == parts[i + 1][0] for i in range(W - 1))
+
+
+# ---------------------------------------------------------------------------------------------------
+# data-sharded mode: host logic on CPU — row plan, and "DataSharding" under gloo, world_size 2
+def test_shard_rows_plan():
+    from bayesianinference_b200.engine import shard_rows
+    for n, W in [(10, 2), (11, 3), (1_000_000, 8), (7, 7)]:
+        parts = [shard_rows(n, r, W) for r in range(W)]
+        assert parts[0][0] == 0 and parts[-1][1] == n
+        assert all(parts[i][1] == parts[i + 1][0] for i in range(W - 1))
+        sizes = [b - a for a, b in parts]
+        assert max(sizes) - min(sizes) <= 1
+    # series of increments (GBM): consecutive shards share exactly one point, every increment counted once
+    for n, W in [(16385, 8), (9, 4)]:
+        parts = [shard_rows(n, r, W, overlap=1) for r in range(W)]
+        assert parts[0][0] == 0 and parts[-1][1] == n
+        assert all(parts[i][1] - 1 == parts[i + 1][0] for i in range(W - 1))
+        assert sum(b - a - 1 for a, b in parts) == n - 1
+    with pytest.raises(ValueError):
+        shard_rows(3, 0, 4)
+
+
+def _sharded_objs():
+    c2 = cfg.c2_polyreg(N=4001)
+    o2 = api.defineInferenceProblem(
+        Data=(c2.inputs[:, 0], c2.outputs[:, 0]), GeneratingDistribution=api.NormalDistribution(
+            api.Polynomial("x", ("c0", "c1", "c2", "c3")), "sigma"),
+        Parameters=[(n, lo, hi) for n, lo, hi in zip(c2.names, c2.lo, c2.hi)], IndependentVariables=["x"],
+        PriorDistribution=["LocationParameter"] * 4 + ["ScaleParameter"], DataSharding="Automatic",
+        _backend_override=OB)
+    c4 = cfg.c4_gbm(T=1000)
+    o4 = api.defineInferenceProblem(
+        Data=(c4.inputs[:, 0], c4.outputs[:, 0]), GeneratingDistribution=api.GeometricBrownianMotionProcess("mu", "sigma"),
+        Parameters=[("mu", -1, 1), ("sigma", 0.01, 2)], PriorDistribution=["LocationParameter", "ScaleParameter"],
+        DataSharding="Automatic", _backend_override=OB)
+    th2 = OB.Problem(c2.op, c2.inputs, c2.outputs, c2.iparam, c2.kinds, c2.lo, c2.hi).sample_prior(6, 3)
+    th2[5, 4] = -1.0  # constraint violation -> logzero on every rank
+    th4 = np.array([[0.1, 0.3], [-0.5, 1.0]])
+    return o2, th2, o4, th4
+
+
+def _shard_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    o2, th2, o4, th4 = _sharded_objs()
+    assert o2["DataSharding"].world == world
+    q.put((rank, o2["LogLikelihoodFunction"](th2), o4["LogLikelihoodFunction"](th4)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_data_sharding_gloo_matches_unsharded():
+    import torch.multiprocessing as tmp
+    o2, th2, o4, th4 = _sharded_objs()  # no process group here: "Automatic" -> unsharded
+    assert o2["DataSharding"] is None
+    ref2, ref4 = o2["LogLikelihoodFunction"](th2), o4["LogLikelihoodFunction"](th4)
+    assert ref2[5] < -1e300
+    ctx = tmp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_shard_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    out = sorted(q.get(timeout=240) for _ in procs)
+    [p.join(60) for p in procs]
+    for _, l2, l4 in out:
+        np.testing.assert_allclose(l2[:5], ref2[:5], rtol=1e-12)
+        assert l2[5] < -1e300
+        np.testing.assert_allclose(l4, ref4, rtol=1e-12)
+    assert np.array_equal(out[0][1], out[1][1])  # same numbers in the same order on every rank
