@@ -11,6 +11,7 @@
 #include "evidence.cuh"
 #include "problem.cuh"
 #include "walk.cuh"
+#include "walk_grid.cuh"
 #include "walk_resident.cuh"
 
 namespace binest {
@@ -33,6 +34,11 @@ struct binest_run {
     int res_cs = 1;             // cluster size of the resident kernel
     long long res_rpc = 0;      // data rows per CTA of the cluster
     size_t res_smem = 0;
+    bool grid = false;          // whole walk in one persistent cooperative launch, data resident in all SMs' smem
+    int grid_G = 0, grid_Gs = 0, grid_tw = 1, grid_passes = 0, grid_passesA = 0;
+    long long grid_rpc = 0;
+    size_t grid_smem = 0;
+    unsigned *h_abort = nullptr;  // pinned
     bool first = true;
     bool finished = false;
     int64_t evals = 0;
@@ -49,6 +55,7 @@ struct binest_run {
     DevBuf<double> dead_theta, dead_logL, dead_logPr, dead_acc, dead_logX;
     DevBuf<int> dead_pool, order, kill_slot, w_flags, w_nacc, w_steps, n_unfrozen;
     DevBuf<RunState> state;
+    DevBuf<GridSync> gsync;
     DevBuf<double> w_theta, w_logL, w_logPr, w_prop, w_prop_logPr, w_mean, w_cov, partials;
 
     ~binest_run() {
@@ -57,6 +64,7 @@ struct binest_run {
         if (ev1) cudaEventDestroy(ev1);
         if (h_state) cudaFreeHost(h_state);
         if (h_unfrozen) cudaFreeHost(h_unfrozen);
+        if (h_abort) cudaFreeHost(h_abort);
     }
 };
 
@@ -98,6 +106,92 @@ void ensure_dead_capacity(binest_run &r, int64_t need) {
     bind_arrays(r);
 }
 
+// Geometry of the persistent grid-resident walk (walk_grid.cuh): G = SMs x resident CTAs, every CTA keeps
+// rows/G data rows in shared memory; walkers are tiled TW per lane and split into two alternating sets.
+// Returns false when the data do not fit (the stepped graph is used instead).
+// a walker warp keeps at most kGridMaxOwn walkers per set (G >= num_sms CTAs)
+inline bool G_own_too_many(int num_sms, int PA, int P) {
+    const int a = std::min(PA, P), b = P - a;
+    return (a + num_sms - 1) / num_sms > kGridMaxOwn || (b + num_sms - 1) / num_sms > kGridMaxOwn;
+}
+
+template <class OP>
+bool plan_grid_walk(binest_run &r, int P) {
+    binest_problem &p = *r.prob;
+    int coop = 0;
+    BN_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, p.device));
+    if (!coop) return false;
+    const char *e = std::getenv("BINEST_GRID_SETS");
+    const int nsets = (e && std::atoi(e) == 1) ? 1 : 2;
+    const int lanesets = (P + 31) / 32;
+    int tw = 1;
+    while (tw * 2 <= OP::TW_MAX && tw * 2 * nsets <= lanesets) tw <<= 1;
+    const int passes = (P + 32 * tw - 1) / (32 * tw);
+    const int passesA = nsets == 2 ? (passes + 1) / 2 : passes;
+    bool ok = false;
+    if (G_own_too_many(p.num_sms, 32 * tw * passesA, P)) return false;
+    dispatch_tw<OP>(tw, [&](auto twc) {
+        constexpr int TW = decltype(twc)::value;
+        for (int occ = 2; occ >= 1 && !ok; --occ) {
+            const int G = p.num_sms * occ;
+            long long rpc = ((p.rows + G - 1) / G + 1) & ~1LL;
+            rpc = std::max<long long>(rpc, 2);
+            const size_t smem = grid_smem_bytes<OP, TW>(rpc);
+            if (smem > (occ == 2 ? 110u * 1024u : 224u * 1024u)) continue;
+            BN_CUDA(cudaFuncSetAttribute(walk_grid_kernel<OP, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int nb = 0;
+            BN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, walk_grid_kernel<OP, TW>, kGridThreads, smem));
+            if (nb < occ) continue;
+            r.grid_G = G;
+            r.grid_Gs = (G + 3) & ~3;
+            r.grid_rpc = rpc;
+            r.grid_smem = smem;
+            ok = true;
+        }
+    });
+    if (!ok) return false;
+    r.grid = true;
+    r.grid_tw = tw;
+    r.grid_passes = passes;
+    r.grid_passesA = passesA;
+    r.partials.alloc((size_t)r.grid_Gs * r.prm.Ps);
+    r.gsync.alloc(1);
+    BN_CUDA(cudaHostAlloc((void **)&r.h_abort, sizeof(unsigned), cudaHostAllocDefault));
+    *r.h_abort = 0;
+    return true;
+}
+
+template <class OP>
+void launch_grid_walk(binest_run &r) {
+    binest_problem &p = *r.prob;
+    BN_CUDA(cudaMemsetAsync(r.gsync.p, 0, sizeof(GridSync), r.stream));
+    dispatch_tw<OP>(r.grid_tw, [&](auto twc) {
+        constexpr int TW = decltype(twc)::value;
+        cudaLaunchConfig_t cfg{};
+        cudaLaunchAttribute attr[1];
+        cfg.gridDim = dim3(r.grid_G);
+        cfg.blockDim = dim3(kGridThreads);
+        cfg.dynamicSmemBytes = r.grid_smem;
+        cfg.stream = r.stream;
+        attr[0].id = cudaLaunchAttributeCooperative;  // all CTAs co-resident, or the launch fails
+        attr[0].val.cooperative = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        const double *data = p.data.p;
+        long long rows = p.rows, rpc = r.grid_rpc;
+        double cst = p.cst;
+        double *partials = r.partials.p;
+        int Gs = r.grid_Gs, passes = r.grid_passes, passesA = r.grid_passesA;
+        GridSync *gs = r.gsync.p;
+        const char *e = std::getenv("BINEST_GRID_SYNC_ROWS");
+        int sync_rows = e ? std::atoi(e) : 64;
+        BN_CUDA(cudaLaunchKernelEx(&cfg, walk_grid_kernel<OP, TW>, r.prm, r.A, p.prior, data, rows, rpc, cst, partials, Gs,
+                                   passes, passesA, sync_rows, gs));
+        BN_LAUNCH_CHECK();
+    });
+    BN_CUDA(cudaMemcpyAsync(r.h_abort, &r.gsync.p->abort, sizeof(unsigned), cudaMemcpyDeviceToHost, r.stream));
+}
+
 // the S-step walk as one CUDA graph: [walk_step, loglike_stream] x S, then the final accept
 void build_walk_graph(binest_run &r) {
     binest_problem &p = *r.prob;
@@ -136,6 +230,8 @@ void build_walk_graph(binest_run &r) {
                 return;
             }
         }
+        // data that fits the shared memories of all SMs: one persistent launch per walk (walk_grid.cuh)
+        if (std::getenv("BINEST_NO_GRID") == nullptr && plan_grid_walk<OP>(r, P)) return;
         const dim3 sgrid((P * 32 + 255) / 256), sblock(256);  // one warp per walker
         BN_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
         // every node after the first is a programmatic dependent of its predecessor (PDL): the likelihood
@@ -184,6 +280,10 @@ void walk_block(binest_run &r) {
             BN_CUDA(cudaLaunchKernelEx(&cfg, walk_resident_kernel<OP>, q, r.A, p.prior, data, rows, rpc, cst, cs));
             BN_LAUNCH_CHECK();
         });
+        return;
+    }
+    if (r.grid) {
+        dispatch_op(p, [&](auto op) { launch_grid_walk<decltype(op)>(r); });
         return;
     }
     const int P = q.R * q.K;
@@ -358,6 +458,8 @@ int binest_run_advance(binest_run *r, int64_t max_batches, int32_t *finished) {
                 BN_CUDA(cudaEventElapsedTime(&ms, r->ev0, r->ev1));
                 r->walk_ms += ms;
                 r->walk_graphs += 1;
+                BN_REQUIRE(!(r->grid && *r->h_abort), BINEST_ERR_CUDA,
+                           "walk_grid_kernel: grid barrier timed out (walk aborted)");
                 r->evals += (int64_t)q.S * (int64_t)(blocks == 0 ? active : *r->h_unfrozen);
                 ++blocks;
                 if (!acc_loop) break;

@@ -72,7 +72,10 @@ loglike_stream_kernel(const double *__restrict__ data, long long rows, long long
         const int w = wbase + lane + 32 * t;
         double th[OP::D];
 #pragma unroll
-        for (int j = 0; j < OP::D; ++j) th[j] = (w < P) ? theta[(size_t)j * Ps + w] : 1.0;
+        // ld.global.cg, not the read-only (.nc) path `const __restrict__` would select: under PDL this kernel is
+        // already resident while its predecessor (walk_step) writes theta, and the non-coherent cache of the SM is
+        // not invalidated by griddepcontrol.wait (seen as stale proposals at N = 1e6: stored logL != logL(point))
+        for (int j = 0; j < OP::D; ++j) th[j] = (w < P) ? __ldcg(theta + (size_t)j * Ps + w) : 1.0;
         c[t] = OP::make_row(th);
     }
 
@@ -123,7 +126,16 @@ struct PartialView {
 // fixed-order combine of the partials of one walker by one warp (all lanes get the sum)
 __device__ __forceinline__ double combine_partials_warp(const PartialView &pv, int w, int lane) {
     double s = 0.0;
-    for (int g = lane; g < pv.G; g += 32) s += pv.p[(size_t)w * pv.sw + (size_t)g * pv.sg];
+    // ld.global.cg: the persistent walk kernel re-reads these addresses every step while other SMs rewrite them
+    // batches of 12 independent loads (one L2 round trip per batch instead of per element); same add order
+    const double *base = pv.p + (size_t)w * pv.sw;
+    for (int g0 = lane; g0 < pv.G; g0 += 32 * 12) {
+        double v[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) v[k] = (g0 + 32 * k < pv.G) ? __ldcg(base + (size_t)(g0 + 32 * k) * pv.sg) : 0.0;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) s += v[k];
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     return s;

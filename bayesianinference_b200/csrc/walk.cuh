@@ -326,14 +326,13 @@ __global__ void __launch_bounds__(1024) run_update_kernel(const __grid_constant_
 // lanes sum the per-CTA partials of their walker in a fixed order), then the next proposal.  The scalar
 // chain logic is executed redundantly by every lane (same values); only lane 0 stores.
 // final_step: accept only.
+// walk_step_walker: the step of ONE walker executed by one warp (shared by walk_step_kernel and the persistent
+// walk_grid_kernel, walk_grid.cuh).
 template <class OP>
-__global__ void __launch_bounds__(256)
-walk_step_kernel(const __grid_constant__ RunParams prm, RunArrays A, const __grid_constant__ PriorSpec prior,
-                 const PartialView pv, double rows, double cst, int final_step) {
+__device__ __forceinline__ void walk_step_walker(const RunParams &prm, const RunArrays &A, const PriorSpec &prior,
+                                                 const PartialView &pv, double rows, double cst, int final_step,
+                                                 int w, int lane) {
     constexpr int D = OP::D;
-    pdl_wait();               // partials / walker state of the predecessors are complete and visible
-    pdl_launch_dependents();  // let the next likelihood kernel start prefetching its data tiles
-    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const int K = prm.K, Ps = prm.Ps;
     if (w >= prm.R * K) return;
     const int r = w / K, j = w - r * K;
@@ -435,6 +434,16 @@ walk_step_kernel(const __grid_constant__ RunParams prm, RunArrays A, const __gri
         flags |= WF_HASPROP | pre;
     }
     if (lead) A.w_flags[w] = flags;
+}
+
+template <class OP>
+__global__ void __launch_bounds__(256)
+walk_step_kernel(const __grid_constant__ RunParams prm, RunArrays A, const __grid_constant__ PriorSpec prior,
+                 const PartialView pv, double rows, double cst, int final_step) {
+    pdl_wait();               // partials / walker state of the predecessors are complete and visible
+    pdl_launch_dependents();  // let the next likelihood kernel start prefetching its data tiles
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    walk_step_walker<OP>(prm, A, prior, pv, rows, cst, final_step, w, lane);
 }
 
 }  // namespace binest

@@ -176,6 +176,78 @@ def test_engine_trajectory_matches_oracle(eng, O, K):
     assert abs(got["entropy"] - ref.entropy) < 1e-7
 
 
+WALK_PATHS = {
+    "resident-cluster": {},                                                 # walk_resident.cuh
+    "grid-2sets": {"BINEST_NO_RESIDENT": "1"},                              # walk_grid.cuh, alternating sets
+    "grid-1set": {"BINEST_NO_RESIDENT": "1", "BINEST_GRID_SETS": "1"},
+    "stepped-graph": {"BINEST_NO_RESIDENT": "1", "BINEST_NO_GRID": "1"},    # [walk_step, loglike_stream] x S
+    "stepped-graph-nopdl": {"BINEST_NO_RESIDENT": "1", "BINEST_NO_GRID": "1", "BINEST_NO_PDL": "1"},
+}
+
+
+@pytest.mark.parametrize("path", list(WALK_PATHS))
+@pytest.mark.parametrize("case", ["C2-20k", "C4-2runs"])
+def test_every_walk_path_matches_oracle(eng, O, monkeypatch, path, case):
+    """The three device implementations of the S-step walk (cluster-resident, grid-resident persistent, stepped
+    CUDA graph) share walk_step_walker / the Philox addressing, so each must reproduce the oracle trajectory."""
+    for k in ("BINEST_NO_RESIDENT", "BINEST_NO_GRID", "BINEST_GRID_SETS", "BINEST_NO_PDL"):
+        monkeypatch.delenv(k, raising=False)
+    for k, v in WALK_PATHS[path].items():
+        monkeypatch.setenv(k, v)
+    if case == "C2-20k":
+        c, n, K, S, iters, runs = cfg.c2_polyreg(N=20_000), 256, 96, 25, 1440, 1
+    else:
+        c, n, K, S, iters, runs = cfg.c4_gbm(T=3000), 128, 24, 30, 600, 2
+    gp, op, pr = _pair(eng, O, c)
+    opts = eng.default_options(pool_size=n, batch_k=K, mc_steps=S, max_iter=iters, min_iter=iters, seed=33, n_runs=runs)
+    start = np.stack([pr.sample(n, 33, r) for r in range(runs)])
+    run = eng.RunGroup(gp, opts, start)
+    assert run.advance(0)
+    for r in range(runs):
+        got = run.fetch(r)
+        ref = O.nested_sampling(op, pr, pool_size=n, batch_k=K, mc_steps=S, max_iter=iters, min_iter=iters, seed=33,
+                                adapt_in_walk=False, start_points=start[r], run_id=r)
+        assert got["M"] == ref.logL.size and got["iterations"] == ref.iterations
+        np.testing.assert_allclose(got["logL"], ref.logL, rtol=1e-9)
+        np.testing.assert_allclose(got["points"], ref.points, rtol=1e-7, atol=1e-10)
+        np.testing.assert_allclose(got["acc"][~np.isnan(ref.acc)], ref.acc[~np.isnan(ref.acc)], rtol=1e-12)
+        assert abs(got["crude_logZ"] - ref.crude_logZ) < 1e-9 * abs(ref.crude_logZ)
+    run.close()
+
+
+@pytest.mark.parametrize("path", ["grid-2sets", "grid-1set", "stepped-graph", "stepped-graph-nopdl"])
+def test_full_size_walk_paths_agree_and_store_true_loglike(eng, monkeypatch, path):
+    """C2 at BASELINE size (1e6 rows, n = 1024, K = 256, S = 200), where the oracle is too slow: size-independent
+    properties instead.  (1) every stored sample's logL equals the operator evaluated at the stored point (a stale
+    proposal or a missed partial sum breaks this at once: it caught a PDL race at this size); (2) all walk paths
+    produce the same trajectory; (3) dead logL ascending, live points above the last threshold."""
+    for k in ("BINEST_NO_RESIDENT", "BINEST_NO_GRID", "BINEST_GRID_SETS", "BINEST_NO_PDL"):
+        monkeypatch.delenv(k, raising=False)
+    for k, v in WALK_PATHS[path].items():
+        monkeypatch.setenv(k, v)
+    c = cfg.c2_polyreg()
+    gp = eng.Problem.from_config(c)
+    opts = eng.default_options(pool_size=1024, batch_k=256, mc_steps=200, max_iter=10**9, min_iter=10**9, seed=2026)
+    run = eng.RunGroup(gp, opts)
+    run.advance(4)
+    s = run.fetch(0)
+    run.close()
+    nd = s["n_deleted"]
+    assert s["M"] == 1024 + 4 * 256 and nd == 4 * 256
+    chk = gp.loglike(s["points"])
+    np.testing.assert_allclose(s["logL"], chk, rtol=1e-12)
+    assert np.all(np.diff(s["logL"][:nd]) >= 0) and np.all(s["logL"][nd:] > s["logL"][nd - 1])
+    acc = s["acc"][~np.isnan(s["acc"])]
+    assert acc.size == 4 * 256 and 0.02 < acc.mean() < 0.9
+    key = ("full-size-c2", 2026)
+    ref = _FULL_SIZE_TRAJ.setdefault(key, s)
+    np.testing.assert_allclose(s["logL"], ref["logL"], rtol=1e-11)
+    np.testing.assert_allclose(s["points"], ref["points"], rtol=1e-9, atol=1e-12)
+
+
+_FULL_SIZE_TRAJ = {}
+
+
 def test_engine_logz_c1(eng, O):
     """LogEvidence within 3 sigma of the quadrature value (K4 pin, SURVEY Appendix A: -114.641064)."""
     c = cfg.c1_gaussian()
