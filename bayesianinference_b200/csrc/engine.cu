@@ -132,22 +132,20 @@ bool plan_grid_walk(binest_run &r, int P) {
     if (G_own_too_many(p.num_sms, 32 * tw * passesA, P)) return false;
     dispatch_tw<OP>(tw, [&](auto twc) {
         constexpr int TW = decltype(twc)::value;
-        for (int occ = 2; occ >= 1 && !ok; --occ) {
-            const int G = p.num_sms * occ;
-            long long rpc = ((p.rows + G - 1) / G + 1) & ~1LL;
-            rpc = std::max<long long>(rpc, 2);
-            const size_t smem = grid_smem_bytes<OP, TW>(rpc);
-            if (smem > (occ == 2 ? 110u * 1024u : 224u * 1024u)) continue;
-            BN_CUDA(cudaFuncSetAttribute(walk_grid_kernel<OP, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            int nb = 0;
-            BN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, walk_grid_kernel<OP, TW>, kGridThreads, smem));
-            if (nb < occ) continue;
-            r.grid_G = G;
-            r.grid_Gs = (G + 3) & ~3;
-            r.grid_rpc = rpc;
-            r.grid_smem = smem;
-            ok = true;
-        }
+        const int G = p.num_sms;  // one CTA per SM
+        long long rpc = ((p.rows + G - 1) / G + 1) & ~1LL;
+        rpc = std::max<long long>(rpc, 2);
+        const size_t smem = grid_smem_bytes<OP, TW>(rpc);
+        if (smem > 212u * 1024u) return;
+        BN_CUDA(cudaFuncSetAttribute(walk_grid_kernel<OP, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int nb = 0;
+        BN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, walk_grid_kernel<OP, TW>, kGridThreads, smem));
+        if (nb < 1) return;
+        r.grid_G = G;
+        r.grid_Gs = (G + 3) & ~3;
+        r.grid_rpc = rpc;
+        r.grid_smem = smem;
+        ok = true;
     });
     if (!ok) return false;
     r.grid = true;
@@ -164,6 +162,11 @@ bool plan_grid_walk(binest_run &r, int P) {
 template <class OP>
 void launch_grid_walk(binest_run &r) {
     binest_problem &p = *r.prob;
+    long long *dbg = nullptr;
+    if (std::getenv("BINEST_GRID_TRACE")) {
+        BN_CUDA(cudaMalloc((void **)&dbg, sizeof(long long) * 2 * 2 * 16 * 2 * 4));
+        BN_CUDA(cudaMemset(dbg, 0, sizeof(long long) * 2 * 2 * 16 * 2 * 4));
+    }
     BN_CUDA(cudaMemsetAsync(r.gsync.p, 0, sizeof(GridSync), r.stream));
     dispatch_tw<OP>(r.grid_tw, [&](auto twc) {
         constexpr int TW = decltype(twc)::value;
@@ -183,12 +186,29 @@ void launch_grid_walk(binest_run &r) {
         double *partials = r.partials.p;
         int Gs = r.grid_Gs, passes = r.grid_passes, passesA = r.grid_passesA;
         GridSync *gs = r.gsync.p;
-        const char *e = std::getenv("BINEST_GRID_SYNC_ROWS");
-        int sync_rows = e ? std::atoi(e) : 64;
         BN_CUDA(cudaLaunchKernelEx(&cfg, walk_grid_kernel<OP, TW>, r.prm, r.A, p.prior, data, rows, rpc, cst, partials, Gs,
-                                   passes, passesA, sync_rows, gs));
+                                   passes, passesA, gs, dbg));
         BN_LAUNCH_CHECK();
     });
+    if (dbg) {  // BINEST_GRID_TRACE: print the timeline of CTAs 0 and G/2 (cycles relative to the first event)
+        std::vector<long long> h(2 * 2 * 16 * 2 * 4);
+        BN_CUDA(cudaMemcpyAsync(h.data(), dbg, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost, r.stream));
+        BN_CUDA(cudaStreamSynchronize(r.stream));
+        for (int c = 0; c < 2; ++c) {
+            long long t0 = 0;
+            for (long long v : std::vector<long long>(h.begin() + c * 256, h.begin() + (c + 1) * 256))
+                if (v && (!t0 || v < t0)) t0 = v;
+            for (int role = 0; role < 2; ++role)
+                for (int s = 0; s < 16; ++s)
+                    for (int X = 0; X < 2; ++X) {
+                        const long long *e = &h[((((size_t)c * 2 + role) * 16 + s) * 2 + X) * 4];
+                        std::fprintf(stderr, "trace cta%d %s s=%2d X=%d  %9.2f %9.2f %9.2f %9.2f us\n", c,
+                                     role ? "data  " : "walker", s, X, (e[0] - t0) / 1965.0, (e[1] - t0) / 1965.0,
+                                     (e[2] - t0) / 1965.0, (e[3] - t0) / 1965.0);
+                    }
+        }
+        cudaFree(dbg);
+    }
     BN_CUDA(cudaMemcpyAsync(r.h_abort, &r.gsync.p->abort, sizeof(unsigned), cudaMemcpyDeviceToHost, r.stream));
 }
 

@@ -25,21 +25,20 @@
 
 namespace binest {
 
-constexpr int kGridDataWarps = 8;
-constexpr int kGridThreads = (kGridDataWarps + 1) * 32;
+constexpr int kGridGroupWarps = 8;                            // data warps per walker set
+constexpr int kGridThreads = (2 * kGridGroupWarps + 2) * 32;  // two data groups + two walker warps
 
+// Every counter on its own 256-byte line: polls of one counter do not queue behind the arrivals of another in the
+// same L2 sector (all four in one 32-byte sector made every arrival wait behind ~6 polls/ns of hot-spot traffic).
 struct GridSync {
-    unsigned props_ready[2];     // arrivals of walker warps: proposals of set X for the next step are published
-    unsigned partials_ready[2];  // arrivals of CTAs: partial sums of set X for the current step are published
+    unsigned ctr[4][64];  // [X]: props_ready of set X (arrivals of walker warps: next proposals published)
+                          // [2 + X]: partials_ready of set X (arrivals of CTAs: partial sums published)
     unsigned abort;
-    unsigned pad_[3];
+    unsigned pad_[63];
 };
+__device__ __forceinline__ unsigned *gs_props(GridSync *gs, int X) { return &gs->ctr[X][0]; }
+__device__ __forceinline__ unsigned *gs_partials(GridSync *gs, int X) { return &gs->ctr[2 + X][0]; }
 
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
 __device__ __forceinline__ void red_release_add_u32(unsigned *p, unsigned v) {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -48,16 +47,18 @@ __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p) {
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ void fence_acquire_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 
-// one thread polls until *ctr >= target (monotone counter); false after an abort / time-out
-__device__ __forceinline__ bool grid_wait(const unsigned *ctr, unsigned target, GridSync *gs) {
-    if (ld_acquire_u32(ctr) >= target) return true;
+// one thread polls until *ctr >= target (monotone counter); false after an abort / time-out.  Relaxed polls with
+// exponential back-off (every ld.acquire would also invalidate the SM's L1), one acquire fence on success.
+__device__ __forceinline__ bool grid_wait(const unsigned *ctr, unsigned target, GridSync *gs, unsigned max_ns) {
+    if (ld_relaxed_u32(ctr) >= target) { fence_acquire_gpu(); return true; }
     const long long t0 = clock64();
-    unsigned ns = 32;
+    unsigned ns = 64;
     for (unsigned it = 1;; ++it) {
         __nanosleep(ns);
-        if (ns < 256) ns <<= 1;
-        if (ld_acquire_u32(ctr) >= target) return true;
+        if (ns < max_ns) ns <<= 1;
+        if (ld_relaxed_u32(ctr) >= target) { fence_acquire_gpu(); return true; }
         if ((it & 63u) == 0u) {
             if (ld_relaxed_u32(&gs->abort)) return false;
             if (clock64() - t0 > 4000000000LL) {  // ~2 s at 1.9 GHz
@@ -66,6 +67,12 @@ __device__ __forceinline__ bool grid_wait(const unsigned *ctr, unsigned target, 
             }
         }
     }
+}
+
+// timeline trace: CTAs 0 and G/2, first 16 steps; slot [cta][role][s][X][4]
+__device__ __forceinline__ void grid_trace(long long *dbg, int g, int G, int role, int s, int X, int ev) {
+    if (dbg == nullptr || s >= 16 || (g != 0 && g != G / 2)) return;
+    dbg[((((g ? 1 : 0) * 2 + role) * 16 + s) * 2 + X) * 4 + ev] = clock64();
 }
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -273,29 +280,30 @@ __device__ __forceinline__ void gw_final(GridWalker<OP> &q, const RunParams &prm
     }
 }
 
-// dynamic shared memory (doubles): tile[rows_per_cta * NCOL (even)] | red[kGridDataWarps][32 * TW]
+// dynamic shared memory (doubles): tile[rows_per_cta * NCOL (even)] | red[2 groups][kGridGroupWarps][32 * TW]
 template <class OP, int TW>
 __host__ __device__ inline size_t grid_smem_bytes(long long rows_per_cta) {
     const size_t tile = (((size_t)rows_per_cta * OP::NCOL + 1) & ~(size_t)1);
-    return (tile + (size_t)kGridDataWarps * 32 * TW) * sizeof(double);
+    return (tile + (size_t)2 * kGridGroupWarps * 32 * TW) * sizeof(double);
 }
 
-// passesA: walker passes (of 32*TW walkers each) in set A; the remaining passes form set B (may be empty)
-// register budget: two CTAs per SM (<= 112 registers) whenever the walkers' coefficients are small enough
+// One CTA per SM: warps [0, 8) = data group of set A, [8, 16) = data group of set B, warp 16 / 17 = walker warp of
+// set A / B.  Both groups sweep ALL rows of the CTA's resident slice, each for its own walkers, and run
+// independently of each other: while one group sits in its per-step overhead (grid wait, proposal loads, cross-warp
+// combine, publish) the other has the whole fp64 pipe.  (History, all measured on C2: two alternating sets inside
+// 8-warp CTAs at 2 CTAs/SM fell into a schedule where the co-resident CTAs took turns — each alone on the SM, its
+// overhead never hidden, 87 us/step; 16 warps sweeping one set at a time: no waits but 95 us/step.)
+// passesA: walker passes (of 32*TW walkers each) in set A; the remaining passes form set B (may be empty).
 template <class OP, int TW>
-constexpr int grid_min_ctas() { return sizeof(typename OP::Row) * TW <= 128 ? 2 : 1; }
-
-template <class OP, int TW>
-__global__ void __launch_bounds__(kGridThreads, grid_min_ctas<OP, TW>())
+__global__ void __launch_bounds__(kGridThreads, 1)
 walk_grid_kernel(const __grid_constant__ RunParams prm, RunArrays A, const __grid_constant__ PriorSpec prior,
                  const double *__restrict__ data, long long rows, long long rows_per_cta, double cst,
-                 double *__restrict__ partials /* [Ps][Gs] */, int Gs, int passes, int passesA, int sync_rows,
-                 GridSync *gs) {
-    constexpr int NCOL = OP::NCOL, D = OP::D, WP = 32 * TW;
+                 double *__restrict__ partials /* [Ps][Gs] */, int Gs, int passes, int passesA,
+                 GridSync *gs, long long *dbg /* timeline trace (BINEST_GRID_TRACE), or nullptr */) {
+    constexpr int NCOL = OP::NCOL, D = OP::D, WP = 32 * TW, GW = kGridGroupWarps;
     extern __shared__ __align__(128) double smem[];
     const size_t tile_sz = (((size_t)rows_per_cta * NCOL + 1) & ~(size_t)1);
     double *tile = smem;
-    double *red = smem + tile_sz;
     __shared__ uint64_t full;
     __shared__ GridWalker<OP> slots[2][kGridMaxOwn];
 
@@ -303,7 +311,6 @@ walk_grid_kernel(const __grid_constant__ RunParams prm, RunArrays A, const __gri
     const int G = gridDim.x, g = blockIdx.x;
     const int P = prm.R * prm.K, Ps = prm.Ps, S = (int)prm.S;
     const int PA = min(passesA * WP, P);  // walkers [0, PA) are set A, [PA, P) set B
-    const int set_pass0[2] = {0, passesA}, set_pass1[2] = {passesA, passes};
 
     const long long r0 = (long long)g * rows_per_cta;
     const long long r1 = (r0 + rows_per_cta < rows) ? r0 + rows_per_cta : rows;
@@ -325,98 +332,93 @@ walk_grid_kernel(const __grid_constant__ RunParams prm, RunArrays A, const __gri
     }
     __syncthreads();
 
-    if (wid == kGridDataWarps) {
-        // =============================== walker warp ===============================
+    if (wid >= 2 * GW) {
+        // =============================== walker warp of set X ===============================
+        const int X = wid - 2 * GW;
+        const int wlo = X ? PA : 0, whi = X ? P : PA;
+        if (wlo >= whi) return;  // empty set: nobody waits on its counters
         const PartialView pv{partials, G, (long long)Gs, 1};
-        int w0[2], nown[2];
-#pragma unroll
-        for (int X = 0; X < 2; ++X) {
-            const int wlo = X ? PA : 0, whi = X ? P : PA;
-            int w = g;
-            while (w < wlo) w += G;
-            w0[X] = w;
-            nown[X] = w < whi ? (whi - w + G - 1) / G : 0;
+        int w0 = g;
+        while (w0 < wlo) w0 += G;
+        const int nown = w0 < whi ? (whi - w0 + G - 1) / G : 0;
+        for (int k = 0; k < nown; ++k) {
+            gw_init<OP>(slots[X][k], prm, A, w0 + k * G, lane);
+            gw_pre<OP>(slots[X][k], prm, A, prior, lane);
         }
-        for (int X = 0; X < 2; ++X)
-            for (int k = 0; k < nown[X]; ++k) {
-                gw_init<OP>(slots[X][k], prm, A, w0[X] + k * G, lane);
-                gw_pre<OP>(slots[X][k], prm, A, prior, lane);
-            }
         for (int s = 0; s <= S; ++s) {
-#pragma unroll 1
-            for (int X = 0; X < 2; ++X) {
-                if ((X ? P : PA) <= (X ? PA : 0)) continue;  // empty set: nobody waits on its counters
-                if (s > 0) {
-                    if (lane == 0) grid_wait(&gs->partials_ready[X], (unsigned)G * (unsigned)s, gs);
-                    __syncwarp();
-                }
-                for (int k = 0; k < nown[X]; ++k) gw_post<OP>(slots[X][k], prm, A, pv, (double)rows, cst, s < S, lane);
-                if (s < S && lane == 0) {
-                    __threadfence();
-                    red_release_add_u32(&gs->props_ready[X], 1u);
-                }
-                // off the critical path: bookkeeping, then the draws and candidates of the next step
-                for (int k = 0; k < nown[X]; ++k) {
-                    gw_update<OP>(slots[X][k], lane);
-                    if (s < S) gw_pre<OP>(slots[X][k], prm, A, prior, lane);
-                    else gw_final<OP>(slots[X][k], prm, A, lane);
-                }
+            if (lane == 0) grid_trace(dbg, g, G, 0, s, X, 0);
+            if (s > 0) {
+                if (lane == 0) grid_wait(gs_partials(gs, X), (unsigned)G * (unsigned)s, gs, 512u);
+                __syncwarp();
             }
+            if (lane == 0) grid_trace(dbg, g, G, 0, s, X, 1);
+            for (int k = 0; k < nown; ++k) gw_post<OP>(slots[X][k], prm, A, pv, (double)rows, cst, s < S, lane);
+            if (s < S && lane == 0) {
+                __threadfence();
+                red_release_add_u32(gs_props(gs, X), 1u);
+            }
+            if (lane == 0) grid_trace(dbg, g, G, 0, s, X, 2);
+            // off the critical path: bookkeeping, then the draws and candidates of the next step
+            for (int k = 0; k < nown; ++k) {
+                gw_update<OP>(slots[X][k], lane);
+                if (s < S) gw_pre<OP>(slots[X][k], prm, A, prior, lane);
+                else gw_final<OP>(slots[X][k], prm, A, lane);
+            }
+            if (lane == 0) grid_trace(dbg, g, G, 0, s, X, 3);
         }
         return;
     }
 
-    // =============================== data warps ===============================
-    // The 8 warps split the rows of the slice; they meet at a named barrier every `sync_rows` rows per warp (the
-    // warp scheduler is not fair between fp64-bound warps: without the meeting points a warp can fall a whole set
-    // behind and then runs alone, latency-bound, while the grid waits for it — measured 114-152 us/step without
-    // barriers against 90 with them), combine their sums in shared memory in a fixed order and publish
-    // partials[walker][g].
+    // =============================== data group of set X ===============================
+    // The 8 warps of the group split the rows of the slice, combine their sums in shared memory in a fixed order and
+    // publish partials[walker][g].  (Barrier-free variants — one partial per warp, or the last warp combining — were
+    // slower: the walker then sums 8x more partials, or the kernel needs too many registers.)
+    const int X = wid / GW, gwid = wid - X * GW, gtid = tid - X * GW * 32;
+    const int pass0 = X ? passesA : 0, pass1 = X ? passes : passesA;
+    if (pass0 >= pass1) return;
+    double *red = smem + tile_sz + (size_t)X * GW * WP;  // [GW][WP]
+    const int bar_id = 1 + X;
     if (nr > 0) mbar_wait(&full, 0);
-    const int chunk = (sync_rows > 0 ? sync_rows : (1 << 28) / kGridDataWarps) * kGridDataWarps;
     for (int s = 0; s < S; ++s) {
-#pragma unroll 1
-        for (int X = 0; X < 2; ++X) {
-            if (set_pass0[X] >= set_pass1[X]) continue;
-            if (tid == 0) grid_wait(&gs->props_ready[X], (unsigned)G * (unsigned)(s + 1), gs);
-            named_bar_sync(1, kGridDataWarps * 32);
-            for (int pass = set_pass0[X]; pass < set_pass1[X]; ++pass) {
-                const int wbase = pass * WP;
-                typename OP::Row c[TW];
+        if (gtid == 0) {
+            grid_trace(dbg, g, G, 1, s, X, 0);
+            grid_wait(gs_props(gs, X), (unsigned)G * (unsigned)(s + 1), gs, 256u);
+            grid_trace(dbg, g, G, 1, s, X, 1);
+        }
+        named_bar_sync(bar_id, GW * 32);
+        for (int pass = pass0; pass < pass1; ++pass) {
+            const int wbase = pass * WP;
+            typename OP::Row c[TW];
 #pragma unroll
-                for (int t = 0; t < TW; ++t) {
-                    const int w = wbase + lane + 32 * t;
-                    double th[D];
+            for (int t = 0; t < TW; ++t) {
+                const int w = wbase + lane + 32 * t;
+                double th[D];
 #pragma unroll
-                    for (int j = 0; j < D; ++j) th[j] = (w < P) ? __ldcg(A.w_prop + (size_t)j * Ps + w) : 1.0;
-                    c[t] = OP::make_row(th);
-                }
-                typename OP::Acc acc[TW];
+                for (int j = 0; j < D; ++j) th[j] = (w < P) ? __ldcg(A.w_prop + (size_t)j * Ps + w) : 1.0;
+                c[t] = OP::make_row(th);
+            }
+            typename OP::Acc acc[TW];
 #pragma unroll
-                for (int t = 0; t < TW; ++t) acc[t] = OP::acc_init();
-#pragma unroll 1
-                for (int i0 = 0; i0 < nr; i0 += chunk) {
-                    const int i1 = min(nr, i0 + chunk);
+            for (int t = 0; t < TW; ++t) acc[t] = OP::acc_init();
 #pragma unroll 2
-                    for (int i = i0 + wid; i < i1; i += kGridDataWarps) OP::template rows<TW>(c, tile + (size_t)i * NCOL, acc);
-                    if (i1 < nr) named_bar_sync(1, kGridDataWarps * 32);
-                }
+            for (int i = gwid; i < nr; i += GW) OP::template rows<TW>(c, tile + (size_t)i * NCOL, acc);
 #pragma unroll
-                for (int u = 0; u < TW; ++u) red[wid * WP + lane + 32 * u] = OP::acc_value(acc[u]);
-                named_bar_sync(1, kGridDataWarps * 32);
-                for (int k = tid; k < WP; k += kGridDataWarps * 32) {
-                    double sum = 0.0;
+            for (int u = 0; u < TW; ++u) red[gwid * WP + lane + 32 * u] = OP::acc_value(acc[u]);
+            named_bar_sync(bar_id, GW * 32);
+            for (int k = gtid; k < WP; k += GW * 32) {
+                double sum = 0.0;
 #pragma unroll
-                    for (int q = 0; q < kGridDataWarps; ++q) sum += red[q * WP + k];
-                    const int w = wbase + k;
-                    if (w < Ps) __stcg(partials + (size_t)w * Gs + g, sum);
-                }
-                named_bar_sync(1, kGridDataWarps * 32);  // red is free again; all partial stores are issued
+                for (int q = 0; q < GW; ++q) sum += red[q * WP + k];
+                const int w = wbase + k;
+                if (w < Ps) __stcg(partials + (size_t)w * Gs + g, sum);
             }
-            if (tid == 0) {
-                __threadfence();
-                red_release_add_u32(&gs->partials_ready[X], 1u);
-            }
+            named_bar_sync(bar_id, GW * 32);  // red is free again; all partial stores are issued
+        }
+        if (gtid == 0) {
+            grid_trace(dbg, g, G, 1, s, X, 2);
+            __threadfence();
+            red_release_add_u32(gs_partials(gs, X), 1u);
+            grid_trace(dbg, g, G, 1, s, X, 3);
         }
     }
 }
