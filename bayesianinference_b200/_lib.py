@@ -60,6 +60,8 @@ SIGNATURES = {
     "binest_crude_weights": (C.c_int, [C.c_int64, _dp, _ip, C.c_int64, _dp, _dp, _dp]),
     "binest_bench_loglike": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int64, C.c_int, _dp, _dp]),
     "binest_run_timing": (C.c_int, [_vp, _dp, _ip, _ip]),
+    "binest_run_path": (C.c_int, [_vp, C.POINTER(C.c_int)]),
+    "binest_problem_stream": (C.c_int, [_vp, C.POINTER(C.c_void_p)]),
     "binest_comm_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),
     "binest_comm_create": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_uint8), C.POINTER(_vp)]),
     "binest_comm_info": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),

@@ -587,6 +587,24 @@ int binest_run_timing(binest_run *r, double *walk_ms, int64_t *walk_graphs, int6
     });
 }
 
+int binest_run_path(const binest_run *r, int *path) {
+    return guard([&] {
+        BN_REQUIRE(r && path, BINEST_ERR_TYPE, "null run");
+        if (r->prob->op == BINEST_OP_GP_SE) *path = BINEST_WALK_STEPPED_GP;
+        else if (r->prob->comm) *path = BINEST_WALK_STEPPED_SHARDED;
+        else if (r->resident) *path = BINEST_WALK_CLUSTER_RESIDENT;
+        else if (r->grid) *path = BINEST_WALK_GRID_RESIDENT;
+        else *path = BINEST_WALK_STEPPED_GRAPH;
+    });
+}
+
+int binest_problem_stream(const binest_problem *p, void **stream) {
+    return guard([&] {
+        BN_REQUIRE(p && stream, BINEST_ERR_TYPE, "null problem");
+        *stream = (void *)p->stream;
+    });
+}
+
 int binest_run_free(binest_run *r) {
     return guard([&] {
         if (r) { cudaSetDevice(r->prob->device); cudaStreamSynchronize(r->stream); }

@@ -149,6 +149,12 @@ class Problem:
         check(_lib.load().binest_sample_prior(self.h, n, seed, run_id, dptr(out)))
         return out
 
+    def stream(self) -> int:
+        """cudaStream_t (as an integer) all kernels of this problem and of its runs are launched on."""
+        st = C.c_void_p()
+        check(_lib.load().binest_problem_stream(self.h, C.byref(st)))
+        return int(st.value or 0)
+
     def bench_loglike(self, P, reps=20, warmup=3, flush_l2=True):
         a, b = C.c_double(), C.c_double()
         check(_lib.load().binest_bench_loglike(self.h, P, reps, warmup, 1 if flush_l2 else 0, C.byref(a), C.byref(b)))
@@ -194,6 +200,13 @@ class RunGroup:
         ms, g, b = C.c_double(), C.c_int64(), C.c_int64()
         check(_lib.load().binest_run_timing(self.h, C.byref(ms), C.byref(g), C.byref(b)))
         return dict(walk_ms=ms.value, walk_graphs=g.value, batches=b.value)
+
+    WALK_PATHS = ("stepped-graph", "cluster-resident", "grid-resident", "stepped-sharded", "stepped-gp")
+
+    def walk_path(self) -> str:
+        v = C.c_int()
+        check(_lib.load().binest_run_path(self.h, C.byref(v)))
+        return self.WALK_PATHS[v.value]
 
     def fetch(self, run=0):
         """Sorted sample list of one run + calculateWeightsCrude columns (BS:812-831)."""

@@ -30,6 +30,8 @@ sys.path.insert(0, ROOT)
 from bayesianinference_b200 import configs as cfg  # noqa: E402
 
 MC_STEPS = 200  # "MonteCarloSteps" default, BS:844
+# profiles/r01e_ncu_walk_grid_c2.md: dram__bytes_read.sum + dram__bytes_write.sum of one walk_grid_kernel launch
+NCU_TRAFFIC_C2_GRID = 16.163e6 + 0.065e6
 WORKLOADS = {
     # name: (config factory, batch_k, flop per datum-eval, algorithmic bytes per datum-eval)   SURVEY §8d
     "C1": (cfg.c1_gaussian, 32, 3, 8),
@@ -64,7 +66,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -118,12 +120,13 @@ def run_reference(args):
     for _ in range(max(args.warmup, 0) and 1):  # one short warm-up pass is enough for a CPU loop
         _cpu_leg(c, threads, 1)
     tot_e, tot_t = 0, 0.0
+    reps = 4 if c.inputs.shape[0] >= 100_000 else 400  # ~1 s of CPU work per step
     for _ in range(args.steps):
-        e, t = _cpu_leg(c, threads, 1)
+        e, t = _cpu_leg(c, threads, reps)
         tot_e += e
         tot_t += t
     v = tot_e / tot_t
-    sample = f"{threads} threads x 1 replacement x {MC_STEPS} evals per step on the full {c.inputs.shape[0]}-row data"
+    sample = f"{threads} threads x {reps} replacements x {MC_STEPS} evals per step on the full {c.inputs.shape[0]}-row data"
     print(json.dumps({
         "impl": "reference", "metric": "loglikelihood evals/s", "value": v, "unit": "evals/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True,
@@ -156,10 +159,16 @@ def run_ours(args):
     opts = engine.default_options(pool_size=n, batch_k=K, mc_steps=MC_STEPS, max_iter=10**9, min_iter=10**9,
                                   seed=2026, first_run_id=rank * n_runs, n_runs=n_runs)
     run = engine.RunGroup(gp, opts)  # starting points drawn from the prior on the device
+    path = run.walk_path()
+    # everything of the library runs on the problem's own stream: time with CUDA events recorded on THAT stream, and
+    # put the L2 flush on it too so that it really sits between two iterations
+    lib_stream = torch.cuda.ExternalStream(gp.stream(), device=torch.device("cuda", local_rank))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    torch.cuda.synchronize()
 
     def step():
-        flush.fill_(1)  # L2 flush between timed iterations
+        with torch.cuda.stream(lib_stream):
+            flush.fill_(1)  # L2 flush between timed iterations
         run.advance(1)
 
     for _ in range(args.warmup):
@@ -173,11 +182,15 @@ def run_ours(args):
     t_before = run.timing()
     launches0 = engine.launch_count()
     torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
+    ev0.record(lib_stream)
     for _ in range(args.steps):
         step()
+    ev1.record(lib_stream)
     torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
+    dt_wall = time.perf_counter() - t0
+    dt = ev0.elapsed_time(ev1) * 1e-3  # device time on the launching stream (host gaps between iterations included)
     if use_dist:
         dist.barrier()
     launches = engine.launch_count() - launches0
@@ -246,12 +259,18 @@ def run_ours(args):
         # (S launches of the kernel, interleaved with the small walk_step kernel — so it is an upper bound).
         graphs = t_after["walk_graphs"] - t_before["walk_graphs"]
         walk_ms = t_after["walk_ms"] - t_before["walk_ms"]
-        ms_launch = walk_ms / max(graphs, 1) / MC_STEPS
         peak_tf = engine.fp64_peak()
         iso_kernel_ms, iso_total_ms = gp.bench_loglike(walkers, 20, 3, True)
-        alg_flop = float(flop) * rows * walkers
-        alg_bytes = float(byts) * rows  # the tile is read once per launch and shared by all walkers of a CTA row
+        # dominant kernel.  grid-resident path: ONE launch of walk_grid_kernel scores walkers x S proposals (the whole
+        # walk); stepped path: one launch of loglike_stream_kernel scores `walkers` proposals (one walk step).
+        steps_per_launch = MC_STEPS if path in ("grid-resident", "cluster-resident") else 1
+        kernel = {"grid-resident": "walk_grid_kernel", "cluster-resident": "walk_resident_kernel"}.get(path, "loglike_stream_kernel")
+        ms_launch = walk_ms / max(graphs, 1) / MC_STEPS * steps_per_launch
+        alg_flop = float(flop) * rows * walkers * steps_per_launch
+        alg_bytes = float(byts) * rows  # every data row is read from HBM/L2 once per launch and shared by all walkers
         achieved_tf = alg_flop / (ms_launch * 1e-3) / 1e12
+        # dram__bytes_read.sum + dram__bytes_write.sum of that kernel, one `ncu --set full` capture (profiles/)
+        traffic = {("C2", "walk_grid_kernel"): NCU_TRAFFIC_C2_GRID}.get((args.config, kernel))
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -259,9 +278,11 @@ def run_ours(args):
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         roof = {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved_tf / peak_tf, "traffic": None,
-                "kernel": "loglike_stream_kernel", "ms_per_launch": ms_launch,
-                "ms_per_launch_isolated": iso_kernel_ms, "frac_isolated": alg_flop / (iso_kernel_ms * 1e-3) / 1e12 / peak_tf,
+                "frac": achieved_tf / peak_tf, "traffic": traffic,
+                "kernel": kernel, "walk_path": path, "walk_steps_per_launch": steps_per_launch,
+                "ms_per_launch": ms_launch,
+                "stream_kernel_ms_isolated": iso_kernel_ms,
+                "stream_kernel_frac_isolated": float(flop) * rows * walkers / (iso_kernel_ms * 1e-3) / 1e12 / peak_tf,
                 "alg_flop_per_launch": alg_flop, "alg_bytes_per_launch": alg_bytes,
                 "hbm_time_bound_ms": alg_bytes / (hbm_peak * 1e9) * 1e3,
                 "peak_source": "fp64 DFMA peak measured live by binest_measure_fp64_peak (not in MEASURED_PEAKS.json); "
@@ -270,7 +291,8 @@ def run_ours(args):
         # ---- CPU baseline beside it: oracle port, bounded sample
         from oracle import oracle as O
         threads = len(os.sched_getaffinity(0))  # all host cores, even when torchrun pins OMP_NUM_THREADS=1
-        e, t = _cpu_leg(c, threads, 1 if N >= 100_000 else 200)
+        e1, t1 = _cpu_leg(c, threads, 1 if N >= 100_000 else 200)  # calibration pass, then ~12 s of CPU work
+        e, t = _cpu_leg(c, threads, max(1, int(round(12.0 / max(t1, 1e-3)))) * (1 if N >= 100_000 else 200))
         cpu = {"value": e / t, "unit": "evals/s", "cores": threads, "kind": "port",
                "sample": f"{e} evals ({threads} threads x {e // max(threads, 1) // MC_STEPS} replacements x {MC_STEPS} steps) "
                          f"on the full {N}-row data, {t:.1f} s"}
@@ -281,6 +303,8 @@ def run_ours(args):
             "config": _workload_config(c, K, n_runs, world),
             "replacements_per_s": value / MC_STEPS,
             "device_walk_ms_per_step": walk_ms / max(graphs, 1),
+            "timing": "CUDA events on the library's stream around the K timed steps, max over ranks",
+            "wall_ms_per_step": 1e3 * dt_wall / args.steps,
             "gpu_launches": int(launches),
             "clocks": clocks, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,
         }

@@ -134,6 +134,18 @@ int binest_run_fetch(binest_run *r, int64_t run, double *points, double *logL, d
 int binest_run_estimates(binest_run *r, int64_t run, double *mean, double *cov);
 /* device time spent in the walk graphs so far (CUDA events on the run's stream), graphs launched, batches */
 int binest_run_timing(binest_run *r, double *walk_ms, int64_t *walk_graphs, int64_t *batches);
+/* which device implementation walks this run (measurement / tests): */
+enum binest_walk_path {
+    BINEST_WALK_STEPPED_GRAPH = 0,   /* CUDA graph of [walk_step, loglike_stream] x S                     */
+    BINEST_WALK_CLUSTER_RESIDENT = 1,/* one launch per walk, data in the shared memories of a CTA cluster */
+    BINEST_WALK_GRID_RESIDENT = 2,   /* one persistent cooperative launch per walk, data in all SMs' smem  */
+    BINEST_WALK_STEPPED_SHARDED = 3, /* data-sharded: stepped with an all-gather per step                 */
+    BINEST_WALK_STEPPED_GP = 4       /* GP operator: stepped, hundreds of launches per likelihood          */
+};
+int binest_run_path(const binest_run *r, int *path);
+/* the CUDA stream (cudaStream_t) every kernel of this problem and of its runs is launched on, so that callers
+ * can record their own events / order their own work on it */
+int binest_problem_stream(const binest_problem *p, void **stream);
 int binest_run_free(binest_run *r);
 
 /* ---- evidenceSampling (BS:1158-1291) on a sorted sample list ------------------------------ */
