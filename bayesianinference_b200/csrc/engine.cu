@@ -2,6 +2,7 @@
 // plus the evidence entry points (BS:812-831, 1158-1291).  One process drives one GPU; runs are sharded
 // across GPUs by the caller (first_run_id / n_runs) and merged on the host (combineRuns BS:1293-1315).
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <functional>
@@ -22,6 +23,8 @@ void gp_loglike_device_strided(binest_problem &p, const double *theta_dev, int P
 }  // namespace binest
 
 using namespace binest;
+
+constexpr int kMaxRetry = 20;  // outer acceptance-retry rounds (1.25^20 = 87 x S steps in the last one)
 
 struct binest_run {
     binest_problem *prob = nullptr;
@@ -160,7 +163,7 @@ bool plan_grid_walk(binest_run &r, int P) {
 }
 
 template <class OP>
-void launch_grid_walk(binest_run &r) {
+void launch_grid_walk(binest_run &r, const RunParams &q) {
     binest_problem &p = *r.prob;
     long long *dbg = nullptr;
     if (std::getenv("BINEST_GRID_TRACE")) {
@@ -186,7 +189,7 @@ void launch_grid_walk(binest_run &r) {
         double *partials = r.partials.p;
         int Gs = r.grid_Gs, passes = r.grid_passes, passesA = r.grid_passesA;
         GridSync *gs = r.gsync.p;
-        BN_CUDA(cudaLaunchKernelEx(&cfg, walk_grid_kernel<OP, TW>, r.prm, r.A, p.prior, data, rows, rpc, cst, partials, Gs,
+        BN_CUDA(cudaLaunchKernelEx(&cfg, walk_grid_kernel<OP, TW>, q, r.A, p.prior, data, rows, rpc, cst, partials, Gs,
                                    passes, passesA, gs, dbg));
         BN_LAUNCH_CHECK();
     });
@@ -273,10 +276,10 @@ void build_walk_graph(binest_run &r) {
     });
 }
 
-// one block of S walk steps for every active walker
-void walk_block(binest_run &r) {
+// one block of q.S walk steps for every active walker.  q = r.prm, or its copy for an outer acceptance-retry round
+// (attempt > 0: more steps, shifted Philox counters); the pre-built CUDA graph only serves q.S == r.prm.S.
+void walk_block(binest_run &r, const RunParams &q) {
     binest_problem &p = *r.prob;
-    const RunParams &q = r.prm;
     if (r.resident) {
         dispatch_op(p, [&](auto op) {
             using OP = decltype(op);
@@ -303,40 +306,42 @@ void walk_block(binest_run &r) {
         return;
     }
     if (r.grid) {
-        dispatch_op(p, [&](auto op) { launch_grid_walk<decltype(op)>(r); });
+        dispatch_op(p, [&](auto op) { launch_grid_walk<decltype(op)>(r, q); });
         return;
     }
     const int P = q.R * q.K;
     const dim3 sgrid((P * 32 + 255) / 256), sblock(256);
-    if (p.comm) {
-        // data-sharded: every rank walks the same chains (same Philox counters) on its own rows; after each
-        // likelihood launch the per-rank sums are all-gathered and combined in rank order (shard_exchange)
-        dispatch_op(p, [&](auto op) {
-            using OP = decltype(op);
-            PartialView pv{p.sh_recv.p, p.comm->world, 1, q.Ps};
-            for (int step = 0; step <= q.S; ++step) {
-                walk_step_kernel<OP><<<sgrid, sblock, 0, r.stream>>>(q, r.A, p.prior, pv, p.rows_eff(), p.cst_eff(),
-                                                                    step == q.S ? 1 : 0);
-                BN_LAUNCH_CHECK();
-                if (step < q.S) {
-                    launch_loglike<OP>(p, r.w_prop.p, P, q.Ps, r.partials.p, r.geom, r.stream);
-                    pv = shard_exchange(p, r.partials.p, q.Ps, r.geom, r.stream);
-                }
-            }
-        });
+    if (p.op == BINEST_OP_GP_SE) {
+        for (int step = 0; step <= q.S; ++step) {
+            walk_step_kernel<OpGpSe><<<sgrid, sblock, 0, r.stream>>>(q, r.A, p.prior, PartialView{r.partials.p, r.geom.G, r.geom.Gs, 1},
+                                                                     (double)p.rows, p.cst, step == q.S ? 1 : 0);
+            BN_LAUNCH_CHECK();
+            if (step < q.S) gp_loglike_device_strided(p, r.w_prop.p, P, q.Ps, r.partials.p, r.geom.Gs, false);
+        }
         return;
     }
-    if (p.op != BINEST_OP_GP_SE) {
+    if (!p.comm && q.attempt == 0 && r.walk_graph) {
         BN_CUDA(cudaGraphLaunch(r.walk_graph, r.stream));
         count_launch(2 * (int)q.S + 1);
         return;
     }
-    for (int step = 0; step <= q.S; ++step) {
-        walk_step_kernel<OpGpSe><<<sgrid, sblock, 0, r.stream>>>(q, r.A, p.prior, PartialView{r.partials.p, r.geom.G, r.geom.Gs, 1},
-                                                                 (double)p.rows, p.cst, step == q.S ? 1 : 0);
-        BN_LAUNCH_CHECK();
-        if (step < q.S) gp_loglike_device_strided(p, r.w_prop.p, P, q.Ps, r.partials.p, r.geom.Gs, false);
-    }
+    // stepped directly: data-sharded (every rank walks the same chains (same Philox counters) on its own rows; after
+    // each likelihood launch the per-rank sums are all-gathered and combined in rank order, shard_exchange), and the
+    // retry rounds of the graph path
+    dispatch_op(p, [&](auto op) {
+        using OP = decltype(op);
+        PartialView pv = p.comm ? PartialView{p.sh_recv.p, p.comm->world, 1, q.Ps}
+                                : PartialView{r.partials.p, r.geom.G, r.geom.Gs, 1};
+        for (int step = 0; step <= q.S; ++step) {
+            walk_step_kernel<OP><<<sgrid, sblock, 0, r.stream>>>(q, r.A, p.prior, pv, p.rows_eff(), p.cst_eff(),
+                                                                step == q.S ? 1 : 0);
+            BN_LAUNCH_CHECK();
+            if (step < q.S) {
+                launch_loglike<OP>(p, r.w_prop.p, P, q.Ps, r.partials.p, r.geom, r.stream);
+                if (p.comm) pv = shard_exchange(p, r.partials.p, q.Ps, r.geom, r.stream);
+            }
+        }
+    });
 }
 
 void launch_update(binest_run &r, bool insert_only = false) {
@@ -468,24 +473,47 @@ int binest_run_advance(binest_run *r, int64_t max_batches, int32_t *finished) {
             for (int i = 0; i < q.R; ++i) active += r->h_state[i].done ? 0 : r->h_state[i].Kb;
             r->dead_upper += q.K;
             // S steps; then extra S-step blocks while some walker's acceptance is out of range (BS:730-736)
-            int blocks = 0;
-            do {
-                BN_CUDA(cudaEventRecord(r->ev0, r->stream));
-                walk_block(*r);
-                BN_CUDA(cudaEventRecord(r->ev1, r->stream));
-                BN_CUDA(cudaEventSynchronize(r->ev1));
-                float ms = 0;
-                BN_CUDA(cudaEventElapsedTime(&ms, r->ev0, r->ev1));
-                r->walk_ms += ms;
-                r->walk_graphs += 1;
-                BN_REQUIRE(!(r->grid && *r->h_abort), BINEST_ERR_CUDA,
-                           "walk_grid_kernel: grid barrier timed out (walk aborted)");
-                r->evals += (int64_t)q.S * (int64_t)(blocks == 0 ? active : *r->h_unfrozen);
-                ++blocks;
-                if (!acc_loop) break;
-                BN_CUDA(cudaMemcpyAsync(r->h_unfrozen, r->n_unfrozen.p, sizeof(int), cudaMemcpyDeviceToHost, r->stream));
-                BN_CUDA(cudaStreamSynchronize(r->stream));
-            } while (*r->h_unfrozen > 0 && blocks < 5);
+            auto walk_until_frozen = [&](const RunParams &qq, int64_t unfrozen0) {
+                int blocks = 0;
+                do {
+                    BN_CUDA(cudaEventRecord(r->ev0, r->stream));
+                    walk_block(*r, qq);
+                    BN_CUDA(cudaEventRecord(r->ev1, r->stream));
+                    BN_CUDA(cudaEventSynchronize(r->ev1));
+                    float ms = 0;
+                    BN_CUDA(cudaEventElapsedTime(&ms, r->ev0, r->ev1));
+                    r->walk_ms += ms;
+                    r->walk_graphs += 1;
+                    BN_REQUIRE(!(r->grid && *r->h_abort), BINEST_ERR_CUDA,
+                               "walk_grid_kernel: grid barrier timed out (walk aborted)");
+                    r->evals += (int64_t)qq.S * (int64_t)(blocks == 0 ? unfrozen0 : *r->h_unfrozen);
+                    ++blocks;
+                    if (!acc_loop) break;
+                    BN_CUDA(cudaMemcpyAsync(r->h_unfrozen, r->n_unfrozen.p, sizeof(int), cudaMemcpyDeviceToHost, r->stream));
+                    BN_CUDA(cudaStreamSynchronize(r->stream));
+                } while (*r->h_unfrozen > 0 && blocks < 5);
+            };
+            walk_until_frozen(q, active);
+            // outer retry (BS:995-1004): walkers still outside the range start again from a fresh live point with
+            // Ceiling[1.25^k S] steps; the reference loops without bound, here at most kMaxRetry rounds
+            if (acc_loop) {
+                double factor = 1.0;
+                for (int attempt = 1; attempt <= kMaxRetry; ++attempt) {
+                    factor *= 1.25;
+                    RunParams qq = q;
+                    qq.attempt = attempt;
+                    qq.S = (long long)std::ceil(factor * (double)q.S);
+                    qq.maxS = 5 * qq.S;
+                    const int P = q.R * q.K;
+                    BN_CUDA(cudaMemsetAsync(r->n_unfrozen.p, 0, sizeof(int), r->stream));
+                    walk_retry_kernel<<<(P + 127) / 128, 128, 0, r->stream>>>(qq, r->A);
+                    BN_LAUNCH_CHECK();
+                    BN_CUDA(cudaMemcpyAsync(r->h_unfrozen, r->n_unfrozen.p, sizeof(int), cudaMemcpyDeviceToHost, r->stream));
+                    BN_CUDA(cudaStreamSynchronize(r->stream));
+                    if (*r->h_unfrozen <= 0) break;
+                    walk_until_frozen(qq, *r->h_unfrozen);
+                }
+            }
             ++done_batches;
             ++r->batches;
         }

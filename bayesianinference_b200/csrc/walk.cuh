@@ -42,6 +42,7 @@ struct RunParams {
     unsigned long long seed;
     unsigned first_run_id;
     double logzero;
+    int attempt;  // outer acceptance retry round (BS:1000-1003): offsets the Philox counter word 0 by 16 * attempt
 };
 
 struct RunArrays {
@@ -408,7 +409,8 @@ __device__ __forceinline__ void walk_step_walker(const RunParams &prm, const Run
         double z[D + 1];
 #pragma unroll
         for (int b = 0; b < (D + 1) / 2; ++b)
-            rng_normal2(prm.seed, (uint32_t)b, (uint32_t)steps, walk_id, TAG_NORMAL, run_id, z[2 * b], z[2 * b + 1]);
+            rng_normal2(prm.seed, (uint32_t)(b + 16 * prm.attempt), (uint32_t)steps, walk_id, TAG_NORMAL, run_id, z[2 * b],
+                        z[2 * b + 1]);
         double xn[D];
 #pragma unroll
         for (int a = 0; a < D; ++a) {
@@ -421,7 +423,7 @@ __device__ __forceinline__ void walk_step_walker(const RunParams &prm, const Run
             if (lead) A.w_prop[(size_t)a * Ps + w] = s;
         }
         double u0, u1;
-        rng_uniform2(prm.seed, 0u, (uint32_t)steps, walk_id, TAG_ACCEPT, run_id, u0, u1);
+        rng_uniform2(prm.seed, (uint32_t)(16 * prm.attempt), (uint32_t)steps, walk_id, TAG_ACCEPT, run_id, u0, u1);
         int pre = 0;
         if (in_box<D>(prior, xn)) {
             double nPr = 0.0;
@@ -434,6 +436,36 @@ __device__ __forceinline__ void walk_step_walker(const RunParams &prm, const Run
         flags |= WF_HASPROP | pre;
     }
     if (lead) A.w_flags[w] = flags;
+}
+
+// Outer acceptance retry (BS:995-1004): a walker whose final acceptance rate is outside "MinMaxAcceptanceRate" is
+// restarted from a fresh RandomChoice of the survivors (BS:993) with its own chain estimates (BS:999) and — set by
+// the host for the whole round — Ceiling[1.25^attempt S] steps.  One thread per walker; counts the restarted
+// walkers in n_unfrozen.
+static __global__ void walk_retry_kernel(const __grid_constant__ RunParams prm, RunArrays A) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    const int K = prm.K, d = prm.d, n = prm.n;
+    if (w >= prm.R * K) return;
+    const int r = w / K, j = w - r * K;
+    const RunState &st = A.state[r];
+    if (st.done || j >= st.Kb) return;
+    const int steps = A.w_steps[w];
+    if (steps <= 0) return;
+    const double rate = (double)A.w_nacc[w] / (double)steps;
+    if (rate >= prm.acc_min && rate <= prm.acc_max) return;
+    double u0, u1;
+    rng_uniform2(prm.seed, (uint32_t)prm.attempt, 0u, (uint32_t)(st.walk_base + j), TAG_START, prm.first_run_id + r, u0, u1);
+    int pick = st.Kb + (int)(u0 * (double)(n - st.Kb));
+    if (pick > n - 1) pick = n - 1;
+    const int src = A.order[(size_t)r * n + pick];
+    const double *lth = A.live_theta + ((size_t)r * n + src) * d;
+    for (int a = 0; a < d; ++a) A.w_theta[(size_t)w * d + a] = lth[a];
+    A.w_logL[w] = A.live_logL[(size_t)r * n + src];
+    A.w_logPr[w] = A.live_logPr[(size_t)r * n + src];
+    A.w_nacc[w] = 0;
+    A.w_steps[w] = 0;
+    A.w_flags[w] = 0;
+    atomicAdd(A.n_unfrozen, 1);
 }
 
 template <class OP>

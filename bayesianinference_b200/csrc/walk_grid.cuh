@@ -139,12 +139,12 @@ __device__ __forceinline__ void gw_pre(GridWalker<OP> &q, const RunParams &prm, 
 #pragma unroll
         for (int b = 0; b < NZ; ++b) {
             double za, zb;
-            rng_normal2(prm.seed, (uint32_t)b, c, q.walk_id, TAG_NORMAL, q.run_id, za, zb);
+            rng_normal2(prm.seed, (uint32_t)(b + 16 * prm.attempt), c, q.walk_id, TAG_NORMAL, q.run_id, za, zb);
             q.z[lane][2 * b] = za;
             q.z[lane][2 * b + 1] = zb;
         }
         double u0, u1;
-        rng_uniform2(prm.seed, 0u, c, q.walk_id, TAG_ACCEPT, q.run_id, u0, u1);
+        rng_uniform2(prm.seed, (uint32_t)(16 * prm.attempt), c, q.walk_id, TAG_ACCEPT, q.run_id, u0, u1);
         q.logu[lane] = log(u0);
         __syncwarp();
     }

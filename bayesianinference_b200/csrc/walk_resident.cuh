@@ -110,7 +110,7 @@ walk_resident_kernel(const __grid_constant__ RunParams prm, RunArrays A, const _
                     double z[D + 1];
 #pragma unroll
                     for (int b = 0; b < (D + 1) / 2; ++b)
-                        rng_normal2(prm.seed, (uint32_t)b, stp, wid_, TAG_NORMAL, rid_, z[2 * b], z[2 * b + 1]);
+                        rng_normal2(prm.seed, (uint32_t)(b + 16 * prm.attempt), stp, wid_, TAG_NORMAL, rid_, z[2 * b], z[2 * b + 1]);
 #pragma unroll
                     for (int a = 0; a < D; ++a) {
                         double dz = 0.0;
@@ -121,7 +121,7 @@ walk_resident_kernel(const __grid_constant__ RunParams prm, RunArrays A, const _
                         s_dz[(sc * D + a) * 32 + wl] = dz;
                     }
                     double u0, u1;
-                    rng_uniform2(prm.seed, 0u, stp, wid_, TAG_ACCEPT, rid_, u0, u1);
+                    rng_uniform2(prm.seed, (uint32_t)(16 * prm.attempt), stp, wid_, TAG_ACCEPT, rid_, u0, u1);
                     s_logu[sc * 32 + wl] = log(u0);
                 }
             }

@@ -31,6 +31,7 @@
 #endif
 
 #define ORC_API __attribute__((visibility("default")))
+#define ORC_MAX_RETRY 20
 #define ORC_MAXD 16
 
 enum { OP_GAUSSIAN_IID = 1, OP_POLYREG = 2, OP_LOGISTIC = 3, OP_GBM = 4, OP_GP_SE = 5 };
@@ -619,7 +620,7 @@ ORC_API orc_run *orc_nested_sampling(const orc_problem *p, const orc_prior *pr, 
                                      const double *start_points) {
     const int d = p->d;
     const int64_t n = o->pool_size;
-    const int64_t S = o->mc_steps, maxS = 5 * S;
+    const int64_t S = o->mc_steps; /* {S, S, 5S} BS:872 */
     const uint32_t run_id = (uint32_t)o->run_id;
     orc_run *r = (orc_run *)calloc(1, sizeof(orc_run));
     r->d = d; r->n = n;
@@ -688,46 +689,69 @@ ORC_API orc_run *orc_nested_sampling(const orc_problem *p, const orc_prior *pr, 
             memcpy(C, covEst, sizeof(double) * d * d);
             memcpy(Lw, Lfac, sizeof(double) * d * d);
             int lw_ok = chol_ok;
-            double t = 10.0; /* startingIteration BS:715 */
-            int64_t steps = 0, accepted = 0, target = S;
-            for (;;) {
-                for (; steps < target; ++steps) {
-                    if (o->adapt_in_walk) lw_ok = proposal_chol(C, d, Lw);
-                    double z[ORC_MAXD + 1];
-                    for (int b = 0; b < (d + 1) / 2; ++b)
-                        orc_normal2(o->seed, (uint32_t)b, (uint32_t)steps, (uint32_t)walk_id, TAG_NORMAL, run_id, z + 2 * b);
-                    for (int a = 0; a < d; ++a) {
-                        double s = x[a];
-                        if (lw_ok) for (int b = 0; b <= a; ++b) s += Lw[a * d + b] * z[b];
-                        xn[a] = s;
-                    }
-                    double ua[2];
-                    orc_uniform2(o->seed, 0, (uint32_t)steps, (uint32_t)walk_id, TAG_ACCEPT, run_id, ua);
-                    /* nsDensity BS:602-617: box && logL > L* (strict) ? logPrior : logzero */
-                    int acc = 0;
-                    double nL = p->logzero, nPr = p->logzero;
-                    if (in_box(pr, xn)) {
-                        nL = orc_loglike(p, pr, xn);
-                        r->evals++;
-                        if (nL > Lstar) {
-                            nPr = orc_logprior(pr, xn);
-                            if (nPr - xPr > log(ua[0])) acc = 1;
+            /* outer loop BS:995-1004: a walk whose acceptance rate ends outside the range is started again from a
+             * fresh RandomChoice with Ceiling[factor S] steps, factor *= 1.25, keeping its own chain estimates
+             * (BS:999).  The reference loops without bound; both sides stop after ORC_MAX_RETRY rounds.  Philox counter
+             * word 0 is shifted by 16 * attempt so that every attempt has its own stream. */
+            int64_t steps = 0, accepted = 0;
+            double factor = 1.0;
+            for (int attempt = 0;; ++attempt) {
+                const int64_t S_k = attempt == 0 ? S : (int64_t)ceil(factor * (double)S);
+                const int64_t maxS_k = 5 * S_k;
+                if (attempt > 0) {
+                    orc_uniform2(o->seed, (uint32_t)attempt, 0, (uint32_t)walk_id, TAG_START, run_id, u);
+                    pick = Kb + (int64_t)(u[0] * (double)(n - Kb));
+                    if (pick > n - 1) pick = n - 1;
+                    const int64_t s2 = ord[pick].idx;
+                    memcpy(x, lp + s2 * d, sizeof(double) * d);
+                    xL = lL[s2]; xPr = lPr[s2];
+                }
+                double t = 10.0; /* startingIteration BS:715 */
+                int64_t target = S_k;
+                steps = 0; accepted = 0;
+                for (;;) {
+                    for (; steps < target; ++steps) {
+                        if (o->adapt_in_walk) lw_ok = proposal_chol(C, d, Lw);
+                        double z[ORC_MAXD + 1];
+                        for (int b = 0; b < (d + 1) / 2; ++b)
+                            orc_normal2(o->seed, (uint32_t)(b + 16 * attempt), (uint32_t)steps, (uint32_t)walk_id, TAG_NORMAL,
+                                        run_id, z + 2 * b);
+                        for (int a = 0; a < d; ++a) {
+                            double s = x[a];
+                            if (lw_ok) for (int b = 0; b <= a; ++b) s += Lw[a * d + b] * z[b];
+                            xn[a] = s;
                         }
+                        double ua[2];
+                        orc_uniform2(o->seed, (uint32_t)(16 * attempt), (uint32_t)steps, (uint32_t)walk_id, TAG_ACCEPT, run_id, ua);
+                        /* nsDensity BS:602-617: box && logL > L* (strict) ? logPrior : logzero */
+                        int acc = 0;
+                        double nL = p->logzero, nPr = p->logzero;
+                        if (in_box(pr, xn)) {
+                            nL = orc_loglike(p, pr, xn);
+                            r->evals++;
+                            if (nL > Lstar) {
+                                nPr = orc_logprior(pr, xn);
+                                if (nPr - xPr > log(ua[0])) acc = 1;
+                            }
+                        }
+                        if (acc) { memcpy(x, xn, sizeof(double) * d); xL = nL; xPr = nPr; ++accepted; }
+                        /* Haario recursion on the chain state */
+                        double mo[ORC_MAXD];
+                        memcpy(mo, m, sizeof(double) * d);
+                        for (int a = 0; a < d; ++a) m[a] += (x[a] - m[a]) / (t + 1.0);
+                        for (int a = 0; a < d; ++a)
+                            for (int b = 0; b < d; ++b)
+                                C[a * d + b] = (t - 1.0) / t * C[a * d + b] + (x[a] - mo[a]) * (x[b] - m[b]) / t;
+                        t += 1.0;
                     }
-                    if (acc) { memcpy(x, xn, sizeof(double) * d); xL = nL; xPr = nPr; ++accepted; }
-                    /* Haario recursion on the chain state */
-                    double mo[ORC_MAXD];
-                    memcpy(mo, m, sizeof(double) * d);
-                    for (int a = 0; a < d; ++a) m[a] += (x[a] - m[a]) / (t + 1.0);
-                    for (int a = 0; a < d; ++a)
-                        for (int b = 0; b < d; ++b)
-                            C[a * d + b] = (t - 1.0) / t * C[a * d + b] + (x[a] - mo[a]) * (x[b] - m[b]) / t;
-                    t += 1.0;
+                    const double rate = (double)accepted / (double)steps;
+                    /* BS:730-736 */
+                    if ((rate >= o->acc_min && rate <= o->acc_max) || steps >= maxS_k) break;
+                    target += S_k;
                 }
                 const double rate = (double)accepted / (double)steps;
-                /* BS:730-736 */
-                if ((rate >= o->acc_min && rate <= o->acc_max) || steps >= maxS) break;
-                target += S;
+                if ((rate >= o->acc_min && rate <= o->acc_max) || attempt >= ORC_MAX_RETRY) break; /* BS:1000-1003 */
+                factor *= 1.25;
             }
             memcpy(wpt + j * d, x, sizeof(double) * d);
             wL[j] = xL; wPr[j] = xPr; wAcc[j] = (double)accepted / (double)steps;

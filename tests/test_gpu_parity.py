@@ -215,6 +215,38 @@ def test_every_walk_path_matches_oracle(eng, O, monkeypatch, path, case):
     run.close()
 
 
+@pytest.mark.parametrize("path", ["resident-cluster", "grid-2sets", "stepped-graph"])
+def test_acceptance_range_loops_match_oracle(eng, O, monkeypatch, path):
+    """"MinMaxAcceptanceRate" (BS:848): the inner loop of nsMCMC (extra S-step blocks until the rate is in range or
+    5S steps, BS:730-736) and the outer retry of nestedSamplingInternal (restart from a fresh live point with
+    Ceiling[1.25^k S] steps, BS:995-1004), on every walk path, against the oracle trajectory."""
+    for k in ("BINEST_NO_RESIDENT", "BINEST_NO_GRID", "BINEST_GRID_SETS", "BINEST_NO_PDL"):
+        monkeypatch.delenv(k, raising=False)
+    for k, v in WALK_PATHS[path].items():
+        monkeypatch.setenv(k, v)
+    c = cfg.c1_gaussian(N=400, seed=5)
+    gp, op, pr = _pair(eng, O, c)
+    n, K, S, iters = 96, 12, 16, 360
+    start = pr.sample(n, 44, 0)
+    opts = eng.default_options(pool_size=n, batch_k=K, mc_steps=S, max_iter=iters, min_iter=iters, seed=44,
+                               acc_min=0.2, acc_max=0.45)
+    run = eng.RunGroup(gp, opts, start)
+    assert run.advance(0)
+    got = run.fetch(0)
+    evals = run.sizes(0)["evals"]
+    run.close()
+    ref = O.nested_sampling(op, pr, pool_size=n, batch_k=K, mc_steps=S, max_iter=iters, min_iter=iters, seed=44,
+                            acc_range=(0.2, 0.45), adapt_in_walk=False, start_points=start)
+    assert got["M"] == ref.logL.size and got["iterations"] == ref.iterations
+    np.testing.assert_allclose(got["logL"], ref.logL, rtol=1e-9)
+    np.testing.assert_allclose(got["points"], ref.points, rtol=1e-7, atol=1e-10)
+    a, b = got["acc"][~np.isnan(ref.acc)], ref.acc[~np.isnan(ref.acc)]
+    np.testing.assert_allclose(a, b, rtol=1e-12)
+    # the loops really ran: more evaluations than the plain S per replacement, and nearly all rates inside the range
+    assert evals > 1.3 * (n + iters * S)
+    assert np.mean((b >= 0.2) & (b <= 0.45)) > 0.9
+
+
 @pytest.mark.parametrize("path", ["grid-2sets", "grid-1set", "stepped-graph", "stepped-graph-nopdl"])
 def test_full_size_walk_paths_agree_and_store_true_loglike(eng, monkeypatch, path):
     """C2 at BASELINE size (1e6 rows, n = 1024, K = 256, S = 200), where the oracle is too slow: size-independent
