@@ -48,6 +48,9 @@ SIGNATURES = {
     "binest_problem_dim": (C.c_int, [_vp, _ip]),
     "binest_loglike": (C.c_int, [_vp, _dp, C.c_int64, _dp]),
     "binest_logprior": (C.c_int, [_vp, _dp, C.c_int64, _dp]),
+    "binest_predictive_width": (C.c_int, [_vp, _ip]),
+    "binest_predictive_components": (C.c_int, [_vp, _dp, C.c_int64, _dp, C.c_int64, _dp]),
+    "binest_gp_predict": (C.c_int, [_vp, _dp, C.c_int64, _dp, C.c_int64, _dp, _dp]),
     "binest_sample_prior": (C.c_int, [_vp, C.c_int64, C.c_uint64, C.c_int64, _dp]),
     "binest_run_create": (C.c_int, [_vp, C.POINTER(Options), _dp, C.POINTER(_vp)]),
     "binest_run_advance": (C.c_int, [_vp, C.c_int64, _i32p]),

@@ -253,8 +253,177 @@ def defineInferenceProblem(rules=None, _backend_override=None, **kw):
 
 def defineGaussianProcess(data, kernel: SquaredExponentialGP, parameters, prior, **rest):
     """GP:201-330 for the squared-exponential kernel + nugget (the operator of BASELINE config C5)."""
-    return defineInferenceProblem(Data=data, GeneratingDistribution=kernel, Parameters=parameters,
-                                  PriorDistribution=prior, **rest)
+    obj = defineInferenceProblem(Data=data, GeneratingDistribution=kernel, Parameters=parameters,
+                                 PriorDistribution=prior, **rest)
+    if not inferenceObjectQ(obj):
+        return obj
+    a = obj.Normal()
+    x = np.asarray(data[0], float)
+    a["Data"] = (x.reshape(-1, 1) if x.ndim == 1 else x, np.asarray(data[1], float).reshape(-1, 1))  # dataNormalForm
+    # GP:312-320: the model functions live in the device operator; the key marks the object as a GP problem
+    a["GaussianProcessData"] = {"ModelFunctions": {"KernelFunction": kernel, "NuggetFunction": kernel.sigma_n,
+                                                   "MeanFunction": 0.0}}
+    return inferenceObject(a)
+
+
+class MixtureDistribution:
+    """MixtureDistribution[weights, {NormalDistribution[mu_m, sigma_m]..}] (GP:357): the posterior predictive at
+    one input, a weighted mixture over the samples of the run."""
+
+    def __init__(self, weights, means, sds):
+        w = np.asarray(weights, float)
+        self.weights, self.means, self.sds = w / w.sum(), np.asarray(means, float), np.asarray(sds, float)
+
+    def mean(self):
+        return float(self.weights @ self.means)
+
+    def variance(self):
+        m = self.mean()
+        return float(self.weights @ (self.sds**2 + (self.means - m) ** 2))
+
+    def sd(self):
+        return float(np.sqrt(self.variance()))
+
+    def pdf(self, x):
+        x = np.asarray(x, float)[..., None]
+        z = (x - self.means) / self.sds
+        return (self.weights * np.exp(-0.5 * z * z) / (self.sds * np.sqrt(2 * np.pi))).sum(-1)
+
+    def cdf(self, x):
+        from math import erf
+        x = np.asarray(x, float)[..., None]
+        z = (x - self.means) / (self.sds * np.sqrt(2.0))
+        return (self.weights * 0.5 * (1.0 + np.vectorize(erf)(z))).sum(-1)
+
+    def quantile(self, q):
+        lo, hi = float((self.means - 10 * self.sds).min()), float((self.means + 10 * self.sds).max())
+        for _ in range(200):
+            mid = 0.5 * (lo + hi)
+            lo, hi = (mid, hi) if self.cdf(mid) < q else (lo, mid)
+        return 0.5 * (lo + hi)
+
+
+class CategoricalMixture:
+    """MixtureDistribution[weights, {CategoricalDistribution[p_m]..}]: class probabilities are the weighted mean."""
+
+    def __init__(self, weights, probs):
+        w = np.asarray(weights, float)
+        self.weights, self.probs = w / w.sum(), np.asarray(probs, float)
+
+    def probabilities(self):
+        return self.weights @ self.probs
+
+    def mode(self):
+        return int(np.argmax(self.probabilities()))
+
+
+class ParameterMixture:
+    """MixtureDistribution[weights, dist /@ points] for a generating distribution without independent variables
+    (BS:1421-1435): the components are the distribution at every sample's parameters."""
+
+    def __init__(self, weights, points, distribution, names):
+        w = np.asarray(weights, float)
+        self.weights, self.points, self.distribution, self.names = w / w.sum(), np.asarray(points, float), distribution, names
+
+
+class Predictive(dict):
+    """Association key -> mixture (BS:1464-1483) plus the arrays behind it: .inputs (Q, F), .weights (M,),
+    .components (M, Q, C)."""
+
+
+def predictiveDistribution(obj, inputs=None, keys=None, point_estimate=None, _backend_override=None):
+    """BS:1373-1483.  point_estimate: None (all samples, weighted by "CrudePosteriorWeight"), "MaximumLikelihood"
+    (BS:1388-1402) or "MAP" (BS:1404-1418).  Without inputs: the mixture over the samples' parameters (i.i.d. data,
+    BS:1420-1435); with inputs (and optional keys, BS:1437-1448): one mixture per input of a regression problem."""
+    if not inferenceObjectQ(obj):
+        return FAILED
+    a = obj.Normal()
+    if "Samples" not in a:
+        warnings.warn("predictiveDistribution::unsampled: Posterior has not been sampled yet")  # BS:1375-1380
+        return FAILED
+    if "GeneratingDistribution" not in a:
+        warnings.warn("predictiveDistribution::MissGenDist: No generating distribution specified")  # BS:1381-1387
+        return FAILED
+    S = a["Samples"]
+    pts = np.asarray(S["Point"], float)
+    if point_estimate in ("MaximumLikelihood", "MAP"):
+        score = S["LogLikelihood"] + (S["LogPriorPDF"] if point_estimate == "MAP" else 0.0)
+        i = int(np.argmax(score))
+        pts, w = pts[i:i + 1], np.ones(1)
+    elif point_estimate is None:
+        if "CrudePosteriorWeight" not in S:
+            return FAILED
+        w = np.asarray(S["CrudePosteriorWeight"], float)
+    else:
+        raise TypeError(f"unknown point estimate {point_estimate!r}")
+    dist, names = a["GeneratingDistribution"], a["ParameterSymbols"]
+    regression = isinstance(a["Data"], tuple) and a.get("IndependentVariables") is not None or isinstance(dist, CategoricalSoftmax)
+    if inputs is None:
+        if regression:
+            return FAILED  # BS:1420: this form needs ListQ data (no independent variables)
+        if isinstance(dist, NormalDistribution):
+            return MixtureDistribution(w, pts[:, 0], pts[:, 1])
+        return ParameterMixture(w, pts, dist, names)
+    if not regression:
+        return FAILED
+    x = np.asarray(inputs, float)
+    x = x.reshape(-1, 1) if x.ndim == 1 else x  # dataNormalForm BS:1437-1441
+    if x.ndim != 2 or not np.all(np.isfinite(x)):
+        return FAILED
+    if keys is None:
+        keys = [float(r[0]) if x.shape[1] == 1 else tuple(float(v) for v in r) for r in x]  # BS:1443-1446
+    if len(keys) != x.shape[0]:
+        return FAILED  # BS:1459
+    comp = a["_problem"].predictive_components(pts, x)
+    out = Predictive()
+    for q, k in enumerate(keys):
+        if isinstance(dist, CategoricalSoftmax):
+            out[k] = CategoricalMixture(w, comp[:, q, :])
+        else:
+            out[k] = MixtureDistribution(w, comp[:, q, 0], comp[:, q, 1])
+    out.inputs, out.weights, out.components = x, w / w.sum(), comp
+    return out
+
+
+class GPPrediction(dict):
+    """Association input -> MixtureDistribution (GP:355-378), plus the columnar arrays it was built from:
+    .points (Q, D), .weights (M,), .means / .sds (M, Q)."""
+
+
+def predictFromGaussianProcess(obj, pts, _backend_override=None):
+    """GP:332-393.  pts: an integer n > 1 (n equally spaced inputs per dimension over the bounds of the data inputs,
+    GP:335-342) or a list / matrix of inputs.  Every sample of the run contributes one NormalDistribution per input
+    (GP:395-420), mixed with the samples' "CrudePosteriorWeight" (GP:353, 357)."""
+    if not inferenceObjectQ(obj):
+        return FAILED
+    a = obj.Normal()
+    if "GaussianProcessData" not in a or "Samples" not in a:
+        return FAILED  # the reference's definition does not match and the call stays unevaluated
+    S = a["Samples"]
+    if "CrudePosteriorWeight" not in S:
+        return FAILED  # needs evidenceSampling with PostProcessSamplingRuns > 0 (BS:1237)
+    xin = a["Data"][0]
+    D = xin.shape[1]
+    if isinstance(pts, (int, np.integer)) and not isinstance(pts, bool):
+        if pts <= 1 or "Data" not in a:
+            return FAILED
+        axes = [np.linspace(xin[:, j].min(), xin[:, j].max(), int(pts)) for j in range(D)]  # CoordinateBoundsArray
+        grid = np.stack(np.meshgrid(*axes, indexing="ij"), -1).reshape(-1, D)
+    else:
+        grid = np.asarray(pts, float)
+        grid = grid.reshape(-1, 1) if grid.ndim == 1 else grid  # dataNormalForm
+        if grid.ndim != 2 or grid.shape[1] != D or not np.all(np.isfinite(grid)):
+            return FAILED
+    _, first = np.unique(grid, axis=0, return_index=True)  # association keys: a repeated input appears once
+    grid = grid[np.sort(first)]
+    mean, sd = a["_problem"].gp_predict(S["Point"], grid)
+    w = np.asarray(S["CrudePosteriorWeight"], float)
+    out = GPPrediction()
+    for q in range(grid.shape[0]):
+        key = float(grid[q, 0]) if D == 1 else tuple(float(v) for v in grid[q])
+        out[key] = MixtureDistribution(w, mean[:, q], sd[:, q])
+    out.points, out.weights, out.means, out.sds = grid, w / w.sum(), mean, sd
+    return out
 
 
 def generateStartingPoints(obj, n, seed=1):

@@ -5,6 +5,7 @@
 #include <functional>
 #include <memory>
 
+#include "predictive.cuh"
 #include "problem.cuh"
 
 namespace binest {
@@ -306,6 +307,56 @@ int binest_loglike(binest_problem *p, const double *theta, int64_t P, double *ou
         upload_theta(*p, theta, P, Ps);
         loglike_device(*p, p->s_theta.p, (int)P, Ps, p->s_out.p);
         BN_CUDA(cudaMemcpyAsync(out, p->s_out.p, sizeof(double) * P, cudaMemcpyDeviceToHost, p->stream));
+        BN_CUDA(cudaStreamSynchronize(p->stream));
+    });
+}
+
+int binest_gp_predict(binest_problem *p, const double *theta, int64_t M, const double *xstar, int64_t Q, double *mean,
+                      double *sd) {
+    return guard([&] {
+        BN_REQUIRE(p && theta && xstar && mean && sd, BINEST_ERR_TYPE, "null argument");
+        BN_REQUIRE(p->op == BINEST_OP_GP_SE, BINEST_ERR_FUNCTION, "binest_gp_predict needs a Gaussian-process problem");
+        BN_REQUIRE(M < (1LL << 30) && Q < (1LL << 24), BINEST_ERR_DIMENSION, "too many samples or prediction points");
+        if (M <= 0 || Q <= 0) return;
+        BN_CUDA(cudaSetDevice(p->device));
+        const int Ps = (int)((M + 31) & ~31LL);
+        upload_theta(*p, theta, M, Ps);
+        DevBuf<double> xs((size_t)Q * p->gp_dim), dm((size_t)M * Q), ds((size_t)M * Q);
+        BN_CUDA(cudaMemcpyAsync(xs.p, xstar, xs.n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+        gp_predict_device(*p, p->s_theta.p, (int)M, Ps, xs.p, (int)Q, dm.p, ds.p);
+        BN_CUDA(cudaMemcpyAsync(mean, dm.p, dm.n * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+        BN_CUDA(cudaMemcpyAsync(sd, ds.p, ds.n * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+        BN_CUDA(cudaStreamSynchronize(p->stream));
+    });
+}
+
+int binest_predictive_width(const binest_problem *p, int64_t *n_comp) {
+    return guard([&] {
+        BN_REQUIRE(p && n_comp, BINEST_ERR_TYPE, "null argument");
+        *n_comp = p->op == BINEST_OP_POLYREG ? 2 : p->op == BINEST_OP_LOGISTIC ? p->iparam[1] : 0;
+    });
+}
+
+int binest_predictive_components(binest_problem *p, const double *theta, int64_t M, const double *inputs, int64_t Q,
+                                 double *out) {
+    return guard([&] {
+        BN_REQUIRE(p && theta && inputs && out, BINEST_ERR_TYPE, "null argument");
+        BN_REQUIRE(p->op == BINEST_OP_POLYREG || p->op == BINEST_OP_LOGISTIC, BINEST_ERR_FUNCTION,
+                   "predictive components need an operator with independent variables (polynomial regression, softmax)");
+        if (M <= 0 || Q <= 0) return;
+        const int K = (int)p->iparam[1], F = p->op == BINEST_OP_LOGISTIC ? (int)p->iparam[2] : 1;
+        BN_REQUIRE(p->op != BINEST_OP_LOGISTIC || K <= kPredMaxD, BINEST_ERR_DIMENSION, "too many classes");
+        const int64_t C = p->op == BINEST_OP_POLYREG ? 2 : K;
+        BN_CUDA(cudaSetDevice(p->device));
+        const int Ps = (int)((M + 31) & ~31LL);
+        upload_theta(*p, theta, M, Ps);
+        DevBuf<double> xs((size_t)Q * F), o((size_t)M * Q * C);
+        BN_CUDA(cudaMemcpyAsync(xs.p, inputs, xs.n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+        const long long total = (long long)M * Q;
+        const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, (long long)p->num_sms * 8);
+        predictive_kernel<<<grid, 256, 0, p->stream>>>(p->op, (int)p->iparam[0], K, F, p->s_theta.p, M, Ps, xs.p, Q, o.p);
+        BN_LAUNCH_CHECK();
+        BN_CUDA(cudaMemcpyAsync(out, o.p, o.n * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
         BN_CUDA(cudaStreamSynchronize(p->stream));
     });
 }

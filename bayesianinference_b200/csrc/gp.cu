@@ -16,6 +16,12 @@
 //   gp_syrk_kernel    trailing update C -= L21 L21^T: the dense contraction, FP64 tensor-core MMA
 //                     (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4), 128x128 tile per CTA, K streamed in chunks of
 //                     32 through shared memory with cp.async double buffering
+//
+// predictFromGaussianProcess (GP:332-422, compiledKandKappa GP:92-116) rides on the same sweep: the Q prediction inputs
+// are appended as Qp = roundup(Q, 128) extra ROWS below every matrix (leading dimension ld = Np + Qp), filled with
+// the cross-covariances k(x*_q, x_j).  The panel solve then turns those rows into V = (L^-1 K*)^T tile by tile, its
+// fused right-hand-side update accumulates -V z = -k*.K^-1 y (the predictive mean) in y[Np + q], and the row sums of
+// squares of V give k*.K^-1 k* for the predictive variance — no factor is ever re-read and no back substitution runs.
 #include <algorithm>
 #include <vector>
 
@@ -29,14 +35,19 @@ constexpr int KC = 32;         // K chunk of the GEMM kernels
 constexpr int LDS_ = NB + 4;   // smem leading dimension: half-warp fragment loads hit 16 distinct 8-byte banks
 
 struct GpBatch {
-    double *A;        // [B][Np*Np] column-major
-    double *y;        // [B][Np] working right-hand side (consumed by the fused forward solve)
+    double *A;        // [B][ld*Np] column-major: Np columns of ld = Np + Qp rows (Qp = 0 for the likelihood)
+    double *y;        // [B][ld] working right-hand side (consumed by the fused forward solve); rows >= Np: -mean
     double *z;        // [B][NB]  z_k of the current panel
     double *linvT;    // [B][NB*NB] (k, n) -> L11^-1[n][k]
     double *logdet;   // [B]
     double *quad;     // [B]
     int *fail;        // [B]
     int Np, N, B;
+    int ld;           // rows per column
+    int Q;            // prediction inputs (rows Np .. Np + Q - 1 are live, the rest of the Qp block is zero)
+    const double *xs; // [Q][dim] prediction inputs (device) or nullptr
+    double *v2;       // [B][ld] row sums of squares of the solved prediction rows (k*.K^-1 k*), or nullptr
+    __host__ __device__ size_t mat() const { return (size_t)ld * Np; }
 };
 
 __device__ __forceinline__ void dmma_8x8x4(double &d0, double &d1, double a, double b) {
@@ -57,24 +68,33 @@ __global__ void __launch_bounds__(256)
 gp_fill_kernel(GpBatch g, const double *__restrict__ x, int dim, const double *__restrict__ yin,
                const double *__restrict__ theta, int Ps, int b0) {
     const int b = blockIdx.y;
-    // decode the lower-triangular tile index
-    int t = blockIdx.x, ti = 0;
-    while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
-    const int tj = t - ti * (ti + 1) / 2;
+    // decode the tile index: lower-triangular tiles of the square part first, then the Qp x Np prediction rows
+    const int T = g.Np / NB, tri = T * (T + 1) / 2;
+    int t = blockIdx.x, ti = 0, tj;
+    if (t < tri) {
+        while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+        tj = t - ti * (ti + 1) / 2;
+    } else {
+        ti = T + (t - tri) / T;
+        tj = (t - tri) % T;
+    }
+    const bool pred = ti >= T;
     const double sf = theta[0 * (size_t)Ps + b0 + b], ell = theta[1 * (size_t)Ps + b0 + b], sn = theta[2 * (size_t)Ps + b0 + b];
     const double sf2 = sf * sf, il2 = 1.0 / (2.0 * ell * ell), sn2 = sn * sn;
-    double *A = g.A + (size_t)b * g.Np * g.Np;
+    double *A = g.A + (size_t)b * g.mat();
     extern __shared__ double sx[];  // [2][NB][dim]
     double *xi = sx, *xj = sx + NB * dim;
     for (int k = threadIdx.x; k < NB * dim; k += blockDim.x) {
         const int r = k / dim, c = k - r * dim;
         const int gi = ti * NB + r, gj = tj * NB + r;
-        xi[k] = gi < g.N ? x[(size_t)gi * dim + c] : 0.0;
+        if (pred) xi[k] = gi - g.Np < g.Q ? g.xs[(size_t)(gi - g.Np) * dim + c] : 0.0;
+        else xi[k] = gi < g.N ? x[(size_t)gi * dim + c] : 0.0;
         xj[k] = gj < g.N ? x[(size_t)gj * dim + c] : 0.0;
     }
-    if (tj == 0 && ti * NB + threadIdx.x < g.Np && threadIdx.x < NB) {
-        const int gi = ti * NB + threadIdx.x;
-        g.y[(size_t)b * g.Np + gi] = gi < g.N ? yin[gi] : 0.0;
+    if (tj == 0 && threadIdx.x < NB) {
+        const int gi = ti * NB + threadIdx.x;  // < ld
+        g.y[(size_t)b * g.ld + gi] = gi < g.N ? yin[gi] : 0.0;
+        if (g.v2) g.v2[(size_t)b * g.ld + gi] = 0.0;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) { g.logdet[b] = 0.0; g.quad[b] = 0.0; g.fail[b] = 0; }
     __syncthreads();
@@ -83,14 +103,15 @@ gp_fill_kernel(GpBatch g, const double *__restrict__ x, int dim, const double *_
         const int gi = ti * NB + r, gj = tj * NB + c;
         if (gi < gj) continue;
         double v;
-        if (gi >= g.N || gj >= g.N) v = (gi == gj) ? 1.0 : 0.0;
+        const bool live_row = pred ? (gi - g.Np < g.Q) : (gi < g.N);
+        if (!live_row || gj >= g.N) v = (gi == gj) ? 1.0 : 0.0;
         else {
             double d2 = 0.0;
             for (int k = 0; k < dim; ++k) { const double df = xi[r * dim + k] - xj[c * dim + k]; d2 = fma(df, df, d2); }
-            v = sf2 * exp(-d2 * il2);
+            v = sf2 * exp(-d2 * il2);   // prediction rows: the cross-covariance k(x*, x_j), no nugget (GP:103-109)
             if (gi == gj) v += sn2;
         }
-        A[(size_t)gj * g.Np + gi] = v;
+        A[(size_t)gj * g.ld + gi] = v;
     }
 }
 
@@ -103,10 +124,10 @@ __global__ void __launch_bounds__(256) gp_potf2_kernel(GpBatch g, int k0) {
     __shared__ int s_fail;
     const int b = blockIdx.x, tid = threadIdx.x;
     if (g.fail[b]) return;
-    double *A = g.A + (size_t)b * g.Np * g.Np;
+    double *A = g.A + (size_t)b * g.mat();
     for (int e = tid; e < NB * NB; e += blockDim.x) {
         const int c = e / NB, r = e - c * NB;
-        s[r * LD + c] = (r >= c) ? A[(size_t)(k0 + c) * g.Np + k0 + r] : 0.0;
+        s[r * LD + c] = (r >= c) ? A[(size_t)(k0 + c) * g.ld + k0 + r] : 0.0;
     }
     if (tid == 0) s_fail = 0;
     __syncthreads();
@@ -147,7 +168,7 @@ __global__ void __launch_bounds__(256) gp_potf2_kernel(GpBatch g, int k0) {
     // write L11 back
     for (int e = tid; e < NB * NB; e += blockDim.x) {
         const int c = e / NB, r = e - c * NB;
-        if (r >= c) A[(size_t)(k0 + c) * g.Np + k0 + r] = s[r * LD + c];
+        if (r >= c) A[(size_t)(k0 + c) * g.ld + k0 + r] = s[r * LD + c];
     }
     // X = L11^-1, one column per thread (forward substitution), written transposed for the GEMM's B operand
     // The strict upper triangle of s is free: thread c keeps column c of X below the diagonal in row c of it,
@@ -177,7 +198,7 @@ __global__ void __launch_bounds__(256) gp_potf2_kernel(GpBatch g, int k0) {
         linvT[e] = (n > k) ? s[k * LD + n] : (n == k ? 1.0 / s[k * LD + k] : 0.0);
     }
     // z_k = L11^-1 y_k ; logdet += 2 sum log l_jj ; quad += z.z
-    const double *y = g.y + (size_t)b * g.Np + k0;
+    const double *y = g.y + (size_t)b * g.ld + k0;
     if (tid < NB) {
         double acc = y[tid] / s[tid * LD + tid];
         for (int c = 0; c < tid; ++c) acc = fma(s[c * LD + tid], y[c], acc);
@@ -238,13 +259,22 @@ __global__ void __launch_bounds__(256, 2) gp_syrk_kernel(GpBatch g, int k0) {
     extern __shared__ __align__(16) double sm[];  // 2 stages x (A chunk [KC][LDS_] + B chunk [KC][LDSH_])
     const int b = blockIdx.y;
     if (g.fail[b]) return;
-    int t = blockIdx.x, ti = 0;
-    while ((ti + 1) * (ti + 2) <= t) ++ti;
-    const int tj = t - ti * (ti + 1);  // 0 .. 2*ti + 1
+    // tiles of the square trailing part (rest x rest row blocks, lower triangle) first, then the prediction rows
+    // (every 64-column block of the trailing part)
+    const int rest = (g.Np - k0) / NB - 1;
+    int t = blockIdx.x, ti = 0, tj;
+    if (t < rest * (rest + 1)) {
+        while ((ti + 1) * (ti + 2) <= t) ++ti;
+        tj = t - ti * (ti + 1);  // 0 .. 2*ti + 1
+    } else {
+        t -= rest * (rest + 1);
+        ti = rest + t / (2 * rest);
+        tj = t % (2 * rest);
+    }
     const int base = k0 + NB;
     const int i0 = base + ti * NB, j0 = base + tj * NBH;
-    double *A = g.A + (size_t)b * g.Np * g.Np;
-    const size_t ld = g.Np;
+    double *A = g.A + (size_t)b * g.mat();
+    const size_t ld = g.ld;
     const double *PA = A + (size_t)k0 * ld + i0, *PB = A + (size_t)k0 * ld + j0;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wm = warp >> 1, wn = warp & 1;
     const int r = lane >> 2, q = lane & 3;
@@ -296,8 +326,8 @@ __global__ void __launch_bounds__(512) gp_trsm_kernel(GpBatch g, int k0) {
     const int b = blockIdx.y;
     if (g.fail[b]) return;
     const int i0 = k0 + NB + blockIdx.x * NB;
-    double *A = g.A + (size_t)b * g.Np * g.Np;
-    const size_t ld = g.Np;
+    double *A = g.A + (size_t)b * g.mat();
+    const size_t ld = g.ld;
     double *sAfull = sm;                       // [NB (k)][LDS_]
     double *sB[2] = {sm + NB * LDS_, sm + NB * LDS_ + KC * LDS_};
     double *sz = sm + NB * LDS_ + 2 * KC * LDS_;
@@ -342,10 +372,34 @@ __global__ void __launch_bounds__(512) gp_trsm_kernel(GpBatch g, int k0) {
     __syncthreads();
     if (threadIdx.x < NB) {
         const int m = threadIdx.x;
-        double s = 0.0;
-        for (int n = 0; n < NB; ++n) s = fma(sAfull[n * LDS_ + m], sz[n], s);
-        g.y[(size_t)b * g.Np + i0 + m] -= s;
+        double s = 0.0, ss = 0.0;
+        for (int n = 0; n < NB; ++n) {
+            const double l = sAfull[n * LDS_ + m];
+            s = fma(l, sz[n], s);
+            ss = fma(l, l, ss);
+        }
+        g.y[(size_t)b * g.ld + i0 + m] -= s;
+        if (i0 >= g.Np) g.v2[(size_t)b * g.ld + i0 + m] += ss;  // prediction rows: this panel's share of |L^-1 k*|^2
     }
+}
+
+// predictive mean and standard deviation (GP:401-418): mean = k*.K^-1 y, sd = Sqrt[kappa - k*.K^-1 k*] with
+// kappa = k(x*, x*) + nugget = sf^2 + sn^2 (GP:110-113).  A covariance that did not factor gives NaN (the reference
+// Throws out of matrixInverseAndDet, GP:131-135).  Rounding can push the radicand of a point that coincides with a
+// noise-free datum a few ulp below zero, where the reference would return a complex number: clamped to 0 here.
+__global__ void gp_predict_finish_kernel(GpBatch g, const double *__restrict__ theta, int Ps, int b0, int64_t Qtot,
+                                         double *__restrict__ mean, double *__restrict__ sd) {
+    const int b = blockIdx.y, q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= g.Q) return;
+    const double sf = theta[0 * (size_t)Ps + b0 + b], sn = theta[2 * (size_t)Ps + b0 + b], ell = theta[1 * (size_t)Ps + b0 + b];
+    const size_t o = (size_t)(b0 + b) * Qtot + q;
+    if (g.fail[b] || !(sf > 0.0 && ell > 0.0 && sn > 0.0)) {
+        mean[o] = sd[o] = __longlong_as_double(0x7ff8000000000000LL);
+        return;
+    }
+    mean[o] = -g.y[(size_t)b * g.ld + g.Np + q];
+    const double var = fma(sf, sf, sn * sn) - g.v2[(size_t)b * g.ld + g.Np + q];
+    sd[o] = sqrt(fmax(var, 0.0));
 }
 
 __global__ void gp_finish_kernel(GpBatch g, const double *__restrict__ theta, int Ps, int b0,
@@ -366,29 +420,33 @@ __global__ void gp_finish_kernel(GpBatch g, const double *__restrict__ theta, in
 
 }  // namespace
 
-// theta_dev SoA [3][Ps]; out_dev[(w) * out_stride]
-void gp_loglike_device_strided(binest_problem &p, const double *theta_dev, int P, int Ps, double *out_dev,
-                               int out_stride, bool check_box) {
-    const int N = (int)p.gp_n, Np = (N + NB - 1) / NB * NB, T = Np / NB;
-    size_t free_b = 0, total_b = 0;
-    BN_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    const size_t per = (size_t)Np * Np * sizeof(double);
-    // workspace: reuse across calls; sized for as many matrices as fit in 60 % of the free memory
-    static thread_local DevBuf<double> wsA, wsY, wsZ, wsL, wsLd, wsQ;
-    static thread_local DevBuf<int> wsF;
-    static thread_local int ws_cap = 0;
-    static thread_local int ws_np = 0;
-    int want = std::min<int>(P, 512);
-    if (ws_cap < want || ws_np != Np) {
-        wsA.release();
+namespace {
+
+// workspace shared by the likelihood and the prediction entry points: reused across calls, sized for as many
+// matrices as fit in 60 % of the free memory
+struct GpWorkspace {
+    DevBuf<double> A, Y, Z, L, Ld, Qd, V2;
+    DevBuf<int> F;
+    int cap = 0, np = 0, ld = 0;
+    void ensure(int want, int Np, int ld_) {
+        if (cap >= want && np == Np && ld == ld_) return;
+        A.release();
+        size_t free_b = 0, total_b = 0;
         BN_CUDA(cudaMemGetInfo(&free_b, &total_b));
-        int fit = (int)std::min<size_t>((size_t)want, (size_t)(0.6 * (double)free_b) / per);
+        const size_t per = (size_t)ld_ * Np * sizeof(double);
+        const int fit = (int)std::min<size_t>((size_t)want, (size_t)(0.6 * (double)free_b) / per);
         BN_REQUIRE(fit >= 1, BINEST_ERR_MEMORY, "not enough device memory for one GP covariance matrix");
-        wsA.alloc((size_t)fit * Np * Np);
-        wsY.alloc((size_t)fit * Np); wsZ.alloc((size_t)fit * NB); wsL.alloc((size_t)fit * NB * NB);
-        wsLd.alloc(fit); wsQ.alloc(fit); wsF.alloc(fit);
-        ws_cap = fit; ws_np = Np;
+        A.alloc((size_t)fit * ld_ * Np);
+        Y.alloc((size_t)fit * ld_); V2.alloc((size_t)fit * ld_); Z.alloc((size_t)fit * NB); L.alloc((size_t)fit * NB * NB);
+        Ld.alloc(fit); Qd.alloc(fit); F.alloc(fit);
+        cap = fit; np = Np; ld = ld_;
     }
+};
+thread_local GpWorkspace g_ws;
+
+// fill + blocked Cholesky sweep (with the fused forward solve) of one chunk of matrices
+void gp_factor_chunk(binest_problem &p, const GpBatch &g, const double *theta_dev, int Ps, int b0) {
+    const int T = g.Np / NB, Tq = (g.ld - g.Np) / NB, B = g.B;
     const size_t smem_potf2 = (size_t)NB * (NB + 1) * sizeof(double);
     const size_t smem_syrk = (size_t)2 * (KC * LDS_ + KC * LDSH_) * sizeof(double);
     const size_t smem_trsm = ((size_t)NB * LDS_ + 2 * KC * LDS_ + NB) * sizeof(double);
@@ -396,23 +454,37 @@ void gp_loglike_device_strided(binest_problem &p, const double *theta_dev, int P
     BN_CUDA(cudaFuncSetAttribute(gp_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_syrk));
     BN_CUDA(cudaFuncSetAttribute(gp_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_trsm));
     cudaStream_t s = p.stream;
-    for (int b0 = 0; b0 < P; b0 += ws_cap) {
-        const int B = std::min(ws_cap, P - b0);
-        GpBatch g{wsA.p, wsY.p, wsZ.p, wsL.p, wsLd.p, wsQ.p, wsF.p, Np, N, B};
-        gp_fill_kernel<<<dim3(T * (T + 1) / 2, B), 256, 2 * NB * p.gp_dim * sizeof(double), s>>>(
-            g, p.gp_x.p, (int)p.gp_dim, p.gp_y.p, theta_dev, Ps, b0);
+    gp_fill_kernel<<<dim3(T * (T + 1) / 2 + Tq * T, B), 256, 2 * NB * p.gp_dim * sizeof(double), s>>>(
+        g, p.gp_x.p, (int)p.gp_dim, p.gp_y.p, theta_dev, Ps, b0);
+    BN_LAUNCH_CHECK();
+    for (int k = 0; k < T; ++k) {
+        const int k0 = k * NB, rest = T - k - 1;
+        gp_potf2_kernel<<<B, 256, smem_potf2, s>>>(g, k0);
         BN_LAUNCH_CHECK();
-        for (int k = 0; k < T; ++k) {
-            const int k0 = k * NB, rest = T - k - 1;
-            gp_potf2_kernel<<<B, 256, smem_potf2, s>>>(g, k0);
+        if (rest + Tq > 0) {
+            gp_trsm_kernel<<<dim3(rest + Tq, B), 512, smem_trsm, s>>>(g, k0);
             BN_LAUNCH_CHECK();
-            if (rest > 0) {
-                gp_trsm_kernel<<<dim3(rest, B), 512, smem_trsm, s>>>(g, k0);
-                BN_LAUNCH_CHECK();
-                gp_syrk_kernel<<<dim3(rest * (rest + 1), B), 256, smem_syrk, s>>>(g, k0);
-                BN_LAUNCH_CHECK();
-            }
         }
+        if (rest > 0) {
+            gp_syrk_kernel<<<dim3(rest * (rest + 1) + Tq * 2 * rest, B), 256, smem_syrk, s>>>(g, k0);
+            BN_LAUNCH_CHECK();
+        }
+    }
+}
+
+}  // namespace
+
+// theta_dev SoA [3][Ps]; out_dev[(w) * out_stride]
+void gp_loglike_device_strided(binest_problem &p, const double *theta_dev, int P, int Ps, double *out_dev,
+                               int out_stride, bool check_box) {
+    const int N = (int)p.gp_n, Np = (N + NB - 1) / NB * NB;
+    GpWorkspace &ws = g_ws;
+    ws.ensure(std::min<int>(P, 512), Np, Np);
+    cudaStream_t s = p.stream;
+    for (int b0 = 0; b0 < P; b0 += ws.cap) {
+        const int B = std::min(ws.cap, P - b0);
+        GpBatch g{ws.A.p, ws.Y.p, ws.Z.p, ws.L.p, ws.Ld.p, ws.Qd.p, ws.F.p, Np, N, B, Np, 0, nullptr, nullptr};
+        gp_factor_chunk(p, g, theta_dev, Ps, b0);
         gp_finish_kernel<<<(B + 127) / 128, 128, 0, s>>>(g, theta_dev, Ps, b0, p.prior, g_logzero, check_box ? 1 : 0,
                                                          out_dev, out_stride);
         BN_LAUNCH_CHECK();
@@ -421,6 +493,22 @@ void gp_loglike_device_strided(binest_problem &p, const double *theta_dev, int P
 
 void gp_loglike_device(binest_problem &p, const double *theta_dev, int P, int Ps, double *out_dev, bool check_box) {
     gp_loglike_device_strided(p, theta_dev, P, Ps, out_dev, 1, check_box);
+}
+
+// predictFromGaussianProcess (GP:332-422): theta_dev SoA [3][Ps], xs_dev [Q][dim]; mean_dev / sd_dev [P][Q]
+void gp_predict_device(binest_problem &p, const double *theta_dev, int P, int Ps, const double *xs_dev, int Q,
+                       double *mean_dev, double *sd_dev) {
+    const int N = (int)p.gp_n, Np = (N + NB - 1) / NB * NB, Qp = (Q + NB - 1) / NB * NB;
+    GpWorkspace &ws = g_ws;
+    ws.ensure(std::min<int>(P, 512), Np, Np + Qp);
+    cudaStream_t s = p.stream;
+    for (int b0 = 0; b0 < P; b0 += ws.cap) {
+        const int B = std::min(ws.cap, P - b0);
+        GpBatch g{ws.A.p, ws.Y.p, ws.Z.p, ws.L.p, ws.Ld.p, ws.Qd.p, ws.F.p, Np, N, B, Np + Qp, Q, xs_dev, ws.V2.p};
+        gp_factor_chunk(p, g, theta_dev, Ps, b0);
+        gp_predict_finish_kernel<<<dim3((Q + 127) / 128, B), 128, 0, s>>>(g, theta_dev, Ps, b0, (int64_t)Q, mean_dev, sd_dev);
+        BN_LAUNCH_CHECK();
+    }
 }
 
 }  // namespace binest

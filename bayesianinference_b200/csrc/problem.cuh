@@ -153,6 +153,8 @@ inline void launch_loglike(binest_problem &p, const double *theta_dev, int P, in
 }
 
 void gp_loglike_device(binest_problem &p, const double *theta_dev, int P, int Ps, double *out_dev, bool check_box);
+void gp_predict_device(binest_problem &p, const double *theta_dev, int P, int Ps, const double *xs_dev, int Q,
+                       double *mean_dev, double *sd_dev);
 
 // comm.cu: all-gather of `count` doubles per rank on stream s (NCCL over NVLink)
 void comm_allgather_f64(binest_comm &c, const double *send, double *recv, size_t count, cudaStream_t s);

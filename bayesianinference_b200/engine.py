@@ -136,6 +136,36 @@ class Problem:
         check(_lib.load().binest_loglike(self.h, dptr(theta), theta.shape[0], dptr(out)))
         return out
 
+    def predictive_components(self, theta, inputs):
+        """predictiveDistribution (BS:1437-1483): parameters of the mixture components dist[theta_m, x_q] for every
+        sample and input -> (M, Q, C); C = 2 (mean, sd) for polynomial regression, K class probabilities for softmax."""
+        theta = _f64(np.atleast_2d(theta))
+        if theta.shape[1] != self.d:
+            raise ValueError(f"theta must have {self.d} columns")
+        inputs = np.asarray(inputs, dtype=np.float64)
+        inputs = _f64(inputs.reshape(-1, 1) if inputs.ndim == 1 else inputs)
+        w = C.c_int64()
+        check(_lib.load().binest_predictive_width(self.h, C.byref(w)))
+        if w.value == 0:
+            raise ValueError("operator has no independent variables")
+        out = np.empty((theta.shape[0], inputs.shape[0], w.value))
+        check(_lib.load().binest_predictive_components(self.h, dptr(theta), theta.shape[0], dptr(inputs), inputs.shape[0],
+                                                       dptr(out)))
+        return out
+
+    def gp_predict(self, theta, xstar):
+        """predictFromGaussianProcessInternal (GP:395-420) for every parameter vector: theta (M, 3), xstar (Q, D)
+        -> (mean, sd), each (M, Q): the NormalDistribution parameters of the predictive at every input."""
+        theta = _f64(np.atleast_2d(theta))
+        if theta.shape[1] != self.d:
+            raise ValueError(f"theta must have {self.d} columns")
+        xstar = _f64(np.asarray(xstar, dtype=np.float64))
+        xstar = _f64(xstar.reshape(-1, 1) if xstar.ndim == 1 else xstar)
+        M, Q = theta.shape[0], xstar.shape[0]
+        mean, sd = np.empty((M, Q)), np.empty((M, Q))
+        check(_lib.load().binest_gp_predict(self.h, dptr(theta), M, dptr(xstar), Q, dptr(mean), dptr(sd)))
+        return mean, sd
+
     def logprior(self, theta):
         """"LogPriorPDFFunction"."""
         theta = _f64(np.atleast_2d(theta))

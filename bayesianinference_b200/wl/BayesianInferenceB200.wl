@@ -13,6 +13,8 @@
      nestedSamplingInternal   BayesianStatistics.wl:859-1040    parallelNestedSampling  :1317-1371
      evidenceSampling         BayesianStatistics.wl:1158-1291   combineRuns             :1293-1315
      generateStartingPoints   BayesianStatistics.wl:1042-1097   inferenceObject         BayesianUtilities.wl:107-138
+     defineGaussianProcess    BayesianGaussianProcess.wl:201-330  predictFromGaussianProcess :332-422
+     predictiveDistribution   BayesianStatistics.wl:1373-1483
 *)
 
 BeginPackage["BayesianInferenceB200`"];
@@ -25,6 +27,11 @@ combineRuns::usage = "combineRuns[obj1, obj2, ...] merges nested-sampling runs."
 generateStartingPoints::usage = "generateStartingPoints[inferenceObject, n] draws n points from the prior.";
 inferenceObject::usage = "inferenceObject[assoc] wraps the results; obj[\"Key\"] extracts a property.";
 inferenceObjectQ::usage = "inferenceObjectQ[obj]";
+defineGaussianProcess::usage = "defineGaussianProcess[in -> out, squaredExponentialKernel[sf, ell], nuggetVariance[sn], None, {{sf, lo, hi}, {ell, lo, hi}, {sn, lo, hi}}, prior] — GP regression with the squared-exponential kernel sf^2 Exp[-|x - x'|^2/(2 ell^2)] and nugget sn^2 (the GPU operator).";
+predictFromGaussianProcess::usage = "predictFromGaussianProcess[inferenceObject, pts] gives, for every input, the MixtureDistribution of the samples' Gaussian predictives weighted by CrudePosteriorWeight.";
+predictiveDistribution::usage = "predictiveDistribution[inferenceObject] or predictiveDistribution[inferenceObject, inputs] gives the posterior predictive as a MixtureDistribution over the samples (per input for regression problems); a trailing \"MaximumLikelihood\" or \"MAP\" uses the single best sample.";
+squaredExponentialKernel::usage = "squaredExponentialKernel[sf, ell] — kernel descriptor for defineGaussianProcess.";
+nuggetVariance::usage = "nuggetVariance[sn] — nugget sn^2 descriptor for defineGaussianProcess.";
 $binestLibrary::usage = "Path of the compiled LibraryLink shim (binestLink).";
 categoricalSoftmax::usage = "categoricalSoftmax[{{w11,..,w1F,b1},...}, {x1,..,xF}] — softmax classification with reference class K.";
 
@@ -44,6 +51,8 @@ binestProblemCreate := ll["binestProblemCreate", {Integer, {Integer, 1}, {Real, 
     {Integer, 1}, {Real, 1}, {Real, 1}, {Real, 1}, {Real, 1}}, Integer];
 binestLogLike := ll["binestLogLike", {Integer, {Real, 2, "Constant"}}, {Real, 1}];
 binestLogPrior := ll["binestLogPrior", {Integer, {Real, 2, "Constant"}}, {Real, 1}];
+binestPredictiveComponents := ll["binestPredictiveComponents", {Integer, {Real, 2, "Constant"}, {Real, 2, "Constant"}}, {Real, 3}];
+binestGPPredict := ll["binestGPPredict", {Integer, {Real, 2, "Constant"}, {Real, 2, "Constant"}}, {Real, 3}];
 binestSamplePrior := ll["binestSamplePrior", {Integer, Integer, Integer, Integer}, {Real, 2}];
 binestRunCreate := ll["binestRunCreate", {Integer, {Integer, 1}, {Real, 1}, {Real, _, "Constant"}}, Integer];
 binestRunAdvance := ll["binestRunAdvance", {Integer, Integer}, Integer];
@@ -75,6 +84,8 @@ operatorFromDistribution[categoricalSoftmax[blocks_?MatrixQ, vars_List], Rule[in
     {3, {0, Length[blocks] + 1, 0, 0}, N[in], ArrayReshape[N[labels], {Length[labels], 1}]};
 operatorFromDistribution[GeometricBrownianMotionProcess[mu_Symbol, sigma_Symbol, _], ts_TemporalData, {mu_, sigma_}, _] :=
     {4, {0, 0, 0, 0}, List /@ N[ts["Times"]], List /@ N[ts["Values"]]}; (* TemporalData adaptor BS:511-515 *)
+operatorFromDistribution[gpOperator[sf_Symbol, ell_Symbol, sn_Symbol], Rule[in_?MatrixQ, out_?MatrixQ], {sf_, ell_, sn_}, _] :=
+    {5, {0, 0, Last[Dimensions[in]], 0}, N[in], N[out]}; (* GP marginal likelihood, GP:27-61, 130-199 *)
 operatorFromDistribution[dist_, ___] := (Message[defineInferenceProblem::logLike, dist]; $Failed);
 defineInferenceProblem::logLike = "`1` is not in the GPU operator table; there is no CPU fallback."; (* cf. BS:456-459 *)
 defineInferenceProblem::insuffInfo = "Not enough information was provided to define the problem"; (* BS:148-152 *)
@@ -115,6 +126,73 @@ defineInferenceProblem[assoc_?AssociationQ] := Catch[
     ],
     "problemDef", Function[inferenceObject[$Failed]] (* BS:308 *)
 ];
+
+(* ------------------------------------------------------------------ Gaussian processes (GP:201-422) *)
+dataMatrix[v_?VectorQ] := List /@ N[v];
+dataMatrix[m_?MatrixQ] := N[m];
+defineGaussianProcess::outputDim = "Output data has has dimensions `1`. Only 1D output data is supported for GP regression at this time."; (* GP:208 *)
+defineGaussianProcess[Rule[in_, out_], squaredExponentialKernel[sf_Symbol, ell_Symbol], nuggetVariance[sn_Symbol],
+        None | 0 | 0., variables : {paramSpecPattern ..}, prior_, rest___Rule] := With[{
+    x = dataMatrix[in], y = dataMatrix[out]},
+    Which[
+        Last[Dimensions[y]] =!= 1, Message[defineGaussianProcess::outputDim, Dimensions[y]]; inferenceObject[$Failed], (* GP:219-225 *)
+        Length[x] =!= Length[y], inferenceObject[$Failed], (* GP:250-252 *)
+        True, defineInferenceProblem[
+            "Data" -> (x -> y), "PriorDistribution" -> prior, "Parameters" -> variables,
+            "GeneratingDistribution" -> gpOperator[sf, ell, sn],
+            "GaussianProcessData" -> <|"ModelFunctions" -> <|"KernelFunction" -> squaredExponentialKernel[sf, ell],
+                "NuggetFunction" -> nuggetVariance[sn], "MeanFunction" -> (0 &)|>|>, (* GP:312-320 *)
+            rest]]];
+
+predictFromGaussianProcess[inferenceObject[result_?(AssociationQ[#] && KeyExistsQ[#, "GaussianProcessData"] && KeyExistsQ[#, "Samples"] && KeyExistsQ[#, "Data"] &)],
+        n_Integer /; n > 1] := predictFromGaussianProcess[inferenceObject[result],
+    CoordinateBoundsArray[CoordinateBounds[result["Data"][[1]]], Into[n - 1]]]; (* GP:332-342 *)
+predictFromGaussianProcess[inferenceObject[result_?(AssociationQ[#] && KeyExistsQ[#, "GaussianProcessData"] && KeyExistsQ[#, "Samples"] &)],
+        pts_List] := Module[{inputs, weights, ms},
+    inputs = DeleteDuplicates @ With[{flat = If[ArrayDepth[pts] > 2, Flatten[pts, ArrayDepth[pts] - 2], pts]}, dataMatrix[flat]];
+    weights = result["Samples", "CrudePosteriorWeight"]; (* GP:353; "Samples" is columnar in this host *)
+    ms = binestGPPredict[result["binestHandle"], N @ result["Samples", "Point"], inputs];
+    (
+        AssociationThread[inputs,
+            MapThread[Function[{mu, sd}, MixtureDistribution[weights, MapThread[NormalDistribution, {mu, sd}]]], (* GP:357, 401-418 *)
+                {Transpose[ms[[1]]], Transpose[ms[[2]]]}]]
+    ) /; ArrayQ[ms, 3, NumericQ]
+];
+
+(* ------------------------------------------------------------------ predictiveDistribution (BS:1373-1483) *)
+predictiveDistribution::MissGenDist = "No generating distribution specified";
+predictiveDistribution::unsampled = "Posterior has not been sampled yet";
+predictiveDistribution[inferenceObject[result_?(AssociationQ[#] && MissingQ[#["Samples"]] &)], ___] := (
+    Message[predictiveDistribution::unsampled]; $Failed);
+predictiveDistribution[inferenceObject[result_?(AssociationQ[#] && !MissingQ[#["Samples"]] && MissingQ[#["GeneratingDistribution"]] &)], ___] := (
+    Message[predictiveDistribution::MissGenDist]; $Failed);
+(* point estimates keep one sample: "Samples" is columnar in this host, so take one position of every column *)
+bestSample[result_, score_] := With[{i = First @ Ordering[score, -1]},
+    Append[result, "Samples" -> Append[
+        Map[If[AssociationQ[#], Map[Function[v, v[[{i}]]], #], #[[{i}]]] &, result["Samples"]],
+        "CrudePosteriorWeight" -> {1.}]]];
+predictiveDistribution[inferenceObject[result_?(AssociationQ[#] && !MissingQ[#["Samples"]] &)], rest___, "MaximumLikelihood"] :=
+    predictiveDistribution[inferenceObject[bestSample[result, result["Samples", "LogLikelihood"]]], rest]; (* BS:1388-1402 *)
+predictiveDistribution[inferenceObject[result_?(AssociationQ[#] && !MissingQ[#["Samples"]] &)], rest___, "MAP"] :=
+    predictiveDistribution[inferenceObject[bestSample[result,
+        result["Samples", "LogLikelihood"] + result["Samples", "LogPriorPDF"]]], rest]; (* BS:1404-1418 *)
+predictiveDistribution[inferenceObject[result_?(AssociationQ[#] && ListQ[#["Data"]] && !MissingQ[#["Samples"]] && !MissingQ[#["GeneratingDistribution"]] &)]] :=
+    With[{dist = Function[pt, result["GeneratingDistribution"] /. Thread[result["ParameterSymbols"] -> pt]]},
+        MixtureDistribution[result["Samples", "CrudePosteriorWeight"], dist /@ result["Samples", "Point"]]]; (* BS:1420-1435 *)
+predictiveDistribution[fst_, inputs_?VectorQ] := predictiveDistribution[fst, List /@ N[inputs], inputs]; (* BS:1437-1441 *)
+predictiveDistribution[fst_, inputs_?MatrixQ] := predictiveDistribution[fst, N[inputs], inputs];         (* BS:1443-1446 *)
+predictiveDistribution[inferenceObject[result_?(AssociationQ[#] && MatchQ[#["Data"], _Rule] && !MissingQ[#["Samples"]] && !MissingQ[#["GeneratingDistribution"]] &)],
+        inputs_?MatrixQ, keys_List] /; Length[keys] === Length[inputs] := Module[{comp, w = result["Samples", "CrudePosteriorWeight"]},
+    comp = binestPredictiveComponents[result["binestHandle"], N @ result["Samples", "Point"], inputs]; (* M x Q x C *)
+    (
+        AssociationThread[keys,
+            Map[Function[tab, MixtureDistribution[w,
+                    If[Last[Dimensions[comp]] === 2 && !MatchQ[result["GeneratingDistribution"], _categoricalSoftmax],
+                        NormalDistribution @@@ tab,
+                        Map[CategoricalDistribution[Range[Length[#]], #] &, tab]]]],
+                Transpose[comp, {2, 1, 3}]]]
+    ) /; ArrayQ[comp, 3, NumericQ]
+]; (* BS:1448-1483 *)
 
 generateStartingPoints[inferenceObject[assoc_?AssociationQ], n_Integer, seed_Integer : 1] :=
     inferenceObject[Append[assoc, "StartingPoints" -> binestSamplePrior[assoc["binestHandle"], n, seed, 0]]]; (* BS:1046-1068 *)

@@ -95,6 +95,50 @@ DLLEXPORT int binestLogPrior(WolframLibraryData libData, mint Argc, MArgument *A
     return batch_eval(libData, Args, Res, binest_logprior);
 }
 
+/* binestPredictiveComponents[handle, theta {Real,2} (M x d), inputs {Real,2} (Q x F)] -> {Real,3} (M x Q x C)
+ * (predictiveDistribution, BayesianStatistics.wl:1437-1483) */
+DLLEXPORT int binestPredictiveComponents(WolframLibraryData libData, mint Argc, MArgument *Args, MArgument Res) {
+    binest_problem *h = (binest_problem *)(intptr_t)MArgument_getInteger(Args[0]);
+    MTensor th = MArgument_getMTensor(Args[1]), xs = MArgument_getMTensor(Args[2]), out;
+    mint dims[3];
+    int64_t C = 0;
+    int rc;
+    if (libData->MTensor_getRank(th) != 2 || libData->MTensor_getRank(xs) != 2) return LIBRARY_RANK_ERROR;
+    rc = binest_predictive_width(h, &C);
+    if (rc) return st(rc);
+    if (C <= 0) return LIBRARY_FUNCTION_ERROR;
+    dims[0] = libData->MTensor_getDimensions(th)[0];
+    dims[1] = libData->MTensor_getDimensions(xs)[0];
+    dims[2] = (mint)C;
+    rc = libData->MTensor_new(MType_Real, 3, dims, &out);
+    if (rc) return rc;
+    rc = binest_predictive_components(h, libData->MTensor_getRealData(th), dims[0], libData->MTensor_getRealData(xs),
+                                      dims[1], libData->MTensor_getRealData(out));
+    if (rc) { libData->MTensor_free(out); return st(rc); }
+    MArgument_setMTensor(Res, out);
+    return LIBRARY_NO_ERROR;
+}
+
+/* binestGPPredict[handle, theta {Real,2} (M x 3), xstar {Real,2} (Q x D)] -> {Real,3}: {means (M x Q), sds (M x Q)}
+ * (predictFromGaussianProcess, BayesianGaussianProcess.wl:332-422) */
+DLLEXPORT int binestGPPredict(WolframLibraryData libData, mint Argc, MArgument *Args, MArgument Res) {
+    binest_problem *h = (binest_problem *)(intptr_t)MArgument_getInteger(Args[0]);
+    MTensor th = MArgument_getMTensor(Args[1]), xs = MArgument_getMTensor(Args[2]), out;
+    mint dims[3];
+    int rc;
+    if (libData->MTensor_getRank(th) != 2 || libData->MTensor_getRank(xs) != 2) return LIBRARY_RANK_ERROR;
+    dims[0] = 2;
+    dims[1] = libData->MTensor_getDimensions(th)[0];
+    dims[2] = libData->MTensor_getDimensions(xs)[0];
+    rc = libData->MTensor_new(MType_Real, 3, dims, &out);
+    if (rc) return rc;
+    rc = binest_gp_predict(h, libData->MTensor_getRealData(th), dims[1], libData->MTensor_getRealData(xs), dims[2],
+                           libData->MTensor_getRealData(out), libData->MTensor_getRealData(out) + dims[1] * dims[2]);
+    if (rc) { libData->MTensor_free(out); return st(rc); }
+    MArgument_setMTensor(Res, out);
+    return LIBRARY_NO_ERROR;
+}
+
 /* binestSamplePrior[handle, n, seed, runId] -> {Real,2} (generateStartingPoints) */
 DLLEXPORT int binestSamplePrior(WolframLibraryData libData, mint Argc, MArgument *Args, MArgument Res) {
     binest_problem *h = (binest_problem *)(intptr_t)MArgument_getInteger(Args[0]);

@@ -106,6 +106,25 @@ int binest_problem_dim(const binest_problem *p, int64_t *d);
 /* "LogLikelihoodFunction" (Listable, BS:499): theta P x d -> out[P].  Box / operator constraints
  * violated -> logzero (BS:491-494, 580-583). */
 int binest_loglike(binest_problem *p, const double *theta, int64_t P, double *out);
+/* predictFromGaussianProcess (GP:332-422, predictFromGaussianProcessInternal GP:395-420) for a BINEST_OP_GP_SE
+ * problem (squared-exponential kernel + nugget, zero mean function): for every parameter vector theta_m (the
+ * samples' points, M x 3) and every prediction input x*_q (Q x n_in, row-major)
+ *   mean[m*Q + q] = k_q . K^-1 y,   sd[m*Q + q] = Sqrt[kappa - k_q . K^-1 k_q],
+ *   k_q = (k(x_i, x*_q))_i,  kappa = k(x*, x*) + nugget = sf^2 + sn^2  (compiledKandKappa GP:92-116)
+ * — the parameters of the NormalDistribution components the reference mixes with the samples' weights (GP:357).
+ * A covariance matrix that cannot be factored gives NaN for that theta. */
+int binest_gp_predict(binest_problem *p, const double *theta, int64_t M, const double *xstar, int64_t Q,
+                      double *mean, double *sd);
+/* predictiveDistribution for regression problems (BS:1437-1483): the parameters of the mixture components
+ * dist[theta_m, x_q] ("GeneratingDistribution" with sample m's parameters at input q, BS:1450-1462) for every
+ * sample (theta M x d) and input (Q x n_in): out[(m*Q + q)*C + c] with
+ *   BINEST_OP_POLYREG:  C = 2, (mean, sd) of NormalDistribution[Sum_j c_j x^j, sigma]
+ *   BINEST_OP_LOGISTIC: C = K, class probabilities (softmax with reference class K)
+ * binest_predictive_width returns C (0 for operators without independent variables, whose mixture components
+ * are the samples' parameters themselves, BS:1421-1435). */
+int binest_predictive_width(const binest_problem *p, int64_t *n_comp);
+int binest_predictive_components(binest_problem *p, const double *theta, int64_t M, const double *inputs,
+                                 int64_t Q, double *out);
 /* "LogPriorPDFFunction" (BS:410-426). */
 int binest_logprior(binest_problem *p, const double *theta, int64_t P, double *out);
 /* generateStartingPoints (BS:1055-1068): n i.i.d. prior draws, out n x d. */

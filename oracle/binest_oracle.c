@@ -447,6 +447,165 @@ static long double gp_loglike_chol_ld(const orc_problem *p, const double *th, in
     return res;
 }
 
+/* predictFromGaussianProcessInternal GP:395-420 with compiledKandKappa GP:92-116, squared-exponential kernel,
+ * zero mean function:  invCov = LinearSolve[K] (LU, GP:132);  k_q = (k(x_i, x*_q))_i;  kappa = k(x*,x*) + nugget;
+ *   mean_q = (invCov[y]) . k_q        sd_q = Sqrt[kappa - k_q . invCov[k_q]]
+ * One LU factorisation (partial pivoting, as LinearSolve does for a dense real matrix), then one solve per
+ * right-hand side.  use_ld != 0: the same quantities by long-double Cholesky (precision reference).
+ * Returns 0 when the matrix is singular / not positive definite (the reference Throws, GP:131-135). */
+ORC_API int orc_gp_predict(const orc_problem *p, const double *th, const double *xs, int64_t Q, int use_ld,
+                           double *mean, double *sd) {
+    const int64_t n = p->n;
+    const int D = p->n_in;
+    const long double sf2 = (long double)th[0] * th[0], il2 = 1.0L / (2.0L * th[1] * th[1]),
+                      sn2 = (long double)th[2] * th[2];
+    int ok = 1;
+    if (use_ld) {
+        long double *A = (long double *)malloc(sizeof(long double) * n * n);
+        long double *z = (long double *)malloc(sizeof(long double) * n);
+        long double *v = (long double *)malloc(sizeof(long double) * n);
+        gp_fill_ld(p, th, A);
+        for (int64_t j = 0; j < n && ok; ++j) {
+            long double s = A[j * n + j];
+            for (int64_t k = 0; k < j; ++k) s -= A[j * n + k] * A[j * n + k];
+            if (!(s > 0)) { ok = 0; break; }
+            const long double l = sqrtl(s);
+            A[j * n + j] = l;
+            for (int64_t i = j + 1; i < n; ++i) {
+                long double t = A[i * n + j];
+                for (int64_t k = 0; k < j; ++k) t -= A[i * n + k] * A[j * n + k];
+                A[i * n + j] = t / l;
+            }
+        }
+        if (ok) {
+            for (int64_t i = 0; i < n; ++i) {   /* z = L^-1 y */
+                long double s = p->out[i];
+                for (int64_t k = 0; k < i; ++k) s -= A[i * n + k] * z[k];
+                z[i] = s / A[i * n + i];
+            }
+            for (int64_t q = 0; q < Q; ++q) {
+                long double m = 0, vv = 0;
+                for (int64_t i = 0; i < n; ++i) {   /* v = L^-1 k_q */
+                    long double d2 = 0;
+                    for (int k = 0; k < D; ++k) { const long double df = (long double)p->in[i * D + k] - xs[q * D + k]; d2 += df * df; }
+                    long double s = sf2 * expl(-d2 * il2);
+                    for (int64_t k = 0; k < i; ++k) s -= A[i * n + k] * v[k];
+                    v[i] = s / A[i * n + i];
+                    m += v[i] * z[i];
+                    vv += v[i] * v[i];
+                }
+                mean[q] = (double)m;
+                sd[q] = (double)sqrtl(fmaxl(sf2 + sn2 - vv, 0.0L));
+            }
+        }
+        free(A); free(z); free(v);
+        return ok;
+    }
+    double *A = (double *)malloc(sizeof(double) * n * n);
+    int64_t *perm = (int64_t *)malloc(sizeof(int64_t) * n);
+    double *a = (double *)malloc(sizeof(double) * n), *b = (double *)malloc(sizeof(double) * n),
+           *kq = (double *)malloc(sizeof(double) * n);
+    for (int64_t i = 0; i < n; ++i)
+        for (int64_t j = 0; j <= i; ++j) {
+            double d2 = 0;
+            for (int k = 0; k < D; ++k) { const double df = p->in[i * D + k] - p->in[j * D + k]; d2 += df * df; }
+            double v = (double)sf2 * exp(-d2 * (double)il2);
+            if (i == j) v += (double)sn2;
+            A[i * n + j] = A[j * n + i] = v;
+        }
+    for (int64_t i = 0; i < n; ++i) perm[i] = i;
+    for (int64_t k = 0; k < n && ok; ++k) {   /* P A = L U in place */
+        int64_t piv = k;
+        double mx = fabs(A[k * n + k]);
+        for (int64_t i = k + 1; i < n; ++i)
+            if (fabs(A[i * n + k]) > mx) { mx = fabs(A[i * n + k]); piv = i; }
+        if (!(mx > 0.0) || !isfinite(mx)) { ok = 0; break; }
+        if (piv != k) {
+            for (int64_t j = 0; j < n; ++j) { const double t = A[k * n + j]; A[k * n + j] = A[piv * n + j]; A[piv * n + j] = t; }
+            const int64_t t = perm[k]; perm[k] = perm[piv]; perm[piv] = t;
+        }
+        const double inv = 1.0 / A[k * n + k];
+        for (int64_t i = k + 1; i < n; ++i) {
+            const double f = A[i * n + k] * inv;
+            A[i * n + k] = f;
+            if (f != 0.0)
+                for (int64_t j = k + 1; j < n; ++j) A[i * n + j] -= f * A[k * n + j];
+        }
+    }
+    if (ok) {
+#define ORC_LU_SOLVE(rhs, out)                                                      \
+        for (int64_t i = 0; i < n; ++i) {                                           \
+            double s_ = (rhs)[perm[i]];                                             \
+            for (int64_t j = 0; j < i; ++j) s_ -= A[i * n + j] * (out)[j];          \
+            (out)[i] = s_;                                                          \
+        }                                                                           \
+        for (int64_t i = n - 1; i >= 0; --i) {                                      \
+            double s_ = (out)[i];                                                   \
+            for (int64_t j = i + 1; j < n; ++j) s_ -= A[i * n + j] * (out)[j];      \
+            (out)[i] = s_ / A[i * n + i];                                           \
+        }
+        ORC_LU_SOLVE(p->out, a)   /* a = invCov[y] */
+        for (int64_t q = 0; q < Q; ++q) {
+            for (int64_t i = 0; i < n; ++i) {
+                double d2 = 0;
+                for (int k = 0; k < D; ++k) { const double df = p->in[i * D + k] - xs[q * D + k]; d2 += df * df; }
+                kq[i] = (double)sf2 * exp(-d2 * (double)il2);
+            }
+            ORC_LU_SOLVE(kq, b)
+            double m = 0.0, kk = 0.0;
+            for (int64_t i = 0; i < n; ++i) { m += a[i] * kq[i]; kk += kq[i] * b[i]; }
+            mean[q] = m;
+            const double var = ((double)sf2 + (double)sn2) - kk;
+            sd[q] = var > 0.0 ? sqrt(var) : 0.0;
+        }
+#undef ORC_LU_SOLVE
+    }
+    free(A); free(perm); free(a); free(b); free(kq);
+    return ok;
+}
+
+/* predictiveDistribution for regression problems, BS:1437-1483: the mixture components are the generating
+ * distribution with sample m's parameters substituted at input q (expressionToFunction, BS:1450-1462).
+ * POLYREG: NormalDistribution[Sum_j c_j x^j, sigma] -> (mean, sd); LOGISTIC: class probabilities (K of them).
+ * out[(m*Q + q)*C + c]; returns C (0: operator without independent variables). */
+ORC_API int orc_predictive_components(const orc_problem *p, const double *theta, int64_t M, const double *xin,
+                                      int64_t Q, double *out) {
+    const int d = p->d;
+    if (p->op == OP_POLYREG) {
+        const int deg = p->iparam[0];
+        for (int64_t m = 0; m < M; ++m)
+            for (int64_t q = 0; q < Q; ++q) {
+                const double *th = theta + m * d;
+                double t = th[deg];
+                for (int j = deg - 1; j >= 0; --j) t = t * xin[q] + th[j];
+                const int ok = th[deg + 1] > 0.0;
+                out[(m * Q + q) * 2 + 0] = ok ? t : NAN;
+                out[(m * Q + q) * 2 + 1] = ok ? th[deg + 1] : NAN;
+            }
+        return 2;
+    }
+    if (p->op == OP_LOGISTIC) {
+        const int K = p->iparam[1], F = p->n_in;
+        for (int64_t m = 0; m < M; ++m)
+            for (int64_t q = 0; q < Q; ++q) {
+                const double *th = theta + m * d;
+                double *o = out + (m * Q + q) * K;
+                double zmax = 0.0, den = 0.0;
+                for (int k = 0; k < K - 1; ++k) {
+                    double z = th[k * (F + 1) + F];
+                    for (int f = 0; f < F; ++f) z += th[k * (F + 1) + f] * xin[q * F + f];
+                    o[k] = z;
+                    if (z > zmax) zmax = z;
+                }
+                o[K - 1] = 0.0;
+                for (int k = 0; k < K; ++k) { o[k] = exp(o[k] - zmax); den += o[k]; }
+                for (int k = 0; k < K; ++k) o[k] /= den;
+            }
+        return K;
+    }
+    return 0;
+}
+
 /* BS:491-494 / BS:580-583: If[constraints[theta], Sum[...], logzero]; RuntimeErrorHandler -> logzero */
 ORC_API double orc_loglike(const orc_problem *p, const orc_prior *pr, const double *th) {
     if (pr && !in_box(pr, th)) return p->logzero;

@@ -66,6 +66,10 @@ def lib():
         L.orc_loglike_q.argtypes = [C.c_void_p, dp, dp, dp]
         L.orc_loglike_batch.argtypes = [C.c_void_p, C.c_void_p, dp, C.c_int64, dp, C.c_int]
         L.orc_logprior_batch.argtypes = [C.c_void_p, dp, C.c_int64, dp]
+        L.orc_predictive_components.restype = C.c_int
+        L.orc_predictive_components.argtypes = [C.c_void_p, dp, C.c_int64, dp, C.c_int64, dp]
+        L.orc_gp_predict.restype = C.c_int
+        L.orc_gp_predict.argtypes = [C.c_void_p, dp, dp, C.c_int64, C.c_int, dp, dp]
         L.orc_sample_prior.argtypes = [C.c_void_p, C.c_int64, C.c_uint64, C.c_uint32, dp]
         L.orc_nested_sampling.restype = C.c_void_p
         L.orc_nested_sampling.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, dp]
@@ -199,6 +203,34 @@ class Problem:
         out = np.empty(theta.shape[0])
         lib().orc_loglike_batch(self.h, prior.h if prior else None, _dp(theta), theta.shape[0], _dp(out), threads)
         return out
+
+    def predictive_components(self, theta, inputs):
+        """BS:1437-1483: (M, Q, C) component parameters; C = 2 (mean, sd) or K class probabilities."""
+        theta = _f64(np.atleast_2d(theta))
+        inputs = _f64(np.asarray(inputs, dtype=np.float64).reshape(-1, self.inputs.shape[1]))
+        M, Q = theta.shape[0], inputs.shape[0]
+        Cw = {2: 2, 3: None}.get(self.op, 0)
+        if Cw is None:
+            Cw = (theta.shape[1] // (self.inputs.shape[1] + 1)) + 1
+        if not Cw:
+            raise ValueError("operator has no independent variables")
+        out = np.empty((M, Q, Cw))
+        got = lib().orc_predictive_components(self.h, _dp(theta), M, _dp(inputs), Q, _dp(out))
+        assert got == Cw, (got, Cw)
+        return out
+
+    def gp_predict(self, theta, xstar, long_double=False):
+        """predictFromGaussianProcessInternal (GP:395-420): (mean, sd), each M x Q; NaN rows where K is singular."""
+        theta = _f64(np.atleast_2d(theta))
+        xstar = _f64(np.asarray(xstar, dtype=np.float64).reshape(-1, self.inputs.shape[1]))
+        M, Q = theta.shape[0], xstar.shape[0]
+        mean, sd = np.full((M, Q), np.nan), np.full((M, Q), np.nan)
+        for i in range(M):
+            row = np.ascontiguousarray(theta[i])
+            m, s = np.empty(Q), np.empty(Q)
+            if lib().orc_gp_predict(self.h, _dp(row), _dp(xstar), Q, int(long_double), _dp(m), _dp(s)):
+                mean[i], sd[i] = m, s
+        return mean, sd
 
     def loglike_quad(self, theta):
         """__float128 value of the sum, returned as (hi, lo) double-double."""

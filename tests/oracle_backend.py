@@ -64,6 +64,12 @@ class Problem:
     def logprior(self, theta):
         return self.prior.logpdf(theta)
 
+    def predictive_components(self, theta, inputs):
+        return self.prob.predictive_components(theta, inputs)
+
+    def gp_predict(self, theta, xstar):
+        return self.prob.gp_predict(theta, xstar)
+
     def sample_prior(self, n, seed=1, run_id=0):
         return self.prior.sample(n, seed, run_id)
 

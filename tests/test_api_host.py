@@ -135,6 +135,81 @@ def test_parallel_nested_sampling_sharded_gloo_matches_single_process():
         assert abs(s - single["Samples"]["LogLikelihood"].sum()) < 1e-6
 
 
+def test_predictive_distribution_host_logic():
+    """predictiveDistribution (BS:1373-1483) on the oracle backend: i.i.d., regression, point estimates, failures."""
+    obj = _c1_obj()
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        assert api.predictiveDistribution(obj) == api.FAILED
+    assert any("unsampled" in str(x.message) for x in w)
+    res = api.nestedSampling(obj, SamplePoolSize=30, MaxIterations=60, MinIterations=60, MonteCarloSteps=20, PostProcessSamplingRuns=5)
+    mix = api.predictiveDistribution(res)
+    S = res["Samples"]
+    wts = S["CrudePosteriorWeight"] / S["CrudePosteriorWeight"].sum()
+    np.testing.assert_allclose(mix.mean(), wts @ S["Point"][:, 0])
+    ml = api.predictiveDistribution(res, point_estimate="MaximumLikelihood")
+    i = int(np.argmax(S["LogLikelihood"]))
+    assert ml.means.shape == (1,) and ml.means[0] == S["Point"][i, 0] and ml.sds[0] == S["Point"][i, 1]
+    assert api.predictiveDistribution(res, [1.0]) == api.FAILED  # no independent variables
+
+    c = cfg.c2_polyreg(N=300)
+    reg = api.defineInferenceProblem(
+        Data=(c.inputs[:, 0], c.outputs[:, 0]), IndependentVariables=["x"],
+        GeneratingDistribution=api.NormalDistribution(api.Polynomial("x", tuple(c.names[:4])), "sigma"),
+        Parameters=[(nm, lo, hi) for nm, lo, hi in zip(c.names, c.lo, c.hi)],
+        PriorDistribution=["LocationParameter"] * 4 + ["ScaleParameter"], _backend_override=OB)
+    rr = api.nestedSampling(reg, SamplePoolSize=40, BatchSize=8, MaxIterations=30, MinIterations=30, MonteCarloSteps=20,
+                            PostProcessSamplingRuns=5)
+    xs = np.array([-0.5, 0.0, 0.75])
+    pd_ = api.predictiveDistribution(rr, xs)
+    P = rr["Samples"]["Point"]
+    assert pd_.components.shape == (P.shape[0], 3, 2) and list(pd_.keys()) == [-0.5, 0.0, 0.75]
+    np.testing.assert_allclose(pd_.components[:, 2, 0], P[:, 0] + P[:, 1] * 0.75 + P[:, 2] * 0.75**2 + P[:, 3] * 0.75**3, rtol=1e-13)
+    np.testing.assert_array_equal(pd_.components[:, 1, 1], P[:, 4])
+    named = api.predictiveDistribution(rr, xs, keys=["a", "b", "c"], point_estimate="MAP")
+    assert list(named.keys()) == ["a", "b", "c"] and named["a"].means.shape == (1,)
+    assert api.predictiveDistribution(rr, xs, keys=["a"]) == api.FAILED
+    assert api.predictiveDistribution(rr) == api.FAILED
+
+
+def test_predict_from_gaussian_process_host_logic():
+    """predictFromGaussianProcess (GP:332-393) on the oracle backend: grid construction, weights, mixture moments."""
+    c = cfg.c5_gp(N=40)
+    pars = [(nm, lo, hi) for nm, lo, hi in zip(c.names, c.lo, c.hi)]
+    obj = api.defineGaussianProcess((c.inputs[:, 0], c.outputs[:, 0]), api.SquaredExponentialGP(*c.names), pars,
+                                    ["ScaleParameter"] * 3, _backend_override=OB)
+    assert api.inferenceObjectQ(obj) and "GaussianProcessData" in obj
+    assert api.predictFromGaussianProcess(obj, 5) == api.FAILED  # no "Samples" yet: the definition does not match
+    res = api.nestedSampling(obj, SamplePoolSize=20, BatchSize=5, MonteCarloSteps=10, MaxIterations=8, MinIterations=8,
+                             PostProcessSamplingRuns=5, Seed=3)
+    pred = api.predictFromGaussianProcess(res, 6)
+    x = c.inputs[:, 0]
+    np.testing.assert_allclose(pred.points[:, 0], np.linspace(x.min(), x.max(), 6))
+    assert list(pred.keys()) == [float(v) for v in pred.points[:, 0]]
+    S = res["Samples"]
+    M = S["Point"].shape[0]
+    assert pred.means.shape == (M, 6) and pred.sds.shape == (M, 6)
+    w = S["CrudePosteriorWeight"] / S["CrudePosteriorWeight"].sum()
+    np.testing.assert_allclose(pred.weights, w)
+    # one component by hand (closed form with numpy): sample 0, input 2
+    sf, ell, sn = S["Point"][0]
+    K = sf**2 * np.exp(-(x[:, None] - x[None]) ** 2 / (2 * ell**2)) + sn**2 * np.eye(x.size)
+    ks = sf**2 * np.exp(-(x - pred.points[2, 0]) ** 2 / (2 * ell**2))
+    np.testing.assert_allclose(pred.means[0, 2], ks @ np.linalg.solve(K, c.outputs[:, 0]), rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(pred.sds[0, 2], np.sqrt(sf**2 + sn**2 - ks @ np.linalg.solve(K, ks)), rtol=1e-7)
+    mix = pred[float(pred.points[2, 0])]
+    np.testing.assert_allclose(mix.mean(), w @ pred.means[:, 2])
+    np.testing.assert_allclose(mix.variance(), w @ (pred.sds[:, 2] ** 2 + pred.means[:, 2] ** 2) - mix.mean() ** 2, rtol=1e-9)
+    assert abs(mix.cdf(mix.quantile(0.3)) - 0.3) < 1e-9
+    xs = np.linspace(mix.mean() - 8 * mix.sd(), mix.mean() + 8 * mix.sd(), 4001)
+    assert abs(np.trapezoid(mix.pdf(xs), xs) - 1.0) < 1e-6
+    # explicit inputs, duplicates collapse like association keys; wrong dimension fails
+    p2 = api.predictFromGaussianProcess(res, [1.0, 2.5, 1.0])
+    assert list(p2.keys()) == [1.0, 2.5]
+    assert api.predictFromGaussianProcess(res, np.zeros((3, 2))) == api.FAILED
+    assert api.predictFromGaussianProcess(res, 1) == api.FAILED
+
+
 def test_shard_plan():
     for R, W in [(64, 8), (4, 3), (1, 2), (5, 5)]:
         parts = [api._shard(R, r, W) for r in range(W)]

@@ -349,3 +349,74 @@ def test_gp_nested_sampling_small(eng, O):
     assert got["M"] == ref.logL.size
     np.testing.assert_allclose(got["logL"], ref.logL, rtol=1e-8)
     np.testing.assert_allclose(got["points"], ref.points, rtol=1e-7, atol=1e-9)
+
+
+@pytest.mark.parametrize("N,Q", [(200, 1), (200, 37), (512, 300), (130, 129)])
+def test_gp_predict_matches_oracle(eng, O, N, Q):
+    """predictFromGaussianProcess (GP:332-422): predictive mean / sd of every parameter vector at
+    every input from the augmented Cholesky sweep, against the oracle's long-double Cholesky and its fp64 LU
+    restatement of GP:395-420.  Ragged sizes: N and Q not multiples of the 128-wide panel."""
+    c = cfg.c5_gp(N=N)
+    gp, op, pr = _pair(eng, O, c)
+    th = pr.sample(9, 41)
+    th[0] = [1.0, 0.8, 0.3]
+    rng = np.random.default_rng(5)
+    xs = np.concatenate([rng.uniform(-1.0, 11.0, Q - 1), c.inputs[3]])  # one input coincides with a datum
+    mean, sd = gp.gp_predict(th, xs)
+    rm, rs = op.gp_predict(th, xs, long_double=True)
+    lm, ls = op.gp_predict(th, xs)
+    scale = np.abs(rm).max()
+    assert np.abs(mean - rm).max() <= 1e-9 * scale, np.abs(mean - rm).max()
+    np.testing.assert_allclose(sd, rs, rtol=1e-7, atol=1e-9)
+    # the reference's own LU arithmetic is no closer to the long-double value than the GPU sweep is (x10 slack)
+    assert np.abs(mean - rm).max() <= 10 * np.abs(lm - rm).max() + 1e-13 * scale
+    # a box/constraint violation or an unfactorable covariance gives NaN for that parameter vector only
+    bad = th.copy()
+    bad[2, 1] = -1.0
+    m2, s2 = gp.gp_predict(bad, xs)
+    assert np.isnan(m2[2]).all() and np.isnan(s2[2]).all()
+    np.testing.assert_allclose(m2[[0, 1, 3]], mean[[0, 1, 3]], rtol=1e-13, atol=1e-15)
+    # the likelihood entry point shares the workspace and the sweep: unchanged after a prediction call
+    np.testing.assert_allclose(gp.loglike(th), op.loglike_quad(th)[0], rtol=1e-10)
+
+
+def test_predict_from_gaussian_process_api(eng):
+    """The reference-facing call on a finished run: mixture over all samples with their CrudePosteriorWeight."""
+    from bayesianinference_b200 import api
+    c = cfg.c5_gp(N=256)
+    obj = api.defineGaussianProcess((c.inputs[:, 0], c.outputs[:, 0]), api.SquaredExponentialGP(*c.names),
+                                    [(nm, lo, hi) for nm, lo, hi in zip(c.names, c.lo, c.hi)], ["ScaleParameter"] * 3)
+    res = api.nestedSampling(obj, SamplePoolSize=128, BatchSize=32, MaxIterations=10**6, Seed=9)
+    pred = api.predictFromGaussianProcess(res, 25)
+    xs = pred.points[:, 0]
+    truth = np.sin(xs) + 0.5 * np.cos(2.3 * xs)
+    mu = np.array([pred[float(v)].mean() for v in xs])
+    sdv = np.array([pred[float(v)].sd() for v in xs])
+    assert np.all(np.isfinite(mu)) and np.all(sdv > 0.05) and np.all(sdv < 0.4)  # noise sd 0.1 + function uncertainty
+    assert np.abs(mu - truth).max() < 0.25 and np.mean(np.abs(mu - truth) < 2.5 * sdv) > 0.9
+
+
+def test_predictive_components_match_oracle(eng, O):
+    """predictiveDistribution (BS:1437-1483): (mean, sd) / class-probability tables of every
+    sample at every input against the oracle restatement; ragged M, Q."""
+    rng = np.random.default_rng(11)
+    c = cfg.c2_polyreg(N=1000)
+    gp, op, pr = _pair(eng, O, c)
+    th = pr.sample(333, 4)
+    xs = rng.uniform(-1, 1, 77)
+    got, ref = gp.predictive_components(th, xs), op.predictive_components(th, xs)
+    assert got.shape == (333, 77, 2)
+    np.testing.assert_allclose(got[:, :, 0], ref[:, :, 0], rtol=1e-14, atol=1e-15)  # Horner with FMA vs without
+    np.testing.assert_array_equal(got[:, :, 1], ref[:, :, 1])
+    th[5, 4] = -1.0
+    assert np.isnan(gp.predictive_components(th, xs)[5]).all()
+    c = cfg.c3_logistic(N=1000)
+    gp, op, pr = _pair(eng, O, c)
+    th = pr.sample(65, 4)
+    X = rng.normal(size=(31, 4))
+    got, ref = gp.predictive_components(th, X), op.predictive_components(th, X)
+    assert got.shape == (65, 31, 3)
+    np.testing.assert_allclose(got, ref, rtol=2e-12, atol=1e-300)  # |z| up to ~100: FMA vs plain dot in the logits
+    np.testing.assert_allclose(got.sum(-1), 1.0, rtol=1e-14)
+    with pytest.raises(ValueError):
+        eng.Problem.from_config(cfg.c4_gbm(T=64)).predictive_components(np.ones((1, 2)), np.ones(3))

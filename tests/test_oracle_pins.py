@@ -202,3 +202,52 @@ def test_k9_combine_runs_invariants():
     assert m["logL"].size == total - dup and m["n_deleted"] == m["logL"].size - 120  # BS:1294-1309
     assert np.all(np.diff(m["logL"]) >= 0)
     assert m["pool"][0] == 120 and m["pool"].max() == 120
+
+
+def test_gp_predict_oracle_matches_closed_form():
+    """predictFromGaussianProcessInternal (GP:395-420) restated with LU (fp64) and long-double Cholesky against the
+    textbook formulas evaluated with scipy."""
+    from scipy.linalg import cho_factor, cho_solve
+    from bayesianinference_b200 import configs as cfg
+    c = cfg.c5_gp(N=150)
+    op = O.Problem(c.op, c.d, c.inputs, c.outputs, c.iparam)
+    th = np.array([[1.0, 0.8, 0.3], [0.7, 1.5, 0.05], [2.0, 0.3, 0.1]])
+    xs = np.linspace(-0.5, 10.5, 17)
+    m, s = op.gp_predict(th, xs)
+    ml, sl = op.gp_predict(th, xs, long_double=True)
+    x, y = c.inputs[:, 0], c.outputs[:, 0]
+    for i, (sf, ell, sn) in enumerate(th):
+        K = sf**2 * np.exp(-(x[:, None] - x[None]) ** 2 / (2 * ell * ell)) + sn**2 * np.eye(x.size)
+        ks = sf**2 * np.exp(-(x[:, None] - xs[None]) ** 2 / (2 * ell * ell))
+        cf = cho_factor(K)
+        mm = ks.T @ cho_solve(cf, y)
+        vv = sf**2 + sn**2 - np.sum(ks * cho_solve(cf, ks), 0)
+        np.testing.assert_allclose(m[i], mm, rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(ml[i], mm, rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(s[i], np.sqrt(vv), rtol=1e-9)
+        np.testing.assert_allclose(sl[i], np.sqrt(vv), rtol=1e-9)
+    bad = op.gp_predict(np.array([[1.0, 0.8, 0.3], [0.0, 1.0, 0.0]]), xs[:3])  # K = 0: singular -> the reference Throws
+    assert np.isnan(bad[0][1]).all()
+
+
+def test_predictive_components_oracle_matches_numpy():
+    """BS:1437-1483 restated: component parameters of the predictive mixture (polynomial regression, softmax)."""
+    from bayesianinference_b200 import configs as cfg
+    rng = np.random.default_rng(3)
+    c = cfg.c2_polyreg(N=50)
+    op = O.Problem(c.op, c.d, c.inputs, c.outputs, c.iparam)
+    th = O.Prior(c.kinds, c.lo, c.hi).sample(7, 2)
+    xs = rng.uniform(-1, 1, 5)
+    out = op.predictive_components(th, xs)
+    np.testing.assert_allclose(out[:, :, 0], np.polynomial.polynomial.polyval(xs, th[:, :4].T), rtol=1e-14)
+    np.testing.assert_array_equal(out[:, :, 1], np.repeat(th[:, 4:5], 5, 1))
+    c = cfg.c3_logistic(N=50)
+    op = O.Problem(c.op, c.d, c.inputs, c.outputs, c.iparam)
+    th = rng.normal(size=(6, 10))
+    X = rng.normal(size=(4, 4))
+    out = op.predictive_components(th, X)
+    W = th.reshape(6, 2, 5)
+    z = np.concatenate([np.einsum("mkf,qf->mqk", W[:, :, :4], X) + W[:, None, :, 4], np.zeros((6, 4, 1))], -1)
+    pr = np.exp(z - z.max(-1, keepdims=True))
+    pr /= pr.sum(-1, keepdims=True)
+    np.testing.assert_allclose(out, pr, rtol=1e-13)
