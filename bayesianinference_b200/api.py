@@ -23,6 +23,7 @@ import numpy as np
 from . import configs as _cfg
 
 FAILED = "$Failed"
+LOGZERO_HOST = -1.7976931348623157e308  # $MachineLogZero, BU:47
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -382,6 +383,115 @@ def predictiveDistribution(obj, inputs=None, keys=None, point_estimate=None, _ba
         else:
             out[k] = MixtureDistribution(w, comp[:, q, 0], comp[:, q, 1])
     out.inputs, out.weights, out.components = x, w / w.sum(), comp
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------
+# Laplace evidence: mode + Hessian of the log posterior on the GPU operators
+def laplaceLogEvidence(maximum, precisionMatrix):
+    """LA:22-30: max + (n Log[2 Pi] - Log[Det[precision]]) / 2, Missing[] unless the determinant is positive."""
+    P = np.atleast_2d(np.asarray(precisionMatrix, float))
+    sign, logdet = np.linalg.slogdet(P)
+    if not (sign > 0 and np.isfinite(logdet)):
+        return Missing("NotPositiveDefinite")
+    return float(maximum + 0.5 * (P.shape[0] * np.log(2 * np.pi) - logdet))
+
+
+def approximateEvidence(obj, InitialGuess=None, MaxIterations=50, _backend_override=None):
+    """approximateEvidence of the reference (LA:177-238) on an inferenceObject: maximise the unnormalised log
+    posterior "LogLikelihoodFunction" + "LogPriorPDFFunction" inside the parameter box, take minus its Hessian at the
+    maximum as the precision matrix, and return <|"LogEvidence", "Maximum", "Mean", "PrecisionMatrix", "Parameters"|>
+    (LA:219-234).  The reference differentiates the symbolic density (FindMaximum + numericD "Hessian"); the operators
+    here are device code, so gradient and Hessian are central differences — all 2 d^2 + 2 d + 1 stencil points of a Newton
+    iteration go through ONE batched "LogLikelihoodFunction" call, the shape the GPU operators are built for.
+    InitialGuess: a point, or None = the best sample of a finished run / of 4096 prior draws."""
+    if not inferenceObjectQ(obj):
+        return FAILED
+    a = obj.Normal()
+    ll, lp = a["LogLikelihoodFunction"], a["LogPriorPDFFunction"]
+    lo = np.array([p[1] for p in a["Parameters"]], float)
+    hi = np.array([p[2] for p in a["Parameters"]], float)
+    d = lo.size
+
+    def f(X):
+        X = np.atleast_2d(X)
+        inside = np.all((X > lo) & (X < hi), axis=1)
+        v = np.full(X.shape[0], -np.inf)
+        if inside.any():
+            v[inside] = ll(X[inside]) + lp(X[inside])
+        v[v <= 0.5 * LOGZERO_HOST] = -np.inf
+        return v
+
+    if InitialGuess is not None:
+        x = np.asarray(InitialGuess, float).reshape(d)
+    elif "Samples" in a:
+        S = a["Samples"]
+        x = np.asarray(S["Point"][int(np.argmax(S["LogLikelihood"] + S["LogPriorPDF"]))], float)
+    else:
+        cand = a["_problem"].sample_prior(4096, seed=77, run_id=0)
+        x = cand[int(np.argmax(f(cand)))]
+    if "Samples" in a and "CrudePosteriorWeight" in a["Samples"]:
+        w = a["Samples"]["CrudePosteriorWeight"]
+        w = w / w.sum()
+        m = w @ a["Samples"]["Point"]
+        h = 0.3 * np.sqrt(np.maximum(w @ (a["Samples"]["Point"] - m) ** 2, 1e-300))  # 0.3 posterior sd
+    else:
+        h = 1e-4 * np.where(np.isfinite(hi - lo), hi - lo, 1.0)
+    E = np.eye(d)
+    pairs = [(i, j) for i in range(d) for j in range(i + 1, d)]
+
+    def derivatives(x, h):
+        pts = [x] + [x + s * h[i] * E[i] for i in range(d) for s in (1, -1)]
+        for i, j in pairs:
+            pts += [x + si * h[i] * E[i] + sj * h[j] * E[j] for si in (1, -1) for sj in (1, -1)]
+        n2 = len(pts)
+        pts += [x + s * 0.5 * h[i] * E[i] for i in range(d) for s in (1, -1)]  # half steps: 5-point gradient, O(h^4)
+        v = f(np.array(pts))
+        f0, fp, fm = v[0], v[1:2 * d + 1:2], v[2:2 * d + 1:2]
+        hp, hm = v[n2::2], v[n2 + 1::2]
+        g = (8.0 * (hp - hm) - (fp - fm)) / (6.0 * h)
+        H = np.diag((fp - 2 * f0 + fm) / h**2)
+        for k, (i, j) in enumerate(pairs):
+            q = v[2 * d + 1 + 4 * k: 2 * d + 5 + 4 * k]  # (+,+), (+,-), (-,+), (-,-)
+            H[i, j] = H[j, i] = (q[0] - q[1] - q[2] + q[3]) / (4 * h[i] * h[j])
+        return f0, g, H, bool(np.all(np.isfinite(v)))
+
+    fx = f(x)[0]
+    if not np.isfinite(fx):
+        return FAILED
+    # two passes: stencil at ~0.3 sd of the local Gaussian to get there robustly, then at ~0.05 sd so that the
+    # O(h^2) bias of the central differences is far below the Monte Carlo error anything is compared with
+    for rel in (0.3, 0.05):
+        if rel != 0.3:
+            h = h * (rel / 0.3)
+        for _ in range(int(MaxIterations)):
+            f0, g, H, ok = derivatives(x, h)
+            if not ok:
+                h = 0.5 * h  # a stencil point left the box / the operator's domain
+                continue
+            ev, V = np.linalg.eigh(-H)
+            if ev.min() > 0:
+                h = np.clip(rel / np.sqrt(np.diag(-H)), 0.1 * h, 4.0 * h)
+                step = V @ ((V.T @ g) / ev)  # Newton
+            else:
+                step = g * h * h  # not concave here: scaled gradient ascent
+            ts = 2.0 ** -np.arange(0, 12)
+            vals = f(x + ts[:, None] * step)  # the whole line search is one batched call
+            k = int(np.argmax(vals))
+            if not (vals[k] > f0):
+                break
+            x = x + ts[k] * step
+            if vals[k] - f0 < 1e-12 + 8 * np.finfo(float).eps * abs(f0) and ev.min() > 0:
+                break
+    f0, g, H, ok = derivatives(x, h)
+    if not ok:
+        return FAILED
+    prec = -0.5 * (H + H.T)
+    names = a["ParameterSymbols"]
+    out = {"LogEvidence": laplaceLogEvidence(f0, prec), "Maximum": (float(f0), dict(zip(names, x.tolist()))),
+           "Mean": x, "PrecisionMatrix": prec, "Parameters": names}
+    if not np.all(np.linalg.eigvalsh(prec) > 0):
+        warnings.warn("approximateEvidence::nonposdef: the Hessian at the maximum is not negative definite")  # LA:214-216
     return out
 
 

@@ -23,6 +23,7 @@
 // fused right-hand-side update accumulates -V z = -k*.K^-1 y (the predictive mean) in y[Np + q], and the row sums of
 // squares of V give k*.K^-1 k* for the predictive variance — no factor is ever re-read and no back substitution runs.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "problem.cuh"
@@ -33,6 +34,8 @@ namespace {
 constexpr int NB = 128;        // panel width / tile edge
 constexpr int KC = 32;         // K chunk of the GEMM kernels
 constexpr int LDS_ = NB + 4;   // smem leading dimension: half-warp fragment loads hit 16 distinct 8-byte banks
+constexpr int kGpBlockPanels = 4;
+constexpr int kGpStreams = 4;      // sub-batches of a chunk swept on separate streams (BINEST_GP_STREAMS overrides, 1..8)  // panels per group of the two-level blocking (BINEST_GP_BLOCK overrides, 1..8)
 
 struct GpBatch {
     double *A;        // [B][ld*Np] column-major: Np columns of ld = Np + Qp rows (Qp = 0 for the likelihood)
@@ -255,23 +258,28 @@ __device__ __forceinline__ void load_chunk_async(double *sdst, const double *__r
 // pipe idle 38 % of the time while C moved).
 constexpr int NBH = NB / 2;
 constexpr int LDSH_ = NBH + 4;
-__global__ void __launch_bounds__(256, 2) gp_syrk_kernel(GpBatch g, int k0) {
+// Two-level blocking.  Panels are factored in groups of `nblk`: inside a group panel j only updates the column
+// blocks of its own group (narrow != 0: the trapezoid rows >= base, columns [base, base + 64 ncol64)), and when the
+// group is done ONE pass with K = kw = nblk * 128 updates everything to the right of it — the trailing matrix
+// crosses HBM once per group instead of once per panel (the DMMA work is unchanged).
+__global__ void __launch_bounds__(256, 2) gp_syrk_kernel(GpBatch g, int k0, int kw, int base, int ncol64) {
     extern __shared__ __align__(16) double sm[];  // 2 stages x (A chunk [KC][LDS_] + B chunk [KC][LDSH_])
     const int b = blockIdx.y;
     if (g.fail[b]) return;
-    // tiles of the square trailing part (rest x rest row blocks, lower triangle) first, then the prediction rows
-    // (every 64-column block of the trailing part)
-    const int rest = (g.Np - k0) / NB - 1;
+    const int rest = (g.Np - base) / NB;  // row blocks of the square part at and below `base`
     int t = blockIdx.x, ti = 0, tj;
-    if (t < rest * (rest + 1)) {
+    if (ncol64 > 0) {  // narrow: ti over all row blocks (prediction rows included), tj < ncol64
+        ti = t / ncol64;
+        tj = t - ti * ncol64;
+        if (tj * NBH > ti * NB + NB - 1) return;  // tile entirely above the diagonal
+    } else if (t < rest * (rest + 1)) {  // lower-triangular tiles of the square trailing part ...
         while ((ti + 1) * (ti + 2) <= t) ++ti;
         tj = t - ti * (ti + 1);  // 0 .. 2*ti + 1
-    } else {
+    } else {                     // ... then the prediction rows (every 64-column block of the trailing part)
         t -= rest * (rest + 1);
         ti = rest + t / (2 * rest);
         tj = t % (2 * rest);
     }
-    const int base = k0 + NB;
     const int i0 = base + ti * NB, j0 = base + tj * NBH;
     double *A = g.A + (size_t)b * g.mat();
     const size_t ld = g.ld;
@@ -294,7 +302,7 @@ __global__ void __launch_bounds__(256, 2) gp_syrk_kernel(GpBatch g, int k0) {
                 const int gi = i0 + wm * 32 + i * 8 + r, gj = j0 + wn * 32 + j * 8 + 2 * q + h;
                 acc[i][j][h] = (gi >= gj) ? A[(size_t)gj * ld + gi] : 0.0;
             }
-    constexpr int NCH = NB / KC;
+    const int NCH = kw / KC;
 #pragma unroll 1
     for (int c = 0; c < NCH; ++c) {
         if (c + 1 < NCH) {
@@ -444,7 +452,62 @@ struct GpWorkspace {
 };
 thread_local GpWorkspace g_ws;
 
-// fill + blocked Cholesky sweep (with the fused forward solve) of one chunk of matrices
+// auxiliary streams of the batch split (below): created once per host thread and device
+struct GpStreams {
+    int device = -1;
+    std::vector<cudaStream_t> aux;
+    std::vector<cudaEvent_t> done;
+    cudaEvent_t fork = nullptr;
+    void ensure(int dev, int n) {
+        if (device != dev) { aux.clear(); done.clear(); fork = nullptr; device = dev; }  // (a thread serves one device)
+        if (!fork) BN_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+        while ((int)aux.size() < n) {
+            cudaStream_t st; cudaEvent_t ev;
+            BN_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+            BN_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            aux.push_back(st); done.push_back(ev);
+        }
+    }
+};
+thread_local GpStreams g_streams;
+
+// blocked Cholesky sweep (with the fused forward solve) of matrices [h0, h0 + Bh) of the chunk on stream s
+void gp_sweep(const GpBatch &gc, int h0, int Bh, int nblk, cudaStream_t s, size_t smem_potf2, size_t smem_trsm,
+              size_t smem_syrk) {
+    GpBatch g = gc;
+    g.A += (size_t)h0 * gc.mat(); g.y += (size_t)h0 * gc.ld; g.z += (size_t)h0 * NB; g.linvT += (size_t)h0 * NB * NB;
+    g.logdet += h0; g.quad += h0; g.fail += h0; g.B = Bh;
+    if (g.v2) g.v2 += (size_t)h0 * gc.ld;
+    const int T = g.Np / NB, Tq = (g.ld - g.Np) / NB, rows_all = T + Tq, B = Bh;
+    for (int kb = 0; kb < T; kb += nblk) {
+        const int kend = std::min(kb + nblk, T);  // panels [kb, kend) form one group
+        for (int k = kb; k < kend; ++k) {
+            const int k0 = k * NB, below = rows_all - k - 1;
+            gp_potf2_kernel<<<B, 256, smem_potf2, s>>>(g, k0);
+            BN_LAUNCH_CHECK();
+            if (below > 0) {
+                gp_trsm_kernel<<<dim3(below, B), 512, smem_trsm, s>>>(g, k0);
+                BN_LAUNCH_CHECK();
+            }
+            const int ncol64 = 2 * (kend - k - 1);  // the group's own remaining column blocks
+            if (ncol64 > 0) {
+                gp_syrk_kernel<<<dim3(below * ncol64, B), 256, smem_syrk, s>>>(g, k0, NB, k0 + NB, ncol64);
+                BN_LAUNCH_CHECK();
+            }
+        }
+        const int rest = T - kend;
+        if (rest > 0) {
+            gp_syrk_kernel<<<dim3(rest * (rest + 1) + Tq * 2 * rest, B), 256, smem_syrk, s>>>(
+                g, kb * NB, (kend - kb) * NB, kend * NB, 0);
+            BN_LAUNCH_CHECK();
+        }
+    }
+}
+
+// fill + sweep of one chunk of matrices.  The chunk is split into `nsplit` sub-batches that run their sweeps on
+// separate streams: the diagonal-block kernel is a latency-bound serial column sweep (one CTA per matrix, ~0.25 ms per
+// panel, 22 % of a B = 32 sweep when it runs alone), and with the sub-batches drifting out of phase it executes under
+// another sub-batch's trailing update instead of leaving the SMs idle.
 void gp_factor_chunk(binest_problem &p, const GpBatch &g, const double *theta_dev, int Ps, int b0) {
     const int T = g.Np / NB, Tq = (g.ld - g.Np) / NB, B = g.B;
     const size_t smem_potf2 = (size_t)NB * (NB + 1) * sizeof(double);
@@ -457,17 +520,26 @@ void gp_factor_chunk(binest_problem &p, const GpBatch &g, const double *theta_de
     gp_fill_kernel<<<dim3(T * (T + 1) / 2 + Tq * T, B), 256, 2 * NB * p.gp_dim * sizeof(double), s>>>(
         g, p.gp_x.p, (int)p.gp_dim, p.gp_y.p, theta_dev, Ps, b0);
     BN_LAUNCH_CHECK();
-    for (int k = 0; k < T; ++k) {
-        const int k0 = k * NB, rest = T - k - 1;
-        gp_potf2_kernel<<<B, 256, smem_potf2, s>>>(g, k0);
-        BN_LAUNCH_CHECK();
-        if (rest + Tq > 0) {
-            gp_trsm_kernel<<<dim3(rest + Tq, B), 512, smem_trsm, s>>>(g, k0);
-            BN_LAUNCH_CHECK();
-        }
-        if (rest > 0) {
-            gp_syrk_kernel<<<dim3(rest * (rest + 1) + Tq * 2 * rest, B), 256, smem_syrk, s>>>(g, k0);
-            BN_LAUNCH_CHECK();
+    static const int nblk_env = [] { const char *e = getenv("BINEST_GP_BLOCK"); return e ? atoi(e) : 0; }();
+    static const int nsplit_env = [] { const char *e = getenv("BINEST_GP_STREAMS"); return e ? atoi(e) : 0; }();
+    const int nblk = std::max(1, std::min(nblk_env > 0 ? nblk_env : kGpBlockPanels, 8));
+    int nsplit = std::max(1, std::min(nsplit_env > 0 ? nsplit_env : kGpStreams, 8));
+    nsplit = std::min(nsplit, std::max(1, B / 4));  // tiny batches stay whole
+    if (nsplit == 1) {
+        gp_sweep(g, 0, B, nblk, s, smem_potf2, smem_trsm, smem_syrk);
+        return;
+    }
+    GpStreams &st = g_streams;
+    st.ensure(p.device, nsplit - 1);
+    BN_CUDA(cudaEventRecord(st.fork, s));
+    for (int h = 0; h < nsplit; ++h) {
+        const int h0 = (int)((long long)B * h / nsplit), h1 = (int)((long long)B * (h + 1) / nsplit);
+        cudaStream_t sh = h == 0 ? s : st.aux[h - 1];
+        if (h > 0) BN_CUDA(cudaStreamWaitEvent(sh, st.fork, 0));
+        gp_sweep(g, h0, h1 - h0, nblk, sh, smem_potf2, smem_trsm, smem_syrk);
+        if (h > 0) {
+            BN_CUDA(cudaEventRecord(st.done[h - 1], sh));
+            BN_CUDA(cudaStreamWaitEvent(s, st.done[h - 1], 0));
         }
     }
 }

@@ -30,6 +30,8 @@ inferenceObjectQ::usage = "inferenceObjectQ[obj]";
 defineGaussianProcess::usage = "defineGaussianProcess[in -> out, squaredExponentialKernel[sf, ell], nuggetVariance[sn], None, {{sf, lo, hi}, {ell, lo, hi}, {sn, lo, hi}}, prior] — GP regression with the squared-exponential kernel sf^2 Exp[-|x - x'|^2/(2 ell^2)] and nugget sn^2 (the GPU operator).";
 predictFromGaussianProcess::usage = "predictFromGaussianProcess[inferenceObject, pts] gives, for every input, the MixtureDistribution of the samples' Gaussian predictives weighted by CrudePosteriorWeight.";
 predictiveDistribution::usage = "predictiveDistribution[inferenceObject] or predictiveDistribution[inferenceObject, inputs] gives the posterior predictive as a MixtureDistribution over the samples (per input for regression problems); a trailing \"MaximumLikelihood\" or \"MAP\" uses the single best sample.";
+laplaceLogEvidence::usage = "laplaceLogEvidence[max, precisionMatrix] = max + (n Log[2 Pi] - Log[Det[precisionMatrix]])/2.";
+approximateEvidence::usage = "approximateEvidence[inferenceObject] maximises the log posterior of the GPU operators and returns the Laplace evidence, the maximum and the precision matrix.";
 squaredExponentialKernel::usage = "squaredExponentialKernel[sf, ell] — kernel descriptor for defineGaussianProcess.";
 nuggetVariance::usage = "nuggetVariance[sn] — nugget sn^2 descriptor for defineGaussianProcess.";
 $binestLibrary::usage = "Path of the compiled LibraryLink shim (binestLink).";
@@ -193,6 +195,35 @@ predictiveDistribution[inferenceObject[result_?(AssociationQ[#] && MatchQ[#["Dat
                 Transpose[comp, {2, 1, 3}]]]
     ) /; ArrayQ[comp, 3, NumericQ]
 ]; (* BS:1448-1483 *)
+
+(* ------------------------------------------------------------------ Laplace evidence (LaplaceApproximation.wl:22-30, 177-238) *)
+laplaceLogEvidence[max_?NumericQ, prec_?(MatrixQ[#, NumericQ] &)] := With[{det = Det[prec]},
+    max + (Length[prec] * Log[2 * Pi] - Log[det])/2 /; TrueQ[det > 0]];
+laplaceLogEvidence[__] := Missing[];
+approximateEvidence::nonposdef = "The Hessian at the maximum `1` is not negative definite."; (* LA:214-216 *)
+approximateEvidence[inferenceObject[assoc_?AssociationQ]] := Module[{
+    h = assoc["binestHandle"], names = assoc["ParameterSymbols"], d, logPost, start, max, mean, step, pts, v, hess, prec},
+    d = Length[names];
+    (* all stencil points of one evaluation go through ONE batched library call *)
+    logPost[m_?(MatrixQ[#, NumericQ] &)] := binestLogLike[h, m] + binestLogPrior[h, m];
+    logPost[p_?(VectorQ[#, NumericQ] &)] := First @ logPost[{p}];
+    start = If[KeyExistsQ[assoc, "Samples"],
+        assoc["Samples", "Point"][[First @ Ordering[assoc["Samples", "LogLikelihood"] + assoc["Samples", "LogPriorPDF"], -1]]],
+        With[{c = binestSamplePrior[h, 4096, 77, 0]}, c[[First @ Ordering[logPost[c], -1]]]]];
+    max = FindMaximum[logPost[Array[\[FormalX], d]], Transpose[{Array[\[FormalX], d], start}]]; (* LA:193-201 *)
+    mean = Array[\[FormalX], d] /. Last[max];
+    step = If[KeyExistsQ[assoc, "Samples"] && KeyExistsQ[assoc["Samples"], "CrudePosteriorWeight"],
+        0.05 * Sqrt @ Diagonal @ Covariance @ WeightedData[assoc["Samples", "Point"], assoc["Samples", "CrudePosteriorWeight"]],
+        10.^-4 * Abs[mean] + 10.^-6];
+    pts = Flatten[Table[mean + si * step[[i]] * UnitVector[d, i] + sj * step[[j]] * UnitVector[d, j],
+        {i, d}, {j, d}, {si, {1, -1}}, {sj, {1, -1}}], 3];
+    v = ArrayReshape[logPost[pts], {d, d, 2, 2}];
+    hess = Table[(v[[i, j, 1, 1]] - v[[i, j, 1, 2]] - v[[i, j, 2, 1]] + v[[i, j, 2, 2]])/(4 * step[[i]] * step[[j]]), {i, d}, {j, d}];
+    prec = -(hess + Transpose[hess])/2; (* LA:209-213: minus the Hessian of the log posterior *)
+    If[!PositiveDefiniteMatrixQ[prec], Message[approximateEvidence::nonposdef, mean]];
+    <|"LogEvidence" -> laplaceLogEvidence[First[max], prec], "Maximum" -> {First[max], Thread[names -> mean]},
+        "Mean" -> mean, "PrecisionMatrix" -> prec, "Parameters" -> names|> (* LA:219-234 *)
+];
 
 generateStartingPoints[inferenceObject[assoc_?AssociationQ], n_Integer, seed_Integer : 1] :=
     inferenceObject[Append[assoc, "StartingPoints" -> binestSamplePrior[assoc["binestHandle"], n, seed, 0]]]; (* BS:1046-1068 *)

@@ -172,6 +172,29 @@ def test_predictive_distribution_host_logic():
     assert api.predictiveDistribution(rr) == api.FAILED
 
 
+def test_approximate_evidence_laplace_matches_quadrature_scale():
+    """approximateEvidence / laplaceLogEvidence (LA:22-30, 177-238) on the oracle backend: C1 has the quadrature pin
+    -114.641064; the Laplace value of this skewed 2-parameter posterior sits within ~0.1 of it, and the mode is the MAP
+    of mu (sample mean) and of sigma under the 1/sigma prior."""
+    assert abs(api.laplaceLogEvidence(-3.0, [[2.0, 0.0], [0.0, 8.0]]) - (-3.0 + np.log(2 * np.pi) - 0.5 * np.log(16.0))) < 1e-14
+    assert not api.laplaceLogEvidence(0.0, [[1.0, 2.0], [2.0, 1.0]])  # Missing[]: determinant < 0
+    obj = _c1_obj()
+    res = api.approximateEvidence(obj)  # no samples: starts from the best of 4096 prior draws
+    c = cfg.c1_gaussian()
+    x = c.inputs[:, 0]
+    N = x.size
+    assert abs(res["Mean"][0] - x.mean()) < 1e-6
+    assert abs(res["Mean"][1] - np.sqrt(((x - x.mean()) ** 2).sum() / (N + 1))) < 1e-6  # d/ds [-(N+1) log s - S/(2 s^2)] = 0
+    np.testing.assert_allclose(res["PrecisionMatrix"][0, 0], N / res["Mean"][1] ** 2, rtol=1e-5)
+    assert abs(res["LogEvidence"] - c.truth["logZ"]) < 0.1
+    assert res["Parameters"] == ["mu", "sigma"] and set(res["Maximum"][1]) == {"mu", "sigma"}
+    # from a finished run the best sample is the start and the posterior spread sets the stencil
+    run = api.nestedSampling(obj, SamplePoolSize=40, MaxIterations=300, MonteCarloSteps=30, PostProcessSamplingRuns=5)
+    res2 = api.approximateEvidence(run)
+    np.testing.assert_allclose(res2["Mean"], res["Mean"], atol=1e-6)
+    np.testing.assert_allclose(res2["LogEvidence"], res["LogEvidence"], atol=1e-6)
+
+
 def test_predict_from_gaussian_process_host_logic():
     """predictFromGaussianProcess (GP:332-393) on the oracle backend: grid construction, weights, mixture moments."""
     c = cfg.c5_gp(N=40)

@@ -57,7 +57,13 @@ def test_c2_full_size_log_evidence():
     assert abs(res["LogLikelihoodMaximum"] - c.truth["logLmax"]) < 0.5
     assert 34.0 < res["RelativeEntropy"]["Mean"] < 47.0
     assert res["TotalSamples"] > 1024 * 30
-    print("C2 full run:", z, "truth", c.truth["logZ"], "samples", res["TotalSamples"])
+    # the Laplace evidence from the GPU operators (mode + finite-difference Hessian, every stencil
+    # of a Newton iteration one batched likelihood call) against the host-side Newton value of make_laplace_pins.py
+    lap = api.approximateEvidence(res)
+    assert abs(lap["LogEvidence"] - PINS["C2"]["logZ_laplace"]) < 1e-4, lap["LogEvidence"]
+    np.testing.assert_allclose(lap["Mean"], PINS["C2"]["mode"], rtol=0, atol=2e-7)
+    assert abs(lap["LogEvidence"] - z["Mean"]) < 3.0 * z["StandardError"]
+    print("C2 full run:", z, "truth", c.truth["logZ"], "laplace(GPU)", lap["LogEvidence"], "samples", res["TotalSamples"])
 
 
 def test_c3_full_size_log_evidence():
@@ -74,7 +80,10 @@ def test_c3_full_size_log_evidence():
     z = _check(res, PINS["C3"]["logZ_laplace"], PINS["C3"]["mode"], names, 0.15, 0.42)
     # the best of ~60 000 samples of a 10-D posterior sits a little below the mode (chi^2_10 / 2 ~ 5 for a typical one)
     assert -4.0 < res["LogLikelihoodMaximum"] - PINS["C3"]["logL_mode"] <= 1e-6
-    print("C3 full run:", z, "laplace", PINS["C3"]["logZ_laplace"], "samples", res["TotalSamples"])
+    lap = api.approximateEvidence(res)
+    assert abs(lap["LogEvidence"] - PINS["C3"]["logZ_laplace"]) < 1e-3, lap["LogEvidence"]
+    np.testing.assert_allclose(lap["Mean"], PINS["C3"]["mode"], rtol=0, atol=2e-6)
+    print("C3 full run:", z, "laplace", PINS["C3"]["logZ_laplace"], "laplace(GPU)", lap["LogEvidence"], "samples", res["TotalSamples"])
 
 
 def test_c5_small_log_evidence_against_quadrature():

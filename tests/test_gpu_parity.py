@@ -406,7 +406,7 @@ def test_predictive_components_match_oracle(eng, O):
     xs = rng.uniform(-1, 1, 77)
     got, ref = gp.predictive_components(th, xs), op.predictive_components(th, xs)
     assert got.shape == (333, 77, 2)
-    np.testing.assert_allclose(got[:, :, 0], ref[:, :, 0], rtol=1e-14, atol=1e-15)  # Horner with FMA vs without
+    np.testing.assert_allclose(got[:, :, 0], ref[:, :, 0], rtol=1e-14, atol=1e-14)  # Horner with FMA vs without; |c_j| <= 5
     np.testing.assert_array_equal(got[:, :, 1], ref[:, :, 1])
     th[5, 4] = -1.0
     assert np.isnan(gp.predictive_components(th, xs)[5]).all()
