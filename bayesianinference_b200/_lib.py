@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbinest.so")
+LIB_PATH = os.environ.get("BINEST_LIB") or os.path.join(_HERE, "libbinest.so")  # BINEST_LIB: A/B builds (csrc/Makefile)
 
 LOGZERO = -1.7976931348623157e308  # -$MaxMachineNumber, what BU:47 evaluates to on IEEE hardware
 
@@ -58,6 +58,10 @@ SIGNATURES = {
     "binest_run_fetch": (C.c_int, [_vp, C.c_int64, _dp, _dp, _dp, _dp, _ip, _dp, _dp, _dp]),
     "binest_run_estimates": (C.c_int, [_vp, C.c_int64, _dp, _dp]),
     "binest_run_free": (C.c_int, [_vp]),
+    "binest_chain_create": (C.c_int, [_vp, _dp, C.c_int64, _dp, C.c_int64, C.c_uint64, C.POINTER(_vp)]),
+    "binest_chain_iterate": (C.c_int, [_vp, C.c_int64, _dp]),
+    "binest_chain_state": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _ip, _ip]),
+    "binest_chain_free": (C.c_int, [_vp]),
     "binest_evidence_sampling": (C.c_int, [C.c_int64, C.c_int64, _dp, _dp, _ip, C.c_int64, C.c_int64, C.c_uint64,
                                            _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
     "binest_crude_weights": (C.c_int, [C.c_int64, _dp, _ip, C.c_int64, _dp, _dp, _dp]),

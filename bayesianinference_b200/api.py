@@ -387,6 +387,75 @@ def predictiveDistribution(obj, inputs=None, keys=None, point_estimate=None, _ba
 
 
 # ----------------------------------------------------------------------------------------------------
+# posterior sampler
+class MarkovChain:
+    """The chain object of createMCMCChain: chain["AcceptanceRate"], chain["StateData"] = (x, t, mean, cov)."""
+
+    def __init__(self, backend_chain, names):
+        self._c, self.names = backend_chain, names
+
+    def __getitem__(self, key):
+        st = self._c.state()
+        one = self._c.n_chains == 1
+        if key == "AcceptanceRate":
+            r = st["accepted"] / np.maximum(st["t"] - 1, 1)
+            return float(r[0]) if one else r
+        if key == "StateData":
+            return tuple(v[0] if one else v for v in (st["x"], st["t"], st["mean"], st["cov"]))
+        return Missing("KeyAbsent")
+
+
+def createMCMCChain(obj, startPt=None, _backend_override=None, **opts):
+    """BS:651-701.  Options "InitialCovariance" (number, vector or matrix; default 1, BS:676-683) and
+    "CovarianceLearnDelay" (default 20), plus "Seed" and "Chains" (independent chains advanced in lock-step on the
+    GPU; 1 is the reference).  startPt defaults to the first of obj["StartingPoints"] (BS:657-658); without either
+    the reference issues createMCMCChain::start and returns inferenceObject[$Failed]."""
+    o = {"InitialCovariance": 1, "CovarianceLearnDelay": 20, "Seed": 1, "Chains": 1}
+    bad = [k for k in opts if k not in o]
+    if bad:
+        raise TypeError(f"Unknown option(s) {bad}")
+    o.update(opts)
+    if not inferenceObjectQ(obj):
+        return inferenceObject(FAILED)
+    a = obj.Normal()
+    d = len(a["Parameters"])
+    nch = int(o["Chains"])
+    if startPt is None:
+        sp = a.get("StartingPoints")
+        if sp is None or np.ndim(sp) != 2:
+            warnings.warn("createMCMCChain::start: Please specify a starting point")  # BS:651-655
+            return inferenceObject(FAILED)
+        startPt = np.asarray(sp, float)[:nch]
+    start = np.atleast_2d(np.asarray(startPt, float))
+    if start.shape != (nch, d):
+        return inferenceObject(FAILED)
+    ic = o["InitialCovariance"]
+    if np.ndim(ic) == 0 and isinstance(ic, (int, float, np.integer, np.floating)):
+        cov = np.eye(d) * float(ic)                       # n -> DiagonalMatrix[ConstantArray[n, dim]]
+    elif np.ndim(ic) == 1 and len(ic) == d:
+        cov = np.diag(np.asarray(ic, float))              # vector -> DiagonalMatrix
+    elif np.ndim(ic) == 2 and np.shape(ic) == (d, d):
+        cov = np.asarray(ic, float)
+    else:
+        cov = np.eye(d)                                   # anything else -> identity (BS:681)
+    delay = o["CovarianceLearnDelay"]
+    delay = int(delay) if isinstance(delay, (int, np.integer)) else 20  # BS:684-690
+    be = _backend(_backend_override or a.get("_backend"))
+    return MarkovChain(be.Chain(a["_problem"], start, cov, delay, int(o["Seed"])), a["ParameterSymbols"])
+
+
+def iterateMCMC(chain, spec):
+    """Statistics`MCMC`MarkovChainIterate (BS:703): spec = n -> the next n states; {n, thin} -> n states, one every
+    `thin` steps (the forms used at BS:729 and BS:1089-1090).  One chain: (n, d); several: (n, chains, d)."""
+    if isinstance(spec, (int, np.integer)):
+        n, thin = int(spec), 1
+    else:
+        n, thin = int(spec[0]), int(spec[1])
+    out = chain._c.iterate(n * thin)[thin - 1::thin]
+    return out[:, 0, :] if chain._c.n_chains == 1 else out
+
+
+# ----------------------------------------------------------------------------------------------------
 # Laplace evidence (SURVEY §8f rank 4): mode + Hessian of the log posterior on the GPU operators
 def laplaceLogEvidence(maximum, precisionMatrix):
     """LA:22-30: max + (n Log[2 Pi] - Log[Det[precision]]) / 2, Missing[] unless the determinant is positive."""

@@ -744,3 +744,6 @@ int binest_bench_loglike(binest_problem *p, int64_t P, int64_t reps, int64_t war
 }
 
 }  // extern "C"
+
+// posterior sampler (createMCMCChain / iterateMCMC, BS:630-703): kernels + C ABI
+#include "mcmc.cuh"

@@ -150,6 +150,91 @@ __device__ __forceinline__ void exp_bounded(const double (&x)[N], double (&out)[
     for (int i = 0; i < N; ++i) out[i] = __hiloint2double(__double2hiint(p[i]) + (k[i] << 20), __double2loint(p[i]));
 }
 
+// Table-driven variant (the one the softmax operator uses): x = (32 k + j) ln2/32 + r with |r| <= ln2/64, so
+// exp(x) = 2^k * 2^(j/32) * exp(r) and a degree-5 polynomial suffices (scripts/gen_exp_poly.py 5 64: max relative error
+// 1.4e-16) — 10 fp64-pipe instructions per exp instead of 14 (the operator is fp64-issue bound: 41 -> 33 per datum).
+// 2^(j/32) comes from a 256-byte table read through the L1 (per-lane index, so not the constant bank).
+__constant__ double kExpTabPoly[4] = {
+    0.49999999998924655,   // 0x3fdffffffffd0b4b
+    0.16666666666513047,   // 0x3fc5555555547d22
+    0.04166691108715919,   // 0x3fa5555d88e3ae37
+    0.008333368250528262,  // 0x3f811115c0cff61a
+};
+__constant__ double kExpTabRed[3] = {
+    46.166241308446828,                  // 32 / ln2
+    -6.93147180369123816490e-01 / 32.0,  // -ln2/32, high part (exact scaling of the Cody-Waite split above)
+    -1.90821492927058770002e-10 / 32.0,  // -ln2/32, low part
+};
+__device__ const double kExp2Tab[32] = {
+    1.0,  // 0x3ff0000000000000
+    1.0218971486541166,  // 0x3ff059b0d3158574
+    1.0442737824274138,  // 0x3ff0b5586cf9890f
+    1.0671404006768237,  // 0x3ff11301d0125b51
+    1.0905077326652577,  // 0x3ff172b83c7d517b
+    1.1143867425958924,  // 0x3ff1d4873168b9aa
+    1.1387886347566916,  // 0x3ff2387a6e756238
+    1.1637248587775775,  // 0x3ff29e9df51fdee1
+    1.189207115002721,  // 0x3ff306fe0a31b715
+    1.215247359980469,  // 0x3ff371a7373aa9cb
+    1.241857812073484,  // 0x3ff3dea64c123422
+    1.2690509571917332,  // 0x3ff44e086061892d
+    1.2968395546510096,  // 0x3ff4bfdad5362a27
+    1.3252366431597413,  // 0x3ff5342b569d4f82
+    1.3542555469368927,  // 0x3ff5ab07dd485429
+    1.383909881963832,  // 0x3ff6247eb03a5585
+    1.4142135623730951,  // 0x3ff6a09e667f3bcd
+    1.4451808069770467,  // 0x3ff71f75e8ec5f74
+    1.4768261459394993,  // 0x3ff7a11473eb0187
+    1.5091644275934228,  // 0x3ff82589994cce13
+    1.5422108254079407,  // 0x3ff8ace5422aa0db
+    1.5759808451078865,  // 0x3ff93737b0cdc5e5
+    1.6104903319492543,  // 0x3ff9c49182a3f090
+    1.645755478153965,  // 0x3ffa5503b23e255d
+    1.681792830507429,  // 0x3ffae89f995ad3ad
+    1.718619298122478,  // 0x3ffb7f76f2fb5e47
+    1.7562521603732995,  // 0x3ffc199bdd85529c
+    1.7947090750031072,  // 0x3ffcb720dcef9069
+    1.8340080864093424,  // 0x3ffd5818dcfba487
+    1.8741676341103,  // 0x3ffdfc97337b9b5f
+    1.9152065613971474,  // 0x3ffea4afa2a490da
+    1.9571441241754002,  // 0x3fff50765b6e4540
+};
+template <int N>
+__device__ __forceinline__ void exp_bounded_tab(const double (&x)[N], double (&out)[N]) {
+    double t[N], r[N], p[N], s[N];
+    int n[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) t[i] = fma(x[i], kExpTabRed[0], kExpRed[1]);
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        n[i] = __double2loint(t[i]);
+        s[i] = __ldg(&kExp2Tab[n[i] & 31]);
+        t[i] -= kExpRed[1];
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) r[i] = fma(t[i], kExpTabRed[1], x[i]);
+#pragma unroll
+    for (int i = 0; i < N; ++i) r[i] = fma(t[i], kExpTabRed[2], r[i]);
+#pragma unroll
+    for (int i = 0; i < N; ++i) p[i] = fma(r[i], kExpTabPoly[3], kExpTabPoly[2]);
+#pragma unroll
+    for (int i = 0; i < N; ++i) p[i] = fma(p[i], r[i], kExpTabPoly[1]);
+#pragma unroll
+    for (int i = 0; i < N; ++i) p[i] = fma(p[i], r[i], kExpTabPoly[0]);
+#pragma unroll
+    for (int i = 0; i < N; ++i) p[i] = fma(p[i], r[i], 1.0);
+#pragma unroll
+    for (int i = 0; i < N; ++i) p[i] = fma(p[i], r[i], 1.0);
+#pragma unroll
+    for (int i = 0; i < N; ++i) p[i] *= s[i];
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+        out[i] = __hiloint2double(__double2hiint(p[i]) + ((n[i] >> 5) << 20), __double2loint(p[i]));
+}
+#ifndef BINEST_EXP_TAB
+#define BINEST_EXP_TAB 1
+#endif
+
 template <int F, int K>
 struct OpLogistic {
     static constexpr int D = (K - 1) * (F + 1), NCOL = (F + 2) & ~1, TW_MAX = 2;
@@ -212,7 +297,11 @@ struct OpLogistic {
             for (int k = 0; k < E; ++k) fast = fast && exp_arg_bounded(dz[u * E + k]);
         }
         if (__builtin_expect(fast, 1)) {
+#if BINEST_EXP_TAB
+            exp_bounded_tab<TW * E>(dz, ex);
+#else
             exp_bounded<TW * E>(dz, ex);
+#endif
 #pragma unroll
             for (int u = 0; u < TW; ++u) {
                 double s = 1.0 + ex[u * E];

@@ -273,6 +273,45 @@ class RunGroup:
             pass
 
 
+class Chain:
+    """createMCMCChain (BS:630-703): adaptive-Metropolis chains on the log posterior of a Problem."""
+
+    def __init__(self, problem: Problem, start, init_cov, learn_delay=20, seed=1):
+        self.problem = problem
+        start = _f64(np.atleast_2d(np.asarray(start, dtype=np.float64)))
+        if start.shape[1] != problem.d:
+            raise ValueError(f"starting points must have {problem.d} columns")
+        init_cov = _f64(np.asarray(init_cov, dtype=np.float64).reshape(problem.d, problem.d))
+        self.n_chains, self.d = start.shape[0], problem.d
+        self.h = C.c_void_p()
+        check(_lib.load().binest_chain_create(problem.h, dptr(start), self.n_chains, dptr(init_cov), int(learn_delay),
+                                              int(seed), C.byref(self.h)))
+
+    def iterate(self, n_steps, record=True):
+        """n_steps of every chain -> states (n_steps, n_chains, d) (or None with record=False)."""
+        out = np.empty((int(n_steps), self.n_chains, self.d)) if record else None
+        check(_lib.load().binest_chain_iterate(self.h, int(n_steps), dptr(out)))
+        return out
+
+    def state(self):
+        Cn, d = self.n_chains, self.d
+        x, lp, mean, cov = np.empty((Cn, d)), np.empty(Cn), np.empty((Cn, d)), np.empty((Cn, d, d))
+        t, acc = np.empty(Cn, dtype=np.int64), np.empty(Cn, dtype=np.int64)
+        check(_lib.load().binest_chain_state(self.h, dptr(x), dptr(lp), dptr(mean), dptr(cov), iptr(t), iptr(acc)))
+        return dict(x=x, logdensity=lp, mean=mean, cov=cov, t=t, accepted=acc)
+
+    def close(self):
+        if getattr(self, "h", None):
+            _lib.load().binest_chain_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def evidence_sampling(points, logL, pool, n_live, post_runs=100, seed=1):
     """evidenceSampling (BS:1158-1291) on a sorted sample list; raw per-draw outputs."""
     _ensure_init()

@@ -14,7 +14,7 @@
      evidenceSampling         BayesianStatistics.wl:1158-1291   combineRuns             :1293-1315
      generateStartingPoints   BayesianStatistics.wl:1042-1097   inferenceObject         BayesianUtilities.wl:107-138
      defineGaussianProcess    BayesianGaussianProcess.wl:201-330  predictFromGaussianProcess :332-422
-     predictiveDistribution   BayesianStatistics.wl:1373-1483
+     predictiveDistribution   BayesianStatistics.wl:1373-1483     createMCMCChain / iterateMCMC :630-703
 *)
 
 BeginPackage["BayesianInferenceB200`"];
@@ -30,6 +30,8 @@ inferenceObjectQ::usage = "inferenceObjectQ[obj]";
 defineGaussianProcess::usage = "defineGaussianProcess[in -> out, squaredExponentialKernel[sf, ell], nuggetVariance[sn], None, {{sf, lo, hi}, {ell, lo, hi}, {sn, lo, hi}}, prior] — GP regression with the squared-exponential kernel sf^2 Exp[-|x - x'|^2/(2 ell^2)] and nugget sn^2 (the GPU operator).";
 predictFromGaussianProcess::usage = "predictFromGaussianProcess[inferenceObject, pts] gives, for every input, the MixtureDistribution of the samples' Gaussian predictives weighted by CrudePosteriorWeight.";
 predictiveDistribution::usage = "predictiveDistribution[inferenceObject] or predictiveDistribution[inferenceObject, inputs] gives the posterior predictive as a MixtureDistribution over the samples (per input for regression problems); a trailing \"MaximumLikelihood\" or \"MAP\" uses the single best sample.";
+createMCMCChain::usage = "createMCMCChain[inferenceObject, startPt, opts] creates an adaptive-Metropolis chain on the log posterior (GPU operators); options \"InitialCovariance\", \"CovarianceLearnDelay\", \"Seed\".";
+iterateMCMC::usage = "iterateMCMC[chain, n] advances the chain and returns the n visited states; iterateMCMC[chain, {n, thin}] keeps one state every thin steps.";
 laplaceLogEvidence::usage = "laplaceLogEvidence[max, precisionMatrix] = max + (n Log[2 Pi] - Log[Det[precisionMatrix]])/2.";
 approximateEvidence::usage = "approximateEvidence[inferenceObject] maximises the log posterior of the GPU operators and returns the Laplace evidence, the maximum and the precision matrix.";
 squaredExponentialKernel::usage = "squaredExponentialKernel[sf, ell] — kernel descriptor for defineGaussianProcess.";
@@ -53,6 +55,10 @@ binestProblemCreate := ll["binestProblemCreate", {Integer, {Integer, 1}, {Real, 
     {Integer, 1}, {Real, 1}, {Real, 1}, {Real, 1}, {Real, 1}}, Integer];
 binestLogLike := ll["binestLogLike", {Integer, {Real, 2, "Constant"}}, {Real, 1}];
 binestLogPrior := ll["binestLogPrior", {Integer, {Real, 2, "Constant"}}, {Real, 1}];
+binestChainCreate := ll["binestChainCreate", {Integer, {Real, 2, "Constant"}, {Real, 2, "Constant"}, Integer, Integer}, Integer];
+binestChainIterate := ll["binestChainIterate", {Integer, Integer, Integer, Integer}, {Real, 3}];
+binestChainState := ll["binestChainState", {Integer, Integer, Integer}, {Real, 1}];
+binestChainFree := ll["binestChainFree", {Integer}, Integer];
 binestPredictiveComponents := ll["binestPredictiveComponents", {Integer, {Real, 2, "Constant"}, {Real, 2, "Constant"}}, {Real, 3}];
 binestGPPredict := ll["binestGPPredict", {Integer, {Real, 2, "Constant"}, {Real, 2, "Constant"}}, {Real, 3}];
 binestSamplePrior := ll["binestSamplePrior", {Integer, Integer, Integer, Integer}, {Real, 2}];
@@ -195,6 +201,31 @@ predictiveDistribution[inferenceObject[result_?(AssociationQ[#] && MatchQ[#["Dat
                 Transpose[comp, {2, 1, 3}]]]
     ) /; ArrayQ[comp, 3, NumericQ]
 ]; (* BS:1448-1483 *)
+
+(* ------------------------------------------------------------------ posterior sampler (BS:630-703) *)
+createMCMCChain::start = "Please specify a starting point"; (* BS:650 *)
+Options[createMCMCChain] = {"CovarianceLearnDelay" -> 20, "InitialCovariance" -> 1, "Seed" -> 1}; (* BS:698-701 *)
+createMCMCChain[obj_?inferenceObjectQ, opts : OptionsPattern[]] /; !MatrixQ[obj["StartingPoints"], NumericQ] := (
+    Message[createMCMCChain::start]; inferenceObject[$Failed]); (* BS:651-655 *)
+createMCMCChain[obj_?inferenceObjectQ, opts : OptionsPattern[]] /; MatrixQ[obj["StartingPoints"], NumericQ] :=
+    createMCMCChain[obj, First[obj["StartingPoints"]], opts]; (* BS:657-658 *)
+createMCMCChain[obj_?inferenceObjectQ, startPt_?(VectorQ[#, NumericQ] &), opts : OptionsPattern[]] := With[{
+    dim = Length[startPt]},
+    With[{
+        cov = Replace[OptionValue["InitialCovariance"], {   (* BS:676-683 *)
+            n_?NumericQ :> DiagonalMatrix[ConstantArray[n, dim]],
+            lst_?(VectorQ[#, NumericQ] &) /; Length[lst] === dim :> DiagonalMatrix[lst],
+            Except[_?(MatrixQ[#, NumericQ] &)] :> DiagonalMatrix[ConstantArray[1, dim]]}],
+        delay = Replace[OptionValue["CovarianceLearnDelay"], Except[_Integer] :> 20]}, (* BS:684-690 *)
+        With[{h = check @ binestChainCreate[obj["binestHandle"], {N[startPt]}, N[cov], delay, OptionValue["Seed"]]},
+            If[h === $Failed, inferenceObject[$Failed], markovChain[<|"Handle" -> h, "Dimension" -> dim|>]]]]];
+markovChain[a_]["StateData"] := With[{v = binestChainState[a["Handle"], 1, a["Dimension"]], d = a["Dimension"]},
+    {v[[;; d]], Round[v[[2 d + d^2 + 1]]], v[[d + 1 ;; 2 d]], Partition[v[[2 d + 1 ;; 2 d + d^2]], d]}]; (* {x, t, mean, cov} *)
+markovChain[a_]["AcceptanceRate"] := With[{v = binestChainState[a["Handle"], 1, a["Dimension"]], d = a["Dimension"]},
+    v[[2 d + d^2 + 2]]/Max[v[[2 d + d^2 + 1]] - 1, 1]];
+iterateMCMC[markovChain[a_], n_Integer?Positive] := binestChainIterate[a["Handle"], n, 1, a["Dimension"]][[All, 1]]; (* BS:703 *)
+iterateMCMC[markovChain[a_], {n_Integer?Positive, thin_Integer?Positive}] :=
+    binestChainIterate[a["Handle"], n * thin, 1, a["Dimension"]][[thin ;; ;; thin, 1]];
 
 (* ------------------------------------------------------------------ Laplace evidence (LaplaceApproximation.wl:22-30, 177-238) *)
 laplaceLogEvidence[max_?NumericQ, prec_?(MatrixQ[#, NumericQ] &)] := With[{det = Det[prec]},

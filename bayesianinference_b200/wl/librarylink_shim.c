@@ -22,6 +22,8 @@
 #include <stdint.h>
 #include <string.h>
 
+static int st(int code);
+static int st_(int code) { return st(code); }
 static int st(int code) { return code == 0 ? LIBRARY_NO_ERROR : (code <= 6 ? code : LIBRARY_FUNCTION_ERROR); }
 
 DLLEXPORT mint WolframLibrary_getVersion(void) { return WolframLibraryVersion; }
@@ -93,6 +95,64 @@ DLLEXPORT int binestLogLike(WolframLibraryData libData, mint Argc, MArgument *Ar
 }
 DLLEXPORT int binestLogPrior(WolframLibraryData libData, mint Argc, MArgument *Args, MArgument Res) {
     return batch_eval(libData, Args, Res, binest_logprior);
+}
+
+/* binestChainCreate[problem, start {Real,2} (chains x d), initCov {Real,2}, learnDelay, seed] -> chain handle
+ * (createMCMCChain, BayesianStatistics.wl:651-701) */
+DLLEXPORT int binestChainCreate(WolframLibraryData libData, mint Argc, MArgument *Args, MArgument Res) {
+    binest_problem *h = (binest_problem *)(intptr_t)MArgument_getInteger(Args[0]);
+    MTensor st = MArgument_getMTensor(Args[1]), cv = MArgument_getMTensor(Args[2]);
+    binest_chain *c = 0;
+    int rc;
+    if (libData->MTensor_getRank(st) != 2 || libData->MTensor_getRank(cv) != 2) return LIBRARY_RANK_ERROR;
+    rc = binest_chain_create(h, libData->MTensor_getRealData(st), libData->MTensor_getDimensions(st)[0],
+                             libData->MTensor_getRealData(cv), MArgument_getInteger(Args[3]),
+                             (uint64_t)MArgument_getInteger(Args[4]), &c);
+    if (rc) return st_(rc);
+    MArgument_setInteger(Res, (mint)(intptr_t)c);
+    return LIBRARY_NO_ERROR;
+}
+
+/* binestChainIterate[chain, n, chains, d] -> {Real,3} (n x chains x d): the state after every step (iterateMCMC, :703) */
+DLLEXPORT int binestChainIterate(WolframLibraryData libData, mint Argc, MArgument *Args, MArgument Res) {
+    binest_chain *c = (binest_chain *)(intptr_t)MArgument_getInteger(Args[0]);
+    mint dims[3];
+    MTensor out;
+    int rc;
+    dims[0] = MArgument_getInteger(Args[1]);
+    dims[1] = MArgument_getInteger(Args[2]);
+    dims[2] = MArgument_getInteger(Args[3]);
+    rc = libData->MTensor_new(MType_Real, 3, dims, &out);
+    if (rc) return rc;
+    rc = binest_chain_iterate(c, dims[0], libData->MTensor_getRealData(out));
+    if (rc) { libData->MTensor_free(out); return st_(rc); }
+    MArgument_setMTensor(Res, out);
+    return LIBRARY_NO_ERROR;
+}
+
+/* binestChainState[chain, chains, d] -> flat {x (chains d), mean (chains d), cov (chains d d), t (chains), accepted (chains)} */
+DLLEXPORT int binestChainState(WolframLibraryData libData, mint Argc, MArgument *Args, MArgument Res) {
+    binest_chain *c = (binest_chain *)(intptr_t)MArgument_getInteger(Args[0]);
+    const mint C = MArgument_getInteger(Args[1]), d = MArgument_getInteger(Args[2]);
+    mint len = 2 * C * d + C * d * d + 2 * C, i;
+    MTensor out;
+    double *o;
+    int64_t tt[64], aa[64];
+    int rc;
+    if (C > 64) return LIBRARY_DIMENSION_ERROR;
+    rc = libData->MTensor_new(MType_Real, 1, &len, &out);
+    if (rc) return rc;
+    o = libData->MTensor_getRealData(out);
+    rc = binest_chain_state(c, o, 0, o + C * d, o + 2 * C * d, tt, aa);
+    if (rc) { libData->MTensor_free(out); return st_(rc); }
+    for (i = 0; i < C; ++i) { o[2 * C * d + C * d * d + i] = (double)tt[i]; o[2 * C * d + C * d * d + C + i] = (double)aa[i]; }
+    MArgument_setMTensor(Res, out);
+    return LIBRARY_NO_ERROR;
+}
+
+DLLEXPORT int binestChainFree(WolframLibraryData libData, mint Argc, MArgument *Args, MArgument Res) {
+    MArgument_setInteger(Res, binest_chain_free((binest_chain *)(intptr_t)MArgument_getInteger(Args[0])));
+    return LIBRARY_NO_ERROR;
 }
 
 /* binestPredictiveComponents[handle, theta {Real,2} (M x d), inputs {Real,2} (Q x F)] -> {Real,3} (M x Q x C)

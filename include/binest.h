@@ -167,6 +167,26 @@ int binest_run_path(const binest_run *r, int *path);
 int binest_problem_stream(const binest_problem *p, void **stream);
 int binest_run_free(binest_run *r);
 
+/* ---- posterior sampler: createMCMCChain / iterateMCMC (BS:630-703) ------------------------ */
+/* n_chains adaptive-Metropolis chains (1 = the reference) on the unnormalised log posterior
+ * posteriorDensity = If[box, logPrior + logL, logzero] (BS:630-649), advanced in lock-step: one batched
+ * likelihood launch scores all proposals of a step.  start: n_chains x d; init_cov: d x d "InitialCovariance"
+ * (BS:676-683, already expanded to a matrix by the host); learn_delay: "CovarianceLearnDelay" (BS:684-690,
+ * default 20): the proposal covariance is init_cov until that many states exist, then 2.4^2/d times the running
+ * sample covariance (Haario et al. 2001 — the Wolfram sampler is closed source).
+ * BINEST_ERR_BAD_LIKELIHOOD: a starting point outside the support (createMCMCChain::start, BS:651-655). */
+typedef struct binest_chain binest_chain;
+int binest_chain_create(binest_problem *p, const double *start, int64_t n_chains, const double *init_cov,
+                        int64_t learn_delay, uint64_t seed, binest_chain **out);
+/* iterateMCMC[chain, n] (BS:703): n steps of every chain; out (may be NULL): n_steps x n_chains x d, the state
+ * after each step.  Thinning / burn-in ({n, thin} forms) are slices the host takes. */
+int binest_chain_iterate(binest_chain *c, int64_t n_steps, double *out);
+/* chain["StateData"] = {x, t, mean, cov} and the accepted-move count behind chain["AcceptanceRate"];
+ * any output may be NULL.  x, mean: n_chains x d; cov: n_chains x d x d; t = states seen (start included). */
+int binest_chain_state(binest_chain *c, double *x, double *logdensity, double *mean, double *cov, int64_t *t,
+                       int64_t *accepted);
+int binest_chain_free(binest_chain *c);
+
 /* ---- evidenceSampling (BS:1158-1291) on a sorted sample list ------------------------------ */
 /* pool: per-sample pool sizes (first M - n_live entries used); outputs may be NULL:
  *  z[post_runs]; logw_mean/sd[M] (LogPosteriorWeight); slx_mean/sd[M] (SampledLogX);

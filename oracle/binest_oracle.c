@@ -1106,6 +1106,79 @@ ORC_API int64_t orc_bench_walks(const orc_problem *p, const orc_prior *pr, const
     return total;
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/* createMCMCChain / iterateMCMC — BS:630-703                                                  */
+/* ------------------------------------------------------------------------------------------ */
+/* One adaptive-Metropolis chain on posteriorDensity = If[box, logPrior + logL, logzero] (BS:630-649), started at
+ * `start` with {InitialCovariance, CovarianceLearnDelay} (BS:673-696).  The sampler itself is the closed-source
+ * Statistics`MCMC`BuildMarkovChain[{"AdaptiveMetropolis","Log"}]; restated from Haario et al. (2001) like the
+ * nested-sampling walk above: proposal N(x, C0) while fewer than `delay` states have been seen, then
+ * N(x, s_d (C_t + eps I)); C_t by the same recursion, started at t = 1 with mean = start (=> unbiased sample
+ * covariance of the visited states).  Philox: (pair, step, chain) under tags 9 / 10.
+ * out: n_steps x d (state after every step); mean d, cov d x d, t_out, acc_out: final chain estimates. */
+enum { TAG_MC_NORMAL = 9, TAG_MC_ACCEPT = 10 };
+ORC_API int orc_mcmc_chain(const orc_problem *p, const orc_prior *pr, const double *start, const double *init_cov,
+                           int64_t delay, uint64_t seed, uint32_t chain_id, int64_t n_steps, double *out,
+                           double *mean, double *cov, int64_t *t_out, int64_t *acc_out) {
+    const int d = p->d;
+    double x[ORC_MAXD], xn[ORC_MAXD], m[ORC_MAXD], mo[ORC_MAXD], C[ORC_MAXD * ORC_MAXD], L0[ORC_MAXD * ORC_MAXD],
+        L[ORC_MAXD * ORC_MAXD];
+    if (delay < 2) delay = 2;
+    memset(L0, 0, sizeof L0);
+    for (int j = 0; j < d; ++j) {
+        double s = init_cov[j * d + j];
+        for (int k = 0; k < j; ++k) s -= L0[j * d + k] * L0[j * d + k];
+        if (!(s > 0.0)) return 0;
+        const double l = sqrt(s);
+        L0[j * d + j] = l;
+        for (int i = j + 1; i < d; ++i) {
+            double t = 0.5 * (init_cov[i * d + j] + init_cov[j * d + i]);
+            for (int k = 0; k < j; ++k) t -= L0[i * d + k] * L0[j * d + k];
+            L0[i * d + j] = t / l;
+        }
+    }
+    memcpy(x, start, sizeof(double) * d);
+    memcpy(m, start, sizeof(double) * d);
+    memset(C, 0, sizeof C);
+    if (!in_box(pr, x)) return 0;
+    double lp = orc_logprior(pr, x) + orc_loglike(p, pr, x);
+    if (!(lp > 0.5 * p->logzero) || !isfinite(lp)) return 0;
+    int64_t t = 1, acc = 0;
+    for (int64_t k = 0; k < n_steps; ++k) {
+        const double *Lw = L0;
+        if (t >= delay && proposal_chol(C, d, L)) Lw = L;
+        double z[ORC_MAXD + 1], ua[2];
+        const uint32_t hi = (uint32_t)((uint64_t)k >> 32);
+        for (int b = 0; b < (d + 1) / 2; ++b) orc_normal2(seed, (uint32_t)b, (uint32_t)k, chain_id, TAG_MC_NORMAL, hi, z + 2 * b);
+        for (int a = 0; a < d; ++a) {
+            double s = x[a];
+            for (int b = 0; b <= a; ++b) s += Lw[a * d + b] * z[b];
+            xn[a] = s;
+        }
+        orc_uniform2(seed, 0u, (uint32_t)k, chain_id, TAG_MC_ACCEPT, hi, ua);
+        if (in_box(pr, xn)) {
+            const double nPr = orc_logprior(pr, xn), nL = orc_loglike(p, pr, xn);
+            if (nPr > 0.5 * p->logzero && nL > 0.5 * p->logzero && (nPr + nL) - lp > log(ua[0])) {
+                memcpy(x, xn, sizeof(double) * d);
+                lp = nPr + nL;
+                ++acc;
+            }
+        }
+        const double tf = (double)t;
+        memcpy(mo, m, sizeof(double) * d);
+        for (int a = 0; a < d; ++a) m[a] += (x[a] - m[a]) / (tf + 1.0);
+        for (int a = 0; a < d; ++a)
+            for (int b = 0; b < d; ++b) C[a * d + b] = (tf - 1.0) / tf * C[a * d + b] + (x[a] - mo[a]) * (x[b] - m[b]) / tf;
+        t += 1;
+        if (out) memcpy(out + k * d, x, sizeof(double) * d);
+    }
+    if (mean) memcpy(mean, m, sizeof(double) * d);
+    if (cov) memcpy(cov, C, sizeof(double) * d * d);
+    if (t_out) *t_out = t;
+    if (acc_out) *acc_out = acc;
+    return 1;
+}
+
 ORC_API int orc_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -68,6 +68,9 @@ def lib():
         L.orc_logprior_batch.argtypes = [C.c_void_p, dp, C.c_int64, dp]
         L.orc_predictive_components.restype = C.c_int
         L.orc_predictive_components.argtypes = [C.c_void_p, dp, C.c_int64, dp, C.c_int64, dp]
+        L.orc_mcmc_chain.restype = C.c_int
+        L.orc_mcmc_chain.argtypes = [C.c_void_p, C.c_void_p, dp, dp, C.c_int64, C.c_uint64, C.c_uint32, C.c_int64, dp, dp, dp,
+                                     ip, ip]
         L.orc_gp_predict.restype = C.c_int
         L.orc_gp_predict.argtypes = [C.c_void_p, dp, dp, C.c_int64, C.c_int, dp, dp]
         L.orc_sample_prior.argtypes = [C.c_void_p, C.c_int64, C.c_uint64, C.c_uint32, dp]
@@ -354,3 +357,17 @@ def bench_walks(problem: Problem, prior: Prior, start_points, Lstar, reps_per_th
 
 def max_threads():
     return int(lib().orc_max_threads())
+
+
+def mcmc_chain(problem, prior, start, init_cov, delay=20, seed=1, chain_id=0, n_steps=100):
+    """createMCMCChain + iterateMCMC (BS:630-703) restated: states (n_steps, d) and the final chain estimates."""
+    d = problem.d
+    start = _f64(np.asarray(start, dtype=np.float64).reshape(d))
+    init_cov = _f64(np.asarray(init_cov, dtype=np.float64).reshape(d, d))
+    out, mean, cov = np.empty((n_steps, d)), np.empty(d), np.empty((d, d))
+    t, acc = C.c_int64(), C.c_int64()
+    ok = lib().orc_mcmc_chain(problem.h, prior.h, _dp(start), _dp(init_cov), delay, seed, chain_id, n_steps, _dp(out), _dp(mean),
+                              _dp(cov), C.byref(t), C.byref(acc))
+    if not ok:
+        raise ValueError("bad starting point or InitialCovariance")
+    return dict(states=out, mean=mean, cov=cov, t=t.value, accepted=acc.value)

@@ -102,6 +102,32 @@ class RunGroup:
         pass
 
 
+class Chain:
+    """engine.Chain served by the oracle restatement (one chain at a time, run from scratch on every call)."""
+
+    def __init__(self, problem, start, init_cov, learn_delay=20, seed=1):
+        self.p, self.start = problem, np.atleast_2d(np.asarray(start, float))
+        self.cov0, self.delay, self.seed = np.asarray(init_cov, float), learn_delay, seed
+        self.n_chains, self.d, self.steps, self.last = self.start.shape[0], problem.d, 0, None
+
+    def iterate(self, n_steps, record=True):
+        tot = self.steps + int(n_steps)
+        self.last = [O.mcmc_chain(self.p.prob, self.p.prior, self.start[c], self.cov0, self.delay, self.seed, c, tot)
+                     for c in range(self.n_chains)]
+        out = np.stack([r["states"][self.steps:] for r in self.last], 1)
+        self.steps = tot
+        return out if record else None
+
+    def state(self):
+        r = self.last
+        return dict(x=np.stack([q["states"][-1] for q in r]), mean=np.stack([q["mean"] for q in r]),
+                    cov=np.stack([q["cov"] for q in r]), t=np.array([q["t"] for q in r]),
+                    accepted=np.array([q["accepted"] for q in r]))
+
+    def close(self):
+        pass
+
+
 def crude_weights(logL, pool, n_live):
     logL = np.asarray(logL, float)
     M = logL.size

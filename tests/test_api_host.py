@@ -195,6 +195,34 @@ def test_approximate_evidence_laplace_matches_quadrature_scale():
     np.testing.assert_allclose(res2["LogEvidence"], res["LogEvidence"], atol=1e-6)
 
 
+def test_create_mcmc_chain_and_iterate_host_logic():
+    """createMCMCChain / iterateMCMC (BS:651-703) on the oracle backend: option forms, thinning, failure modes."""
+    obj = _c1_obj()
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        assert not api.inferenceObjectQ(api.createMCMCChain(obj))  # createMCMCChain::start
+    assert any("createMCMCChain::start" in str(x.message) for x in w)
+    ch = api.createMCMCChain(obj, [1.5, 0.7], InitialCovariance=0.01, Seed=3)
+    a = api.iterateMCMC(ch, 40)
+    b = api.iterateMCMC(ch, (10, 5))  # 10 states, one every 5 steps
+    assert a.shape == (40, 2) and b.shape == (10, 2)
+    ref = api.iterateMCMC(api.createMCMCChain(obj, [1.5, 0.7], InitialCovariance=[0.01, 0.01], Seed=3), 90)
+    np.testing.assert_array_equal(a, ref[:40])
+    np.testing.assert_array_equal(b, ref[40:][4::5])
+    x, t, mean, cov = ch["StateData"]
+    assert t == 91 and x.shape == (2,) and cov.shape == (2, 2)
+    np.testing.assert_array_equal(x, ref[-1])
+    assert 0.0 < ch["AcceptanceRate"] <= 1.0
+    # starting points from the object (BS:657-658), several chains
+    sp = api.generateStartingPoints(obj, 3, seed=2)
+    ch3 = api.createMCMCChain(sp, Chains=3, InitialCovariance=np.eye(2) * 0.01)
+    assert api.iterateMCMC(ch3, 7).shape == (7, 3, 2)
+    with pytest.raises(TypeError):
+        api.createMCMCChain(obj, [1.5, 0.7], Nope=1)
+    with pytest.raises(ValueError):
+        api.iterateMCMC(api.createMCMCChain(obj, [1.5, -0.7]), 3)  # start outside the box
+
+
 def test_predict_from_gaussian_process_host_logic():
     """predictFromGaussianProcess (GP:332-393) on the oracle backend: grid construction, weights, mixture moments."""
     c = cfg.c5_gp(N=40)

@@ -251,3 +251,33 @@ def test_predictive_components_oracle_matches_numpy():
     pr = np.exp(z - z.max(-1, keepdims=True))
     pr /= pr.sum(-1, keepdims=True)
     np.testing.assert_allclose(out, pr, rtol=1e-13)
+
+
+def test_mcmc_chain_oracle_samples_the_known_posterior():
+    """createMCMCChain / iterateMCMC restated (BS:630-703): on C1 (flat prior on mu, 1/sigma prior on sigma) the
+    marginal posterior of mu is Student t_{N-1}(xbar, s^2/N): mean xbar, variance s^2/N (N-1)/(N-3)."""
+    from bayesianinference_b200 import configs as cfg
+    c = cfg.c1_gaussian()
+    op = O.Problem(c.op, c.d, c.inputs, c.outputs, c.iparam)
+    pr = O.Prior(c.kinds, c.lo, c.hi)
+    x = c.inputs[:, 0]
+    N = x.size
+    r = O.mcmc_chain(op, pr, [1.0, 1.0], np.eye(2) * 0.01, delay=20, seed=5, chain_id=0, n_steps=40000)
+    st = r["states"][4000:]
+    assert r["t"] == 40001 and 0.15 < r["accepted"] / 40000 < 0.6
+    sd_mu = np.sqrt(x.var(ddof=1) / N * (N - 1) / (N - 3))
+    assert abs(st[:, 0].mean() - x.mean()) < 0.1 * sd_mu      # ~ 3 sigma of a chain with ESS ~ 1000
+    assert abs(st[:, 0].std() / sd_mu - 1.0) < 0.1
+    # E[sigma^2 | data] = S / (N - 3) for the 1/sigma prior (scaled inverse chi^2 with N - 1 dof)
+    assert abs((st[:, 1] ** 2).mean() / (((x - x.mean()) ** 2).sum() / (N - 3)) - 1.0) < 0.05
+    # chain estimates = running moments of ALL visited states (start included)
+    allst = np.vstack([[1.0, 1.0], r["states"]])
+    np.testing.assert_allclose(r["mean"], allst.mean(0), rtol=1e-10)
+    np.testing.assert_allclose(r["cov"], np.cov(allst.T), rtol=1e-8)
+    # same seed -> same chain; other chain id -> another stream
+    r2 = O.mcmc_chain(op, pr, [1.0, 1.0], np.eye(2) * 0.01, delay=20, seed=5, chain_id=0, n_steps=50)
+    np.testing.assert_array_equal(r2["states"], r["states"][:50])
+    r3 = O.mcmc_chain(op, pr, [1.0, 1.0], np.eye(2) * 0.01, delay=20, seed=5, chain_id=1, n_steps=50)
+    assert not np.array_equal(r3["states"], r2["states"])
+    with pytest.raises(ValueError):
+        O.mcmc_chain(op, pr, [1.0, -1.0], np.eye(2), n_steps=5)  # outside the box
