@@ -219,6 +219,177 @@ __global__ void __launch_bounds__(256) gp_potf2_kernel(GpBatch g, int k0) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// diagonal block, register-tiled (the default).  The column sweep of gp_potf2_kernel is a chain of long dot
+// products (2 threads per row) and its inverse a chain of 128 dependent substitutions per thread: 0.25 ms per panel,
+// 22 % of a B = 32 sweep (profiles/r01f_gp_launches.md).  Here both are right-looking outer-product sweeps over a
+// register-resident tile: thread (tx, ty) of a 16 x 16 grid owns the elements (i, c) = (ty + 16 a, tx + 16 b),
+// a, b = 0..7 — cyclic, so the shrinking trailing matrix stays balanced — and every step is one barrier:
+//   factor, step j:  the warp that owns column j scales it (diagonal broadcast by shuffle, rsqrt) and publishes it in
+//                    shared memory (column j of Ls); after the barrier everybody applies the rank-1 update to the
+//                    elements it owns right of column j (<= 36 independent DFMAs per thread);
+//   invert, step k:  R starts as I; the owners of row k scale it by 1/l_kk (that is row k of X = L^-1) and publish it;
+//                    after the barrier rows i > k subtract l_ik x_k,: .
+// tid = 16 tx + ty: the owners of a column sit in one warp (shuffle), the owners of a row are spread over all warps.
+__global__ void __launch_bounds__(256, 1) gp_potf2_reg_kernel(GpBatch g, int k0) {
+    extern __shared__ __align__(16) double sm2[];
+    double *Ls = sm2;                 // [NB (column j)][NB (row i)]: L, column-major
+    double *rowbuf = Ls + NB * NB;    // [2][NB] row k of X, double buffered
+    double *dg = rowbuf + 2 * NB;     // [NB] l_jj
+    double *zp = dg + NB;             // [NB][17] partial sums of z = X y
+    __shared__ double s_z[NB];
+    __shared__ int s_fail[2];  // alternating: a fast warp may already be flagging step j + 1 while a slow one reads step j
+    const int b = blockIdx.x, tid = threadIdx.x, tx = tid >> 4, ty = tid & 15;
+    if (g.fail[b]) return;
+    double *A = g.A + (size_t)b * g.mat();
+    const size_t ld = g.ld;
+    double acc[8][8];
+#pragma unroll
+    for (int bb = 0; bb < 8; ++bb)
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+            const int i = ty + 16 * a, c = tx + 16 * bb;
+            acc[a][bb] = (i >= c) ? A[(size_t)(k0 + c) * ld + k0 + i] : 0.0;
+        }
+    if (tid == 0) s_fail[0] = s_fail[1] = 0;
+    __syncthreads();
+
+    // ---- factor
+    bool failed = false;
+#pragma unroll
+    for (int jb = 0; jb < 8; ++jb) {
+        if (failed) break;
+#pragma unroll 1
+        for (int jt = 0; jt < 16; ++jt) {
+            const int j = 16 * jb + jt;
+            if ((tx >> 1) == (jt >> 1)) {  // the warp holding column j
+                double d = acc[jb][jb];
+                d = __shfl_sync(0xffffffffu, d, ((jt & 1) << 4) | jt);  // a_jj lives at tx == ty == jt
+                const bool bad = !(d > 0.0) || !isfinite(d);
+                const double rinv = rsqrt(d);
+                if (tx == jt) {
+#pragma unroll
+                    for (int a = 0; a < 8; ++a) {
+                        const int i = ty + 16 * a;
+                        double l = 0.0;
+                        if (a >= jb && i >= j) {
+                            l = acc[a][jb] * rinv;   // i == j: d / sqrt(d) = sqrt(d)
+                            acc[a][jb] = l;
+                        }
+                        Ls[j * NB + i] = l;
+                    }
+                    if (ty == jt) {
+                        dg[j] = d * rinv;
+                        if (bad) s_fail[j & 1] = 1;  // not positive definite -> logzero (GP:131-135)
+                    }
+                }
+            }
+            __syncthreads();
+            if (s_fail[j & 1]) { failed = true; break; }
+            double lr[8], lc[8];
+#pragma unroll
+            for (int a = jb; a < 8; ++a) lr[a] = Ls[j * NB + ty + 16 * a];
+#pragma unroll
+            for (int bb = jb; bb < 8; ++bb) lc[bb] = Ls[j * NB + tx + 16 * bb];
+#pragma unroll
+            for (int bb = jb; bb < 8; ++bb) {
+                if (bb > jb || tx > jt) {  // columns right of j only
+#pragma unroll
+                    for (int a = bb; a < 8; ++a) acc[a][bb] = fma(-lr[a], lc[bb], acc[a][bb]);
+                }
+            }
+        }
+    }
+    if (failed) {
+        if (tid == 0) g.fail[b] = 1;
+        return;
+    }
+    // L11 back to the matrix
+#pragma unroll
+    for (int bb = 0; bb < 8; ++bb)
+#pragma unroll
+        for (int a = bb; a < 8; ++a) {
+            const int i = ty + 16 * a, c = tx + 16 * bb;
+            if (i >= c) A[(size_t)(k0 + c) * ld + k0 + i] = acc[a][bb];
+        }
+
+    // ---- invert: X = L^-1 (lower triangular), R = I to start with
+#pragma unroll
+    for (int bb = 0; bb < 8; ++bb)
+#pragma unroll
+        for (int a = 0; a < 8; ++a) acc[a][bb] = (a == bb && tx == ty) ? 1.0 : 0.0;
+#pragma unroll
+    for (int kb = 0; kb < 8; ++kb) {
+#pragma unroll 1
+        for (int kt = 0; kt < 16; ++kt) {
+            const int k = 16 * kb + kt;
+            double *rb = rowbuf + (k & 1) * NB;
+            if (ty == kt) {  // owners of row k: x_k,c = r_k,c / l_kk for c <= k
+                const double dinv = 1.0 / dg[k];
+#pragma unroll
+                for (int bb = 0; bb <= kb; ++bb) {
+                    const int c = tx + 16 * bb;
+                    const double x = (c <= k) ? acc[kb][bb] * dinv : 0.0;
+                    acc[kb][bb] = x;
+                    rb[c] = x;
+                }
+            }
+            __syncthreads();
+            double lr[8], xc[8];
+#pragma unroll
+            for (int a = kb; a < 8; ++a) lr[a] = Ls[k * NB + ty + 16 * a];
+#pragma unroll
+            for (int bb = 0; bb <= kb; ++bb) xc[bb] = rb[tx + 16 * bb];
+#pragma unroll
+            for (int a = kb; a < 8; ++a) {
+                if (a > kb || ty > kt) {  // rows below k only
+#pragma unroll
+                    for (int bb = 0; bb <= kb; ++bb) acc[a][bb] = fma(-lr[a], xc[bb], acc[a][bb]);
+                }
+            }
+        }
+    }
+    // transposed inverse for the panel GEMM: linvT[(k, n)] = X[n][k]
+    double *linvT = g.linvT + (size_t)b * NB * NB;
+#pragma unroll
+    for (int bb = 0; bb < 8; ++bb)
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+            const int i = ty + 16 * a, c = tx + 16 * bb;
+            linvT[c * NB + i] = (i >= c) ? acc[a][bb] : 0.0;
+        }
+    // z_k = X y_k ; logdet += 2 sum log l_jj ; quad += z.z
+    {
+        const double *y = g.y + (size_t)b * ld + k0;
+        double yc[8];
+#pragma unroll
+        for (int bb = 0; bb < 8; ++bb) yc[bb] = y[tx + 16 * bb];
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+            double s = 0.0;
+#pragma unroll
+            for (int bb = 0; bb <= a; ++bb) s = fma(acc[a][bb], yc[bb], s);  // acc is 0 above the diagonal
+            zp[(ty + 16 * a) * 17 + tx] = s;
+        }
+    }
+    __syncthreads();
+    if (tid < NB) {
+        double s = 0.0;
+#pragma unroll
+        for (int t = 0; t < 16; ++t) s += zp[tid * 17 + t];
+        s_z[tid] = s;
+        g.z[(size_t)b * NB + tid] = s;
+    }
+    __syncthreads();
+    if (tid < 32) {
+        double ldt = 0.0, q = 0.0;
+        for (int i = tid; i < NB; i += 32) { ldt += log(dg[i]); q = fma(s_z[i], s_z[i], q); }
+        ldt = warp_sum(ldt);
+        q = warp_sum(q);
+        if (tid == 0) { g.logdet[b] += 2.0 * ldt; g.quad[b] += q; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // shared GEMM core: acc[4][4][2] (32x32 per warp, 16 warps -> 128x128) += sign * A(128 x KC) B(128 x KC)^T
 // sA, sB: [KC][LDS_] (k-major).  Fragment maps of mma.m8n8k4.f64: a[row = lane/4][k = lane%4],
 // b[k = lane%4][col = lane/4], c[row = lane/4][col = 2*(lane%4) + {0,1}].
@@ -479,11 +650,14 @@ void gp_sweep(const GpBatch &gc, int h0, int Bh, int nblk, cudaStream_t s, size_
     g.logdet += h0; g.quad += h0; g.fail += h0; g.B = Bh;
     if (g.v2) g.v2 += (size_t)h0 * gc.ld;
     const int T = g.Np / NB, Tq = (g.ld - g.Np) / NB, rows_all = T + Tq, B = Bh;
+    static const bool potf2_reg = [] { const char *e = getenv("BINEST_GP_POTF2"); return !(e && atoi(e) == 1); }();  // 1: column sweep
+    const size_t smem_potf2_reg = (size_t)(NB * NB + 2 * NB + NB + NB * 17) * sizeof(double);
     for (int kb = 0; kb < T; kb += nblk) {
         const int kend = std::min(kb + nblk, T);  // panels [kb, kend) form one group
         for (int k = kb; k < kend; ++k) {
             const int k0 = k * NB, below = rows_all - k - 1;
-            gp_potf2_kernel<<<B, 256, smem_potf2, s>>>(g, k0);
+            if (potf2_reg) gp_potf2_reg_kernel<<<B, 256, smem_potf2_reg, s>>>(g, k0);
+            else gp_potf2_kernel<<<B, 256, smem_potf2, s>>>(g, k0);
             BN_LAUNCH_CHECK();
             if (below > 0) {
                 gp_trsm_kernel<<<dim3(below, B), 512, smem_trsm, s>>>(g, k0);
@@ -514,6 +688,8 @@ void gp_factor_chunk(binest_problem &p, const GpBatch &g, const double *theta_de
     const size_t smem_syrk = (size_t)2 * (KC * LDS_ + KC * LDSH_) * sizeof(double);
     const size_t smem_trsm = ((size_t)NB * LDS_ + 2 * KC * LDS_ + NB) * sizeof(double);
     BN_CUDA(cudaFuncSetAttribute(gp_potf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_potf2));
+    BN_CUDA(cudaFuncSetAttribute(gp_potf2_reg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)((NB * NB + 2 * NB + NB + NB * 17) * sizeof(double))));
     BN_CUDA(cudaFuncSetAttribute(gp_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_syrk));
     BN_CUDA(cudaFuncSetAttribute(gp_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_trsm));
     cudaStream_t s = p.stream;

@@ -4,6 +4,7 @@
 #pragma once
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <type_traits>
 #include <vector>
 
@@ -61,7 +62,8 @@ inline StreamGeom stream_geom(const binest_problem &p, int P) {
     StreamGeom g;
     const int lanesets = (P + 31) / 32;
     g.tw = 1;
-    while (g.tw < OP::TW_MAX && g.tw < lanesets) g.tw <<= 1;
+    static const int tw_cap = [] { const char *e = getenv("BINEST_TW_MAX"); return e ? atoi(e) : 8; }();  // experiments
+    while (g.tw < OP::TW_MAX && g.tw < lanesets && 2 * g.tw <= tw_cap) g.tw <<= 1;
     g.pgroups = (P + 32 * g.tw - 1) / (32 * g.tw);
     // exactly one wave: grid = SMs x resident CTAs of this instantiation, all slices the same size
     // (a 592-CTA grid at 3 resident CTAs/SM ran 1.33 waves and left the fp64 pipe 22 % idle in the tail)
