@@ -715,7 +715,7 @@ def evidenceSampling(obj_or_assoc, paramNames=None, _backend_override=None, **op
     S = a["Samples"]
     n = int(a["SamplePoolSize"])
     # calculateWeightsCrude: samples must be sorted by {logL, point} (BS:814) — restore that order first
-    order = np.lexsort(tuple(S["Point"][:, j] for j in range(S["Point"].shape[1] - 1, -1, -1)) + (S["LogLikelihood"],))
+    order = _lex_order(S["Point"], S["LogLikelihood"])
     S = {k: v[order] for k, v in S.items()}
     pool = S.get("PoolSize")
     M = S["LogLikelihood"].size
@@ -753,28 +753,60 @@ def evidenceSampling(obj_or_assoc, paramNames=None, _backend_override=None, **op
     return inferenceObject(out) if wrap else out
 
 
+def _lex_order(pts, logL=None):
+    """Stable order by (logL, point) — SortBy[{#LogLikelihood, #Point}&] (BS:814) — or by point alone.
+    One argsort on the leading key; only the (rare) runs of equal leading keys are refined with a lexsort."""
+    lead = logL if logL is not None else pts[:, 0]
+    o = np.argsort(lead, kind="stable")
+    sl = lead[o]
+    tie = sl[1:] == sl[:-1]
+    if tie.any():
+        m = np.zeros(o.size, dtype=bool)
+        m[1:] |= tie
+        m[:-1] |= tie
+        sub = o[m]
+        keys = tuple(pts[sub, j] for j in range(pts.shape[1] - 1, -1, -1)) + (lead[sub],)
+        o[m] = sub[np.lexsort(keys)]
+    return o
+
+
 def _merge_samples(tables, pool_sizes):
     """combineRuns BS:1293-1297: Join, DeleteDuplicatesBy Point (first kept), SortBy {logL, Point};
-    per-sample pool size = sum over runs of that run's pool size at the sample's likelihood level."""
+    per-sample pool size = sum over runs of that run's pool size at the sample's likelihood level.
+    O(M log M) for M samples in total, whatever the number of runs: every run's pool size is a step function of the
+    likelihood level that changes at its own samples, so the sum over runs is one cumulative sum over all samples
+    sorted by level (the reference recomputes X from scratch instead, calculateXValues BS:785-799)."""
     pts = np.concatenate([t["Point"] for t in tables])
     cols = {k: np.concatenate([t[k] for t in tables]) for k in ("LogLikelihood", "LogPriorPDF", "AcceptanceRate")}
     rid = np.concatenate([np.full(t["LogLikelihood"].size, i) for i, t in enumerate(tables)])
-    _, first = np.unique(pts, axis=0, return_index=True)
-    keep = np.sort(first)
-    pts, rid = pts[keep], rid[keep]
-    cols = {k: v[keep] for k, v in cols.items()}
-    order = np.lexsort(tuple(pts[:, j] for j in range(pts.shape[1] - 1, -1, -1)) + (cols["LogLikelihood"],))
-    pts, rid = pts[order], rid[order]
-    cols = {k: v[order] for k, v in cols.items()}
-    pool = np.zeros(pts.shape[0], dtype=np.int64)
+    # pool-size step functions: run r contributes tp_r[i] while i of its samples lie strictly below the level
+    base, ev_level, ev_delta = 0, [], []
     for t, n in zip(tables, pool_sizes):
-        o = np.lexsort(tuple(t["Point"][:, j] for j in range(t["Point"].shape[1] - 1, -1, -1)) + (t["LogLikelihood"],))
+        o = _lex_order(t["Point"], t["LogLikelihood"])
         tl = t["LogLikelihood"][o]
         tp = t.get("PoolSize")
         tp = tp[o] if tp is not None else np.concatenate([np.full(tl.size - n, n), np.arange(n, 0, -1)])
-        idx = np.searchsorted(tl, cols["LogLikelihood"], side="left")
-        pool += np.where(idx < tl.size, tp[np.minimum(idx, tl.size - 1)], 0)
-    out = {"Point": pts, "PoolSize": pool, "RunIndex": rid}
+        tp = np.asarray(tp, dtype=np.int64)
+        if tl.size:
+            base += int(tp[0])
+            ev_level.append(tl)
+            ev_delta.append(np.diff(np.concatenate([tp, [0]])))
+    ev_level, ev_delta = np.concatenate(ev_level), np.concatenate(ev_delta)
+    eo = np.argsort(ev_level, kind="stable")
+    ev_level, csum = ev_level[eo], np.concatenate([[0], np.cumsum(ev_delta[eo])])
+    # DeleteDuplicatesBy[Point]: the first of equal points in Join order survives
+    po = _lex_order(pts)
+    sp = pts[po]
+    dup_sorted = np.concatenate([[False], np.all(sp[1:] == sp[:-1], axis=1)])
+    keep = np.ones(pts.shape[0], dtype=bool)
+    keep[po[dup_sorted]] = False
+    pts, rid = pts[keep], rid[keep]
+    cols = {k: v[keep] for k, v in cols.items()}
+    order = _lex_order(pts, cols["LogLikelihood"])
+    pts, rid = pts[order], rid[order]
+    cols = {k: v[order] for k, v in cols.items()}
+    pool = base + csum[np.searchsorted(ev_level, cols["LogLikelihood"], side="left")]
+    out = {"Point": pts, "PoolSize": pool.astype(np.int64), "RunIndex": rid}
     out.update(cols)
     return out
 

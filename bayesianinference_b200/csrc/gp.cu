@@ -34,7 +34,7 @@ namespace {
 constexpr int NB = 128;        // panel width / tile edge
 constexpr int KC = 32;         // K chunk of the GEMM kernels
 constexpr int LDS_ = NB + 4;   // smem leading dimension: half-warp fragment loads hit 16 distinct 8-byte banks
-constexpr int kGpBlockPanels = 4;
+constexpr int kGpBlockPanels = 8;
 constexpr int kGpStreams = 4;      // sub-batches of a chunk swept on separate streams (BINEST_GP_STREAMS overrides, 1..8)  // panels per group of the two-level blocking (BINEST_GP_BLOCK overrides, 1..8)
 
 struct GpBatch {
@@ -429,10 +429,10 @@ __device__ __forceinline__ void load_chunk_async(double *sdst, const double *__r
 // pipe idle 38 % of the time while C moved).
 constexpr int NBH = NB / 2;
 constexpr int LDSH_ = NBH + 4;
-// Two-level blocking.  Panels are factored in groups of `nblk`: inside a group panel j only updates the column
-// blocks of its own group (narrow != 0: the trapezoid rows >= base, columns [base, base + 64 ncol64)), and when the
-// group is done ONE pass with K = kw = nblk * 128 updates everything to the right of it — the trailing matrix
-// crosses HBM once per group instead of once per panel (the DMMA work is unchanged).
+// Two-level blocking.  Panels are factored in groups of `nblk`: inside a group the finished panels only update the
+// column blocks of their own group (ncol64 != 0: the trapezoid rows >= base, columns [base, base + 64 ncol64), see the
+// binary schedule in gp_sweep), and when the group is done ONE pass with K = kw = nblk * 128 updates everything to the
+// right of it — the trailing matrix crosses HBM once per group instead of once per panel (the DMMA work is unchanged).
 __global__ void __launch_bounds__(256, 2) gp_syrk_kernel(GpBatch g, int k0, int kw, int base, int ncol64) {
     extern __shared__ __align__(16) double sm[];  // 2 stages x (A chunk [KC][LDS_] + B chunk [KC][LDSH_])
     const int b = blockIdx.y;
@@ -663,9 +663,14 @@ void gp_sweep(const GpBatch &gc, int h0, int Bh, int nblk, cudaStream_t s, size_
                 gp_trsm_kernel<<<dim3(below, B), 512, smem_trsm, s>>>(g, k0);
                 BN_LAUNCH_CHECK();
             }
-            const int ncol64 = 2 * (kend - k - 1);  // the group's own remaining column blocks
-            if (ncol64 > 0) {
-                gp_syrk_kernel<<<dim3(below * ncol64, B), 256, smem_syrk, s>>>(g, k0, NB, k0 + NB, ncol64);
+            // in-group updates, binary schedule: with o panels of the group done, the last w = lowbit(o) of them
+            // update the next w column blocks (all rows below) in one K = 128 w pass.  Every column block has then
+            // received all earlier panels of its group when its turn comes (the o's that reach it are the prefixes
+            // of its binary offset), in fewer and wider passes than panel-by-panel updates.
+            const int o = k - kb + 1;
+            if (o < kend - kb) {
+                const int w = o & -o, cols = std::min(w, kend - (k + 1));
+                gp_syrk_kernel<<<dim3(below * 2 * cols, B), 256, smem_syrk, s>>>(g, (k + 1 - w) * NB, w * NB, k0 + NB, 2 * cols);
                 BN_LAUNCH_CHECK();
             }
         }
