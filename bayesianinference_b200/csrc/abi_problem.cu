@@ -49,6 +49,37 @@ __global__ void pack_rows_kernel(const double *__restrict__ in, int n_in, const 
     }
 }
 
+// data moments of the polynomial-regression epilogue (operators.cuh): m[0] = Sum y, m[k] = Sum x^k, k = 1..deg.
+// Sum t enters the log-likelihood multiplied by 2 c_0 h ~ 10, next to terms of 5e5: it has to be good to ~1e-15
+// relative.  Every thread accumulates in double-double (TwoSum), a block combines its 256 pairs the same way and
+// writes (hi, lo) per moment; the host adds the few hundred block results in long double.
+__device__ __forceinline__ void dd_add(double &hi, double &lo, double v) {
+    const double s = hi + v, bb = s - hi;
+    lo += (hi - (s - bb)) + (v - bb);
+    hi = s;
+}
+__global__ void __launch_bounds__(256)
+polyreg_moments_kernel(const double *__restrict__ x, const double *__restrict__ y, long long rows, int deg,
+                       double *__restrict__ out /* [gridDim.x][6][2] */) {
+    double hi[6] = {0, 0, 0, 0, 0, 0}, lo[6] = {0, 0, 0, 0, 0, 0};
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += (long long)gridDim.x * blockDim.x) {
+        const double xv = x[i];
+        dd_add(hi[0], lo[0], y[i]);
+        double xp = xv;
+        for (int k = 1; k <= deg; ++k) { dd_add(hi[k], lo[k], xp); xp *= xv; }
+    }
+    __shared__ double sh[256][12];
+    for (int k = 0; k < 6; ++k) { sh[threadIdx.x][2 * k] = hi[k]; sh[threadIdx.x][2 * k + 1] = lo[k]; }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        const int k = threadIdx.x;
+        double h = 0.0, l = 0.0;
+        for (int t = 0; t < 256; ++t) { dd_add(h, l, sh[t][2 * k]); l += sh[t][2 * k + 1]; }
+        out[((size_t)blockIdx.x * 6 + k) * 2] = h;
+        out[((size_t)blockIdx.x * 6 + k) * 2 + 1] = l;
+    }
+}
+
 static double norm_cdf(double z) { return 0.5 * std::erfc(-z * 0.70710678118654752440084436210485); }
 
 static void fill_prior(PriorSpec &pr, int d, const int32_t *kind, const double *lo, const double *hi,
@@ -239,7 +270,7 @@ int binest_problem_create(int op_id, const int64_t *iparam, const double *inputs
                 cst += -logl((long double)outputs[i]) - 0.5L * logl(dt);
             }
             cst -= (long double)p->rows * (long double)kHalfLog2Pi;
-            p->cst = (double)cst;
+            p->cst.c = (double)cst;
             break;
         }
         case BINEST_OP_GP_SE: {
@@ -277,10 +308,24 @@ int binest_problem_create(int op_id, const int64_t *iparam, const double *inputs
                 pack_rows_kernel<<<grid, 256, 0, p->stream>>>(raw_in.p, (int)n_in, raw_out.p, p->rows, p->ncol, n_classes,
                                                             p->data.p, bad.p);
                 BN_LAUNCH_CHECK();
+                const int mom_blocks = p->op == BINEST_OP_POLYREG ? 2 * p->num_sms : 0;
+                DevBuf<double> mom((size_t)mom_blocks * 12);
+                std::vector<double> h_mom((size_t)mom_blocks * 12);
+                if (mom_blocks) {
+                    polyreg_moments_kernel<<<mom_blocks, 256, 0, p->stream>>>(raw_in.p, raw_out.p, p->rows, (int)p->iparam[0], mom.p);
+                    BN_LAUNCH_CHECK();
+                    BN_CUDA(cudaMemcpyAsync(h_mom.data(), mom.p, h_mom.size() * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+                }
                 int h_bad = 0;
                 BN_CUDA(cudaMemcpyAsync(&h_bad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
                 BN_CUDA(cudaStreamSynchronize(p->stream));
                 BN_REQUIRE(!h_bad, BINEST_ERR_NUMERICAL, "logistic: class labels must be integers 0..K-1");
+                for (int k = 0; k < 6 && mom_blocks; ++k) {
+                    long double m = 0.0L;
+                    for (int b = 0; b < mom_blocks; ++b)
+                        m += (long double)h_mom[((size_t)b * 6 + k) * 2] + (long double)h_mom[((size_t)b * 6 + k) * 2 + 1];
+                    p->cst.m[k] = (double)m;
+                }
             }
         }
         *out = p.release();

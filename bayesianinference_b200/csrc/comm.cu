@@ -120,17 +120,21 @@ int binest_problem_shard(binest_problem *p, binest_comm *c) {
                    "the GP operator does not shard by rows (replicas only); shard the theta batch instead");
         BN_REQUIRE(p->device == c->device, BINEST_ERR_CUDA, "problem and communicator live on different devices");
         BN_CUDA(cudaSetDevice(p->device));
-        DevBuf<double> send(2), recv((size_t)2 * c->world);
-        const double h[2] = {(double)p->rows, p->cst};
+        constexpr int NV = 8;  // rows, additive constant, 6 data moments
+        DevBuf<double> send(NV), recv((size_t)NV * c->world);
+        const double h[NV] = {(double)p->rows, p->cst.c, p->cst.m[0], p->cst.m[1], p->cst.m[2], p->cst.m[3], p->cst.m[4],
+                              p->cst.m[5]};
         BN_CUDA(cudaMemcpyAsync(send.p, h, sizeof(h), cudaMemcpyHostToDevice, p->stream));
-        comm_allgather_f64(*c, send.p, recv.p, 2, p->stream);
-        std::vector<double> all((size_t)2 * c->world);
+        comm_allgather_f64(*c, send.p, recv.p, NV, p->stream);
+        std::vector<double> all((size_t)NV * c->world);
         BN_CUDA(cudaMemcpyAsync(all.data(), recv.p, sizeof(double) * all.size(), cudaMemcpyDeviceToHost, p->stream));
         BN_CUDA(cudaStreamSynchronize(p->stream));
-        long double rows = 0.0L, cst = 0.0L;
-        for (int r = 0; r < c->world; ++r) { rows += all[2 * r]; cst += all[2 * r + 1]; }
-        p->rows_total = (double)rows;
-        p->cst_total = (double)cst;
+        long double tot[NV] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int r = 0; r < c->world; ++r)
+            for (int v = 0; v < NV; ++v) tot[v] += all[(size_t)NV * r + v];
+        p->rows_total = (double)tot[0];
+        p->cst_total.c = (double)tot[1];
+        for (int k = 0; k < 6; ++k) p->cst_total.m[k] = (double)tot[2 + k];
         p->comm = c;
     });
 }

@@ -185,7 +185,7 @@ void launch_grid_walk(binest_run &r, const RunParams &q) {
         cfg.numAttrs = 1;
         const double *data = p.data.p;
         long long rows = p.rows, rpc = r.grid_rpc;
-        double cst = p.cst;
+        OpCst cst = p.cst;
         double *partials = r.partials.p;
         int Gs = r.grid_Gs, passes = r.grid_passes, passesA = r.grid_passesA;
         GridSync *gs = r.gsync.p;
@@ -265,7 +265,8 @@ void build_walk_graph(binest_run &r) {
             PdlConfig lc(sgrid, sblock, s, pdl && step > 0);
             const PartialView pv{r.partials.p, r.geom.G, r.geom.Gs, 1};
             int fin = step == S ? 1 : 0;
-            double rows = (double)p.rows, cst = p.cst;
+            double rows = (double)p.rows;
+            OpCst cst = p.cst;
             BN_CUDA(cudaLaunchKernelEx(&lc.cfg, walk_step_kernel<OP>, r.prm, r.A, p.prior, pv, rows, cst, fin));
             if (step < S) launch_loglike<OP>(p, r.w_prop.p, P, r.prm.Ps, r.partials.p, r.geom, s, false, pdl);
         }
@@ -298,7 +299,7 @@ void walk_block(binest_run &r, const RunParams &q) {
             cfg.numAttrs = r.res_cs > 1 ? 1 : 0;
             const double *data = p.data.p;
             long long rows = p.rows, rpc = r.res_rpc;
-            double cst = p.cst;
+            OpCst cst = p.cst;
             int cs = r.res_cs;
             BN_CUDA(cudaLaunchKernelEx(&cfg, walk_resident_kernel<OP>, q, r.A, p.prior, data, rows, rpc, cst, cs));
             BN_LAUNCH_CHECK();

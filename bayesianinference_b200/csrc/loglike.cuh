@@ -144,7 +144,7 @@ __device__ __forceinline__ double combine_partials_warp(const PartialView &pv, i
 
 // operator epilogue + operator constraints (RuntimeErrorHandler -> logzero, BS:500-503)
 template <class OP>
-__device__ __forceinline__ double loglike_finish(const double (&th)[OP::D], double sum, double rows, double cst,
+__device__ __forceinline__ double loglike_finish(const double (&th)[OP::D], double sum, double rows, const OpCst &cst,
                                                  double logzero) {
     bool ok;
     const typename OP::Coef c = OP::prepare(th, ok);
@@ -155,7 +155,7 @@ __device__ __forceinline__ double loglike_finish(const double (&th)[OP::D], doub
 // one warp per walker
 template <class OP>
 __global__ void loglike_finalize_kernel(const double *__restrict__ theta, int P, int Ps,
-                                        const PartialView pv, double rows, double cst,
+                                        const PartialView pv, double rows, const OpCst cst,
                                         const __grid_constant__ PriorSpec prior, double logzero,
                                         double *__restrict__ out) {
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;

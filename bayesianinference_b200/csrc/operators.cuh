@@ -22,6 +22,15 @@
 
 namespace binest {
 
+// parameter-independent constants of a problem's data, fixed at upload and handed to every operator epilogue:
+//   c     additive constant (GBM: Sum_i(-log x_i - 1/2 log dt_i) - rows 1/2 log 2pi)
+//   m[k]  data moments (polynomial regression: m[0] = Sum y, m[k] = Sum x^k, k = 1..degree)
+// In the data-sharded mode these are the totals over all shards.
+struct OpCst {
+    double c;
+    double m[6];
+};
+
 // ------------------------------------------------------------------ NormalDistribution[mu, sigma], i.i.d. data
 struct OpGaussian {
     static constexpr int D = 2, NCOL = 1, TW_MAX = 8;
@@ -44,16 +53,24 @@ struct OpGaussian {
 #pragma unroll
         for (int u = 0; u < TW; ++u) acc[u] = fma(e[u], e[u], acc[u]);
     }
-    __device__ static double finish(const Coef &c, double acc, double rows, double) {
+    __device__ static double finish(const Coef &c, double acc, double rows, const OpCst &) {
         return rows * c.lognorm - c.h * acc;
     }
 };
 
 // ------------------------------------------------------------------ NormalDistribution[Sum_j c_j x^j, sigma]
+// Per datum the reference evaluates -(y - Sum_j c_j x^j)^2 / (2 sigma^2) - log sigma - 1/2 log 2pi.  Here
+//     t_i = x_i (c_1 + c_2 x_i + ... + c_deg x_i^(deg-1)) - y_i        (Horner on c_deg..c_1, last FMA adds -y)
+// and the residual is e_i = t_i + c_0, so Sum e^2 = Sum t^2 + 2 c_0 Sum t + N c_0^2 with
+//     Sum t = Sum_k c_k m[k] - m[0]
+// from the walker-independent data moments (OpCst).  The per-datum chain is deg FMAs + the FMA-accumulate: 4 fp64
+// pipe slots at degree 3 instead of 5 (3 Horner FMA, subtract, FMA-accumulate) for the same 9 algorithmic flop of
+// SURVEY §8d.  Sum t^2 <= Sum e^2 + N c_0^2 terms of the same sign: no cancellation beyond the ~1 digit of the
+// final three-term sum (|logL| error ~1e-13 relative at the C2 posterior, parity bar 1e-12).
 template <int DEG>
 struct OpPolyReg {
     static constexpr int D = DEG + 2, NCOL = 2, TW_MAX = 8;
-    struct Coef { double h, lognorm; };
+    struct Coef { double h, lognorm, c[DEG + 1]; };
     struct Row { double c[DEG + 1]; };
     using Acc = double;
     __device__ __forceinline__ static Acc acc_init() { return 0.0; }
@@ -70,26 +87,36 @@ struct OpPolyReg {
         ok = sg > 0.0;  // BS:523
         c.h = 1.0 / (2.0 * sg * sg);
         c.lognorm = -log(sg) - kHalfLog2Pi;
+#pragma unroll
+        for (int j = 0; j <= DEG; ++j) c.c[j] = th[j];
         return c;
     }
-    // 9 flop per datum-walker at DEG = 3: 3 Horner FMA, 1 subtract, 1 FMA-accumulate
     template <int TW>
     __device__ __forceinline__ static void rows(const Row (&c)[TW], const double *__restrict__ r, double (&acc)[TW]) {
         const double x = r[0], y = r[1];
         double t[TW];
+        if (DEG >= 2) {
 #pragma unroll
-        for (int u = 0; u < TW; ++u) t[u] = fma(c[u].c[DEG], x, c[u].c[DEG - 1]);
+            for (int u = 0; u < TW; ++u) t[u] = fma(c[u].c[DEG], x, c[u].c[DEG - 1]);
 #pragma unroll
-        for (int j = DEG - 2; j >= 0; --j)
+            for (int j = DEG - 2; j >= 1; --j)
 #pragma unroll
-            for (int u = 0; u < TW; ++u) t[u] = fma(t[u], x, c[u].c[j]);
+                for (int u = 0; u < TW; ++u) t[u] = fma(t[u], x, c[u].c[j]);
+        } else {
 #pragma unroll
-        for (int u = 0; u < TW; ++u) t[u] = y - t[u];
+            for (int u = 0; u < TW; ++u) t[u] = c[u].c[1];
+        }
+#pragma unroll
+        for (int u = 0; u < TW; ++u) t[u] = fma(t[u], x, -y);
 #pragma unroll
         for (int u = 0; u < TW; ++u) acc[u] = fma(t[u], t[u], acc[u]);
     }
-    __device__ static double finish(const Coef &c, double acc, double rows, double) {
-        return rows * c.lognorm - c.h * acc;
+    __device__ static double finish(const Coef &c, double acc, double rows, const OpCst &k) {
+        double st = -k.m[0];
+#pragma unroll
+        for (int j = 1; j <= DEG; ++j) st = fma(c.c[j], k.m[j], st);
+        const double sse = fma(c.c[0], fma(rows, c.c[0], 2.0 * st), acc);  // Sum t^2 + c0 (2 Sum t + N c0)
+        return rows * c.lognorm - c.h * sse;
     }
 };
 
@@ -322,7 +349,7 @@ struct OpLogistic {
             }
         }
     }
-    __device__ static double finish(const Coef &, double acc, double, double) { return acc; }
+    __device__ static double finish(const Coef &, double acc, double, const OpCst &) { return acc; }
 };
 
 // ------------------------------------------------------------------ GeometricBrownianMotionProcess[mu, sigma, x0]
@@ -349,8 +376,8 @@ struct OpGbm {
 #pragma unroll
         for (int u = 0; u < TW; ++u) acc[u] = fma(e[u], e[u], acc[u]);
     }
-    __device__ static double finish(const Coef &c, double acc, double rows, double cst) {
-        return rows * c.lognorm + cst - c.h * acc;
+    __device__ static double finish(const Coef &c, double acc, double rows, const OpCst &cst) {
+        return rows * c.lognorm + cst.c - c.h * acc;
     }
 };
 
@@ -364,7 +391,7 @@ struct OpGpSe {
         ok = th[0] > 0.0 && th[1] > 0.0 && th[2] > 0.0;
         return Coef{0};
     }
-    __device__ static double finish(const Coef &, double acc, double, double) { return acc; }
+    __device__ static double finish(const Coef &, double acc, double, const OpCst &) { return acc; }
 };
 
 // ------------------------------------------------------------------ priors (BS:25-64, BS:365-427)

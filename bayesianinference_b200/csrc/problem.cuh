@@ -22,7 +22,7 @@ struct binest_problem {
     int d = 0;
     int64_t rows = 0;      // device rows (GBM: increments = n_rows - 1)
     int ncol = 0;          // fp64 columns per device row
-    double cst = 0.0;      // parameter-independent additive constant
+    binest::OpCst cst{};   // parameter-independent constants of the data (additive constant, moments)
     binest::DevBuf<double> data;
     binest::PriorSpec prior{};
     int device = 0;
@@ -35,10 +35,11 @@ struct binest_problem {
     binest::DevBuf<double> s_theta, s_partials, s_out;
     // data-sharded mode: this problem holds rows [shard of the data]; logL = Sum over ranks of the shard sums
     binest_comm *comm = nullptr;
-    double rows_total = 0.0, cst_total = 0.0;   // over all shards (operator epilogues need the global values)
+    double rows_total = 0.0;
+    binest::OpCst cst_total{};                  // over all shards (operator epilogues need the global values)
     binest::DevBuf<double> sh_send, sh_recv;    // [Ps], [world][Ps]
     double rows_eff() const { return comm ? rows_total : (double)rows; }
-    double cst_eff() const { return comm ? cst_total : cst; }
+    const binest::OpCst &cst_eff() const { return comm ? cst_total : cst; }
 
     ~binest_problem() {
         if (stream) cudaStreamDestroy(stream);

@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(1024) run_update_kernel(const __grid_constant_
 // walk_grid_kernel, walk_grid.cuh).
 template <class OP>
 __device__ __forceinline__ void walk_step_walker(const RunParams &prm, const RunArrays &A, const PriorSpec &prior,
-                                                 const PartialView &pv, double rows, double cst, int final_step,
+                                                 const PartialView &pv, double rows, const OpCst &cst, int final_step,
                                                  int w, int lane) {
     constexpr int D = OP::D;
     const int K = prm.K, Ps = prm.Ps;
@@ -471,7 +471,7 @@ static __global__ void walk_retry_kernel(const __grid_constant__ RunParams prm, 
 template <class OP>
 __global__ void __launch_bounds__(256)
 walk_step_kernel(const __grid_constant__ RunParams prm, RunArrays A, const __grid_constant__ PriorSpec prior,
-                 const PartialView pv, double rows, double cst, int final_step) {
+                 const PartialView pv, double rows, const OpCst cst, int final_step) {
     pdl_wait();               // partials / walker state of the predecessors are complete and visible
     pdl_launch_dependents();  // let the next likelihood kernel start prefetching its data tiles
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;

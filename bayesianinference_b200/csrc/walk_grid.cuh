@@ -186,7 +186,7 @@ __device__ __forceinline__ void gw_pre(GridWalker<OP> &q, const RunParams &prm, 
 // after the partial sums of the current proposal arrived: decide, publish the next proposal
 template <class OP>
 __device__ __forceinline__ void gw_post(GridWalker<OP> &q, const RunParams &prm, const RunArrays &A, const PartialView &pv,
-                                        double rows, double cst, bool publish, int lane) {
+                                        double rows, const OpCst &cst, bool publish, int lane) {
     constexpr int D = OP::D;
     if (!q.active) return;
     int sel = 0;
@@ -297,7 +297,7 @@ __host__ __device__ inline size_t grid_smem_bytes(long long rows_per_cta) {
 template <class OP, int TW>
 __global__ void __launch_bounds__(kGridThreads, 1)
 walk_grid_kernel(const __grid_constant__ RunParams prm, RunArrays A, const __grid_constant__ PriorSpec prior,
-                 const double *__restrict__ data, long long rows, long long rows_per_cta, double cst,
+                 const double *__restrict__ data, long long rows, long long rows_per_cta, const OpCst cst,
                  double *__restrict__ partials /* [Ps][Gs] */, int Gs, int passes, int passesA,
                  GridSync *gs, long long *dbg /* timeline trace (BINEST_GRID_TRACE), or nullptr */) {
     constexpr int NCOL = OP::NCOL, D = OP::D, WP = 32 * TW, GW = kGridGroupWarps;

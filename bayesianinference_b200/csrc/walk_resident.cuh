@@ -35,7 +35,7 @@ __host__ __device__ inline size_t resident_smem_doubles(long long rows_per_cta, 
 template <class OP>
 __global__ void __launch_bounds__(kResWarps * 32)
 walk_resident_kernel(const __grid_constant__ RunParams prm, RunArrays A, const __grid_constant__ PriorSpec prior,
-                     const double *__restrict__ data, long long rows, long long rows_per_cta, double cst, int CS) {
+                     const double *__restrict__ data, long long rows, long long rows_per_cta, const OpCst cst, int CS) {
     constexpr int D = OP::D, NCOL = OP::NCOL;
     extern __shared__ __align__(16) double smem[];
     const size_t tile_sz = ((size_t)rows_per_cta * NCOL + 1) & ~(size_t)1;
