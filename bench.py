@@ -30,8 +30,8 @@ sys.path.insert(0, ROOT)
 from bayesianinference_b200 import configs as cfg  # noqa: E402
 
 MC_STEPS = 200  # "MonteCarloSteps" default, BS:844
-# profiles/r01e_ncu_walk_grid_c2.md: dram__bytes_read.sum + dram__bytes_write.sum of one walk_grid_kernel launch
-NCU_TRAFFIC_C2_GRID = 16.163e6 + 0.065e6
+# profiles/r01g_ncu_walk_grid_c2.md: dram__bytes_read.sum + dram__bytes_write.sum of one walk_grid_kernel launch
+NCU_TRAFFIC_C2_GRID = 16.165e6 + 0.088e6
 WORKLOADS = {
     # name: (config factory, batch_k, flop per datum-eval, algorithmic bytes per datum-eval)   SURVEY §8d
     "C1": (cfg.c1_gaussian, 32, 3, 8),
