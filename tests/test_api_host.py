@@ -117,6 +117,50 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _merge_reference(tables, pool_sizes):
+    """combineRuns' merge the slow, literal way (BS:1293-1297): one searchsorted per run."""
+    lex = lambda P, L: np.lexsort(tuple(P[:, j] for j in range(P.shape[1] - 1, -1, -1)) + (L,))
+    pts = np.concatenate([t["Point"] for t in tables])
+    L = np.concatenate([t["LogLikelihood"] for t in tables])
+    _, first = np.unique(pts, axis=0, return_index=True)
+    keep = np.sort(first)
+    pts, L = pts[keep], L[keep]
+    o = lex(pts, L)
+    pts, L = pts[o], L[o]
+    pool = np.zeros(L.size, dtype=np.int64)
+    for t, n in zip(tables, pool_sizes):
+        oo = lex(t["Point"], t["LogLikelihood"])
+        tl, tp = t["LogLikelihood"][oo], t["PoolSize"][oo]
+        idx = np.searchsorted(tl, L, side="left")
+        pool += np.where(idx < tl.size, tp[np.minimum(idx, tl.size - 1)], 0)
+    return pts, L, pool
+
+
+def test_merge_samples_matches_literal_merge():
+    """The O(M log M) merge (one cumulative sum over all samples) equals the per-run formulation: duplicate points
+    (first kept), ties in logL within and across runs, K > 1 pool patterns, unsorted input tables."""
+    rng = np.random.default_rng(4)
+    for R, M, n, K in [(3, 60, 10, 1), (6, 300, 32, 8), (9, 1000, 100, 25)]:
+        tables = []
+        for r in range(R):
+            L = np.sort(np.round(rng.normal(size=M), 2 if r % 2 else 12))
+            P = np.round(rng.normal(size=(M, 2)), 1 if r % 3 == 0 else 9)
+            for _ in range(4):
+                a, b = rng.integers(0, M, 2)
+                P[b] = P[a]
+            nd = M - n
+            pool = np.concatenate([np.tile(np.arange(n, n - K, -1), nd // K + 1)[:nd], np.arange(n, 0, -1)])
+            perm = rng.permutation(M)
+            tables.append({"Point": P[perm], "LogLikelihood": L[perm], "LogPriorPDF": rng.normal(size=M),
+                           "AcceptanceRate": rng.uniform(size=M), "PoolSize": pool[perm]})
+        got = api._merge_samples(tables, [n] * R)
+        pts, L, pool = _merge_reference(tables, [n] * R)
+        np.testing.assert_array_equal(got["Point"], pts)
+        np.testing.assert_array_equal(got["LogLikelihood"], L)
+        np.testing.assert_array_equal(got["PoolSize"], pool)
+        assert got["PoolSize"][0] == R * n  # below every sample all runs are complete: K9, pool = sum n_r
+
+
 def test_parallel_nested_sampling_sharded_gloo_matches_single_process():
     """Runs are keyed by (seed, run id): sharding them over 2 ranks must give the same merged object."""
     import torch.multiprocessing as tmp

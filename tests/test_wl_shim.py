@@ -25,9 +25,10 @@ def test_shim_compiles_links_and_exports(tmp_path):
 def test_wl_package_keeps_the_reference_api_surface():
     src = open(WL).read()
     for sym in ("defineInferenceProblem", "nestedSampling", "parallelNestedSampling", "evidenceSampling", "combineRuns",
-                "generateStartingPoints", "inferenceObject"):
+                "generateStartingPoints", "inferenceObject", "defineGaussianProcess", "predictFromGaussianProcess",
+                "predictiveDistribution", "createMCMCChain", "iterateMCMC", "approximateEvidence", "laplaceLogEvidence"):
         assert re.search(rf"^{sym}::usage", src, flags=re.M), sym
     for opt in ('"SamplePoolSize" -> 100', '"MaxIterations" -> 10000', '"MinIterations" -> 100', '"MonteCarloSteps" -> 200',
                 '"TerminationFraction" -> 0.01', '"MinMaxAcceptanceRate" -> {0, 1}', '"PostProcessSamplingRuns" -> 100',
-                '"ParallelRuns" :> 4'):
+                '"ParallelRuns" :> 4', '"CovarianceLearnDelay" -> 20', '"InitialCovariance" -> 1'):
         assert opt in src, opt  # Options of BS:833-851, 1366-1371
