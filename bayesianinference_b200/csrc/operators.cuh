@@ -279,11 +279,16 @@ struct OpLogistic {
         ok = true;
         return Coef{0};
     }
-    // Per datum, with the label's own logit z_y as the shift:  log p_y = -log(1 + Sum_{k != y} exp(z_k - z_y)).
-    // Every term has the same sign (no cancellation against a separate Sum z_y), K-1 exps, no max/sort.
+    // Per datum  log p_y = z_y - log(1 + Sum_k exp z_k)  (z_K = 0).  The exps do not depend on the label, and z_y is
+    // picked with 0/1 indicators formed once per row (i_k = [label == k]), so the per-walker code has no label-dependent
+    // branch or select at all (an earlier form shifted by z_y first — log p_y = -log(1 + Sum_{k != y} exp(z_k - z_y)) —
+    // and paid ~25 integer/branch instructions per walker and datum for the permutation; this kernel is bound by issue
+    // slots and fixed latencies, not by the fp64 pipe: profiles/r01g_ncu_loglike_c3.md).
     // Sum_i log s_i = log Prod_i s_i: the running product is renormalised to [1, 2) after every factor by moving
     // its exponent field into an integer (4 ALU instructions instead of a log per datum); one log at the end.
-    // |z_k - z_y| >= 700 (overflow / subnormal territory, NaN) takes the slow path: max-shifted libdevice exp/log.
+    // Sum z_y and Sum log s are accumulated separately and subtracted once; with |z| <= a few hundred at most that
+    // costs < 3 digits of the 16 (parity bar 1e-12).  |z_k| >= 700 (overflow / subnormal territory, NaN) takes the slow
+    // path: max-shifted libdevice exp/log.
     struct Acc { double lin, prod; long long e2; };
     __device__ __forceinline__ static Acc acc_init() { return Acc{0.0, 1.0, 0}; }
     __device__ __forceinline__ static double acc_value(const Acc &a) {
@@ -293,41 +298,35 @@ struct OpLogistic {
     __device__ __forceinline__ static void rows(const Row (&c)[TW], const double *__restrict__ r, Acc (&acc)[TW]) {
         static_assert(K == 2 || K == 3, "softmax operator is specialised for 2 or 3 classes");
         constexpr int E = K - 1;  // exps per datum
-        double z[TW][E];
-        const int lab = (int)r[F];
+        double z[TW * E], ex[TW * E], zy[TW];
+        const double labv = r[F];
+        const double i0 = (labv == 0.0) ? 1.0 : 0.0;
+        const double i1 = (K == 3 && labv == 1.0) ? 1.0 : 0.0;  // the last class is the reference class (z = 0)
 #pragma unroll
         for (int k = 0; k < E; ++k)
 #pragma unroll
-            for (int u = 0; u < TW; ++u) z[u][k] = c[u].w[k][F];
+            for (int u = 0; u < TW; ++u) z[u * E + k] = c[u].w[k][F];
 #pragma unroll
         for (int f = 0; f < F; ++f) {
             const double x = r[f];
 #pragma unroll
             for (int k = 0; k < E; ++k)
 #pragma unroll
-                for (int u = 0; u < TW; ++u) z[u][k] = fma(c[u].w[k][f], x, z[u][k]);
+                for (int u = 0; u < TW; ++u) z[u * E + k] = fma(c[u].w[k][f], x, z[u * E + k]);
         }
-        double dz[TW * E], ex[TW * E];
         bool fast = true;
 #pragma unroll
         for (int u = 0; u < TW; ++u) {
-            if (K == 2) {
-                dz[u] = (lab == 0) ? -z[u][0] : z[u][0];  // label 1 is the reference class (z = 0)
-            } else {
-                const double zy = (lab == 0) ? z[u][0] : ((lab == 1) ? z[u][1] : 0.0);
-                const double za = (lab == 0) ? z[u][1] : z[u][0];
-                const double zb = (lab == 2) ? z[u][1] : 0.0;
-                dz[u * E] = za - zy;
-                dz[u * E + 1] = zb - zy;
-            }
+            zy[u] = i0 * z[u * E];
+            if (K == 3) zy[u] = fma(i1, z[u * E + 1], zy[u]);
 #pragma unroll
-            for (int k = 0; k < E; ++k) fast = fast && exp_arg_bounded(dz[u * E + k]);
+            for (int k = 0; k < E; ++k) fast = fast && exp_arg_bounded(z[u * E + k]);
         }
         if (__builtin_expect(fast, 1)) {
 #if BINEST_EXP_TAB
-            exp_bounded_tab<TW * E>(dz, ex);
+            exp_bounded_tab<TW * E>(z, ex);
 #else
-            exp_bounded<TW * E>(dz, ex);
+            exp_bounded<TW * E>(z, ex);
 #endif
 #pragma unroll
             for (int u = 0; u < TW; ++u) {
@@ -337,15 +336,16 @@ struct OpLogistic {
                 const int hi = __double2hiint(p), e = (hi >> 20) - 1023;
                 acc[u].e2 += e;
                 acc[u].prod = __hiloint2double(hi - (e << 20), __double2loint(p));
+                acc[u].lin += zy[u];
             }
         } else {
 #pragma unroll
             for (int u = 0; u < TW; ++u) {
-                double mx = fmax(dz[u * E], 0.0);
-                if (K == 3) mx = fmax(mx, dz[u * E + 1]);
-                double s = exp(-mx) + exp(dz[u * E] - mx);
-                if (K == 3) s += exp(dz[u * E + 1] - mx);
-                acc[u].lin -= mx + log(s);
+                double mx = fmax(z[u * E], 0.0);
+                if (K == 3) mx = fmax(mx, z[u * E + 1]);
+                double s = exp(-mx) + exp(z[u * E] - mx);
+                if (K == 3) s += exp(z[u * E + 1] - mx);
+                acc[u].lin += zy[u] - (mx + log(s));
             }
         }
     }
