@@ -16,7 +16,7 @@ evaluate: message + inferenceObject[$Failed] (BS:456-459, 308).  There is no CPU
 from __future__ import annotations
 
 import warnings
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 
 import numpy as np
 
