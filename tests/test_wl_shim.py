@@ -32,3 +32,45 @@ def test_wl_package_keeps_the_reference_api_surface():
                 '"TerminationFraction" -> 0.01', '"MinMaxAcceptanceRate" -> {0, 1}', '"PostProcessSamplingRuns" -> 100',
                 '"ParallelRuns" :> 4', '"CovarianceLearnDelay" -> 20', '"InitialCovariance" -> 1'):
         assert opt in src, opt  # Options of BS:833-851, 1366-1371
+
+
+def test_wl_package_brackets_balance():
+    """The package cannot be parsed here (no Wolfram Engine); at least every bracket, association delimiter, string and
+    comment must close — the class of slip a kernel would report first."""
+    src = open(WL).read()
+    pairs = {")": "(", "]": "[", "}": "{"}
+    stack, i, line, depth, in_str = [], 0, 1, 0, False
+    while i < len(src):
+        c = src[i]
+        line += c == "\n"
+        if in_str:
+            if c == "\\":
+                i += 2
+                continue
+            in_str = c != '"'
+        elif depth:
+            if src.startswith("(*", i):
+                depth += 1
+                i += 1
+            elif src.startswith("*)", i):
+                depth -= 1
+                i += 1
+        elif src.startswith("(*", i):
+            depth = 1
+            i += 1
+        elif c == '"':
+            in_str = True
+        elif src.startswith("<|", i):
+            stack.append(("<|", line))
+            i += 1
+        elif src.startswith("|>", i):
+            assert stack and stack[-1][0] == "<|", f"unmatched |> at line {line}"
+            stack.pop()
+            i += 1
+        elif c in "([{":
+            stack.append((c, line))
+        elif c in ")]}":
+            assert stack and stack[-1][0] == pairs[c], f"unmatched {c} at line {line} (open: {stack[-1:]})"
+            stack.pop()
+        i += 1
+    assert not stack and not in_str and depth == 0, (stack[:3], in_str, depth)
