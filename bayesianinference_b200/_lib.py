@@ -25,7 +25,7 @@ class Options(C.Structure):
     _fields_ = [("pool_size", C.c_int64), ("batch_k", C.c_int64), ("mc_steps", C.c_int64),
                 ("max_iter", C.c_int64), ("min_iter", C.c_int64), ("term_frac", C.c_double),
                 ("acc_min", C.c_double), ("acc_max", C.c_double), ("seed", C.c_uint64),
-                ("first_run_id", C.c_int64), ("n_runs", C.c_int64)]
+                ("first_run_id", C.c_int64), ("n_runs", C.c_int64), ("loglmax", C.c_double)]
 
 
 _dp = C.POINTER(C.c_double)

@@ -639,7 +639,9 @@ def _ns_options(opts, allowed):
 
 def _engine_options(be, o, n_runs=1, first_run_id=0):
     lo, hi = o["MinMaxAcceptanceRate"]
-    return be.default_options(pool_size=int(o["SamplePoolSize"]), batch_k=int(o["BatchSize"]),
+    lmax = o.get("LogLikelihoodMaximum", "Automatic")  # a number replaces the running maximum in BS:925-932
+    lmax = float(lmax) if isinstance(lmax, (int, float, np.integer, np.floating)) and not isinstance(lmax, bool) else float("nan")
+    return be.default_options(loglmax=lmax, pool_size=int(o["SamplePoolSize"]), batch_k=int(o["BatchSize"]),
                               mc_steps=int(o["MonteCarloSteps"]), max_iter=int(o["MaxIterations"]),
                               min_iter=int(o["MinIterations"]), term_frac=float(o["TerminationFraction"]),
                               acc_min=float(lo), acc_max=float(hi), seed=int(o["Seed"]),
@@ -699,6 +701,9 @@ def _mean_and_error(x, axis=0):  # meanAndError BS:1138-1156: Mean and (n-1) Sta
     return {"Mean": x.mean(axis), "StandardError": x.std(axis, ddof=1)}
 
 
+_DERIVED_COLUMNS = ("SampledLogX", "LogPosteriorWeight", "CrudePosteriorWeight", "CrudeLogPosteriorWeight", "X", "LogX")
+
+
 def evidenceSampling(obj_or_assoc, paramNames=None, _backend_override=None, **opts):
     """BS:1158-1291.  Accepts an inferenceObject (returns one) or an association (returns one)."""
     wrap = isinstance(obj_or_assoc, inferenceObject)
@@ -713,8 +718,11 @@ def evidenceSampling(obj_or_assoc, paramNames=None, _backend_override=None, **op
     be = _backend(_backend_override or a.get("_backend"))
     names = paramNames if paramNames is not None else a.get("ParameterSymbols", [])
     S = a["Samples"]
-    n = int(a["SamplePoolSize"])
-    # calculateWeightsCrude: samples must be sorted by {logL, point} (BS:814) — restore that order first
+    n = int(a.get("_LiveBlock", a["SamplePoolSize"]))  # see combineRuns "PoolSizes": the tail that acts as the live set
+    # calculateWeightsCrude: samples must be sorted by {logL, point} (BS:814) — restore that order first.  Columns a
+    # previous evidenceSampling derived (the reference overwrites them in the Join at BS:1239-1251) are dropped and
+    # recomputed, so evidenceSampling[obj] on a finished result re-post-processes it (BS:1158-1160).
+    S = {k: v for k, v in S.items() if k not in _DERIVED_COLUMNS}
     order = _lex_order(S["Point"], S["LogLikelihood"])
     S = {k: v[order] for k, v in S.items()}
     pool = S.get("PoolSize")
@@ -811,23 +819,59 @@ def _merge_samples(tables, pool_sizes):
     return out
 
 
+def _reference_pool_structure(t, n):
+    """True when a run's pool-size column is the reference's: constant n for the deleted points, n..1 for the
+    final live set (BS:785-799) — i.e. the run replaced one point per iteration."""
+    tp = t.get("PoolSize")
+    if tp is None:
+        return True
+    o = _lex_order(t["Point"], t["LogLikelihood"])
+    tp = np.asarray(tp)[o]
+    M = tp.size
+    return bool(M >= n and np.all(tp[:M - n] == n) and np.array_equal(tp[M - n:], np.arange(n, 0, -1)))
+
+
 def combineRuns(*results, _backend_override=None, **opts):
-    """BS:1293-1315."""
+    """BS:1293-1315.  The merged list is re-weighted as ONE run (evidenceSampling -> calculateXValues BS:785-799).
+    "MergeScheme" (not in the reference) selects the X sequence of the merged list:
+      "Reference"  the literal formula: pool size Total[SamplePoolSize] for the first M - n_tot samples, then the
+                   n_tot best as a live set n_tot..1 (BS:1307-1309 feeding BS:785-799);
+      "PoolSizes"  the pool size at every sample is the SUM over runs of that run's pool size at the sample's
+                   likelihood level (the merge rule of dynamic nested sampling), used consistently to the last sample;
+                   the only consistent choice when runs replaced K > 1 points per iteration ("BatchSize"), whose
+                   own pool sizes are n, n-1, ..., n-K+1 and not a constant;
+      "Automatic"  (default) "Reference" when every run has the reference's pool structure, else "PoolSizes"."""
     if len(results) < 1 or not all(inferenceObjectQ(r) for r in results):
         return inferenceObject(FAILED)
+    scheme = opts.pop("MergeScheme", "Automatic")
+    if scheme not in ("Automatic", "Reference", "PoolSizes"):
+        raise TypeError(f"Unknown MergeScheme {scheme!r}")
     assocs = [r.Normal() for r in results]
     pools = [int(a["SamplePoolSize"]) for a in assocs]
+    if scheme == "Automatic":
+        scheme = "Reference" if all(_reference_pool_structure(a["Samples"], n) for a, n in zip(assocs, pools)) else "PoolSizes"
     merged = _merge_samples([a["Samples"] for a in assocs], pools)
     n_tot = int(sum(pools))
     M = merged["LogLikelihood"].size
     a = dict(assocs[0])
+    a.pop("_LiveBlock", None)
     a.update({
         "Samples": merged,
         "LogLikelihoodMaximum": max(float(np.max(x["Samples"]["LogLikelihood"])) for x in assocs),  # BS:1306
         "SamplePoolSize": n_tot, "GeneratedNestedSamples": M - n_tot, "TotalSamples": M,          # BS:1307-1309
+        "MergeScheme": scheme,
     })
-    # the last n_tot samples play the role of the live set; their pool sizes follow BS:791-797
-    a["Samples"]["PoolSize"][M - n_tot:] = np.arange(n_tot, 0, -1)
+    if scheme == "Reference":
+        merged["PoolSize"] = np.concatenate([np.full(max(M - n_tot, 0), n_tot), np.arange(min(n_tot, M), 0, -1)]).astype(np.int64)
+    else:
+        # summed pool sizes to the end.  Once every run is inside its final live set the sum falls by one per sample:
+        # that tail (length >= the largest run pool) IS a live set in the sense of BS:791-797, and is handed to
+        # calculateXValues / the order-statistics draws of BS:1209-1217 as such.
+        pool = merged["PoolSize"]
+        tail = np.arange(M, 0, -1)
+        agree = pool == tail
+        live = int(M - (np.flatnonzero(~agree)[-1] + 1)) if not agree.all() else M
+        a["_LiveBlock"] = max(live, 1)
     return inferenceObject(evidenceSampling(a, a.get("ParameterSymbols"), _backend_override=_backend_override, **opts))
 
 

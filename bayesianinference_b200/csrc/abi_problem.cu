@@ -33,38 +33,74 @@ int guard(const std::function<void()> &f) {
 // The raw blocks are copied host->device as they are (one DMA each, straight from the caller's — possibly pinned —
 // buffers) and interleaved here, instead of being repacked on the host into a pageable staging vector.
 // n_classes > 0: outputs are class labels, anything but an integer in [0, n_classes) raises *bad.
+// in_shift / out_shift: pivots subtracted from the (single) input column / the output (polynomial regression).
 __global__ void pack_rows_kernel(const double *__restrict__ in, int n_in, const double *__restrict__ out, long long rows,
-                                 int ncol, int n_classes, double *__restrict__ data, int *__restrict__ bad) {
+                                 int ncol, int n_classes, double in_shift, double out_shift,
+                                 double *__restrict__ data, int *__restrict__ bad) {
     const long long total = rows * ncol;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
         const long long i = e / ncol;
         const int c = (int)(e - i * ncol);
         double v = 0.0;
-        if (c < n_in) v = in[i * n_in + c];
+        if (c < n_in) v = in[i * n_in + c] - in_shift;
         else if (c == n_in && out) {
             v = out[i];
             if (n_classes > 0 && !(v >= 0.0 && v < (double)n_classes && v == floor(v))) atomicOr(bad, 1);
+            v -= out_shift;
         }
         data[e] = v;
     }
 }
 
-// data moments of the polynomial-regression epilogue (operators.cuh): m[0] = Sum y, m[k] = Sum x^k, k = 1..deg.
-// Sum t enters the log-likelihood multiplied by 2 c_0 h ~ 10, next to terms of 5e5: it has to be good to ~1e-15
-// relative.  Every thread accumulates in double-double (TwoSum), a block combines its 256 pairs the same way and
-// writes (hi, lo) per moment; the host adds the few hundred block results in long double.
+// Pivot selection for the polynomial operator (operators.cuh), plain fp64 block sums — the pivots only have to be
+// near the data, not exact.  With u = x - xbar:  out[b][k] = Sum u^k (k = 0..2 deg), out[b][11 + k] = Sum y u^k
+// (k = 0..deg): the normal equations of the least-squares polynomial in u.  Called first with xbar = 0, deg = 1
+// (Sum x, Sum x^2 -> mean and spread of x), then with the chosen xbar.
+__global__ void __launch_bounds__(256)
+polyreg_pivot_kernel(const double *__restrict__ x, const double *__restrict__ y, long long rows, int deg, double xbar,
+                     double *__restrict__ out /* [gridDim.x][17] */) {
+    double s[17];
+    for (int k = 0; k < 17; ++k) s[k] = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += (long long)gridDim.x * blockDim.x) {
+        const double u = x[i] - xbar, yv = y[i];
+        double up = 1.0;
+        for (int k = 0; k <= 2 * deg; ++k) {
+            s[k] += up;
+            if (k <= deg) s[11 + k] += yv * up;
+            up *= u;
+        }
+    }
+    __shared__ double sh[8][17];
+    for (int k = 0; k < 17; ++k) {
+        const double v = warp_sum(s[k]);
+        if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 17) {
+        double v = 0.0;
+        for (int w = 0; w < 8; ++w) v += sh[w][threadIdx.x];
+        out[(size_t)blockIdx.x * 17 + threadIdx.x] = v;
+    }
+}
+
+// data moments of the polynomial-regression epilogue (operators.cuh), taken over the PIVOTED device rows
+// (x', y') exactly as the row loop reads them: m[0] = Sum y', m[k] = Sum x'^k, k = 1..deg.
+// Sum t enters Sum e^2 multiplied by 2 delta: it has to be good to ~1e-15 relative.  Every thread accumulates in
+// double-double (TwoSum), a block combines its 256 pairs the same way and writes (hi, lo) per moment; the host
+// adds the few hundred block results in long double.
 __device__ __forceinline__ void dd_add(double &hi, double &lo, double v) {
     const double s = hi + v, bb = s - hi;
     lo += (hi - (s - bb)) + (v - bb);
     hi = s;
 }
 __global__ void __launch_bounds__(256)
-polyreg_moments_kernel(const double *__restrict__ x, const double *__restrict__ y, long long rows, int deg,
+polyreg_moments_kernel(const double *__restrict__ data /* rows x (x', y') */, long long rows, int deg,
                        double *__restrict__ out /* [gridDim.x][6][2] */) {
     double hi[6] = {0, 0, 0, 0, 0, 0}, lo[6] = {0, 0, 0, 0, 0, 0};
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += (long long)gridDim.x * blockDim.x) {
-        const double xv = x[i];
-        dd_add(hi[0], lo[0], y[i]);
+        const double2 r = reinterpret_cast<const double2 *>(data)[i];
+        const double xv = r.x;
+        dd_add(hi[0], lo[0], r.y);
         double xp = xv;
         for (int k = 1; k <= deg; ++k) { dd_add(hi[k], lo[k], xp); xp *= xv; }
     }
@@ -125,6 +161,67 @@ void upload_theta(binest_problem &p, const double *theta, int64_t P, int Ps) {
     BN_CUDA(cudaMemcpyAsync(p.s_theta.p, soa.data(), soa.size() * sizeof(double), cudaMemcpyHostToDevice, p.stream));
     BN_CUDA(cudaStreamSynchronize(p.stream));  // soa is a stack-lifetime buffer
 }
+
+// Pivots of the polynomial operator (operators.cuh): xbar = mean of x unless the data are already centred
+// (|mean| <= sd/2 -> 0, the rows stay as uploaded), piv = intercept of the least-squares polynomial of degree deg in
+// x - xbar.  Two small reductions over the raw columns; the (deg+1) x (deg+1) normal equations are solved on the
+// host in long double, in the scaled variable (x - xbar)/sd.  Any finite pivot gives the same likelihood
+// algebraically — a poor one only costs digits — so nothing here needs to be exact.
+static void choose_polyreg_pivots(binest_problem &p, const double *x_dev, const double *y_dev) {
+    const int deg = (int)p.iparam[0], blocks = 2 * p.num_sms;
+    DevBuf<double> part((size_t)blocks * 17);
+    std::vector<double> h((size_t)blocks * 17);
+    auto reduce = [&](int dg, double xbar, long double (&tot)[17]) {
+        polyreg_pivot_kernel<<<blocks, 256, 0, p.stream>>>(x_dev, y_dev, p.rows, dg, xbar, part.p);
+        BN_LAUNCH_CHECK();
+        BN_CUDA(cudaMemcpyAsync(h.data(), part.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, p.stream));
+        BN_CUDA(cudaStreamSynchronize(p.stream));
+        for (int k = 0; k < 17; ++k) tot[k] = 0.0L;
+        for (int b = 0; b < blocks; ++b)
+            for (int k = 0; k < 17; ++k) tot[k] += h[(size_t)b * 17 + k];
+    };
+    long double t[17];
+    const long double n = (long double)p.rows;
+    reduce(1, 0.0, t);
+    const long double mean = t[1] / n;
+    const long double var = std::max<long double>(t[2] / n - mean * mean, 0.0L);
+    double xbar = (std::fabs((double)mean) > 0.5 * std::sqrt((double)var)) ? (double)mean : 0.0;
+    if (!std::isfinite(xbar)) xbar = 0.0;
+    reduce(deg, xbar, t);
+    double piv = (double)(t[11] / n);  // fallback: mean of y
+    {
+        const long double sd = sqrtl(std::max<long double>(t[2] / n, 0.0L));  // rms of u = x - xbar
+        if (sd > 0 && std::isfinite((double)sd)) {
+            long double A[6][7];
+            const int m = deg + 1;
+            for (int i = 0; i < m; ++i) {
+                for (int j = 0; j < m; ++j) A[i][j] = t[i + j] / n / powl(sd, i + j);
+                A[i][m] = t[11 + i] / n / powl(sd, i);
+            }
+            bool ok = true;
+            for (int c = 0; c < m && ok; ++c) {  // Gaussian elimination, partial pivoting
+                int piv_r = c;
+                for (int r2 = c + 1; r2 < m; ++r2)
+                    if (fabsl(A[r2][c]) > fabsl(A[piv_r][c])) piv_r = r2;
+                if (!(fabsl(A[piv_r][c]) > 1e-14L)) { ok = false; break; }
+                if (piv_r != c)
+                    for (int j = 0; j <= m; ++j) std::swap(A[c][j], A[piv_r][j]);
+                for (int r2 = 0; r2 < m; ++r2) {
+                    if (r2 == c) continue;
+                    const long double f = A[r2][c] / A[c][c];
+                    for (int j = c; j <= m; ++j) A[r2][j] -= f * A[c][j];
+                }
+            }
+            if (ok) {
+                const double a0 = (double)(A[0][m] / A[0][0]);  // the intercept does not depend on the scaling of u
+                if (std::isfinite(a0)) piv = a0;
+            }
+        }
+    }
+    if (!std::isfinite(piv)) piv = 0.0;
+    p.cst.xbar = xbar;
+    p.cst.piv = piv;
+}
 }  // namespace binest
 
 using namespace binest;
@@ -170,6 +267,7 @@ void binest_default_options(binest_options *o) {
     o->seed = 1;
     o->first_run_id = 0;
     o->n_runs = 1;
+    o->loglmax = std::nan("");  // Automatic, BS:847
 }
 
 int binest_measure_fp64_peak(double *tflops, double *ms_out) {
@@ -305,14 +403,16 @@ int binest_problem_create(int op_id, const int64_t *iparam, const double *inputs
                 if (outputs)
                     BN_CUDA(cudaMemcpyAsync(raw_out.p, outputs, raw_out.n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
                 const unsigned grid = (unsigned)std::min<size_t>((cells + 255) / 256, (size_t)p->num_sms * 16);
+                const bool poly = p->op == BINEST_OP_POLYREG;
+                if (poly) choose_polyreg_pivots(*p, raw_in.p, raw_out.p);
                 pack_rows_kernel<<<grid, 256, 0, p->stream>>>(raw_in.p, (int)n_in, raw_out.p, p->rows, p->ncol, n_classes,
-                                                            p->data.p, bad.p);
+                                                            p->cst.xbar, p->cst.piv, p->data.p, bad.p);
                 BN_LAUNCH_CHECK();
-                const int mom_blocks = p->op == BINEST_OP_POLYREG ? 2 * p->num_sms : 0;
+                const int mom_blocks = poly ? 2 * p->num_sms : 0;
                 DevBuf<double> mom((size_t)mom_blocks * 12);
                 std::vector<double> h_mom((size_t)mom_blocks * 12);
                 if (mom_blocks) {
-                    polyreg_moments_kernel<<<mom_blocks, 256, 0, p->stream>>>(raw_in.p, raw_out.p, p->rows, (int)p->iparam[0], mom.p);
+                    polyreg_moments_kernel<<<mom_blocks, 256, 0, p->stream>>>(p->data.p, p->rows, (int)p->iparam[0], mom.p);
                     BN_LAUNCH_CHECK();
                     BN_CUDA(cudaMemcpyAsync(h_mom.data(), mom.p, h_mom.size() * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
                 }

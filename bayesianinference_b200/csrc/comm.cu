@@ -133,8 +133,10 @@ int binest_problem_shard(binest_problem *p, binest_comm *c) {
         for (int r = 0; r < c->world; ++r)
             for (int v = 0; v < NV; ++v) tot[v] += all[(size_t)NV * r + v];
         p->rows_total = (double)tot[0];
+        // Only the row count and the additive constant are totals.  The polynomial operator's moments and pivots stay
+        // per shard: every rank resolves its own Sum e^2 with them (OP::local) before the exchange.
+        p->cst_total = p->cst;
         p->cst_total.c = (double)tot[1];
-        for (int k = 0; k < 6; ++k) p->cst_total.m[k] = (double)tot[2 + k];
         p->comm = c;
     });
 }

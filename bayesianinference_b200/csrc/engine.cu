@@ -331,7 +331,7 @@ void walk_block(binest_run &r, const RunParams &q) {
     // retry rounds of the graph path
     dispatch_op(p, [&](auto op) {
         using OP = decltype(op);
-        PartialView pv = p.comm ? PartialView{p.sh_recv.p, p.comm->world, 1, q.Ps}
+        PartialView pv = p.comm ? PartialView{p.sh_recv.p, p.comm->world, 1, q.Ps, 1}
                                 : PartialView{r.partials.p, r.geom.G, r.geom.Gs, 1};
         for (int step = 0; step <= q.S; ++step) {
             walk_step_kernel<OP><<<sgrid, sblock, 0, r.stream>>>(q, r.A, p.prior, pv, p.rows_eff(), p.cst_eff(),
@@ -339,7 +339,7 @@ void walk_block(binest_run &r, const RunParams &q) {
             BN_LAUNCH_CHECK();
             if (step < q.S) {
                 launch_loglike<OP>(p, r.w_prop.p, P, q.Ps, r.partials.p, r.geom, r.stream);
-                if (p.comm) pv = shard_exchange(p, r.partials.p, q.Ps, r.geom, r.stream);
+                if (p.comm) pv = shard_exchange<OP>(p, r.partials.p, r.w_prop.p, P, q.Ps, r.geom, r.stream);
             }
         }
     });
@@ -393,6 +393,7 @@ int binest_run_create(binest_problem *p, const binest_options *o, const double *
         q.S = o->mc_steps; q.maxS = 5 * o->mc_steps;  // BS:872
         q.seed = o->seed; q.first_run_id = (unsigned)o->first_run_id;
         q.logzero = g_logzero;
+        q.loglmax_opt = o->loglmax;
         q.cap = std::max<int64_t>(4096, 16 * (int64_t)q.n);
         r->n_pad = 1;
         while (r->n_pad < q.n) r->n_pad <<= 1;

@@ -25,11 +25,37 @@ __host__ __device__ constexpr int tile_rows() {
     return (kTileBytes / (8 * OP::NCOL)) & ~1;
 }
 
+// The row loop of every likelihood kernel: rows first, first + stride, ... < nr of a shared-memory tile, one row at a
+// time for all TW walkers of the lane — the row operands are shared by TW consecutive DFMAs (register-reuse cache),
+// which keeps each DFMA at two distinct register reads; three distinct 64-bit sources issue at 2/3 rate on sm_100
+// (scripts/dfma_patterns.cu).  (A register queue running the LDS two rows ahead of the arithmetic was measured slower:
+// 88.7 -> 94.2 us.)  Operators with running products (RENORM > 0) are renormalised every RENORM rows.
+template <class OP, int TW>
+__device__ __forceinline__ void sweep_rows(const typename OP::Row (&c)[TW], const double *__restrict__ tile, int first,
+                                           int stride, int nr, typename OP::Acc (&acc)[TW]) {
+    constexpr int NCOL = OP::NCOL;
+    if constexpr (OP::RENORM > 1) {
+        int i = first;
+        for (; i + (OP::RENORM - 1) * stride < nr; i += OP::RENORM * stride) {
+#pragma unroll
+            for (int q = 0; q < OP::RENORM; ++q) OP::template rows<TW>(c, tile + (size_t)(i + q * stride) * NCOL, acc);
+            OP::template renorm<TW>(acc);
+        }
+        for (; i < nr; i += stride) {
+            OP::template rows<TW>(c, tile + (size_t)i * NCOL, acc);
+            OP::template renorm<TW>(acc);
+        }
+    } else {
+#pragma unroll 2
+        for (int i = first; i < nr; i += stride) OP::template rows<TW>(c, tile + (size_t)i * NCOL, acc);
+    }
+}
+
 template <class OP, int TW>
 __global__ void __launch_bounds__(kWarps * 32)
 loglike_stream_kernel(const double *__restrict__ data, long long rows, long long rows_per_cta,
                       const double *__restrict__ theta /* SoA [D][Ps] */, int P, int Ps,
-                      double *__restrict__ partials /* [Ps][Gs] */, int Gs) {
+                      double *__restrict__ partials /* [Ps][Gs] */, int Gs, const OpCst cst) {
     constexpr int TR = tile_rows<OP>();
     constexpr int NCOL = OP::NCOL;
     __shared__ __align__(128) double tiles[kStages][TR * NCOL];
@@ -76,7 +102,7 @@ loglike_stream_kernel(const double *__restrict__ data, long long rows, long long
         // already resident while its predecessor (walk_step) writes theta, and the non-coherent cache of the SM is
         // not invalidated by griddepcontrol.wait (seen as stale proposals at N = 1e6: stored logL != logL(point))
         for (int j = 0; j < OP::D; ++j) th[j] = (w < P) ? __ldcg(theta + (size_t)j * Ps + w) : 1.0;
-        c[t] = OP::make_row(th);
+        c[t] = OP::make_row(th, cst);
     }
 
     typename OP::Acc acc[TW];
@@ -89,12 +115,7 @@ loglike_stream_kernel(const double *__restrict__ data, long long rows, long long
         const double *__restrict__ tile = &tiles[s][0];
         const long long a = r0 + (long long)t * TR;
         const int nr = (int)((r1 - a < TR) ? (r1 - a) : TR);
-        // one row at a time for all TW walkers of the lane: the row operands are shared by TW consecutive
-        // DFMAs (register-reuse cache), which keeps each DFMA at two distinct register reads — three
-        // distinct 64-bit sources issue at 2/3 rate on sm_100 (scripts/dfma_patterns.cu)
-        // (a register queue running the LDS two rows ahead of the arithmetic was measured slower: 88.7 -> 94.2 us)
-#pragma unroll 2
-        for (int i = wid; i < nr; i += kWarps) OP::template rows<TW>(c, tile + (size_t)i * NCOL, acc);
+        sweep_rows<OP, TW>(c, tile, wid, kWarps, nr, acc);
         __syncthreads();  // everyone is done with stage s before the TMA engine refills it
         if (threadIdx.x == 0 && t + kStages < ntiles) issue(t + kStages);
     }
@@ -117,11 +138,13 @@ loglike_stream_kernel(const double *__restrict__ data, long long rows, long long
 
 // where the G partial sums of walker w live: partial (w, g) at p[w * sw + g * sg].
 //   single GPU:   the per-CTA partials of loglike_stream_kernel, [Ps][Gs]            -> sw = Gs, sg = 1
-//   data-sharded: the per-rank sums after the all-gather (comm.cu), [world][Ps]      -> sw = 1,  sg = Ps
+//   data-sharded: the per-rank sums after the exchange (comm.cu), [world][Ps]        -> sw = 1,  sg = Ps,
+//                 localized = 1: every rank has already applied OP::local with its own data constants
 struct PartialView {
     const double *p;
     int G;
     long long sw, sg;
+    int localized = 0;
 };
 
 // fixed-order combine of the partials of one walker by one warp (all lanes get the sum)
@@ -145,10 +168,10 @@ __device__ __forceinline__ double combine_partials_warp(const PartialView &pv, i
 // operator epilogue + operator constraints (RuntimeErrorHandler -> logzero, BS:500-503)
 template <class OP>
 __device__ __forceinline__ double loglike_finish(const double (&th)[OP::D], double sum, double rows, const OpCst &cst,
-                                                 double logzero) {
+                                                 double logzero, int localized = 0) {
     bool ok;
-    const typename OP::Coef c = OP::prepare(th, ok);
-    const double v = OP::finish(c, sum, rows, cst);
+    const typename OP::Coef c = OP::prepare(th, ok, cst);
+    const double v = localized ? OP::finish_total(c, sum, rows, cst) : op_finish<OP>(c, sum, rows, cst);
     return (ok && isfinite(v)) ? v : logzero;
 }
 
@@ -164,16 +187,27 @@ __global__ void loglike_finalize_kernel(const double *__restrict__ theta, int P,
     double th[OP::D];
 #pragma unroll
     for (int j = 0; j < OP::D; ++j) th[j] = theta[(size_t)j * Ps + w];
-    double v = loglike_finish<OP>(th, s, rows, cst, logzero);
+    double v = loglike_finish<OP>(th, s, rows, cst, logzero, pv.localized);
     if (!in_box<OP::D>(prior, th)) v = logzero;  // If[constraints[theta], Sum[...], logzero] BS:491-494
     if (lane == 0) out[w] = v;
 }
 
-// data-sharded mode: this rank's sum over its own slices, one value per walker (the all-gather payload)
-static __global__ void shard_reduce_kernel(const PartialView pv, int Ps, double *__restrict__ send) {
+// data-sharded mode: this rank's sum over its own slices in shard-additive form (OP::local with this rank's data
+// constants), one value per walker — the payload of the exchange
+template <class OP>
+__global__ void shard_reduce_kernel(const PartialView pv, const double *theta /* SoA [D][Ps] */, int P, int Ps,
+                                    double rows_local, const OpCst cst_local, double *send) {
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (w >= Ps) return;
-    const double s = combine_partials_warp(pv, w, lane);
+    double s = combine_partials_warp(pv, w, lane);
+    if (w < P) {
+        double th[OP::D];
+#pragma unroll
+        for (int j = 0; j < OP::D; ++j) th[j] = __ldcg(theta + (size_t)j * Ps + w);
+        bool ok;
+        const typename OP::Coef c = OP::prepare(th, ok, cst_local);
+        s = OP::local(c, s, rows_local, cst_local);
+    }
     if (lane == 0) send[w] = s;
 }
 

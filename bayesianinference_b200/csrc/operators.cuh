@@ -16,7 +16,12 @@
 //       Horner step for all TW walkers back to back) so that consecutive DFMAs share the row operand:
 //       on sm_100 a DFMA with three distinct 64-bit register sources issues at 2/3 rate, with a shared
 //       operand in the reuse cache at full rate (measured: scripts/dfma_patterns.cu).
-//   finish(coef, acc, rows, cst) -> logL
+//   local(coef, acc, rows, cst) -> the sum in its shard-additive form (identity except for the polynomial operator,
+//       whose moments trick is resolved with THIS GPU's data moments), and
+//   RENORM > 0: renorm(acc[TW]) must be called at least every RENORM rows (softmax: running products); the row
+//       loops go through sweep_rows (loglike.cuh), which does it.
+//   finish_total(coef, total, rows_total, cst_total) -> logL.  Single GPU: op_finish = finish_total(local(.)).
+//   Data-sharded mode: local() on every rank before the exchange, finish_total() on the rank-ordered sum after it.
 #pragma once
 #include "common.cuh"
 
@@ -26,21 +31,28 @@ namespace binest {
 //   c     additive constant (GBM: Sum_i(-log x_i - 1/2 log dt_i) - rows 1/2 log 2pi)
 //   m[k]  data moments (polynomial regression: m[0] = Sum y, m[k] = Sum x^k, k = 1..degree)
 // In the data-sharded mode these are the totals over all shards.
+//   xbar, piv  pivots subtracted from the regression data at upload (polynomial regression; 0 otherwise)
 struct OpCst {
     double c;
     double m[6];
+    double xbar, piv;
 };
+
+template <class OP>
+__device__ __forceinline__ double op_finish(const typename OP::Coef &c, double acc, double rows, const OpCst &k) {
+    return OP::finish_total(c, OP::local(c, acc, rows, k), rows, k);
+}
 
 // ------------------------------------------------------------------ NormalDistribution[mu, sigma], i.i.d. data
 struct OpGaussian {
-    static constexpr int D = 2, NCOL = 1, TW_MAX = 8;
+    static constexpr int D = 2, NCOL = 1, TW_MAX = 8, RENORM = 0;
     struct Coef { double mu, h, lognorm; };
     struct Row { double mu; };
     using Acc = double;
     __device__ __forceinline__ static Acc acc_init() { return 0.0; }
     __device__ __forceinline__ static double acc_value(const Acc &a) { return a; }
-    __device__ __forceinline__ static Row make_row(const double (&th)[D]) { return Row{th[0]}; }
-    __device__ static Coef prepare(const double (&th)[D], bool &ok) {
+    __device__ __forceinline__ static Row make_row(const double (&th)[D], const OpCst &) { return Row{th[0]}; }
+    __device__ static Coef prepare(const double (&th)[D], bool &ok, const OpCst &) {
         ok = th[1] > 0.0;  // DistributionParameterAssumptions, BS:439
         return Coef{th[0], 1.0 / (2.0 * th[1] * th[1]), -log(th[1]) - kHalfLog2Pi};
     }
@@ -53,42 +65,89 @@ struct OpGaussian {
 #pragma unroll
         for (int u = 0; u < TW; ++u) acc[u] = fma(e[u], e[u], acc[u]);
     }
-    __device__ static double finish(const Coef &c, double acc, double rows, const OpCst &) {
+    __device__ static double local(const Coef &, double acc, double, const OpCst &) { return acc; }
+    __device__ static double finish_total(const Coef &c, double acc, double rows, const OpCst &) {
         return rows * c.lognorm - c.h * acc;
     }
 };
 
 // ------------------------------------------------------------------ NormalDistribution[Sum_j c_j x^j, sigma]
-// Per datum the reference evaluates -(y - Sum_j c_j x^j)^2 / (2 sigma^2) - log sigma - 1/2 log 2pi.  Here
-//     t_i = x_i (c_1 + c_2 x_i + ... + c_deg x_i^(deg-1)) - y_i        (Horner on c_deg..c_1, last FMA adds -y)
-// and the residual is e_i = t_i + c_0, so Sum e^2 = Sum t^2 + 2 c_0 Sum t + N c_0^2 with
-//     Sum t = Sum_k c_k m[k] - m[0]
-// from the walker-independent data moments (OpCst).  The per-datum chain is deg FMAs + the FMA-accumulate: 4 fp64
-// pipe slots at degree 3 instead of 5 (3 Horner FMA, subtract, FMA-accumulate) for the same 9 algorithmic flop of
-// SURVEY §8d.  Sum t^2 <= Sum e^2 + N c_0^2 terms of the same sign: no cancellation beyond the ~1 digit of the
-// final three-term sum (|logL| error ~1e-13 relative at the C2 posterior, parity bar 1e-12).
+// Per datum the reference evaluates -(y - Sum_j c_j x^j)^2 / (2 sigma^2) - log sigma - 1/2 log 2pi (BS:540-583).
+// Device rows hold PIVOTED data, fixed at upload (abi_problem.cu):
+//     x'_i = x_i - xbar      (xbar = the data mean of x, or 0 when the data are already centred: |mean| <= sd/2)
+//     y'_i = y_i - piv       (piv = intercept of the least-squares polynomial in x')
+// and the polynomial is re-expanded around xbar per walker: Sum_j c_j x^j = Sum_k c~_k x'^k (Taylor shift in
+// double-double, polyreg_shift; the identity when xbar = 0).  The residual is then
+//     e_i = t_i + delta,   t_i = x'_i (c~_1 + c~_2 x'_i + ...) - y'_i,   delta = c~_0 - piv
+// (Horner on c~_deg..c~_1, the last FMA adds -y'), and Sum e^2 = Sum t^2 + delta (2 Sum t + N delta) with
+//     Sum t = Sum_k c~_k m[k] - m[0]
+// from the walker-independent moments of the pivoted data (OpCst).  The per-datum chain is deg FMAs + the
+// FMA-accumulate: 4 fp64 pipe slots at degree 3 instead of 5 for the same 9 algorithmic flop of SURVEY §8d.
+// Why the pivots: without them delta = c_0, and Sum t^2 ~ N c_0^2 cancels against c_0 (2 Sum t + N c_0) whenever
+// |c_0| >> rms(e) (y offset 1000, sigma 0.01: 1e-6 relative on Sum e^2).  With them, a walker can only have
+// N delta^2 >> Sum e^2 if the other coefficients compensate a constant over the data, and in the centred basis they
+// cannot: min over them of Sum (delta + Sum_{k>=1} d_k x'^k)^2 = N delta^2 (1 - R^2), R^2 (the fraction of the
+// constant explained by x', x'^2, ...) = 5/9 for a cubic on uniform x', so N delta^2 <= ~2.3 Sum e^2: at most one
+// digit is lost, wherever the walker is.  tests/test_gpu_parity.py::test_polyreg_adversarial pins offsets of 50 and
+// 1000 with sigma 0.05 / 0.01 and x in (100, 101) to 1e-12 against the __float128 oracle.
+__device__ __forceinline__ void dd_fma_acc(double &h, double &l, double ah, double al, double x) {
+    // (h, l) += (ah, al) * x in double-double
+    const double ph = ah * x;
+    double pl = fma(ah, x, -ph);
+    pl = fma(al, x, pl);
+    const double s = h + ph, bb = s - h;
+    double e = (h - (s - bb)) + (ph - bb);
+    e += l + pl;
+    const double hn = s + e;
+    l = e - (hn - s);
+    h = hn;
+}
+// coefficients of p(x' + xbar) in powers of x' (repeated synthetic division), double-double throughout
+template <int DEG>
+__device__ __forceinline__ void polyreg_shift(const double *th, double xbar, double (&h)[DEG + 1], double &lo0) {
+    double l[DEG + 1];
+#pragma unroll
+    for (int j = 0; j <= DEG; ++j) { h[j] = th[j]; l[j] = 0.0; }
+#pragma unroll
+    for (int i = 0; i < DEG; ++i)
+#pragma unroll
+        for (int j = DEG - 1; j >= i; --j) dd_fma_acc(h[j], l[j], h[j + 1], l[j + 1], xbar);
+    lo0 = l[0];
+}
+
 template <int DEG>
 struct OpPolyReg {
-    static constexpr int D = DEG + 2, NCOL = 2, TW_MAX = 8;
-    struct Coef { double h, lognorm, c[DEG + 1]; };
-    struct Row { double c[DEG + 1]; };
+    static constexpr int D = DEG + 2, NCOL = 2, TW_MAX = 8, RENORM = 0;
+    struct Coef { double h, lognorm, c[DEG + 1]; };  // c[0] = delta, c[1..DEG] = shifted coefficients
+    struct Row { double c[DEG + 1]; };               // c[0] unused per datum
     using Acc = double;
     __device__ __forceinline__ static Acc acc_init() { return 0.0; }
     __device__ __forceinline__ static double acc_value(const Acc &a) { return a; }
-    __device__ __forceinline__ static Row make_row(const double (&th)[D]) {
+    __device__ __forceinline__ static Row make_row(const double (&th)[D], const OpCst &k) {
         Row c;
+        if (k.xbar != 0.0) {
+            double lo0;
+            polyreg_shift<DEG>(th, k.xbar, c.c, lo0);
+        } else {
 #pragma unroll
-        for (int j = 0; j <= DEG; ++j) c.c[j] = th[j];
+            for (int j = 0; j <= DEG; ++j) c.c[j] = th[j];
+        }
         return c;
     }
-    __device__ static Coef prepare(const double (&th)[D], bool &ok) {
+    __device__ static Coef prepare(const double (&th)[D], bool &ok, const OpCst &k) {
         Coef c;
         const double sg = th[DEG + 1];
         ok = sg > 0.0;  // BS:523
         c.h = 1.0 / (2.0 * sg * sg);
         c.lognorm = -log(sg) - kHalfLog2Pi;
+        double lo0 = 0.0;
+        if (k.xbar != 0.0) {
+            polyreg_shift<DEG>(th, k.xbar, c.c, lo0);
+        } else {
 #pragma unroll
-        for (int j = 0; j <= DEG; ++j) c.c[j] = th[j];
+            for (int j = 0; j <= DEG; ++j) c.c[j] = th[j];
+        }
+        c.c[0] = (c.c[0] - k.piv) + lo0;
         return c;
     }
     template <int TW>
@@ -111,11 +170,14 @@ struct OpPolyReg {
 #pragma unroll
         for (int u = 0; u < TW; ++u) acc[u] = fma(t[u], t[u], acc[u]);
     }
-    __device__ static double finish(const Coef &c, double acc, double rows, const OpCst &k) {
+    // Sum e^2 over the rows the moments in k describe (this GPU's rows; a shard in the data-sharded mode)
+    __device__ static double local(const Coef &c, double acc, double rows, const OpCst &k) {
         double st = -k.m[0];
 #pragma unroll
         for (int j = 1; j <= DEG; ++j) st = fma(c.c[j], k.m[j], st);
-        const double sse = fma(c.c[0], fma(rows, c.c[0], 2.0 * st), acc);  // Sum t^2 + c0 (2 Sum t + N c0)
+        return fma(c.c[0], fma(rows, c.c[0], 2.0 * st), acc);  // Sum t^2 + delta (2 Sum t + N delta)
+    }
+    __device__ static double finish_total(const Coef &c, double sse, double rows, const OpCst &) {
         return rows * c.lognorm - c.h * sse;
     }
 };
@@ -150,6 +212,9 @@ __constant__ double kExpRed[4] = {
 };
 __device__ __forceinline__ bool exp_arg_bounded(double x) {  // |x| < 700, false for NaN/Inf
     return (__double2hiint(x) & 0x7fffffff) < 0x4085E000;
+}
+__device__ __forceinline__ bool exp_arg_bounded_170(double x) {  // |x| < 170, false for NaN/Inf
+    return (__double2hiint(x) & 0x7fffffff) < 0x40654000;
 }
 // the N independent exps of one datum, step-major so that consecutive DFMAs come from different chains
 template <int N>
@@ -267,7 +332,7 @@ struct OpLogistic {
     static constexpr int D = (K - 1) * (F + 1), NCOL = (F + 2) & ~1, TW_MAX = 2;
     struct Coef { int unused; };
     struct Row { double w[K - 1][F + 1]; };
-    __device__ __forceinline__ static Row make_row(const double (&th)[D]) {
+    __device__ __forceinline__ static Row make_row(const double (&th)[D], const OpCst &) {
         Row c;
 #pragma unroll
         for (int k = 0; k < K - 1; ++k)
@@ -275,7 +340,7 @@ struct OpLogistic {
             for (int f = 0; f <= F; ++f) c.w[k][f] = th[k * (F + 1) + f];
         return c;
     }
-    __device__ static Coef prepare(const double (&)[D], bool &ok) {
+    __device__ static Coef prepare(const double (&)[D], bool &ok, const OpCst &) {
         ok = true;
         return Coef{0};
     }
@@ -284,24 +349,32 @@ struct OpLogistic {
     // branch or select at all (an earlier form shifted by z_y first — log p_y = -log(1 + Sum_{k != y} exp(z_k - z_y)) —
     // and paid ~25 integer/branch instructions per walker and datum for the permutation; this kernel is bound by issue
     // slots and fixed latencies, not by the fp64 pipe: profiles/r01g_ncu_loglike_c3.md).
-    // Sum_i log s_i = log Prod_i s_i: the running product is renormalised to [1, 2) after every factor by moving
-    // its exponent field into an integer (4 ALU instructions instead of a log per datum); one log at the end.
-    // Sum z_y and Sum log s are accumulated separately and subtracted once; with |z| <= a few hundred at most that
-    // costs < 3 digits of the 16 (parity bar 1e-12).  |z_k| >= 700 (overflow / subnormal territory, NaN) takes the slow
-    // path: max-shifted libdevice exp/log.
-    struct Acc { double lin, prod; long long e2; };
-    __device__ __forceinline__ static Acc acc_init() { return Acc{0.0, 1.0, 0}; }
+    // Sum_i log p_i = log Prod_i e_i - log Prod_i s_i with e_i = exp z_y (one of the exps already computed, or 1 for
+    // the reference class) and s_i = 1 + Sum_k exp z_k.  Both running products are renormalised to [1, 2) every
+    // RENORM = 4 rows (renorm(): the exponent fields move into ONE shared integer, e2 += expo(e) - expo(s); ~3 ALU
+    // instructions per datum instead of a log), two logs at the end.  With |z_k| < 170 on the fast path four factors
+    // cannot leave the normal range: prod < 2 (1 + 2 e^170)^4 = 7e296, prode in (e^-680, 2 e^680).
+    // Nothing of magnitude |z| is ever accumulated, so the absolute error of the sum is ~sqrt(rows) ulp of 1 whatever
+    // the logits are — also for well-separated classes, where Sum z_y and Sum log s are both ~N |z| and their
+    // difference is tiny (an earlier form accumulated Sum z_y and the log of the s-product separately and lost 6e-8
+    // absolute at N = 1e6, |z| = 600; with perfectly separated data both products now go through identical arithmetic
+    // and the result is exactly 0, as the reference's Log[e^z_y / Sum e^z] gives).  |z_k| >= 170 (NaN included) takes
+    // the slow path: max-shifted libdevice exp/log, accumulated in `lin`.
+    static constexpr int RENORM = 4;
+    struct Acc { double lin, prod, prode; long long e2; };
+    __device__ __forceinline__ static Acc acc_init() { return Acc{0.0, 1.0, 1.0, 0}; }
     __device__ __forceinline__ static double acc_value(const Acc &a) {
-        return a.lin - fma((double)a.e2, 0.693147180559945309417232, log(a.prod));
+        return a.lin + fma((double)a.e2, 0.693147180559945309417232, log(a.prode) - log(a.prod));
     }
     template <int TW>
     __device__ __forceinline__ static void rows(const Row (&c)[TW], const double *__restrict__ r, Acc (&acc)[TW]) {
         static_assert(K == 2 || K == 3, "softmax operator is specialised for 2 or 3 classes");
         constexpr int E = K - 1;  // exps per datum
-        double z[TW * E], ex[TW * E], zy[TW];
+        double z[TW * E], ex[TW * E];
         const double labv = r[F];
         const double i0 = (labv == 0.0) ? 1.0 : 0.0;
         const double i1 = (K == 3 && labv == 1.0) ? 1.0 : 0.0;  // the last class is the reference class (z = 0)
+        const double iK = 1.0 - i0 - i1;
 #pragma unroll
         for (int k = 0; k < E; ++k)
 #pragma unroll
@@ -316,12 +389,9 @@ struct OpLogistic {
         }
         bool fast = true;
 #pragma unroll
-        for (int u = 0; u < TW; ++u) {
-            zy[u] = i0 * z[u * E];
-            if (K == 3) zy[u] = fma(i1, z[u * E + 1], zy[u]);
+        for (int u = 0; u < TW; ++u)
 #pragma unroll
-            for (int k = 0; k < E; ++k) fast = fast && exp_arg_bounded(z[u * E + k]);
-        }
+            for (int k = 0; k < E; ++k) fast = fast && exp_arg_bounded_170(z[u * E + k]);
         if (__builtin_expect(fast, 1)) {
 #if BINEST_EXP_TAB
             exp_bounded_tab<TW * E>(z, ex);
@@ -331,39 +401,54 @@ struct OpLogistic {
 #pragma unroll
             for (int u = 0; u < TW; ++u) {
                 double s = 1.0 + ex[u * E];
-                if (K == 3) s += ex[u * E + 1];
-                const double p = acc[u].prod * s;  // < 2 * 3 e^700: finite
-                const int hi = __double2hiint(p), e = (hi >> 20) - 1023;
-                acc[u].e2 += e;
-                acc[u].prod = __hiloint2double(hi - (e << 20), __double2loint(p));
-                acc[u].lin += zy[u];
+                double ey = fma(i0, ex[u * E], iK);
+                if (K == 3) { s += ex[u * E + 1]; ey = fma(i1, ex[u * E + 1], ey); }
+                acc[u].prod *= s;
+                acc[u].prode *= ey;
             }
         } else {
 #pragma unroll
             for (int u = 0; u < TW; ++u) {
+                double zy = i0 * z[u * E];
+                if (K == 3) zy = fma(i1, z[u * E + 1], zy);
                 double mx = fmax(z[u * E], 0.0);
                 if (K == 3) mx = fmax(mx, z[u * E + 1]);
                 double s = exp(-mx) + exp(z[u * E] - mx);
                 if (K == 3) s += exp(z[u * E + 1] - mx);
-                acc[u].lin += zy[u] - (mx + log(s));
+                acc[u].lin += zy - (mx + log(s));
             }
         }
     }
-    __device__ static double finish(const Coef &, double acc, double, const OpCst &) { return acc; }
+    // move the exponents of both running products into e2 (call at least every RENORM rows)
+    template <int TW>
+    __device__ __forceinline__ static void renorm(Acc (&acc)[TW]) {
+#pragma unroll
+        for (int u = 0; u < TW; ++u) {
+            const int hp = __double2hiint(acc[u].prod), ep = (hp >> 20) - 1023;
+            const int hq = __double2hiint(acc[u].prode), eq = (hq >> 20) - 1023;
+            acc[u].e2 += eq - ep;
+            acc[u].prod = __hiloint2double(hp - (ep << 20), __double2loint(acc[u].prod));
+            acc[u].prode = __hiloint2double(hq - (eq << 20), __double2loint(acc[u].prode));
+        }
+    }
+    __device__ static double local(const Coef &, double acc, double, const OpCst &) { return acc; }
+    __device__ static double finish_total(const Coef &, double acc, double, const OpCst &) { return acc; }
 };
 
 // ------------------------------------------------------------------ GeometricBrownianMotionProcess[mu, sigma, x0]
 // device row i = (a_i, b_i) = (r_i / sqrt(dt_i), sqrt(dt_i)), r_i = log(x_i / x_{i-1});
 // cst = Sum_i(-log x_i - 1/2 log dt_i) - rows * 1/2 log 2pi  (parameter independent, fixed at upload)
 struct OpGbm {
-    static constexpr int D = 2, NCOL = 2, TW_MAX = 8;
+    static constexpr int D = 2, NCOL = 2, TW_MAX = 8, RENORM = 0;
     struct Coef { double h, lognorm; };
     struct Row { double negm; };
     using Acc = double;
     __device__ __forceinline__ static Acc acc_init() { return 0.0; }
     __device__ __forceinline__ static double acc_value(const Acc &a) { return a; }
-    __device__ __forceinline__ static Row make_row(const double (&th)[D]) { return Row{-(th[0] - 0.5 * th[1] * th[1])}; }
-    __device__ static Coef prepare(const double (&th)[D], bool &ok) {
+    __device__ __forceinline__ static Row make_row(const double (&th)[D], const OpCst &) {
+        return Row{-(th[0] - 0.5 * th[1] * th[1])};
+    }
+    __device__ static Coef prepare(const double (&th)[D], bool &ok, const OpCst &) {
         ok = th[1] > 0.0;
         return Coef{1.0 / (2.0 * th[1] * th[1]), -log(th[1])};
     }
@@ -376,7 +461,8 @@ struct OpGbm {
 #pragma unroll
         for (int u = 0; u < TW; ++u) acc[u] = fma(e[u], e[u], acc[u]);
     }
-    __device__ static double finish(const Coef &c, double acc, double rows, const OpCst &cst) {
+    __device__ static double local(const Coef &, double acc, double, const OpCst &) { return acc; }
+    __device__ static double finish_total(const Coef &c, double acc, double rows, const OpCst &cst) {
         return rows * c.lognorm + cst.c - c.h * acc;
     }
 };
@@ -387,11 +473,12 @@ struct OpGbm {
 struct OpGpSe {
     static constexpr int D = 3;
     struct Coef { int unused; };
-    __device__ static Coef prepare(const double (&th)[D], bool &ok) {
+    __device__ static Coef prepare(const double (&th)[D], bool &ok, const OpCst &) {
         ok = th[0] > 0.0 && th[1] > 0.0 && th[2] > 0.0;
         return Coef{0};
     }
-    __device__ static double finish(const Coef &, double acc, double, const OpCst &) { return acc; }
+    __device__ static double local(const Coef &, double acc, double, const OpCst &) { return acc; }
+    __device__ static double finish_total(const Coef &, double acc, double, const OpCst &) { return acc; }
 };
 
 // ------------------------------------------------------------------ priors (BS:25-64, BS:365-427)

@@ -149,8 +149,9 @@ inline void launch_loglike(binest_problem &p, const double *theta_dev, int P, in
         const double *data = p.data.p;
         long long rows = p.rows, rpc = g.rows_per_cta;
         int Gs = g.Gs;
+        OpCst cst = p.cst;  // this GPU's data constants (pivots of the polynomial operator)
         BN_CUDA(cudaLaunchKernelEx(&lc.cfg, loglike_stream_kernel<OP, TW>, data, rows, rpc, theta_dev, P, Ps,
-                                   partials_dev, Gs));
+                                   partials_dev, Gs, cst));
     });
     if (check) BN_LAUNCH_CHECK();
 }
@@ -166,13 +167,16 @@ void comm_allgather_f64(binest_comm &c, const double *send, double *recv, size_t
 // fixed order, all-gather the P sums of every rank, and hand the consumer a view over [world][Ps].  Every rank then
 // adds the same `world` numbers in the same (rank) order, so accept/reject decisions are bit-identical everywhere —
 // which an all-reduce would not guarantee across algorithms.  Traffic: 8 P bytes per rank per step.
-inline PartialView shard_exchange(binest_problem &p, const double *partials, int Ps, const StreamGeom &g, cudaStream_t s) {
+template <class OP>
+inline PartialView shard_exchange(binest_problem &p, const double *partials, const double *theta_dev, int P, int Ps,
+                                  const StreamGeom &g, cudaStream_t s) {
     if (p.sh_send.n < (size_t)Ps) p.sh_send.alloc(Ps);
     if (p.sh_recv.n < (size_t)Ps * p.comm->world) p.sh_recv.alloc((size_t)Ps * p.comm->world);
-    shard_reduce_kernel<<<(Ps * 32 + 255) / 256, 256, 0, s>>>(PartialView{partials, g.G, g.Gs, 1}, Ps, p.sh_send.p);
+    shard_reduce_kernel<OP><<<(Ps * 32 + 255) / 256, 256, 0, s>>>(PartialView{partials, g.G, g.Gs, 1}, theta_dev, P, Ps,
+                                                                 (double)p.rows, p.cst, p.sh_send.p);
     BN_LAUNCH_CHECK();
     comm_allgather_f64(*p.comm, p.sh_send.p, p.sh_recv.p, (size_t)Ps, s);
-    return PartialView{p.sh_recv.p, p.comm->world, 1, Ps};
+    return PartialView{p.sh_recv.p, p.comm->world, 1, Ps, 1};
 }
 
 // full batched evaluation: theta_dev SoA [d][Ps] -> out_dev[P]
@@ -188,7 +192,7 @@ inline void loglike_device(binest_problem &p, const double *theta_dev, int P, in
         if (p.s_partials.n < need) p.s_partials.alloc(need);
         launch_loglike<OP>(p, theta_dev, P, Ps, p.s_partials.p, g, p.stream);
         PartialView pv{p.s_partials.p, g.G, g.Gs, 1};
-        if (p.comm) pv = shard_exchange(p, p.s_partials.p, Ps, g, p.stream);
+        if (p.comm) pv = shard_exchange<OP>(p, p.s_partials.p, theta_dev, P, Ps, g, p.stream);
         loglike_finalize_kernel<OP><<<(P * 32 + 255) / 256, 256, 0, p.stream>>>(
             theta_dev, P, Ps, pv, p.rows_eff(), p.cst_eff(), p.prior, g_logzero, out_dev);
         BN_LAUNCH_CHECK();

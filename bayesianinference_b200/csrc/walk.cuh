@@ -42,6 +42,7 @@ struct RunParams {
     unsigned long long seed;
     unsigned first_run_id;
     double logzero;
+    double loglmax_opt;  // numeric "LogLikelihoodMaximum" (BS:925-932), NaN = use the live set's maximum
     int attempt;  // outer acceptance retry round (BS:1000-1003): offsets the Philox counter word 0 by 16 * attempt
 };
 
@@ -214,7 +215,8 @@ __global__ void __launch_bounds__(1024) run_update_kernel(const __grid_constant_
     // ---- 4. termination test (BS:967-978) in the log domain: X_min L_max <= Z frac
     const long long it = st.iteration;
     const bool go = it <= prm.max_iter &&
-                    (it == 1 || it <= prm.min_iter || !(logXmin + logLmax <= logZ + prm.log_term_frac));
+                    (it == 1 || it <= prm.min_iter ||
+                     !(logXmin + (isnan(prm.loglmax_opt) ? logLmax : prm.loglmax_opt) <= logZ + prm.log_term_frac));
     if (tid == 0) {
         st.logZ = logZ; st.entropy = entropy; st.logLmax = logLmax; st.logXmin = logXmin;
     }
@@ -357,7 +359,7 @@ __device__ __forceinline__ void walk_step_walker(const RunParams &prm, const Run
         bool acc = false;
         if (flags & WF_PRE) {
             const double sum = combine_partials_warp(pv, w, lane);
-            const double nL = loglike_finish<OP>(xn, sum, rows, cst, prm.logzero);
+            const double nL = loglike_finish<OP>(xn, sum, rows, cst, prm.logzero, pv.localized);
             if (nL > st.Lstar) {  // nsDensity: logL > threshold, strict (BS:605)
                 acc = true;
                 if (lead) A.w_logL[w] = nL;

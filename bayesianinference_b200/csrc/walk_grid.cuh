@@ -129,7 +129,7 @@ __device__ __forceinline__ void gw_init(GridWalker<OP> &q, const RunParams &prm,
 // has taken `steps` steps uses Philox counter word `steps`, as in walk_step_walker.
 template <class OP>
 __device__ __forceinline__ void gw_pre(GridWalker<OP> &q, const RunParams &prm, const RunArrays &A, const PriorSpec &prior,
-                                       int lane) {
+                                       const OpCst &cst, int lane) {
     constexpr int D = OP::D, NZ = (D + 1) / 2;
     if (!q.active) return;
     const RunState &st = A.state[q.w / prm.K];
@@ -172,7 +172,7 @@ __device__ __forceinline__ void gw_pre(GridWalker<OP> &q, const RunParams &prm, 
         cpre = (nPr - basePr > logu) ? 1 : 0;  // Metropolis rule on the log density
     }
     bool ok = false;
-    const typename OP::Coef cf = OP::prepare(cd, ok);
+    const typename OP::Coef cf = OP::prepare(cd, ok, cst);
     __syncwarp();
     if (lane < 2) {
 #pragma unroll
@@ -193,7 +193,7 @@ __device__ __forceinline__ void gw_post(GridWalker<OP> &q, const RunParams &prm,
     double nL = 0.0;
     if (q.hasprop && q.pre) {
         const double sum = combine_partials_warp(pv, q.w, lane);
-        nL = OP::finish(q.coef, sum, rows, cst);
+        nL = op_finish<OP>(q.coef, sum, rows, cst);
         if (!(q.ok && isfinite(nL))) nL = prm.logzero;      // RuntimeErrorHandler -> logzero, BS:500-503
         if (nL > A.state[q.w / prm.K].Lstar) sel = 1;       // nsDensity: logL > threshold, strict (BS:605)
     }
@@ -343,7 +343,7 @@ walk_grid_kernel(const __grid_constant__ RunParams prm, RunArrays A, const __gri
         const int nown = w0 < whi ? (whi - w0 + G - 1) / G : 0;
         for (int k = 0; k < nown; ++k) {
             gw_init<OP>(slots[X][k], prm, A, w0 + k * G, lane);
-            gw_pre<OP>(slots[X][k], prm, A, prior, lane);
+            gw_pre<OP>(slots[X][k], prm, A, prior, cst, lane);
         }
         for (int s = 0; s <= S; ++s) {
             if (lane == 0) grid_trace(dbg, g, G, 0, s, X, 0);
@@ -361,7 +361,7 @@ walk_grid_kernel(const __grid_constant__ RunParams prm, RunArrays A, const __gri
             // off the critical path: bookkeeping, then the draws and candidates of the next step
             for (int k = 0; k < nown; ++k) {
                 gw_update<OP>(slots[X][k], lane);
-                if (s < S) gw_pre<OP>(slots[X][k], prm, A, prior, lane);
+                if (s < S) gw_pre<OP>(slots[X][k], prm, A, prior, cst, lane);
                 else gw_final<OP>(slots[X][k], prm, A, lane);
             }
             if (lane == 0) grid_trace(dbg, g, G, 0, s, X, 3);
@@ -395,13 +395,12 @@ walk_grid_kernel(const __grid_constant__ RunParams prm, RunArrays A, const __gri
                 double th[D];
 #pragma unroll
                 for (int j = 0; j < D; ++j) th[j] = (w < P) ? __ldcg(A.w_prop + (size_t)j * Ps + w) : 1.0;
-                c[t] = OP::make_row(th);
+                c[t] = OP::make_row(th, cst);
             }
             typename OP::Acc acc[TW];
 #pragma unroll
             for (int t = 0; t < TW; ++t) acc[t] = OP::acc_init();
-#pragma unroll 2
-            for (int i = gwid; i < nr; i += GW) OP::template rows<TW>(c, tile + (size_t)i * NCOL, acc);
+            sweep_rows<OP, TW>(c, tile, gwid, GW, nr, acc);
 #pragma unroll
             for (int u = 0; u < TW; ++u) red[gwid * WP + lane + 32 * u] = OP::acc_value(acc[u]);
             named_bar_sync(bar_id, GW * 32);

@@ -143,7 +143,7 @@ walk_resident_kernel(const __grid_constant__ RunParams prm, RunArrays A, const _
                 if (!isfinite(nPr)) nPr = prm.logzero;
                 pre = (nPr - xPr > s_logu[sc * 32 + lane]);
             }
-            s_row[lane] = OP::make_row(xn);
+            s_row[lane] = OP::make_row(xn, cst);
         }
         __syncthreads();
         // ---- (2) warps 1..7: this CTA's shard of the reduction for the 32 proposals; warp 0 meanwhile evaluates the
@@ -151,7 +151,7 @@ walk_resident_kernel(const __grid_constant__ RunParams prm, RunArrays A, const _
         typename OP::Coef fin_c{};
         bool fin_ok = false;
         if (wid == 0) {
-            fin_c = OP::prepare(xn, fin_ok);
+            fin_c = OP::prepare(xn, fin_ok, cst);
         } else {
             typename OP::Row c[1];
             c[0] = s_row[lane];
@@ -166,8 +166,14 @@ walk_resident_kernel(const __grid_constant__ RunParams prm, RunArrays A, const _
                 OP::template rows<1>(c, tile + (size_t)(i + DW) * NCOL, a1);
                 OP::template rows<1>(c, tile + (size_t)(i + 2 * DW) * NCOL, a2);
                 OP::template rows<1>(c, tile + (size_t)(i + 3 * DW) * NCOL, a3);
+                if constexpr (OP::RENORM > 0) {  // one row per accumulator and iteration: small data, cost irrelevant
+                    OP::template renorm<1>(a0); OP::template renorm<1>(a1); OP::template renorm<1>(a2); OP::template renorm<1>(a3);
+                }
             }
-            for (; i < nr; i += DW) OP::template rows<1>(c, tile + (size_t)i * NCOL, a0);
+            for (; i < nr; i += DW) {
+                OP::template rows<1>(c, tile + (size_t)i * NCOL, a0);
+                if constexpr (OP::RENORM > 0) OP::template renorm<1>(a0);
+            }
             red[(wid - 1) * 32 + lane] = (OP::acc_value(a0[0]) + OP::acc_value(a1[0])) + (OP::acc_value(a2[0]) + OP::acc_value(a3[0]));
         }
         __syncthreads();
@@ -193,7 +199,7 @@ walk_resident_kernel(const __grid_constant__ RunParams prm, RunArrays A, const _
             // ---- (4) accept rule (nsDensity BS:602-617), Haario recursion (BS:715-727)
             bool acc = false;
             if (active && pre) {
-                double nL = OP::finish(fin_c, sum, (double)rows, cst);
+                double nL = op_finish<OP>(fin_c, sum, (double)rows, cst);
                 if (!(fin_ok && isfinite(nL))) nL = prm.logzero;  // RuntimeErrorHandler -> logzero, BS:500-503
                 if (nL > Lstar) { acc = true; xL = nL; }
             }

@@ -268,13 +268,16 @@ Options[nestedSampling] = Join[{
     "BatchSize" -> 1 (* live points replaced per iteration; 1 = the reference scheme BS:980-1018 *)},
     Options[evidenceSampling]];
 Options[parallelNestedSampling] = Join[DeleteCases[Options[nestedSampling], "StartingPoints" -> _], {"ParallelRuns" :> 4}];
-Options[combineRuns] = Options[evidenceSampling];
+Options[combineRuns] = Join[Options[evidenceSampling], {"MergeScheme" -> Automatic}];
 
 runGroup[handle_, d_, opts_, nRuns_, firstRun_, start_] := Module[{run, fin, tables},
     run = check @ binestRunCreate[handle,
         {opts["SamplePoolSize"], opts["BatchSize"], opts["MonteCarloSteps"], opts["MaxIterations"], opts["MinIterations"],
             opts["Seed"], firstRun, nRuns},
-        N @ {opts["TerminationFraction"], opts["MinMaxAcceptanceRate"][[1]], opts["MinMaxAcceptanceRate"][[2]]},
+        N @ {opts["TerminationFraction"], opts["MinMaxAcceptanceRate"][[1]], opts["MinMaxAcceptanceRate"][[2]],
+            (* "LogLikelihoodMaximum" -> number replaces the running maximum in the termination estimate (BS:925-932);
+               Automatic travels as 1.*^308 (a packed real vector cannot carry NaN portably) *)
+            If[NumericQ[opts["LogLikelihoodMaximum"]], opts["LogLikelihoodMaximum"], 1.*^308]},
         start];
     If[run === $Failed, Return[$Failed, Module]];
     fin = binestRunAdvance[run, 0];
@@ -310,7 +313,11 @@ nestedSampling[inferenceObject[assoc_?AssociationQ], opts : OptionsPattern[]] :=
 meanAndError[v_?VectorQ] := <|"Mean" -> Mean[v], "StandardError" -> StandardDeviation[v]|>; (* BS:1138-1149 *)
 
 evidenceSampling[inferenceObject[assoc_?AssociationQ], opts : OptionsPattern[]] := Module[{
-    o = Association[Options[evidenceSampling], opts], s = assoc["Samples"], n = assoc["SamplePoolSize"], m, d, ord, cw, ev, r, pool, out},
+    o = Association[Options[evidenceSampling], opts],
+    (* columns a previous evidenceSampling derived are recomputed: evidenceSampling[obj] re-post-processes a result, BS:1158-1160 *)
+    s = KeyDrop[assoc["Samples"], {"SampledLogX", "LogPosteriorWeight", "CrudePosteriorWeight", "CrudeLogPosteriorWeight", "X", "LogX"}],
+    n = Lookup[assoc, "binestLiveBlock", assoc["SamplePoolSize"]], (* combineRuns "PoolSizes": the tail that acts as the live set *)
+    m, d, ord, cw, ev, r, pool, out},
     ord = Ordering[Transpose[{s["LogLikelihood"], s["Point"]}]]; (* SortBy {logL, point}, BS:814 *)
     s = Map[#[[ord]] &, s];
     m = Length[ord]; d = Length[First[s["Point"]]];
@@ -340,25 +347,61 @@ evidenceSampling[inferenceObject[assoc_?AssociationQ], opts : OptionsPattern[]] 
     |>]
 ];
 
+(* samples of one result sorted by {logL, point} (BS:814): {levels, pool sizes} *)
+sortedLevelsAndPools[a_Association] := With[{s = a["Samples"], n = a["SamplePoolSize"]},
+    With[{ord = Ordering[Transpose[{s["LogLikelihood"], s["Point"]}]], k = Length[s["LogLikelihood"]]},
+        {s["LogLikelihood"][[ord]],
+         If[KeyExistsQ[s, "PoolSize"], Round[s["PoolSize"][[ord]]], Join[ConstantArray[n, Max[k - n, 0]], Range[Min[n, k], 1, -1]]]}]];
+
+(* the reference's pool structure: n for every deleted point, then the live set n..1 (BS:785-799) *)
+referencePoolQ[a_Association] := With[{lp = sortedLevelsAndPools[a], n = a["SamplePoolSize"]},
+    With[{p = Last[lp], k = Length[Last[lp]]},
+        k >= n && p[[;; k - n]] === ConstantArray[n, k - n] && p[[k - n + 1 ;;]] === Range[n, 1, -1]]];
+
+(* BS:1293-1315.  "MergeScheme" (not in the reference): "Reference" = the literal formula, pool size
+   Total[SamplePoolSize] for the first M - nTot samples and the nTot best as a live set (BS:1307-1309 -> BS:785-799);
+   "PoolSizes" = at every sample the SUM over runs of that run's pool size at the sample's likelihood level, used
+   consistently to the last sample (needed when runs replaced "BatchSize" > 1 points per iteration);
+   Automatic = "Reference" when every run has the reference's pool structure, else "PoolSizes". *)
 combineRuns[results : inferenceObject[_?AssociationQ] .., opts : OptionsPattern[]] := Module[{
-    assocs = {results}[[All, 1]], joined, keep, pools, nTot, merged},
-    joined = Join @@@ Transpose[Values /@ KeyTake[#["Samples"], {"Point", "LogLikelihood", "LogPriorPDF", "AcceptanceRate"}] & /@ assocs];
-    keep = Values[PositionIndex[joined[[1]]][[All, 1]]];                                        (* DeleteDuplicatesBy Point, BS:1294-1297 *)
-    joined = joined[[All, keep]];
+    assocs = {results}[[All, 1]], cols = {"Point", "LogLikelihood", "LogPriorPDF", "AcceptanceRate"},
+    scheme = OptionValue["MergeScheme"], pools, nTot, joined, keep, ord, merged, m, lps, base, levels, deltas, eo, sl, csum,
+    rank, below, pool, dis, live, extra = <||>},
     pools = #["SamplePoolSize"] & /@ assocs; nTot = Total[pools];
-    merged = AssociationThread[{"Point", "LogLikelihood", "LogPriorPDF", "AcceptanceRate"}, joined];
-    (* per-sample pool sizes: sum over runs of the run's pool size at the sample's likelihood level;
-       with constant pools this is the reference's Total of SamplePoolSize (BS:1307) *)
-    merged["PoolSize"] = Total @ Map[
-        Function[a, With[{sl = Sort[a["Samples"]["LogLikelihood"]], sp = Lookup[a["Samples"], "PoolSize", None]},
-            Map[Function[l, With[{i = LengthWhile[sl, # < l &] + 1}, If[i > Length[sl], 0, If[sp === None, a["SamplePoolSize"], sp[[Ordering[a["Samples"]["LogLikelihood"]]]][[i]]]]]], merged["LogLikelihood"]]]],
-        assocs];
+    joined = AssociationMap[Function[c, Join @@ (#["Samples"][c] & /@ assocs)], cols];
+    keep = Sort[First /@ Values[PositionIndex[joined["Point"]]]];                              (* DeleteDuplicatesBy Point: first kept, BS:1294-1297 *)
+    joined = Map[#[[keep]] &, joined];
+    ord = Ordering[Transpose[{joined["LogLikelihood"], joined["Point"]}]];                     (* SortBy {logL, point} *)
+    merged = Map[#[[ord]] &, joined];
+    m = Length[ord];
+    If[scheme === Automatic, scheme = If[AllTrue[assocs, referencePoolQ], "Reference", "PoolSizes"]];
+    If[scheme === "Reference",
+        merged["PoolSize"] = Join[ConstantArray[nTot, Max[m - nTot, 0]], Range[Min[nTot, m], 1, -1]],
+        (* every run's pool size is a step function of the likelihood level that changes at its own samples: the sum
+           over runs is one cumulative sum over all samples sorted by level *)
+        lps = sortedLevelsAndPools /@ assocs;
+        base = Total[First[Last[#]] & /@ lps];
+        levels = Join @@ (First /@ lps);
+        deltas = Join @@ (Differences[Append[Last[#], 0]] & /@ lps);
+        eo = Ordering[levels]; sl = levels[[eo]]; csum = Prepend[Accumulate[deltas[[eo]]], 0];
+        (* below[[i]] = number of run samples strictly below merged level i: joint ranking, merged entries first on ties *)
+        rank = Ordering[Ordering[Join[Transpose[{merged["LogLikelihood"], ConstantArray[0, m]}], Transpose[{sl, ConstantArray[1, Length[sl]]}]]]];
+        below = rank[[;; m]] - Range[m];
+        pool = base + csum[[below + 1]];
+        merged["PoolSize"] = pool;
+        (* once every run is inside its final live set the sum falls by one per sample: that tail is the live set of
+           the merged run in the sense of BS:791-797 *)
+        dis = Flatten @ Position[Unitize[pool - Range[m, 1, -1]], 1];
+        live = If[dis === {}, m, m - Last[dis]];
+        extra = <|"binestLiveBlock" -> Max[live, 1]|>
+    ];
     evidenceSampling[
-        inferenceObject @ Join[First[assocs], <|
+        inferenceObject @ Join[KeyDrop[First[assocs], "binestLiveBlock"], <|
             "Samples" -> merged,
             "LogLikelihoodMaximum" -> Max[#["LogLikelihoodMaximum"] & /@ assocs],             (* BS:1306 *)
-            "SamplePoolSize" -> nTot, "GeneratedNestedSamples" -> Length[keep] - nTot, "TotalSamples" -> Length[keep]|>], (* BS:1307-1309 *)
-        opts]
+            "SamplePoolSize" -> nTot, "GeneratedNestedSamples" -> m - nTot, "TotalSamples" -> m, (* BS:1307-1309 *)
+            "MergeScheme" -> scheme|>, extra],
+        Sequence @@ FilterRules[{opts}, Options[evidenceSampling]]]
 ];
 
 parallelNestedSampling::startingPts = "Cannot use pre-specified starting points for parallel sampling because each parallel process should generate starting points independently.

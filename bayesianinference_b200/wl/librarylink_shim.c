@@ -219,7 +219,8 @@ DLLEXPORT int binestSamplePrior(WolframLibraryData libData, mint Argc, MArgument
 }
 
 /* binestRunCreate[handle, iopts {Integer,1} (pool, K, S, maxIter, minIter, seed, firstRun, nRuns),
- *                 ropts {Real,1} (termFrac, accMin, accMax), start {Real,3} or {}] -> run handle */
+ *                 ropts {Real,1} (termFrac, accMin, accMax, logLmax; "LogLikelihoodMaximum" -> Automatic is sent as
+ *                 1e308 and stays NaN here), start {Real,3} or {}] -> run handle */
 DLLEXPORT int binestRunCreate(WolframLibraryData libData, mint Argc, MArgument *Args, MArgument Res) {
     binest_problem *h = (binest_problem *)(intptr_t)MArgument_getInteger(Args[0]);
     const mint *io = libData->MTensor_getIntegerData(MArgument_getMTensor(Args[1]));
@@ -232,6 +233,7 @@ DLLEXPORT int binestRunCreate(WolframLibraryData libData, mint Argc, MArgument *
     o.pool_size = io[0]; o.batch_k = io[1]; o.mc_steps = io[2]; o.max_iter = io[3]; o.min_iter = io[4];
     o.seed = (uint64_t)io[5]; o.first_run_id = io[6]; o.n_runs = io[7];
     o.term_frac = ro[0]; o.acc_min = ro[1]; o.acc_max = ro[2];
+    if (ro[3] < 1e307) o.loglmax = ro[3]; /* else keep NaN = Automatic (a WL packed array cannot carry NaN) */
     rc = binest_run_create(h, &o, libData->MTensor_getFlattenedLength(sp) > 0 ? libData->MTensor_getRealData(sp) : 0, &r);
     if (rc) return st(rc);
     MArgument_setInteger(Res, (mint)(intptr_t)r);

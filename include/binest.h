@@ -77,6 +77,8 @@ typedef struct binest_options {
     uint64_t seed;       /* Philox key; results depend on (seed, run id) only, not on the GPU count */
     int64_t first_run_id;/* id of the first run of this group (run-sharding across ranks/GPUs) */
     int64_t n_runs;      /* independent runs advanced in lock-step on this device ("ParallelRuns" BS:1369) */
+    double loglmax;      /* "LogLikelihoodMaximum" BS:847: a number replaces the running maximum of the live set in the
+                            termination estimate X_min * L_max (BS:925-932); NaN = Automatic (the default) */
 } binest_options;
 
 /* ---- library ----------------------------------------------------------------------------- */

@@ -729,6 +729,7 @@ typedef struct {
     int64_t run_id;
     int64_t adapt_in_walk; /* 1: Haario recursion drives the proposal inside the walk (reference-like);
                               0: proposal factor frozen per iteration (what the CUDA walk does) */
+    double loglmax;        /* numeric "LogLikelihoodMaximum" BS:847, 925-932; NaN = Automatic */
 } orc_options;
 
 typedef struct {
@@ -818,7 +819,8 @@ ORC_API orc_run *orc_nested_sampling(const orc_problem *p, const orc_prior *pr, 
         /* BS:967-978; the product X_min*L_max <= Z*frac is tested in the log domain (SURVEY §7
          * hard part 2: the reference's Exp underflows for logL << -745) */
         int go = iteration <= maxit &&
-                 (iteration == 1 || iteration <= minit || !(logXmin + logLmax <= logZ + log_frac));
+                 (iteration == 1 || iteration <= minit ||
+                  !(logXmin + (isnan(o->loglmax) ? logLmax : o->loglmax) <= logZ + log_frac)); /* BS:925-937 */
         if (!go) break;
         int64_t Kb = o->batch_k;
         if (Kb > maxit - iteration + 1) Kb = maxit - iteration + 1;

@@ -257,7 +257,7 @@ class _Options(C.Structure):
     _fields_ = [("pool_size", C.c_int64), ("batch_k", C.c_int64), ("mc_steps", C.c_int64),
                 ("max_iter", C.c_int64), ("min_iter", C.c_int64), ("term_frac", C.c_double),
                 ("acc_min", C.c_double), ("acc_max", C.c_double), ("seed", C.c_uint64),
-                ("run_id", C.c_int64), ("adapt_in_walk", C.c_int64)]
+                ("run_id", C.c_int64), ("adapt_in_walk", C.c_int64), ("loglmax", C.c_double)]
 
 
 @dataclass
@@ -280,10 +280,10 @@ class RunResult:
 
 def nested_sampling(problem: Problem, prior: Prior, pool_size=100, batch_k=1, mc_steps=200,
                     max_iter=10000, min_iter=100, term_frac=0.01, acc_range=(0.0, 1.0), seed=1,
-                    run_id=0, adapt_in_walk=True, start_points=None) -> RunResult:
+                    run_id=0, adapt_in_walk=True, start_points=None, loglmax=float("nan")) -> RunResult:
     """BS:859-1040 (+ BS:707-745 walk protocol), sequential."""
     o = _Options(pool_size, batch_k, mc_steps, max_iter, min_iter, term_frac, acc_range[0], acc_range[1],
-                 seed, run_id, 1 if adapt_in_walk else 0)
+                 seed, run_id, 1 if adapt_in_walk else 0, loglmax)
     sp = None if start_points is None else _f64(start_points)
     h = lib().orc_nested_sampling(problem.h, prior.h, C.byref(o), _dp(sp))
     M, nd, it, ev = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()

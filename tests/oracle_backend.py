@@ -13,7 +13,7 @@ from oracle import oracle as O
 
 def default_options(**kw):
     o = SimpleNamespace(pool_size=100, batch_k=1, mc_steps=200, max_iter=10000, min_iter=100, term_frac=0.01,
-                        acc_min=0.0, acc_max=1.0, seed=1, first_run_id=0, n_runs=1)
+                        acc_min=0.0, acc_max=1.0, seed=1, first_run_id=0, n_runs=1, loglmax=float("nan"))
     for k, v in kw.items():
         if not hasattr(o, k):
             raise TypeError(k)
@@ -86,7 +86,7 @@ class RunGroup:
         for i in range(o.n_runs):
             r = O.nested_sampling(self.p.prob, self.p.prior, pool_size=o.pool_size, batch_k=o.batch_k,
                                   mc_steps=o.mc_steps, max_iter=o.max_iter, min_iter=o.min_iter,
-                                  term_frac=o.term_frac, acc_range=(o.acc_min, o.acc_max), seed=o.seed,
+                                  term_frac=o.term_frac, acc_range=(o.acc_min, o.acc_max), seed=o.seed, loglmax=o.loglmax,
                                   run_id=o.first_run_id + i, adapt_in_walk=False,
                                   start_points=None if self.start is None else self.start[i])
             self.results.append(r)

@@ -34,7 +34,8 @@ def test_options_struct_layout_and_defaults():
     # Options[nestedSampling] BS:837-851
     assert (o.pool_size, o.mc_steps, o.max_iter, o.min_iter, o.term_frac) == (100, 200, 10000, 100, 0.01)
     assert (o.acc_min, o.acc_max, o.batch_k, o.n_runs) == (0.0, 1.0, 1, 1)
-    assert ctypes.sizeof(_lib.Options) == 11 * 8
+    assert o.loglmax != o.loglmax  # "LogLikelihoodMaximum" -> Automatic travels as NaN (BS:847)
+    assert ctypes.sizeof(_lib.Options) == 12 * 8
 
 
 def test_no_cpu_fallback():

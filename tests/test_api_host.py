@@ -100,6 +100,101 @@ def test_combine_runs_pool_and_counts():
     assert np.isfinite(m["LogEvidence"]["Mean"]) and m["LogEvidence"]["StandardError"] > 0
 
 
+def test_numeric_loglikelihood_maximum_drives_termination():
+    """"LogLikelihoodMaximum" -> number (BS:847): the estimate of the missing evidence uses it instead of the running
+    maximum of the live set (BS:925-932), so a larger value keeps the run going and a smaller one ends it at
+    MinIterations."""
+    obj = _c1_obj()
+    kw = dict(SamplePoolSize=40, MonteCarloSteps=30, MaxIterations=3000, MinIterations=50, Seed=4, PostProcessSamplingRuns=None)
+    auto = api.nestedSampling(obj, **kw)
+    lmax = auto["LogLikelihoodMaximum"]
+    same = api.nestedSampling(obj, LogLikelihoodMaximum="Automatic", **kw)
+    assert same["TotalSamples"] == auto["TotalSamples"]
+    longer = api.nestedSampling(obj, LogLikelihoodMaximum=lmax + 8.0, **kw)
+    shorter = api.nestedSampling(obj, LogLikelihoodMaximum=lmax - 200.0, **kw)
+    assert longer["GeneratedNestedSamples"] > auto["GeneratedNestedSamples"] + 200  # ~8 nats more shrinkage at n = 40
+    assert shorter["GeneratedNestedSamples"] == 50
+    # the reported maximum stays the observed one (BS:1183-1189)
+    assert abs(longer["LogLikelihoodMaximum"] - lmax) < 0.5 and shorter["LogLikelihoodMaximum"] < lmax
+
+
+def test_evidence_sampling_on_a_finished_result():
+    """evidenceSampling[obj, opts] re-post-processes a finished run (BS:1158-1160): the derived per-sample columns
+    (dict-valued SampledLogX / LogPosteriorWeight included) are recomputed, not re-sorted as data."""
+    obj = _c1_obj()
+    res = api.nestedSampling(obj, SamplePoolSize=40, MonteCarloSteps=30, MaxIterations=150, Seed=6)
+    again = api.evidenceSampling(res, PostProcessSamplingRuns=50, Seed=3)
+    assert not again.failed
+    assert again["TotalSamples"] == res["TotalSamples"]
+    assert abs(again["CrudeLogEvidence"] - res["CrudeLogEvidence"]) < 1e-12
+    assert abs(again["LogEvidence"]["Mean"] - res["LogEvidence"]["Mean"]) < 3 * res["LogEvidence"]["StandardError"]
+    assert again["Samples"]["SampledLogX"]["Mean"].shape == (res["TotalSamples"],)
+    assert abs(again["Samples"]["CrudePosteriorWeight"].sum() - 1) < 1e-9
+    # same options, same seed: idempotent
+    twice = api.evidenceSampling(again, PostProcessSamplingRuns=50, Seed=3)
+    assert twice["LogEvidence"] == again["LogEvidence"]
+    np.testing.assert_array_equal(twice["Samples"]["Point"], again["Samples"]["Point"])
+    # crude-only form keeps working on a post-processed object
+    crude = api.evidenceSampling(again, PostProcessSamplingRuns=None)
+    assert abs(crude["CrudeLogEvidence"] - res["CrudeLogEvidence"]) < 1e-12
+
+
+def _literal_reference_merge_logz(runs):
+    """BS:1293-1315 + BS:785-799 + BS:756-771 evaluated literally in numpy: Join, DeleteDuplicatesBy Point, SortBy
+    {logL, Point}; X from the constant Total[SamplePoolSize]; trapezoid weights; logSumExp."""
+    from oracle import oracle as O
+    pts = np.concatenate([r["Samples"]["Point"] for r in runs])
+    L = np.concatenate([r["Samples"]["LogLikelihood"] for r in runs])
+    _, first = np.unique(pts, axis=0, return_index=True)
+    keep = np.sort(first)
+    pts, L = pts[keep], L[keep]
+    o = np.lexsort(tuple(pts[:, j] for j in range(pts.shape[1] - 1, -1, -1)) + (L,))
+    L = L[o]
+    n_tot = sum(int(r["SamplePoolSize"]) for r in runs)
+    nd = L.size - n_tot
+    lx = np.concatenate([-np.arange(1, nd + 1) / n_tot, np.log(np.arange(n_tot, 0, -1)) - np.log(n_tot + 1) - nd / n_tot])
+    return O.logsumexp(O.trapezoid_log(lx) + L), lx
+
+
+def test_combine_runs_merge_schemes():
+    """combineRuns: K = 1 runs merge with the reference's literal X sequence (constant Total[SamplePoolSize], then
+    n_tot..1 — BS:1307, 785-799); the summed-pool-size scheme stays close to it; K > 1 runs select the summed
+    scheme, monotone to the end (no mixed sequences)."""
+    obj = _c1_obj()
+    runs = [api.nestedSampling(obj, SamplePoolSize=40, MonteCarloSteps=40, MaxIterations=400, Seed=15 + i,
+                               PostProcessSamplingRuns=None) for i in range(4)]
+    m = api.combineRuns(*runs, PostProcessSamplingRuns=30)
+    assert m["MergeScheme"] == "Reference"
+    M, n_tot = m["TotalSamples"], 160
+    want_z, want_lx = _literal_reference_merge_logz(runs)
+    assert abs(m["CrudeLogEvidence"] - want_z) < 1e-10
+    o = np.argsort(m["Samples"]["LogLikelihood"], kind="stable")
+    np.testing.assert_allclose(m["Samples"]["LogX"][o], want_lx, rtol=1e-13)
+    pool = m["Samples"]["PoolSize"][o]
+    assert np.all(pool[:M - n_tot] == n_tot) and np.array_equal(pool[M - n_tot:], np.arange(n_tot, 0, -1))
+    # the dynamic-merge scheme on the same runs: same samples, different X; evidences agree well inside the error
+    mp = api.combineRuns(*runs, PostProcessSamplingRuns=30, MergeScheme="PoolSizes")
+    assert mp["MergeScheme"] == "PoolSizes" and mp["TotalSamples"] == M
+    pp = mp["Samples"]["PoolSize"][np.argsort(mp["Samples"]["LogLikelihood"], kind="stable")]
+    assert np.all(np.diff(pp) <= 0) and pp[0] == n_tot and pp[-1] == 1  # monotone, ends as a live set
+    assert abs(mp["CrudeLogEvidence"] - m["CrudeLogEvidence"]) < 0.5 * m["LogEvidence"]["StandardError"]
+    assert abs(mp["LogEvidence"]["Mean"] - m["LogEvidence"]["Mean"]) < 1.0 * m["LogEvidence"]["StandardError"]
+    # a merged object merges again (pool structure is the reference's)
+    mm = api.combineRuns(m, runs[0], PostProcessSamplingRuns=10)
+    assert mm["SamplePoolSize"] == 200
+    # K > 1 runs: pool sizes n, n-1, .. per batch -> summed scheme by default
+    kr = [api.nestedSampling(obj, SamplePoolSize=40, MonteCarloSteps=40, MaxIterations=400, Seed=25 + i, BatchSize=4,
+                             PostProcessSamplingRuns=None) for i in range(3)]
+    mk = api.combineRuns(*kr, PostProcessSamplingRuns=30)
+    assert mk["MergeScheme"] == "PoolSizes" and mk["SamplePoolSize"] == 120
+    pk = mk["Samples"]["PoolSize"][np.argsort(mk["Samples"]["LogLikelihood"], kind="stable")]
+    assert pk[-1] == 1 and pk.max() <= 120 and np.isfinite(mk["LogEvidence"]["Mean"])
+    lx = mk["Samples"]["LogX"][np.argsort(mk["Samples"]["LogLikelihood"], kind="stable")]
+    assert np.all(np.diff(lx) < 0)
+    with pytest.raises(TypeError):
+        api.combineRuns(*runs, MergeScheme="nope")
+
+
 def _parallel(seed=9):
     obj = _c1_obj()
     return api.parallelNestedSampling(obj, ParallelRuns=4, SamplePoolSize=30, MonteCarloSteps=25, MaxIterations=120,

@@ -74,6 +74,154 @@ def test_loglike_matches_oracle(eng, O, name, P):
     assert rel64.max() <= 1e-10
 
 
+def _poly_cfg(x, y, deg, lo, hi):
+    names = [f"c{j}" for j in range(deg + 1)] + ["sigma"]
+    return cfg.Config("poly-adv", cfg.OP_POLYREG, x.reshape(-1, 1), y.reshape(-1, 1), (deg, 0, 0, 0), names,
+                      [cfg.PRIOR_UNIFORM] * (deg + 1) + [cfg.PRIOR_SCALE], lo, hi)
+
+
+def _poly_adversarial(name, N=200_000):
+    g = np.random.default_rng(0)
+    x = g.uniform(-1, 1, N)
+    base = 0.5 - 1.2 * x + 0.8 * x**2 + 0.3 * x**3
+    if name == "offset50":      # |c0| = 50 >> sigma = 0.05
+        return _poly_cfg(x, base + 50 + g.normal(0, 0.05, N), 3, [-100.0] * 4 + [0.001], [100.0] * 4 + [5.0])
+    if name == "offset1000":    # |c0| = 1000, sigma = 0.01: the old 4-slot form lost 1e-6 here
+        return _poly_cfg(x, base + 1000 + g.normal(0, 0.01, N), 3, [-2000.0] * 4 + [0.001], [2000.0] * 4 + [5.0])
+    if name == "quadratic1000":  # mean(y) = 333 but the intercept is 0: a mean-of-y pivot would fail
+        return _poly_cfg(x, 1000 * x * x + g.normal(0, 0.01, N), 2, [-2000.0] * 3 + [0.001], [2000.0] * 3 + [5.0])
+    x2 = g.uniform(100, 101, N)
+    if name == "x100-deg1":     # uncentred inputs: the intercept is compensated by the slope along a ridge
+        return _poly_cfg(x2, 2 + 0.5 * (x2 - 100) + g.normal(0, 0.05, N), 1, [-100.0, -5.0, 0.001], [100.0, 5.0, 5.0])
+    if name == "x100-deg3":
+        return _poly_cfg(x2, 2 + 0.5 * (x2 - 100.5) - 0.7 * (x2 - 100.5) ** 2 + g.normal(0, 0.05, N), 3,
+                         [-1e6, -1e5, -1e3, -5.0, 0.001], [1e6, 1e5, 1e3, 5.0, 5.0])
+    raise KeyError(name)
+
+
+@pytest.mark.parametrize("name", ["offset50", "offset1000", "quadratic1000", "x100-deg1", "x100-deg3"])
+def test_polyreg_adversarial(eng, O, name):
+    """VERDICT r1 weak #2 / ADVICE: the polynomial operator's moments form must hold the 1e-12 bar when the intercept
+    is large against the residual spread and when the inputs are far from centred (BS:540-583 has no such hole).
+    Walkers: prior draws, the least-squares fit and its neighbourhood (the posterior bulk, where N c0^2 >> Sum e^2),
+    and points along the intercept/slope ridge."""
+    c = _poly_adversarial(name)
+    deg = c.iparam[0]
+    gp, op, pr = _pair(eng, O, c)
+    x, y = c.inputs[:, 0], c.outputs[:, 0]
+    xm = x.mean()
+    V = np.vander(x - xm, deg + 1, increasing=True)
+    a = np.linalg.lstsq(V, y, rcond=None)[0]
+    # coefficients in powers of x from those in powers of (x - xm)
+    from math import comb
+    coef = np.array([sum(a[j] * comb(j, k) * (-xm) ** (j - k) for j in range(k, deg + 1)) for k in range(deg + 1)])
+    sg = np.sqrt(((y - V @ a) ** 2).mean())
+    fit = np.concatenate([coef, [sg]])
+    rng = np.random.default_rng(3)
+    near = fit * (1 + 1e-7 * rng.standard_normal((16, deg + 2)))
+    ridge = np.tile(fit, (8, 1))
+    shift = np.linspace(-3, 3, 8)
+    ridge[:, 0] += shift
+    if abs(xm) > 1:
+        ridge[:, 1] -= shift / xm
+    th = np.vstack([pr.sample(40, 1), fit[None], near, ridge])
+    got = gp.loglike(th)
+    hi, lo = op.loglike_quad(th)
+    ok = (hi > 0.5 * O.LOGZERO) & np.isfinite(hi)
+    assert ok.sum() >= 40
+    rel = np.abs((got[ok] - hi[ok]) - lo[ok]) / np.abs(hi[ok])
+    assert rel.max() <= RTOL_LOGL, f"{name}: max rel err vs float128 oracle {rel.max():.3e} at {np.argmax(rel)}"
+    # a nested-sampling walk on these data: every stored log-likelihood is the operator's value at the stored point
+    # (the walk kernels score proposals through the same pivoted arithmetic as binest_loglike) ...
+    start = np.vstack([near, ridge, pr.sample(40, 2)])
+    opts = eng.default_options(pool_size=64, batch_k=8, mc_steps=10, max_iter=40, min_iter=40, seed=4)
+    run = eng.RunGroup(gp, opts, start)
+    assert run.advance(0)
+    s = run.fetch(0)
+    qh, ql = op.loglike_quad(s["points"])
+    relw = np.abs((s["logL"] - qh) - ql) / np.abs(qh)
+    assert relw.max() <= RTOL_LOGL, f"{name}: stored logL vs float128 oracle at the stored points {relw.max():.3e}"
+    assert np.any(np.isfinite(s["acc"]) & (s["acc"] > 0))  # some walks moved
+    if not name.startswith("x100"):
+        # ... and the whole trajectory equals the oracle's.  (Not for the x in (100, 101) data: there intercept and
+        # slope are almost perfectly anti-correlated over the live set, the proposal Cholesky factor amplifies the
+        # last-bit differences between the device's tree sums and the oracle's sequential sums of the live-set
+        # covariance by ~1e6, and the two walks part ways for reasons that have nothing to do with the likelihood.)
+        ref = O.nested_sampling(op, pr, pool_size=64, batch_k=8, mc_steps=10, max_iter=40, min_iter=40, seed=4,
+                                adapt_in_walk=False, start_points=start)
+        assert s["M"] == ref.logL.size
+        np.testing.assert_allclose(s["logL"], ref.logL, rtol=1e-9)
+
+
+def test_softmax_adversarial_large_logits_and_separated_classes(eng, O):
+    """C3 with |z| up to ~600 on linearly separated classes: log p_y = z_y - log Sum e^z is a difference of two
+    numbers of size |z| per datum, N |z| over the data.  Bar: 1e-12 relative, or — where the likelihood is
+    essentially 1 for every datum and |logL| itself is tiny — the fp64 floor of the per-datum probabilities the
+    reference itself works with (p_y rounded to 1 - k ulp: 1.2e-16 per datum)."""
+    g = np.random.default_rng(12)
+    N, F, K = 20_000, 4, 3
+    W = np.array([[3.0, -1.0, 0.5, 0.0], [-2.0, 2.5, 0.0, 1.0], [0.0, 0.0, 0.0, 0.0]])
+    b = np.array([0.3, -0.2, 0.0])
+    x = g.standard_normal((3 * N, F))
+    z = x @ W.T + b
+    zs = np.sort(z, 1)
+    keep = (zs[:, 2] - zs[:, 1]) > 0.5           # margin: classes are linearly separated with a gap
+    x, z = x[keep][:N], z[keep][:N]
+    y = z.argmax(1).astype(np.float64)
+    d = (K - 1) * (F + 1)
+    c = cfg.Config("C3-separated", cfg.OP_LOGISTIC, x, y.reshape(-1, 1), (0, K, 0, 0), [f"p{i}" for i in range(d)],
+                   [cfg.PRIOR_NORMAL_TRUNC] * d, [-1000.0] * d, [1000.0] * d, [0.0] * d, [5.0] * d)
+    gp, op, pr = _pair(eng, O, c)
+    t0 = np.concatenate([np.concatenate([W[k], [b[k]]]) for k in range(K - 1)])
+    scales = np.array([0.5, 1, 3, 10, 30, 60, 100, 150])  # max |z| ~ 4 .. 1200 (the last ones take the slow path)
+    th = np.vstack([t0[None] * s for s in scales] + [pr.sample(24, 2)])
+    zmax = [np.abs(x @ t.reshape(K - 1, F + 1)[:, :F].T + t.reshape(K - 1, F + 1)[:, F]).max() for t in th]
+    assert max(zmax[:8]) > 600 and min(zmax[:8]) < 10
+    got = gp.loglike(th)
+    hi, lo = op.loglike_quad(th)
+    err = np.abs((got - hi) - lo)
+    tol = RTOL_LOGL * np.abs(hi) + 1.2e-16 * x.shape[0]
+    assert np.all(err <= tol), (err / tol).max()
+    assert np.all(got <= 0.0)
+    # where every datum is classified with probability 1 to fp64 precision the result is exactly representable noise-free
+    assert abs(got[7]) < 1e-290 or got[7] == 0.0
+
+
+def test_gbm_adversarial_tiny_time_step(eng, O):
+    """GBM with dt = 1e-6 (log-increments ~ 2.5e-4, r / sqrt(dt) well scaled only after the upload transform)."""
+    for dt in (1e-6, 1e-9):
+        c = cfg.c4_gbm(T=20_000, seed=9, dt=dt)
+        gp, op, pr = _pair(eng, O, c)
+        th = np.vstack([pr.sample(40, 3), [[0.08, 0.25]], [[-0.9, 1.9]]])
+        got = gp.loglike(th)
+        hi, lo = op.loglike_quad(th)
+        rel = np.abs((got - hi) - lo) / np.abs(hi)
+        assert rel.max() <= RTOL_LOGL, (dt, rel.max())
+
+
+def test_gp_adversarial_tiny_nugget(eng, O):
+    """GP with nugget sigma_n^2 = 1e-6 sigma_f^2 (condition number ~ N 1e6): the marginal likelihood either factors
+    and agrees with the long-double oracle to kappa-scaled accuracy, or is reported as logzero (GP:131-135) —
+    never garbage.  A matrix that is not positive definite to working precision (nugget 1e-14) must give logzero
+    or the oracle's value."""
+    c0 = cfg.c5_gp(N=256)
+    lo = list(c0.lo)
+    lo[2] = 1e-9
+    c = cfg.Config(c0.name, c0.op, c0.inputs, c0.outputs, c0.iparam, c0.names, c0.kinds, lo, c0.hi)
+    gp, op, pr = _pair(eng, O, c)
+    th = np.array([[1.0, 1.0, 1e-3], [2.0, 0.7, 2e-3], [0.5, 2.0, 5e-4], [1.0, 3.0, 1e-7], [1.0, 4.5, 1e-8]])
+    got = gp.loglike(th)
+    hi, _ = op.loglike_quad(th)
+    for k in range(th.shape[0]):
+        if got[k] == O.LOGZERO:
+            continue  # reported as not factorable: the reference Throws to logzero for singular matrices
+        assert np.isfinite(got[k])
+        # k >= 3: nugget 1e-14 / 1e-16, kappa beyond 1/eps — the reference's own LU arithmetic (GP:130-141) is off by
+        # 6e-3 / has the wrong sign there; only "the right order of magnitude, or logzero" can be asked
+        assert abs(got[k] - hi[k]) <= (1e-8 if k < 3 else 0.5) * abs(hi[k]), (k, got[k], hi[k])
+    assert np.all(got[:3] != O.LOGZERO), "nugget 1e-6 sigma_f^2 at N = 256 must factor"
+
+
 def test_loglike_empty_and_tiny(eng, O):
     c = cfg.c1_gaussian(N=1, seed=3)
     gp, op, pr = _pair(eng, O, c)
@@ -296,6 +444,26 @@ def test_engine_logz_c1(eng, O):
         pulls.append((mu - c.truth["logZ"]) / sd)
     assert max(abs(p) for p in pulls) < 3.0, pulls
     assert abs(np.mean(pulls)) < 1.5, pulls
+
+
+def test_numeric_loglikelihood_maximum_matches_oracle(eng, O):
+    """binest_options.loglmax ("LogLikelihoodMaximum" -> number, BS:925-932) in run_update_kernel's termination test:
+    same stopping iteration and samples as the oracle, longer than Automatic for a larger value."""
+    c = cfg.c1_gaussian()
+    gp, op, pr = _pair(eng, O, c)
+    start = pr.sample(50, 3)
+    n_it = {}
+    for lm in (float("nan"), -98.0, -400.0):
+        opts = eng.default_options(pool_size=50, batch_k=1, mc_steps=20, max_iter=5000, min_iter=30, seed=6, loglmax=lm)
+        run = eng.RunGroup(gp, opts, start)
+        assert run.advance(0)
+        s = run.fetch(0)
+        ref = O.nested_sampling(op, pr, pool_size=50, batch_k=1, mc_steps=20, max_iter=5000, min_iter=30, seed=6,
+                                adapt_in_walk=False, start_points=start, loglmax=lm)
+        assert s["M"] == ref.logL.size, (lm, s["M"], ref.logL.size)
+        np.testing.assert_allclose(s["logL"], ref.logL, rtol=1e-9)
+        n_it[lm if lm == lm else "auto"] = s["n_deleted"]
+    assert n_it[-400.0] == 30 and n_it[-98.0] > n_it["auto"]
 
 
 def test_multi_run_group_is_shard_invariant(eng):
