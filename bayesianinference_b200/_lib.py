@@ -74,6 +74,8 @@ SIGNATURES = {
     "binest_comm_info": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "binest_comm_free": (C.c_int, [_vp]),
     "binest_problem_shard": (C.c_int, [_vp, _vp]),
+    "binest_problem_shard_batch": (C.c_int, [_vp, _vp]),
+    "binest_comm_stats": (C.c_int, [_vp, _ip, _ip, C.POINTER(C.c_int)]),
 }
 COMM_ID_BYTES = 128
 

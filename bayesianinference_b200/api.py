@@ -208,7 +208,9 @@ def defineInferenceProblem(rules=None, _backend_override=None, **kw):
 
     Extra key "DataSharding" (no reference counterpart; SURVEY §8e "very large N"): None (default), a backend Comm,
     or "Automatic" = one shard per torch.distributed rank.  Every rank passes the full "Data"; only its row block
-    is uploaded, and "LogLikelihoodFunction" / nestedSampling become collectives that all ranks must call alike."""
+    is uploaded, and "LogLikelihoodFunction" / nestedSampling become collectives that all ranks must call alike.
+    The GP operator is batch-sharded instead (§8e row 2): the data stay replicated and every batch of parameter
+    vectors is split across the ranks."""
     a = dict(rules or {})
     a.update(kw)
     try:
@@ -231,7 +233,7 @@ def defineInferenceProblem(rules=None, _backend_override=None, **kw):
                 comm = be.Comm(dist.get_rank(), dist.get_world_size())
         extra = {} if comm is None else {"comm": comm}
         if comm is not None and op == _cfg.OP_GP_SE:
-            raise DefinitionError("defineInferenceProblem::logLike: the GP operator does not shard by rows")
+            extra["shard"] = "batch"  # a covariance matrix does not shard by rows: the theta batch is split instead
         prob = be.Problem(op, inputs, outputs, iparam, kinds, [p[1] for p in params], [p[2] for p in params], p0, p1,
                           **extra)
         a["DataSharding"] = comm
@@ -910,23 +912,37 @@ def parallelNestedSampling(obj, _backend_override=None, **opts):
             rank, world = dist.get_rank(), dist.get_world_size()
     except ImportError:
         pass
+    import time as _time
+    tm = {}
+    t0 = _time.perf_counter()
     first, count = _shard(R, rank, world)
     local = []
     if count > 0:
         grp = be.RunGroup(a["_problem"], _engine_options(be, o, n_runs=count, first_run_id=first), None)
         grp.advance(0)
+        tm["device_loop_s"] = _time.perf_counter() - t0
+        t1 = _time.perf_counter()
         local = [(first + i, grp.fetch(i)) for i in range(count)]
         grp.close()
+        tm["fetch_s"] = _time.perf_counter() - t1
+    t1 = _time.perf_counter()
     if dist is not None and world > 1:
         gathered = [None] * world
         dist.all_gather_object(gathered, local)  # host merge only: no collective on the data path
         local = [x for part in gathered for x in part]
+    tm["gather_s"] = _time.perf_counter() - t1
     local.sort(key=lambda t: t[0])
     n = int(o["SamplePoolSize"])
+    t1 = _time.perf_counter()
     runs = []
     for _, s in local:
         ra = dict(a)
         ra.update(_result_assoc(s, n))
         runs.append(inferenceObject(ra))
-    return combineRuns(*runs, _backend_override=be, PostProcessSamplingRuns=o["PostProcessSamplingRuns"],
-                       EmpiricalPosteriorDistributionType=o["EmpiricalPosteriorDistributionType"], Seed=o["Seed"])
+    res = combineRuns(*runs, _backend_override=be, PostProcessSamplingRuns=o["PostProcessSamplingRuns"],
+                      EmpiricalPosteriorDistributionType=o["EmpiricalPosteriorDistributionType"], Seed=o["Seed"])
+    tm["combine_and_evidence_s"] = _time.perf_counter() - t1
+    tm["total_s"] = _time.perf_counter() - t0
+    if inferenceObjectQ(res):
+        res._assoc["_Timing"] = tm  # wall-clock phases of this call on this rank (bench.py; keys() hides "_" entries)
+    return res

@@ -453,6 +453,8 @@ int binest_loglike(binest_problem *p, const double *theta, int64_t P, double *ou
         loglike_device(*p, p->s_theta.p, (int)P, Ps, p->s_out.p);
         BN_CUDA(cudaMemcpyAsync(out, p->s_out.p, sizeof(double) * P, cudaMemcpyDeviceToHost, p->stream));
         BN_CUDA(cudaStreamSynchronize(p->stream));
+        if (p->comm) comm_check_abort(*p->comm, p->stream);
+        if (p->comm_batch) comm_check_abort(*p->comm_batch, p->stream);
     });
 }
 

@@ -1,19 +1,23 @@
-// comm.cu — data-sharded mode (third row): the data rows are split across the GPUs of one box, every
-// rank evaluates the same proposals on its own rows, and the per-walker partial sums are exchanged once per
-// likelihood launch.  This is the only place the library talks to another GPU; run-sharded jobs
-// (parallelNestedSampling, BS:1349-1357) never come here.
+// comm.cu — the sharded modes: data-sharded (rows split across the GPUs of one box, every rank evaluates
+// the same proposals on its own rows, the per-walker partial sums are exchanged once per likelihood launch) and
+// batch-sharded (GP: the theta batch is split, the finished log-likelihoods are exchanged).  This is the only place the
+// library talks to another GPU; run-sharded jobs (parallelNestedSampling, BS:1349-1357) never come here.
 //
-// NCCL is bound at run time (dlopen of libnccl.so.2 — the copy torch has already loaded when the host is Python, the
-// system one otherwise), so libbinest.so itself has no link-time dependency on it and single-GPU users never load it.
-// The exchange is an all-gather of 8 P bytes per rank followed by a fixed-order sum on every rank
-// (problem.cuh: shard_exchange): latency-bound, NVLink/NVSwitch carries it in one hop.
+// The per-step exchange runs INSIDE our kernels over peer-mapped memory (xchg.cuh): binest_comm_create allocates a
+// receive buffer and a flag line per rank with cudaMalloc, passes their CUDA IPC handles around, and every rank maps
+// every peer's buffer (cudaIpcOpenMemHandle -> P2P over NVLink 5 / NVSwitch).  NCCL carries the set-up traffic (IPC
+// handles, data constants) and remains as the fallback exchange (BINEST_XCHG=nccl, or when peer mapping fails): bound
+// at run time (dlopen of libnccl.so.2 — the copy torch has already loaded when the host is Python, the system one
+// otherwise), so libbinest.so has no link-time dependency on it and single-GPU users never load it.
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <memory>
 #include <mutex>
+#include <vector>
 
 #include "problem.cuh"
 
@@ -60,6 +64,73 @@ void nccl_check(ncclResult_t r, const char *what) {
 
 }  // namespace
 
+// Peer-mapped exchange buffers (xchg.cuh).  Collective.  Any failure on any rank (no P2P between the devices, IPC not
+// permitted in the container, BINEST_XCHG=nccl) leaves EVERY rank on the NCCL fallback: the outcome is agreed with one
+// more all-gather, so the ranks never disagree about the path.
+void setup_peer_exchange(binest_comm &c) {
+    struct Blob { cudaIpcMemHandle_t buf, flag; int ok; int pad[3]; };
+    static_assert(sizeof(Blob) % 8 == 0, "blob travels as doubles");
+    const int W = c.world;
+    BN_REQUIRE(W <= kXchgMaxWorld, BINEST_ERR_DIMENSION, "sharded modes support up to 8 ranks (one box)");
+    const char *e = std::getenv("BINEST_XCHG");
+    bool want = !(e && std::strcmp(e, "nccl") == 0);
+    Blob mine;
+    std::memset(&mine, 0, sizeof(mine));
+    const size_t buf_bytes = sizeof(double) * 2 * (size_t)W * kXchgSlotDoubles;
+    const size_t flag_bytes = sizeof(unsigned) * (size_t)W * kXchgFlagStride;
+    if (want) {
+        want = cudaMalloc((void **)&c.xbuf_local, buf_bytes) == cudaSuccess &&
+               cudaMalloc((void **)&c.xflag_local, flag_bytes) == cudaSuccess &&
+               cudaMalloc((void **)&c.xst, sizeof(XchgState)) == cudaSuccess &&
+               cudaMalloc((void **)&c.xd_dev, sizeof(XchgDev)) == cudaSuccess &&
+               cudaMemset(c.xbuf_local, 0, buf_bytes) == cudaSuccess &&
+               cudaMemset(c.xflag_local, 0, flag_bytes) == cudaSuccess &&
+               cudaMemset(c.xst, 0, sizeof(XchgState)) == cudaSuccess &&
+               cudaIpcGetMemHandle(&mine.buf, c.xbuf_local) == cudaSuccess &&
+               cudaIpcGetMemHandle(&mine.flag, c.xflag_local) == cudaSuccess;
+        cudaGetLastError();
+    }
+    mine.ok = want ? 1 : 0;
+    auto gather = [&](const Blob &in, std::vector<Blob> &all) {
+        constexpr size_t ND = sizeof(Blob) / sizeof(double);
+        DevBuf<double> send(ND), recv(ND * W);
+        BN_CUDA(cudaMemcpy(send.p, &in, sizeof(Blob), cudaMemcpyHostToDevice));
+        nccl_check(nccl().AllGather(send.p, recv.p, ND, ncclFloat64, (ncclComm_t)c.nccl, (cudaStream_t)0), "ncclAllGather");
+        all.resize(W);
+        BN_CUDA(cudaMemcpy(all.data(), recv.p, sizeof(Blob) * W, cudaMemcpyDeviceToHost));
+    };
+    std::vector<Blob> all;
+    gather(mine, all);
+    bool ok = true;
+    for (int r = 0; r < W; ++r) ok = ok && all[r].ok;
+    XchgDev xd;
+    std::memset(&xd, 0, sizeof(xd));
+    xd.rank = c.rank; xd.world = W; xd.st = c.xst;
+    for (int r = 0; r < W && ok; ++r) {
+        if (r == c.rank) { xd.buf[r] = c.xbuf_local; xd.flag[r] = c.xflag_local; continue; }
+        void *pb = nullptr, *pf = nullptr;
+        ok = cudaIpcOpenMemHandle(&pb, all[r].buf, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess &&
+             cudaIpcOpenMemHandle(&pf, all[r].flag, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+        cudaGetLastError();
+        xd.buf[r] = (double *)pb; xd.flag[r] = (unsigned *)pf;
+    }
+    // second round: every rank reports whether ITS mappings succeeded; the peer path is used only if all did.  The
+    // collective also orders every rank's memset before anybody's first push.
+    Blob st2;
+    std::memset(&st2, 0, sizeof(st2));
+    st2.ok = ok ? 1 : 0;
+    gather(st2, all);
+    bool all_ok = true;
+    for (int r = 0; r < W; ++r) all_ok = all_ok && all[r].ok;
+    c.xd = xd;
+    c.peer = all_ok;
+    if (all_ok) {
+        BN_CUDA(cudaMemcpy(c.xd_dev, &xd, sizeof(xd), cudaMemcpyHostToDevice));
+        BN_CUDA(cudaHostAlloc((void **)&c.h_abort, sizeof(unsigned), cudaHostAllocDefault));
+        *c.h_abort = 0;
+    }
+}
+
 void comm_allgather_f64(binest_comm &c, const double *send, double *recv, size_t count, cudaStream_t s) {
     nccl_check(nccl().AllGather(send, recv, count, ncclFloat64, (ncclComm_t)c.nccl, s), "ncclAllGather");
     count_launch();
@@ -95,6 +166,7 @@ int binest_comm_create(int rank, int world, const uint8_t *id, binest_comm **out
         ncclComm_t comm = nullptr;
         nccl_check(nccl().CommInitRank(&comm, world, u, rank), "ncclCommInitRank");
         c->nccl = comm;
+        setup_peer_exchange(*c);
         *out = c.release();
     });
 }
@@ -102,12 +174,37 @@ int binest_comm_create(int rank, int world, const uint8_t *id, binest_comm **out
 int binest_comm_free(binest_comm *c) {
     return guard([&] {
         if (!c) return;
-        if (c->nccl) {
-            cudaSetDevice(c->device);
+        cudaSetDevice(c->device);
+        cudaDeviceSynchronize();
+        if (c->nccl && c->peer) {  // nobody unmaps while a peer may still push: one last collective as a barrier
+            DevBuf<double> a(1), b((size_t)c->world);
+            a.zero();
+            nccl().AllGather(a.p, b.p, 1, ncclFloat64, (ncclComm_t)c->nccl, (cudaStream_t)0);
             cudaDeviceSynchronize();
-            nccl().CommDestroy((ncclComm_t)c->nccl);
         }
+        for (int r = 0; r < c->world && c->peer; ++r) {
+            if (r == c->rank) continue;
+            if (c->xd.buf[r]) cudaIpcCloseMemHandle(c->xd.buf[r]);
+            if (c->xd.flag[r]) cudaIpcCloseMemHandle(c->xd.flag[r]);
+        }
+        if (c->xbuf_local) cudaFree(c->xbuf_local);
+        if (c->xflag_local) cudaFree(c->xflag_local);
+        if (c->xst) cudaFree(c->xst);
+        if (c->xd_dev) cudaFree(c->xd_dev);
+        if (c->h_abort) cudaFreeHost(c->h_abort);
+        if (c->nccl) nccl().CommDestroy((ncclComm_t)c->nccl);
         delete c;
+    });
+}
+
+// traffic counters of the sharded exchange (bench.py): exchanges issued, payload bytes this rank pushed to its peers,
+// and whether the in-kernel peer path (1) or the NCCL fallback (0) is in use
+int binest_comm_stats(const binest_comm *c, int64_t *exchanges, int64_t *bytes_pushed, int *peer_path) {
+    return guard([&] {
+        BN_REQUIRE(c, BINEST_ERR_TYPE, "null argument");
+        if (exchanges) *exchanges = c->exchanges;
+        if (bytes_pushed) *bytes_pushed = c->bytes_pushed;
+        if (peer_path) *peer_path = c->peer ? 1 : 0;
     });
 }
 
@@ -138,6 +235,20 @@ int binest_problem_shard(binest_problem *p, binest_comm *c) {
         p->cst_total = p->cst;
         p->cst_total.c = (double)tot[1];
         p->comm = c;
+    });
+}
+
+// Collective: from now on the GP problem `p` (data replicated on every rank) evaluates every theta batch in slices,
+// one per rank (gp.cu: gp_loglike_device_strided).  binest_loglike / binest_run_* become collectives: all ranks must
+// make the same calls with the same theta / options / seed.
+int binest_problem_shard_batch(binest_problem *p, binest_comm *c) {
+    return guard([&] {
+        BN_REQUIRE(p && c, BINEST_ERR_TYPE, "null argument");
+        BN_REQUIRE(p->op == BINEST_OP_GP_SE, BINEST_ERR_FUNCTION,
+                   "batch sharding is the GP operator's mode; the streaming operators shard by rows (binest_problem_shard)");
+        BN_REQUIRE(p->device == c->device, BINEST_ERR_CUDA, "problem and communicator live on different devices");
+        BN_REQUIRE(!p->comm, BINEST_ERR_FUNCTION, "problem is already data-sharded");
+        p->comm_batch = c;
     });
 }
 

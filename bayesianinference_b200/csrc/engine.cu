@@ -50,6 +50,7 @@ struct binest_run {
     cudaStream_t stream = nullptr;
     cudaGraphExec_t walk_graph = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int64_t graph_exchanges = 0, graph_bytes = 0, graph_launches = 0;  // per launch of the sharded walk graph
     double walk_ms = 0.0;   // device time spent in walk graphs (CUDA events on the run's stream)
     int64_t walk_graphs = 0;
     RunState *h_state = nullptr;  // pinned mirror
@@ -215,6 +216,31 @@ void launch_grid_walk(binest_run &r, const RunParams &q) {
     BN_CUDA(cudaMemcpyAsync(r.h_abort, &r.gsync.p->abort, sizeof(unsigned), cudaMemcpyDeviceToHost, r.stream));
 }
 
+// [walk_step, loglike_stream (, shard exchange)] x S + the final accept, enqueued on the run's stream (directly, or
+// under stream capture).  Data-sharded: every rank walks the same chains (same Philox counters) on its own rows; after
+// each likelihood launch the per-rank sums are exchanged (problem.cuh: shard_exchange — in-kernel pushes over
+// peer-mapped memory, or ncclAllGather on the fallback) and combined in rank order by the next walk_step.
+void stepped_walk(binest_run &r, const RunParams &q) {
+    binest_problem &p = *r.prob;
+    const int P = q.R * q.K;
+    const dim3 sgrid((P * 32 + 255) / 256), sblock(256);
+    dispatch_op(p, [&](auto op) {
+        using OP = decltype(op);
+        PartialView pv = p.comm ? PartialView{p.sh_recv.p, p.comm->world, 1, q.Ps, 1}
+                                : PartialView{r.partials.p, r.geom.G, r.geom.Gs, 1};
+        const XchgDev *xd = (p.comm && p.comm->peer) ? p.comm->xd_dev : nullptr;
+        for (int step = 0; step <= q.S; ++step) {
+            walk_step_kernel<OP><<<sgrid, sblock, 0, r.stream>>>(q, r.A, p.prior, pv, p.rows_eff(), p.cst_eff(),
+                                                                step == q.S ? 1 : 0, xd, step == 0 ? 1 : 0);
+            BN_LAUNCH_CHECK();
+            if (step < q.S) {
+                launch_loglike<OP>(p, r.w_prop.p, P, q.Ps, r.partials.p, r.geom, r.stream);
+                if (p.comm) pv = shard_exchange<OP>(p, r.partials.p, r.w_prop.p, P, q.Ps, r.geom, r.stream);
+            }
+        }
+    });
+}
+
 // the S-step walk as one CUDA graph: [walk_step, loglike_stream] x S, then the final accept
 void build_walk_graph(binest_run &r) {
     binest_problem &p = *r.prob;
@@ -230,8 +256,24 @@ void build_walk_graph(binest_run &r) {
         using OP = decltype(op);
         r.geom = stream_geom<OP>(p, P);
         r.partials.alloc((size_t)r.geom.Gs * r.prm.Ps);
-        // data-sharded: stepped directly (the per-step all-gather is a NCCL call), see walk_block()
-        if (p.comm) return;
+        // data-sharded on the peer path: the whole S-step walk incl. the in-kernel exchanges is ONE graph
+        // (3 S + 1 nodes); on the NCCL fallback it is stepped directly, see walk_block()
+        if (p.comm) {
+            if (!p.comm->peer || std::getenv("BINEST_NO_SHARD_GRAPH")) return;
+            BN_REQUIRE(r.prm.Ps <= kXchgSlotDoubles, BINEST_ERR_DIMENSION, "too many walkers for the sharded exchange buffer");
+            const int64_t ex0 = p.comm->exchanges, by0 = p.comm->bytes_pushed, l0 = g_launches.load();
+            BN_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+            stepped_walk(r, r.prm);
+            cudaGraph_t g;
+            BN_CUDA(cudaStreamEndCapture(s, &g));
+            BN_CUDA(cudaGraphInstantiate(&r.walk_graph, g, 0));
+            cudaGraphDestroy(g);
+            r.graph_exchanges = p.comm->exchanges - ex0;
+            r.graph_bytes = p.comm->bytes_pushed - by0;
+            r.graph_launches = g_launches.load() - l0;
+            p.comm->exchanges = ex0; p.comm->bytes_pushed = by0; g_launches.store(l0);  // capture enqueued nothing
+            return;
+        }
         // small data: the resident cluster kernel replaces the per-step graph (walk_resident.cuh)
         if (std::getenv("BINEST_NO_RESIDENT") == nullptr) {
             const size_t budget = 200 * 1024;
@@ -267,7 +309,9 @@ void build_walk_graph(binest_run &r) {
             int fin = step == S ? 1 : 0;
             double rows = (double)p.rows;
             OpCst cst = p.cst;
-            BN_CUDA(cudaLaunchKernelEx(&lc.cfg, walk_step_kernel<OP>, r.prm, r.A, p.prior, pv, rows, cst, fin));
+            const XchgDev *xd = nullptr;
+            int first = step == 0 ? 1 : 0;
+            BN_CUDA(cudaLaunchKernelEx(&lc.cfg, walk_step_kernel<OP>, r.prm, r.A, p.prior, pv, rows, cst, fin, xd, first));
             if (step < S) launch_loglike<OP>(p, r.w_prop.p, P, r.prm.Ps, r.partials.p, r.geom, s, false, pdl);
         }
         cudaGraph_t g;
@@ -321,28 +365,19 @@ void walk_block(binest_run &r, const RunParams &q) {
         }
         return;
     }
-    if (!p.comm && q.attempt == 0 && r.walk_graph) {
+    if (q.attempt == 0 && q.S == r.prm.S && r.walk_graph) {
         BN_CUDA(cudaGraphLaunch(r.walk_graph, r.stream));
-        count_launch(2 * (int)q.S + 1);
+        if (p.comm) {
+            p.comm->exchanges += r.graph_exchanges;
+            p.comm->bytes_pushed += r.graph_bytes;
+            count_launch((int)r.graph_launches);
+        } else {
+            count_launch(2 * (int)q.S + 1);
+        }
         return;
     }
-    // stepped directly: data-sharded (every rank walks the same chains (same Philox counters) on its own rows; after
-    // each likelihood launch the per-rank sums are all-gathered and combined in rank order, shard_exchange), and the
-    // retry rounds of the graph path
-    dispatch_op(p, [&](auto op) {
-        using OP = decltype(op);
-        PartialView pv = p.comm ? PartialView{p.sh_recv.p, p.comm->world, 1, q.Ps, 1}
-                                : PartialView{r.partials.p, r.geom.G, r.geom.Gs, 1};
-        for (int step = 0; step <= q.S; ++step) {
-            walk_step_kernel<OP><<<sgrid, sblock, 0, r.stream>>>(q, r.A, p.prior, pv, p.rows_eff(), p.cst_eff(),
-                                                                step == q.S ? 1 : 0);
-            BN_LAUNCH_CHECK();
-            if (step < q.S) {
-                launch_loglike<OP>(p, r.w_prop.p, P, q.Ps, r.partials.p, r.geom, r.stream);
-                if (p.comm) pv = shard_exchange<OP>(p, r.partials.p, r.w_prop.p, P, q.Ps, r.geom, r.stream);
-            }
-        }
-    });
+    // stepped directly: the retry rounds of the graph path, and the data-sharded mode on the NCCL fallback
+    stepped_walk(r, q);
 }
 
 void launch_update(binest_run &r, bool insert_only = false) {
@@ -488,6 +523,8 @@ int binest_run_advance(binest_run *r, int64_t max_batches, int32_t *finished) {
                     r->walk_graphs += 1;
                     BN_REQUIRE(!(r->grid && *r->h_abort), BINEST_ERR_CUDA,
                                "walk_grid_kernel: grid barrier timed out (walk aborted)");
+                    if (r->prob->comm) comm_check_abort(*r->prob->comm, r->stream);
+                    if (r->prob->comm_batch) comm_check_abort(*r->prob->comm_batch, r->stream);
                     r->evals += (int64_t)qq.S * (int64_t)(blocks == 0 ? unfrozen0 : *r->h_unfrozen);
                     ++blocks;
                     if (!acc_loop) break;

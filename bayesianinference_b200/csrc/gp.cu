@@ -727,19 +727,60 @@ void gp_factor_chunk(binest_problem &p, const GpBatch &g, const double *theta_de
 
 }  // namespace
 
-// theta_dev SoA [3][Ps]; out_dev[(w) * out_stride]
-void gp_loglike_device_strided(binest_problem &p, const double *theta_dev, int P, int Ps, double *out_dev,
-                               int out_stride, bool check_box) {
+// out[k * stride] = in[k], k < total (NCCL fallback of the batch-sharded gather)
+static __global__ void gp_scatter_kernel(const double *__restrict__ in, int total, double *__restrict__ out, int stride) {
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) out[(size_t)k * stride] = in[k];
+}
+
+// matrices [lo, hi) of the batch: fill + factor + finish, results at out_dev[(w) * out_stride]
+static void gp_loglike_range(binest_problem &p, const double *theta_dev, int lo, int hi, int Ps, double *out_dev,
+                             int out_stride, bool check_box) {
     const int N = (int)p.gp_n, Np = (N + NB - 1) / NB * NB;
+    if (hi <= lo) return;
     GpWorkspace &ws = g_ws;
-    ws.ensure(std::min<int>(P, 512), Np, Np);
+    ws.ensure(std::min<int>(hi - lo, 512), Np, Np);
     cudaStream_t s = p.stream;
-    for (int b0 = 0; b0 < P; b0 += ws.cap) {
-        const int B = std::min(ws.cap, P - b0);
+    for (int b0 = lo; b0 < hi; b0 += ws.cap) {
+        const int B = std::min(ws.cap, hi - b0);
         GpBatch g{ws.A.p, ws.Y.p, ws.Z.p, ws.L.p, ws.Ld.p, ws.Qd.p, ws.F.p, Np, N, B, Np, 0, nullptr, nullptr};
         gp_factor_chunk(p, g, theta_dev, Ps, b0);
         gp_finish_kernel<<<(B + 127) / 128, 128, 0, s>>>(g, theta_dev, Ps, b0, p.prior, g_logzero, check_box ? 1 : 0,
                                                          out_dev, out_stride);
+        BN_LAUNCH_CHECK();
+    }
+}
+
+// theta_dev SoA [3][Ps]; out_dev[(w) * out_stride].
+// Batch-sharded mode (binest_problem_shard_batch): the P parameter vectors are split into `world`
+// contiguous slices of cnt = ceil(P / world); this rank fills and factors only its own (the data are replicated), and
+// the cnt finished log-likelihoods of every rank are exchanged — pushed into all peers' receive buffers by
+// xchg_push_kernel and scattered by xchg_gather_kernel (xchg.cuh; 8 cnt bytes to each peer), or ncclAllGather on the
+// fallback.  All ranks end with the same P values, so a GP walk takes identical decisions everywhere.
+void gp_loglike_device_strided(binest_problem &p, const double *theta_dev, int P, int Ps, double *out_dev,
+                               int out_stride, bool check_box) {
+    binest_comm *c = p.comm_batch;
+    if (c == nullptr || c->world == 1) {
+        gp_loglike_range(p, theta_dev, 0, P, Ps, out_dev, out_stride, check_box);
+        return;
+    }
+    const int W = c->world, cnt = (P + W - 1) / W;
+    const int lo = std::min(P, c->rank * cnt), hi = std::min(P, lo + cnt);
+    cudaStream_t s = p.stream;
+    if (p.sh_send.n < (size_t)cnt) p.sh_send.alloc(cnt);
+    BN_CUDA(cudaMemsetAsync(p.sh_send.p, 0, sizeof(double) * cnt, s));
+    gp_loglike_range(p, theta_dev, lo, hi, Ps, p.sh_send.p - lo, 1, check_box);
+    c->exchanges += 1;
+    c->bytes_pushed += (int64_t)8 * cnt * (W - 1);
+    if (c->peer) {
+        BN_REQUIRE(cnt <= kXchgSlotDoubles, BINEST_ERR_DIMENSION, "batch too large for the sharded exchange buffer");
+        xchg_push_kernel<<<std::max(1, std::min(32, (cnt + 255) / 256)), 256, 0, s>>>(c->xd, p.sh_send.p, cnt);
+        BN_LAUNCH_CHECK();
+        xchg_gather_kernel<<<std::max(1, std::min(32, (P + 255) / 256)), 256, 0, s>>>(c->xd, cnt, P, out_dev, out_stride);
+        BN_LAUNCH_CHECK();
+    } else {
+        if (p.sh_recv.n < (size_t)cnt * W) p.sh_recv.alloc((size_t)cnt * W);
+        comm_allgather_f64(*c, p.sh_send.p, p.sh_recv.p, (size_t)cnt, s);
+        gp_scatter_kernel<<<std::max(1, std::min(32, (P + 255) / 256)), 256, 0, s>>>(p.sh_recv.p, P, out_dev, out_stride);
         BN_LAUNCH_CHECK();
     }
 }

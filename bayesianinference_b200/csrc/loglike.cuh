@@ -13,6 +13,7 @@
 // The fp64 pipe — not HBM/L2 — is the bound when P >= ~11 walkers share a tile.
 #pragma once
 #include "operators.cuh"
+#include "xchg.cuh"
 
 namespace binest {
 
@@ -147,6 +148,19 @@ struct PartialView {
     int localized = 0;
 };
 
+// Consumer side of the in-kernel sharded exchange (xchg.cuh): the first thread of the CTA waits for the flags of the
+// exchange the preceding producer kernel published, then every thread points the view at this rank's receive slot.
+// xd == nullptr: nothing to do (single GPU, or the NCCL fallback whose view already points at the gathered buffer).
+__device__ __forceinline__ bool resolve_exchange(PartialView &pv, const XchgDev *xd) {
+    if (xd == nullptr) return true;
+    __shared__ int s_ok;
+    const unsigned t = xd->st->step;
+    if (threadIdx.x == 0) s_ok = xchg_wait(*xd, t) ? 1 : 0;
+    __syncthreads();
+    pv.p = xd->buf[xd->rank] + xd->slot(t, 0);
+    return s_ok != 0;
+}
+
 // fixed-order combine of the partials of one walker by one warp (all lanes get the sum)
 __device__ __forceinline__ double combine_partials_warp(const PartialView &pv, int w, int lane) {
     double s = 0.0;
@@ -178,11 +192,12 @@ __device__ __forceinline__ double loglike_finish(const double (&th)[OP::D], doub
 // one warp per walker
 template <class OP>
 __global__ void loglike_finalize_kernel(const double *__restrict__ theta, int P, int Ps,
-                                        const PartialView pv, double rows, const OpCst cst,
+                                        PartialView pv, double rows, const OpCst cst,
                                         const __grid_constant__ PriorSpec prior, double logzero,
-                                        double *__restrict__ out) {
+                                        double *__restrict__ out, const XchgDev *xd = nullptr) {
+    const bool xok = resolve_exchange(pv, xd);
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (w >= P) return;
+    if (w >= P || !xok) return;
     const double s = combine_partials_warp(pv, w, lane);
     double th[OP::D];
 #pragma unroll
@@ -209,6 +224,27 @@ __global__ void shard_reduce_kernel(const PartialView pv, const double *theta /*
         s = OP::local(c, s, rows_local, cst_local);
     }
     if (lane == 0) send[w] = s;
+}
+
+// the same, pushing the value into every rank's receive buffer (in-kernel exchange, xchg.cuh)
+template <class OP>
+__global__ void shard_reduce_push_kernel(const PartialView pv, const double *theta /* SoA [D][Ps] */, int P, int Ps,
+                                         double rows_local, const OpCst cst_local, const XchgDev x) {
+    const unsigned t = x.st->step + 1u;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w < Ps) {
+        double s = combine_partials_warp(pv, w, lane);
+        if (w < P) {
+            double th[OP::D];
+#pragma unroll
+            for (int j = 0; j < OP::D; ++j) th[j] = __ldcg(theta + (size_t)j * Ps + w);
+            bool ok;
+            const typename OP::Coef c = OP::prepare(th, ok, cst_local);
+            s = OP::local(c, s, rows_local, cst_local);
+        }
+        if (lane == 0) xchg_store(x, t, (size_t)w, s);
+    }
+    xchg_publish(x, t);
 }
 
 // log prior density for a batch (BS:410-426); theta SoA [d][Ps]

@@ -10,10 +10,22 @@
 
 #include "loglike.cuh"
 
-// data-sharded mode: one communicator per process, created by binest_comm_create (comm.cu)
+#include "xchg.cuh"
+
+// sharded modes: one communicator per process, created by binest_comm_create (comm.cu)
 struct binest_comm {
-    void *nccl = nullptr;  // ncclComm_t
+    void *nccl = nullptr;  // ncclComm_t: set-up traffic (IPC handles, data constants) and the fallback exchange
     int rank = 0, world = 1, device = 0;
+    // in-kernel exchange over peer-mapped memory (xchg.cuh); peer == false: host-issued ncclAllGather per exchange
+    bool peer = false;
+    binest::XchgDev xd{};
+    double *xbuf_local = nullptr;
+    unsigned *xflag_local = nullptr;
+    binest::XchgState *xst = nullptr;
+    unsigned *h_abort = nullptr;  // pinned mirror of xst->abort
+    binest::XchgDev *xd_dev = nullptr;  // device copy of xd (consumer kernels take a pointer: nullptr = unsharded)
+    int64_t exchanges = 0;        // exchanges issued so far (host count; NVLink bytes = 8 * count * (world - 1) each)
+    int64_t bytes_pushed = 0;     // payload bytes this rank has stored into peers' buffers
 };
 
 struct binest_problem {
@@ -35,6 +47,7 @@ struct binest_problem {
     binest::DevBuf<double> s_theta, s_partials, s_out;
     // data-sharded mode: this problem holds rows [shard of the data]; logL = Sum over ranks of the shard sums
     binest_comm *comm = nullptr;
+    binest_comm *comm_batch = nullptr;  // batch-sharded mode (GP): the theta batch is split across the ranks
     double rows_total = 0.0;
     binest::OpCst cst_total{};                  // over all shards (operator epilogues need the global values)
     binest::DevBuf<double> sh_send, sh_recv;    // [Ps], [world][Ps]
@@ -167,16 +180,40 @@ void comm_allgather_f64(binest_comm &c, const double *send, double *recv, size_t
 // fixed order, all-gather the P sums of every rank, and hand the consumer a view over [world][Ps].  Every rank then
 // adds the same `world` numbers in the same (rank) order, so accept/reject decisions are bit-identical everywhere —
 // which an all-reduce would not guarantee across algorithms.  Traffic: 8 P bytes per rank per step.
+// true when a consumer of the in-kernel exchange timed out (a peer died or left the lock step); host side, after a sync
+inline void comm_check_abort(binest_comm &c, cudaStream_t s) {
+    if (!c.peer) return;
+    BN_CUDA(cudaMemcpyAsync(c.h_abort, &c.xst->abort, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+    BN_CUDA(cudaStreamSynchronize(s));
+    BN_REQUIRE(*c.h_abort == 0, BINEST_ERR_CUDA, "sharded exchange timed out: a peer rank did not publish its values");
+}
+
+// Data-sharded exchange after a likelihood launch: reduce this rank's per-CTA partials to one value per walker in
+// shard-additive form (OP::local with this rank's data constants) and make the P values of every rank visible on every
+// rank.  Peer path (default): shard_reduce_push_kernel stores them straight into all peers' receive buffers and raises
+// the flags (xchg.cuh); the consumer kernel gets the XchgDev and waits in-kernel.  Fallback (BINEST_XCHG=nccl or no
+// peer access): ncclAllGather on the stream.  Every rank then adds the same `world` numbers in rank order, so
+// accept/reject decisions are bit-identical everywhere.  Traffic: 8 P bytes to each peer per step.
 template <class OP>
 inline PartialView shard_exchange(binest_problem &p, const double *partials, const double *theta_dev, int P, int Ps,
                                   const StreamGeom &g, cudaStream_t s) {
+    binest_comm &c = *p.comm;
+    c.exchanges += 1;
+    c.bytes_pushed += (int64_t)8 * Ps * (c.world - 1);
+    if (c.peer) {
+        BN_REQUIRE(Ps <= kXchgSlotDoubles, BINEST_ERR_DIMENSION, "too many walkers for the sharded exchange buffer");
+        shard_reduce_push_kernel<OP><<<(Ps * 32 + 255) / 256, 256, 0, s>>>(PartialView{partials, g.G, g.Gs, 1}, theta_dev, P,
+                                                                          Ps, (double)p.rows, p.cst, c.xd);
+        BN_LAUNCH_CHECK();
+        return PartialView{nullptr, c.world, 1, kXchgSlotDoubles, 1};  // resolved in-kernel from the XchgDev
+    }
     if (p.sh_send.n < (size_t)Ps) p.sh_send.alloc(Ps);
-    if (p.sh_recv.n < (size_t)Ps * p.comm->world) p.sh_recv.alloc((size_t)Ps * p.comm->world);
+    if (p.sh_recv.n < (size_t)Ps * c.world) p.sh_recv.alloc((size_t)Ps * c.world);
     shard_reduce_kernel<OP><<<(Ps * 32 + 255) / 256, 256, 0, s>>>(PartialView{partials, g.G, g.Gs, 1}, theta_dev, P, Ps,
                                                                  (double)p.rows, p.cst, p.sh_send.p);
     BN_LAUNCH_CHECK();
-    comm_allgather_f64(*p.comm, p.sh_send.p, p.sh_recv.p, (size_t)Ps, s);
-    return PartialView{p.sh_recv.p, p.comm->world, 1, Ps, 1};
+    comm_allgather_f64(c, p.sh_send.p, p.sh_recv.p, (size_t)Ps, s);
+    return PartialView{p.sh_recv.p, c.world, 1, Ps, 1};
 }
 
 // full batched evaluation: theta_dev SoA [d][Ps] -> out_dev[P]
@@ -193,8 +230,9 @@ inline void loglike_device(binest_problem &p, const double *theta_dev, int P, in
         launch_loglike<OP>(p, theta_dev, P, Ps, p.s_partials.p, g, p.stream);
         PartialView pv{p.s_partials.p, g.G, g.Gs, 1};
         if (p.comm) pv = shard_exchange<OP>(p, p.s_partials.p, theta_dev, P, Ps, g, p.stream);
+        const XchgDev *xd = (p.comm && p.comm->peer) ? p.comm->xd_dev : nullptr;
         loglike_finalize_kernel<OP><<<(P * 32 + 255) / 256, 256, 0, p.stream>>>(
-            theta_dev, P, Ps, pv, p.rows_eff(), p.cst_eff(), p.prior, g_logzero, out_dev);
+            theta_dev, P, Ps, pv, p.rows_eff(), p.cst_eff(), p.prior, g_logzero, out_dev, xd);
         BN_LAUNCH_CHECK();
     });
 }

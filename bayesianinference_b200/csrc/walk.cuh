@@ -473,9 +473,14 @@ static __global__ void walk_retry_kernel(const __grid_constant__ RunParams prm, 
 template <class OP>
 __global__ void __launch_bounds__(256)
 walk_step_kernel(const __grid_constant__ RunParams prm, RunArrays A, const __grid_constant__ PriorSpec prior,
-                 const PartialView pv, double rows, const OpCst cst, int final_step) {
+                 const PartialView pv_in, double rows, const OpCst cst, int final_step, const XchgDev *xd = nullptr,
+                 int first_step = 0) {
     pdl_wait();               // partials / walker state of the predecessors are complete and visible
     pdl_launch_dependents();  // let the next likelihood kernel start prefetching its data tiles
+    PartialView pv = pv_in;
+    // sharded modes: wait (in-kernel) for the exchange the preceding producer kernel published; the first step of a
+    // block has no proposal in flight and nothing to wait for
+    if (xd != nullptr && !first_step && !resolve_exchange(pv, xd)) return;
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     walk_step_walker<OP>(prm, A, prior, pv, rows, cst, final_step, w, lane);
 }

@@ -79,6 +79,13 @@ class Comm:
         check(L.binest_comm_create(rank, world, ident, C.byref(h)))
         self.h, self.rank, self.world = h, rank, world
 
+    def stats(self):
+        """Exchange traffic so far: exchanges issued, payload bytes this rank pushed to its peers, and whether the
+        exchange runs in-kernel over peer-mapped memory (True) or through ncclAllGather (False)."""
+        ex, by, pp = C.c_int64(), C.c_int64(), C.c_int()
+        check(_lib.load().binest_comm_stats(self.h, C.byref(ex), C.byref(by), C.byref(pp)))
+        return dict(exchanges=ex.value, bytes_pushed=by.value, peer_path=bool(pp.value))
+
     def close(self):
         if getattr(self, "h", None):
             _lib.load().binest_comm_free(self.h)
@@ -88,10 +95,13 @@ class Comm:
 class Problem:
     """Device-resident inference problem (the data-carrying half of defineInferenceProblem, BS:167-307).
 
-    comm: data-sharded mode — `inputs`/`outputs` are the FULL data on every rank; only this rank's row block
-    (shard_rows) is uploaded and the problem is declared a shard (binest_problem_shard, collective)."""
+    comm: sharded modes — `inputs`/`outputs` are the FULL data on every rank.
+      shard="rows"  (data-sharded) only this rank's row block (shard_rows) is uploaded and the problem is declared a
+                    shard (binest_problem_shard, collective);
+      shard="batch" (GP operator) the data are replicated and every theta batch is split across the ranks
+                    (binest_problem_shard_batch)."""
 
-    def __init__(self, op, inputs, outputs, iparam, kinds, lo, hi, p0=None, p1=None, comm=None):
+    def __init__(self, op, inputs, outputs, iparam, kinds, lo, hi, p0=None, p1=None, comm=None, shard="rows"):
         _ensure_init()
         L = _lib.load()
         self.op = int(op)
@@ -100,7 +110,9 @@ class Problem:
             inputs = inputs.reshape(-1, 1)
         n = inputs.shape[0]
         outputs = None if outputs is None else _f64(outputs).reshape(n, -1)
-        if comm is not None:
+        if shard not in ("rows", "batch"):
+            raise ValueError("shard must be 'rows' or 'batch'")
+        if comm is not None and shard == "rows":
             from .configs import OP_GBM
             r0, r1 = shard_rows(n, comm.rank, comm.world, overlap=1 if self.op == OP_GBM else 0)
             inputs = np.ascontiguousarray(inputs[r0:r1])
@@ -121,11 +133,12 @@ class Problem:
         self.h = h
         self.n_rows = n
         if comm is not None:
-            check(L.binest_problem_shard(self.h, comm.h))
+            check((L.binest_problem_shard if shard == "rows" else L.binest_problem_shard_batch)(self.h, comm.h))
 
     @classmethod
-    def from_config(cls, cfg, comm=None):
-        return cls(cfg.op, cfg.inputs, cfg.outputs, cfg.iparam, cfg.kinds, cfg.lo, cfg.hi, cfg.p0, cfg.p1, comm=comm)
+    def from_config(cls, cfg, comm=None, shard="rows"):
+        return cls(cfg.op, cfg.inputs, cfg.outputs, cfg.iparam, cfg.kinds, cfg.lo, cfg.hi, cfg.p0, cfg.p1, comm=comm,
+                   shard=shard)
 
     def loglike(self, theta):
         """"LogLikelihoodFunction" (Listable): theta (P, d) -> (P,)."""

@@ -1,22 +1,35 @@
 #!/usr/bin/env python
 """bench.py — the hot path of BASELINE.json: the live-point replacement step of nestedSampling.
 
-A "step" is one nested-sampling iteration of one run group: the K worst live points are deleted, K walkers do
-S = 200 constrained-prior Metropolis steps each (every proposal scores a log-likelihood that is a reduction
-over all N data rows), the new points are inserted and the logX/logZ evidence state is advanced.
-metric = log-likelihood evaluations per second (K*S evals per step); replacements/s = value / S.
+Primary line (what the driver reads).  A "step" is one nested-sampling iteration of one run group: the K worst live
+points are deleted, K walkers do S = 200 constrained-prior Metropolis steps each (every proposal scores a
+log-likelihood that is a reduction over all N data rows), the new points are inserted and the logX/logZ evidence state
+is advanced.  metric = log-likelihood evaluations per second (K*S evals per step); replacements/s = value / S.
+  N = 1 workload: config C2 of BASELINE.json (polynomial regression, 5 parameters, N = 1e6 rows, 1024 live points).
+  N > 1: one process per GPU (torchrun), run-sharded exactly like parallelNestedSampling (BS:1349-1357): every rank
+  advances its own independent run (run id = rank), no data-path collective; "scaling": "weak".
 
-N = 1 workload: config C2 of BASELINE.json (polynomial regression, 5 parameters, N = 1e6 rows, 1024 live points).
-N > 1: one process per GPU (torchrun), run-sharded exactly like parallelNestedSampling (BS:1349-1357): every
-rank advances its own independent run (run id = rank), no data-path collective; "scaling": "weak".
+Secondary objects in the same JSON line ("extras", each measured at the same N GPUs, each a STRONG-scaling point —
+total work fixed, so the driver's 1/2/4/8 sweep yields their curves; skipped with --no-extras):
+  "c5"            config C5: GP marginal likelihood, N = 4096, ONE batched evaluation of 256 hyper-parameter sets
+                  (fill + blocked Cholesky on FP64 DMMA); N > 1: batch-sharded, 256/N matrices per GPU, the finished
+                  values exchanged in-kernel over peer-mapped memory.  Roofline: fp64 tensor pipe.
+  "c4_strong"     config C4 as BASELINE states it: 64 parallelNestedSampling runs x 512 live points through
+                  api.parallelNestedSampling, the WHOLE call timed (device loop + gather + combineRuns +
+                  evidenceSampling); N > 1: 64/N runs per GPU.  Unit: live-point replacements/s.
+  "data_sharded"  the data-sharded mode: C2-shaped data with --rows rows (default 6.4e7) split N ways, K = 256
+                  walkers x 200 steps per iteration, per-step exchange of 8 P bytes to every peer.
+A watchdog bounds the extras: if they do not finish in time the line is printed without the missing ones.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C2]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C1..C5]
+                  [--mode run-sharded|data-sharded] [--rows R] [--no-extras]
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
+import shutil
 import subprocess
 import sys
 import threading
@@ -32,13 +45,17 @@ from bayesianinference_b200 import configs as cfg  # noqa: E402
 MC_STEPS = 200  # "MonteCarloSteps" default, BS:844
 # profiles/r01g_ncu_walk_grid_c2.md: dram__bytes_read.sum + dram__bytes_write.sum of one walk_grid_kernel launch
 NCU_TRAFFIC_C2_GRID = 16.165e6 + 0.088e6
+GP_FLOP_PER_THETA = 2.31e10   # fill 2.1e8 + Cholesky N^3/3 = 2.29e10 + solve/logdet, N = 4096
+GP_BYTES_PER_THETA = 134.2e6  # lower triangle written once + read once (minimum traffic)
 WORKLOADS = {
     # name: (config factory, batch_k, flop per datum-eval, algorithmic bytes per datum-eval)   SURVEY §8d
     "C1": (cfg.c1_gaussian, 32, 3, 8),
     "C2": (cfg.c2_polyreg, 256, 9, 16),
     "C3": (cfg.c3_logistic, 512, 81, 36),
     "C4": (cfg.c4_gbm, 64, 4, 16),
+    "C5": (cfg.c5_gp, 256, None, None),
 }
+EXTRAS_DEADLINE_S = 420.0
 
 
 def _workload_config(c, K, n_runs, world):
@@ -52,6 +69,21 @@ def _workload_config(c, K, n_runs, world):
 
 def _dist_env():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def _peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def _wolfram_probe():
+    """the reference's own Wolfram path can only be timed where a Wolfram Engine exists."""
+    path = shutil.which("wolframscript") or shutil.which("WolframKernel") or shutil.which("wolfram")
+    return {"wolframscript": path,
+            "status": "unavailable: no Wolfram Engine on this machine (BASELINE.md §3)" if path is None else
+                      "found, but the reference paclet is not on this machine (bench.py may not read /root/reference at run time)"}
 
 
 class ClockSampler:
@@ -96,17 +128,34 @@ def _pinned(a):
     return t.numpy(), t
 
 
+# ------------------------------------------------------------------------------------------------- CPU arm
 def _cpu_leg(c, threads, reps_per_thread, seed=77):
-    """The reference scheme (one walker, S sequential evaluations per replacement, BS:729) on host cores —
-    oracle port (the reference is Wolfram Language; no Wolfram Engine offline)."""
+    """The reference scheme (one walker per chain, S sequential density evaluations per replacement, BS:729; a proposal
+    outside the box is rejected without a likelihood evaluation, BS:602-617) on host cores — the oracle port built
+    -O3 -march=native with vectorised sums (oracle/Makefile FAST_*).  The reference itself is Wolfram Language; no
+    Wolfram Engine offline.  Returns (evaluations performed, replacements, seconds)."""
     from oracle import oracle as O
+    O.fast_lib()  # build / load outside the timed region
     op = O.Problem(c.op, c.d, c.inputs, c.outputs, c.iparam)
     pr = O.Prior(c.kinds, c.lo, c.hi, c.p0 or None, c.p1 or None)
     start = pr.sample(64, seed)
     t0 = time.perf_counter()
-    evals = O.bench_walks(op, pr, start, O.LOGZERO, reps_per_thread, MC_STEPS, seed, threads)
+    evals = O.bench_walks(op, pr, start, O.LOGZERO, reps_per_thread, MC_STEPS, seed, threads, fast=True)
     dt = time.perf_counter() - t0
-    return evals, dt
+    return evals, reps_per_thread * threads, dt
+
+
+def _cpu_gp_leg(c, threads, n_theta):
+    """C5 on host cores: the reference's LU path (GP:130-141) restated in the oracle, one theta per thread."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle as O
+    op = O.Problem(c.op, c.d, c.inputs, c.outputs, c.iparam)
+    pr = O.Prior(c.kinds, c.lo, c.hi)
+    th = pr.sample(n_theta, 905)
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:  # ctypes releases the GIL
+        list(ex.map(lambda t: op.loglike(t[None, :], pr), th))
+    return n_theta, time.perf_counter() - t0
 
 
 def run_reference(args):
@@ -117,39 +166,198 @@ def run_reference(args):
     factory, K, flop, byts = WORKLOADS[args.config]
     c = factory()
     threads = len(os.sched_getaffinity(0))  # all host cores, even when torchrun pins OMP_NUM_THREADS=1
+    if args.config == "C5":
+        n, t = _cpu_gp_leg(c, threads, max(threads, 8) if args.steps > 1 else threads)
+        v = n / t
+        line = {"impl": "reference", "metric": "loglikelihood evals/s", "value": v, "unit": "evals/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"C5-gp: N={c.inputs.shape[0]}, batch of 256 hyper-parameter sets"},
+                "cpu_baseline": {"value": v, "unit": "evals/s", "cores": threads, "kind": "port",
+                                 "sample": f"{n} covariance matrices of order {c.inputs.shape[0]} (fill + LU + solve), one per thread"},
+                "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "wolfram": _wolfram_probe()}
+        print(json.dumps(line))
+        return
     for _ in range(max(args.warmup, 0) and 1):  # one short warm-up pass is enough for a CPU loop
         _cpu_leg(c, threads, 1)
-    tot_e, tot_t = 0, 0.0
+    tot_e, tot_r, tot_t = 0, 0, 0.0
     reps = 4 if c.inputs.shape[0] >= 100_000 else 400  # ~1 s of CPU work per step
     for _ in range(args.steps):
-        e, t = _cpu_leg(c, threads, reps)
+        e, r, t = _cpu_leg(c, threads, reps)
         tot_e += e
+        tot_r += r
         tot_t += t
     v = tot_e / tot_t
-    sample = f"{threads} threads x {reps} replacements x {MC_STEPS} evals per step on the full {c.inputs.shape[0]}-row data"
+    sample = (f"{threads} threads x {reps} replacements x {MC_STEPS} walk steps per step on the full {c.inputs.shape[0]}-row data; "
+              f"{tot_e} likelihood evaluations performed (proposals outside the box are rejected without one, BS:602-617); {O.FAST_FLAGS}")
     print(json.dumps({
         "impl": "reference", "metric": "loglikelihood evals/s", "value": v, "unit": "evals/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": _workload_config(c, K, args.runs_per_gpu, max(args.gpus, 1)),
-        "replacements_per_s": v / MC_STEPS,
+        "replacements_per_s": tot_r / tot_t,
         "cpu_baseline": {"value": v, "unit": "evals/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wolfram": _wolfram_probe(),
         "note": "oracle port of BS:859-1040 on host cores; Wolfram reference unavailable offline (BASELINE.md §3)",
     }))
 
 
-def run_ours(args):
-    import torch
-    rank, local_rank, world = _dist_env()
-    torch.cuda.set_device(local_rank)
-    use_dist = world > 1
-    if use_dist:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    from bayesianinference_b200 import engine
-    engine.init(device=local_rank)
+# ------------------------------------------------------------------------------------------------- helpers (GPU)
+class Ctx:
+    """torch / torch.distributed / engine state of one rank."""
 
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.rank, self.local_rank, self.world = _dist_env()
+        torch.cuda.set_device(self.local_rank)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+            self.dist = dist
+        from bayesianinference_b200 import engine
+        engine.init(device=self.local_rank)
+        self.engine = engine
+        self._comm = None
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.dist:
+            self.dist.barrier()
+
+    def max_over_ranks(self, x):
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        if self.dist:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def comm(self):
+        if self._comm is None and self.world > 1:
+            self._comm = self.engine.Comm(self.rank, self.world)
+        return self._comm
+
+
+def measure_c5(ctx, steps, warmup, batch=256):
+    """One batched GP evaluation per step: 256 theta-sets at N = 4096 (BASELINE config C5).  Device-timed value with the
+    data and theta resident (binest_bench_loglike: CUDA events on the library's stream), e2e through binest_loglike
+    with host theta in / host logL out.  N > 1: batch-sharded (strong scaling: the 256 sets are split)."""
+    eng = ctx.engine
+    c = cfg.c5_gp()
+    N = c.inputs.shape[0]
+    comm = ctx.comm()
+    gp = eng.Problem.from_config(c, comm=comm, shard="batch") if comm is not None else eng.Problem.from_config(c)
+    th = gp.sample_prior(batch, seed=905)
+    gp.loglike(th[: max(2 * ctx.world, 8)])  # first touch (kernel attributes, streams)
+    ctx.barrier()
+    ms_k, ms_tot = gp.bench_loglike(batch, reps=max(steps, 1), warmup=max(min(warmup, 2), 1), flush_l2=False)
+    ms = ctx.max_over_ranks(ms_tot)
+    ctx.barrier()
+    t0 = time.perf_counter()
+    e_steps = max(2, min(steps, 3))
+    for _ in range(e_steps):
+        out = gp.loglike(th)
+    ctx.torch.cuda.synchronize()
+    e_dt = ctx.max_over_ranks((time.perf_counter() - t0) / e_steps)
+    stats = comm.stats() if comm is not None else None
+    peak = eng.fp64_peak()
+    per_rank = -(-batch // ctx.world)
+    ach = GP_FLOP_PER_THETA * per_rank / (ms * 1e-3) / 1e12
+    res = {
+        "metric": "loglikelihood evals/s", "unit": "evals/s", "value": batch / (ms * 1e-3), "ms_per_step": ms,
+        "scaling": "strong", "n_gpus": ctx.world,
+        "config": {"workload": f"C5-gp: N={N} points, squared-exponential kernel + nugget, one batched evaluation of {batch} "
+                               f"hyper-parameter sets ({per_rank} matrices of {N}^2 fp64 per GPU, {per_rank * 134.2e6 / 1e9:.1f} GB)",
+                   "parallelism": "single GPU" if ctx.world == 1 else f"batch-sharded x{ctx.world}: theta batch split, values "
+                                  "exchanged in-kernel over peer-mapped memory", "l2": "inputs larger than L2 (134 MB per matrix)"},
+        "e2e": {"value": batch / e_dt, "unit": "evals/s", "h2d_bytes_per_step": int(th.nbytes), "d2h_bytes_per_step": int(out.nbytes),
+                "what": "binest_loglike: host theta in, fill + factor + solve, host logL out"},
+        "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                     "kernel": "gp_syrk_kernel (DMMA.8x8x4) inside the fill + blocked-Cholesky pipeline",
+                     "alg_flop_per_launch": GP_FLOP_PER_THETA * per_rank, "alg_bytes_per_launch": GP_BYTES_PER_THETA * per_rank,
+                     "peak_source": "fp64 peak measured live (register-resident DFMA loop; DMMA shares the pipe); achieved = "
+                                    "2.31e10 flop x matrices per GPU / pipeline time (all kernels of the evaluation)"},
+        "exchange": stats, "finite": int(np.isfinite(out).sum()),
+    }
+    gp.close()
+    return res
+
+
+def measure_c4_strong(ctx, reps=2):
+    """Config C4 as BASELINE states it, through the reference-facing call: parallelNestedSampling with 64 runs x 512 live
+    points (BS:1317-1371), whole call timed on every rank (max over ranks): device loops of this rank's runs, gather of
+    the sample lists, combineRuns (BS:1293-1315), evidenceSampling (BS:1158-1291)."""
+    from bayesianinference_b200 import api
+    c = cfg.c4_gbm()
+    obj = api.defineInferenceProblem(
+        Data=(c.inputs[:, 0], c.outputs[:, 0]), GeneratingDistribution=api.GeometricBrownianMotionProcess("mu", "sigma", 100.0),
+        Parameters=[(nm, lo, hi) for nm, lo, hi in zip(c.names, c.lo, c.hi)],
+        PriorDistribution=["LocationParameter", "ScaleParameter"])
+    best, info = None, None
+    for rep in range(reps + 1):  # first pass warms the library up (kernel attributes, pools)
+        ctx.barrier()
+        t0 = time.perf_counter()
+        res = api.parallelNestedSampling(obj, ParallelRuns=64, SamplePoolSize=512, BatchSize=64, MaxIterations=10**6,
+                                         Seed=2026 + rep, PostProcessSamplingRuns=100)
+        ctx.torch.cuda.synchronize()
+        dt = ctx.max_over_ranks(time.perf_counter() - t0)
+        if rep > 0 and (best is None or dt < best):
+            best = dt
+            info = (res["GeneratedNestedSamples"], res["LogEvidence"], res.get("_Timing"))
+    gen, logz, timing = info
+    pull = (logz["Mean"] - c.truth["logZ"]) / max(logz["StandardError"], 1e-12)
+    return {"metric": "live-point replacements/s", "unit": "replacements/s", "value": gen / best, "s_per_call": best,
+            "scaling": "strong", "n_gpus": ctx.world, "replacements": int(gen),
+            "config": {"workload": "C4-gbm: 64 parallelNestedSampling runs x 512 live points, T=16384 increments, K=64 "
+                                   "replaced per iteration per run, 200 walk steps", "parallelism": f"run-sharded x{ctx.world}: "
+                                   f"{-(-64 // ctx.world)} runs per GPU, host merge (combineRuns)"},
+            "phases_s_rank0": timing, "log_evidence": logz, "pull_vs_quadrature": pull}
+
+
+def measure_data_sharded(ctx, rows, iters=2, K=256):
+    """Data-sharded mode: C2-shaped data, `rows` rows split over the ranks; one iteration = K walkers x
+    200 steps, every step one exchange of the K per-rank sums (8 K bytes to each peer)."""
+    eng = ctx.engine
+    c = cfg.c2_polyreg(N=int(rows))
+    comm = ctx.comm()
+    p = eng.Problem.from_config(c, comm=comm) if comm is not None else eng.Problem.from_config(c)
+    o = eng.default_options(pool_size=1024, batch_k=K, mc_steps=MC_STEPS, max_iter=10**9, min_iter=10**9, seed=3)
+    run = eng.RunGroup(p, o)
+    path = run.walk_path()
+    run.advance(1)
+    ctx.barrier()
+    s0 = comm.stats() if comm is not None else None
+    t0 = time.perf_counter()
+    run.advance(iters)
+    ctx.torch.cuda.synchronize()
+    dt = ctx.max_over_ranks((time.perf_counter() - t0) / iters)
+    s1 = comm.stats() if comm is not None else None
+    tm = run.timing()
+    peak = eng.fp64_peak()
+    evals = K * MC_STEPS / dt
+    flops = evals * 9.0 * rows
+    ex = None
+    if s1 is not None:
+        n_ex = (s1["exchanges"] - s0["exchanges"]) / iters
+        ex = {"peer_path": s1["peer_path"], "exchanges_per_iteration": n_ex,
+              "nvlink_payload_bytes_per_step_per_rank": (s1["bytes_pushed"] - s0["bytes_pushed"]) / max(s1["exchanges"] - s0["exchanges"], 1),
+              "expected_8P_times_peers": 8 * K * (ctx.world - 1)}
+    run.close()
+    p.close()
+    return {"metric": "loglikelihood evals/s", "unit": "evals/s", "value": evals, "ms_per_iteration": 1e3 * dt,
+            "scaling": "strong", "n_gpus": ctx.world, "walk_path": path, "device_walk_ms_per_iteration": tm["walk_ms"] / max(tm["walk_graphs"], 1),
+            "config": {"workload": f"C2-shaped polynomial regression, {int(rows)} rows ({rows * 16 / 1e9:.2f} GB) split over {ctx.world} "
+                                   f"GPU(s), K={K} walkers x {MC_STEPS} steps per iteration", "l2": "inputs larger than L2"},
+            "aggregate_tflops": flops / 1e12, "frac_of_fp64_peak_aggregate": flops / 1e12 / (peak * ctx.world), "exchange": ex}
+
+
+# ------------------------------------------------------------------------------------------------- primary (C1..C4)
+def run_primary(ctx, args):
+    torch, engine, dist = ctx.torch, ctx.engine, ctx.dist
+    rank, local_rank, world = ctx.rank, ctx.local_rank, ctx.world
+    use_dist = world > 1
     factory, K, flop, byts = WORKLOADS[args.config]
     c = factory()
     n, d, N = c.pool_size, c.d, c.inputs.shape[0]
@@ -173,9 +381,7 @@ def run_ours(args):
 
     for _ in range(args.warmup):
         step()
-    torch.cuda.synchronize()
-    if use_dist:
-        dist.barrier()
+    ctx.barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -196,121 +402,181 @@ def run_ours(args):
     launches = engine.launch_count() - launches0
     t_after = run.timing()
     clocks = sampler.stop() if rank == 0 else None
-    tmax = torch.tensor([dt], dtype=torch.float64, device="cuda")
-    if use_dist:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    dt_max = float(tmax.item())
+    dt_max = ctx.max_over_ranks(dt)
     walkers = n_runs * K
     evals_per_step = walkers * MC_STEPS
     value = world * evals_per_step * args.steps / dt_max
 
     # ---- e2e through the C ABI with HOST (pinned) buffers: define the problem (H2D of the data), create the run
     # from host start points, one replacement step, fetch the sample list back (D2H) — every step.
-    e2e = None
-    roof = None
-    cpu = None
-    if True:
-        inp, _k1 = _pinned(c.inputs)
-        out, _k2 = _pinned(c.outputs) if c.outputs is not None else (None, None)
-        sp, _k3 = _pinned(gp.sample_prior(n * n_runs, seed=5, run_id=rank).reshape(n_runs, n, d))
-        e_opts = engine.default_options(pool_size=n, batch_k=K, mc_steps=MC_STEPS, max_iter=10**9, min_iter=10**9,
-                                        seed=11, first_run_id=rank * n_runs, n_runs=n_runs)
+    inp, _k1 = _pinned(c.inputs)
+    out, _k2 = _pinned(c.outputs) if c.outputs is not None else (None, None)
+    sp, _k3 = _pinned(gp.sample_prior(n * n_runs, seed=5, run_id=rank).reshape(n_runs, n, d))
+    e_opts = engine.default_options(pool_size=n, batch_k=K, mc_steps=MC_STEPS, max_iter=10**9, min_iter=10**9,
+                                    seed=11, first_run_id=rank * n_runs, n_runs=n_runs)
 
-        def e2e_step():
-            t = [time.perf_counter()]
-            p2 = engine.Problem(c.op, inp, out, c.iparam, c.kinds, c.lo, c.hi, c.p0, c.p1)
-            t.append(time.perf_counter())
-            r2 = engine.RunGroup(p2, e_opts, sp)
-            t.append(time.perf_counter())
-            r2.advance(1)
-            t.append(time.perf_counter())
-            res = r2.fetch(0)
-            t.append(time.perf_counter())
-            nbytes = sum(v.nbytes for v in res.values() if isinstance(v, np.ndarray))
-            r2.close()
-            p2.close()
-            t.append(time.perf_counter())
-            if os.environ.get("BINEST_E2E_DEBUG"):
-                print("e2e phases ms:", [round(1e3 * (b - a), 2) for a, b in zip(t, t[1:])], file=sys.stderr)
-            return nbytes
+    def e2e_step():
+        t = [time.perf_counter()]
+        p2 = engine.Problem(c.op, inp, out, c.iparam, c.kinds, c.lo, c.hi, c.p0, c.p1)
+        t.append(time.perf_counter())
+        r2 = engine.RunGroup(p2, e_opts, sp)
+        t.append(time.perf_counter())
+        r2.advance(1)
+        t.append(time.perf_counter())
+        res = r2.fetch(0)
+        t.append(time.perf_counter())
+        nbytes = sum(v.nbytes for v in res.values() if isinstance(v, np.ndarray))
+        r2.close()
+        p2.close()
+        t.append(time.perf_counter())
+        if os.environ.get("BINEST_E2E_DEBUG"):
+            print("e2e phases ms:", [round(1e3 * (b - a), 2) for a, b in zip(t, t[1:])], file=sys.stderr)
+        return nbytes
 
-        for _ in range(min(args.warmup, 3)):
-            d2h = e2e_step()
-        torch.cuda.synchronize()
-        if use_dist:
-            dist.barrier()
-        e_steps = max(3, min(args.steps, 10))
-        t0 = time.perf_counter()
-        for _ in range(e_steps):
-            d2h = e2e_step()
-        torch.cuda.synchronize()
-        edt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-        if use_dist:
-            dist.all_reduce(edt, op=dist.ReduceOp.MAX)
-        h2d = inp.nbytes + (out.nbytes if out is not None else 0) + sp.nbytes
-        e2e = {"value": world * evals_per_step * e_steps / float(edt.item()), "unit": "evals/s",
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e_steps,
-               "what": "binest_problem_create (data H2D from pinned host) + binest_run_create (host start points) + "
-                       "binest_run_advance(1) + binest_run_fetch (D2H), per step"}
+    for _ in range(min(args.warmup, 3)):
+        d2h = e2e_step()
+    ctx.barrier()
+    e_steps = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(e_steps):
+        d2h = e2e_step()
+    torch.cuda.synchronize()
+    edt = ctx.max_over_ranks(time.perf_counter() - t0)
+    h2d = inp.nbytes + (out.nbytes if out is not None else 0) + sp.nbytes
+    e2e = {"value": world * evals_per_step * e_steps / edt, "unit": "evals/s",
+           "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e_steps,
+           "what": "binest_problem_create (data H2D from pinned host) + binest_run_create (host start points) + "
+                   "binest_run_advance(1) + binest_run_fetch (D2H), per step"}
+    if rank != 0:
+        return None
+    # ---- roofline of the dominant kernel: algorithmic flop per launch / launch duration.  Duration from CUDA events
+    # recorded on the library's stream around every walk launch of the timed region.
+    graphs = t_after["walk_graphs"] - t_before["walk_graphs"]
+    walk_ms = t_after["walk_ms"] - t_before["walk_ms"]
+    peak_tf = engine.fp64_peak()
+    iso_kernel_ms, iso_total_ms = gp.bench_loglike(walkers, 20, 3, True)
+    # dominant kernel.  grid-resident path: ONE launch of walk_grid_kernel scores walkers x S proposals (the whole
+    # walk); stepped path: one launch of loglike_stream_kernel scores `walkers` proposals (one walk step).
+    steps_per_launch = MC_STEPS if path in ("grid-resident", "cluster-resident") else 1
+    kernel = {"grid-resident": "walk_grid_kernel", "cluster-resident": "walk_resident_kernel"}.get(path, "loglike_stream_kernel")
+    ms_launch = walk_ms / max(graphs, 1) / MC_STEPS * steps_per_launch
+    alg_flop = float(flop) * rows * walkers * steps_per_launch
+    alg_bytes = float(byts) * rows  # every data row is read from HBM/L2 once per launch and shared by all walkers
+    achieved_tf = alg_flop / (ms_launch * 1e-3) / 1e12
+    # dram__bytes_read.sum + dram__bytes_write.sum of that kernel, one `ncu --set full` capture (profiles/)
+    traffic = {("C2", "walk_grid_kernel"): NCU_TRAFFIC_C2_GRID}.get((args.config, kernel))
+    peaks = _peaks()
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    roof = {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+            "frac": achieved_tf / peak_tf, "traffic": traffic,
+            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture "
+                              "profiles/r01g_ncu_walk_grid_c2.md (not re-measured in this run)" if traffic else None,
+            "kernel": kernel, "walk_path": path, "walk_steps_per_launch": steps_per_launch,
+            "ms_per_launch": ms_launch,
+            "pipe_slots_note": "9 algorithmic flop per datum (SURVEY §8d) execute as 4 DFMA = 8 flop: hardware busy fraction = frac * 8/9",
+            "frac_executed_flop": achieved_tf / peak_tf * 8.0 / 9.0 if args.config == "C2" else None,
+            "stream_kernel_ms_isolated": iso_kernel_ms,
+            "stream_kernel_frac_isolated": float(flop) * rows * walkers / (iso_kernel_ms * 1e-3) / 1e12 / peak_tf,
+            "alg_flop_per_launch": alg_flop, "alg_bytes_per_launch": alg_bytes,
+            "hbm_time_bound_ms": alg_bytes / (hbm_peak * 1e9) * 1e3,
+            "peak_source": "fp64 DFMA peak measured live by binest_measure_fp64_peak (not in MEASURED_PEAKS.json); "
+                           f"hbm {hbm_peak} GB/s " + ("of measured" if peaks else "of fallback"),
+            "why": "P walkers share every data tile, intensity = flop*P/bytes >> fp64 ridge (~6 flop/B): fp64-FMA bound"}
+    # ---- CPU baseline beside it: oracle port (-O3 -march=native build), bounded sample
+    from oracle import oracle as O
+    threads = len(os.sched_getaffinity(0))  # all host cores, even when torchrun pins OMP_NUM_THREADS=1
+    big = N >= 100_000
+    e1, r1, t1 = _cpu_leg(c, threads, 1 if big else 200)  # calibration pass, then ~12 s of CPU work
+    e, r, t = _cpu_leg(c, threads, max(1, int(round(12.0 / max(t1, 1e-3)))) * (1 if big else 200))
+    cpu = {"value": e / t, "unit": "evals/s", "cores": threads, "kind": "port", "replacements_per_s": r / t,
+           "sample": f"{r} replacements x {MC_STEPS} walk steps on {threads} threads, full {N}-row data, {t:.1f} s; {e} likelihood "
+                     f"evaluations performed (proposals outside the box are rejected without one, BS:602-617); {O.FAST_FLAGS}"}
+    return {
+        "metric": "loglikelihood evals/s", "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt_max / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": _workload_config(c, K, n_runs, world),
+        "replacements_per_s": value / MC_STEPS,
+        "evals_note": "every proposal of the batch is scored, in or out of the prior box (the reference skips the latter)",
+        "device_walk_ms_per_step": walk_ms / max(graphs, 1),
+        "timing": "CUDA events on the library's stream around the K timed steps, max over ranks",
+        "wall_ms_per_step": 1e3 * dt_wall / args.steps,
+        "gpu_launches": int(launches),
+        "clocks": clocks, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu, "wolfram": _wolfram_probe(),
+    }
 
-    if rank == 0:
-        # ---- roofline of the dominant kernel (loglike_stream_kernel): algorithmic flop per launch / launch duration.
-        # Duration from CUDA events recorded on the library's stream around every walk graph of the timed region
-        # (S launches of the kernel, interleaved with the small walk_step kernel — so it is an upper bound).
-        graphs = t_after["walk_graphs"] - t_before["walk_graphs"]
-        walk_ms = t_after["walk_ms"] - t_before["walk_ms"]
-        peak_tf = engine.fp64_peak()
-        iso_kernel_ms, iso_total_ms = gp.bench_loglike(walkers, 20, 3, True)
-        # dominant kernel.  grid-resident path: ONE launch of walk_grid_kernel scores walkers x S proposals (the whole
-        # walk); stepped path: one launch of loglike_stream_kernel scores `walkers` proposals (one walk step).
-        steps_per_launch = MC_STEPS if path in ("grid-resident", "cluster-resident") else 1
-        kernel = {"grid-resident": "walk_grid_kernel", "cluster-resident": "walk_resident_kernel"}.get(path, "loglike_stream_kernel")
-        ms_launch = walk_ms / max(graphs, 1) / MC_STEPS * steps_per_launch
-        alg_flop = float(flop) * rows * walkers * steps_per_launch
-        alg_bytes = float(byts) * rows  # every data row is read from HBM/L2 once per launch and shared by all walkers
-        achieved_tf = alg_flop / (ms_launch * 1e-3) / 1e12
-        # dram__bytes_read.sum + dram__bytes_write.sum of that kernel, one `ncu --set full` capture (profiles/)
-        traffic = {("C2", "walk_grid_kernel"): NCU_TRAFFIC_C2_GRID}.get((args.config, kernel))
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        roof = {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved_tf / peak_tf, "traffic": traffic,
-                "kernel": kernel, "walk_path": path, "walk_steps_per_launch": steps_per_launch,
-                "ms_per_launch": ms_launch,
-                "stream_kernel_ms_isolated": iso_kernel_ms,
-                "stream_kernel_frac_isolated": float(flop) * rows * walkers / (iso_kernel_ms * 1e-3) / 1e12 / peak_tf,
-                "alg_flop_per_launch": alg_flop, "alg_bytes_per_launch": alg_bytes,
-                "hbm_time_bound_ms": alg_bytes / (hbm_peak * 1e9) * 1e3,
-                "peak_source": "fp64 DFMA peak measured live by binest_measure_fp64_peak (not in MEASURED_PEAKS.json); "
-                               f"hbm {hbm_peak} GB/s " + ("of measured" if peaks else "of fallback"),
-                "why": "P walkers share every data tile, intensity = flop*P/bytes >> fp64 ridge (~6 flop/B): fp64-FMA bound"}
-        # ---- CPU baseline beside it: oracle port, bounded sample
-        from oracle import oracle as O
-        threads = len(os.sched_getaffinity(0))  # all host cores, even when torchrun pins OMP_NUM_THREADS=1
-        e1, t1 = _cpu_leg(c, threads, 1 if N >= 100_000 else 200)  # calibration pass, then ~12 s of CPU work
-        e, t = _cpu_leg(c, threads, max(1, int(round(12.0 / max(t1, 1e-3)))) * (1 if N >= 100_000 else 200))
-        cpu = {"value": e / t, "unit": "evals/s", "cores": threads, "kind": "port",
-               "sample": f"{e} evals ({threads} threads x {e // max(threads, 1) // MC_STEPS} replacements x {MC_STEPS} steps) "
-                         f"on the full {N}-row data, {t:.1f} s"}
-        line = {
-            "metric": "loglikelihood evals/s", "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * dt_max / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": _workload_config(c, K, n_runs, world),
-            "replacements_per_s": value / MC_STEPS,
-            "device_walk_ms_per_step": walk_ms / max(graphs, 1),
-            "timing": "CUDA events on the library's stream around the K timed steps, max over ranks",
-            "wall_ms_per_step": 1e3 * dt_wall / args.steps,
-            "gpu_launches": int(launches),
-            "clocks": clocks, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,
-        }
-        print(json.dumps(line))
-    if use_dist:
-        dist.destroy_process_group()
+
+def _as_primary(extra, args, clocks=None, launches=None):
+    """Promote an extras-style measurement to a full contract line (--config C5 / --mode data-sharded)."""
+    line = {"metric": extra["metric"], "value": extra["value"], "unit": extra["unit"], "n_gpus": extra["n_gpus"],
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": extra.get("ms_per_step", extra.get("ms_per_iteration")),
+            "higher_is_better": True, "scaling": extra["scaling"], "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": extra["config"], "gpu_launches": launches, "clocks": clocks, "wolfram": _wolfram_probe()}
+    for k, v in extra.items():
+        line.setdefault(k, v)
+    return line
+
+
+def run_ours(args):
+    ctx = Ctx()
+    eng = ctx.engine
+    t_start = time.perf_counter()
+    if args.mode == "data-sharded" or args.config == "C5":
+        sampler = ClockSampler(ctx.local_rank)
+        if ctx.rank == 0:
+            sampler.start()
+        l0 = eng.launch_count()
+        if args.config == "C5":
+            ex = measure_c5(ctx, args.steps, args.warmup)
+        else:
+            ex = measure_data_sharded(ctx, args.rows, iters=max(1, min(args.steps, 3)))
+        clocks = sampler.stop() if ctx.rank == 0 else None
+        if ctx.rank == 0:
+            line = _as_primary(ex, args, clocks, int(eng.launch_count() - l0))
+            if args.config == "C5":
+                n, t = _cpu_gp_leg(cfg.c5_gp(), len(os.sched_getaffinity(0)), len(os.sched_getaffinity(0)))
+                line["cpu_baseline"] = {"value": n / t, "unit": "evals/s", "cores": len(os.sched_getaffinity(0)), "kind": "port",
+                                        "sample": f"{n} covariance matrices of order 4096 (fill + LU + solve, GP:130-141), one per thread, {t:.1f} s"}
+            print(json.dumps(line))
+        ctx.barrier()
+        os._exit(0)
+
+    line = run_primary(ctx, args)
+    extras, errors = {}, {}
+    done = threading.Event()
+
+    def emit():
+        if ctx.rank == 0:
+            line["extras"] = extras
+            if errors:
+                line["extras_errors"] = errors
+            line["bench_wall_s"] = time.perf_counter() - t_start
+            print(json.dumps(line), flush=True)
+
+    def watchdog():
+        if not done.wait(EXTRAS_DEADLINE_S):
+            errors["watchdog"] = f"extras did not finish within {EXTRAS_DEADLINE_S:.0f} s; line printed without the missing ones"
+            emit()
+            os._exit(0)
+
+    if not args.no_extras:
+        threading.Thread(target=watchdog, daemon=True).start()
+        plan = [("c5", lambda: measure_c5(ctx, 3, 1)), ("c4_strong", lambda: measure_c4_strong(ctx)),
+                ("data_sharded", lambda: measure_data_sharded(ctx, args.rows))]
+        for name, fn in plan:
+            # all ranks must agree to enter a collective measurement: a rank-local failure aborts the remaining extras
+            try:
+                t0 = time.perf_counter()
+                r = fn()
+                r["measure_wall_s"] = time.perf_counter() - t0
+                extras[name] = r
+            except Exception as e:  # noqa: BLE001
+                errors[name] = f"{type(e).__name__}: {e}"
+                break
+    done.set()
+    emit()
+    sys.stdout.flush()
+    os._exit(0)  # the extras may leave NCCL / IPC teardown work that is not worth risking a hang on
 
 
 def main():
@@ -320,7 +586,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C2", choices=list(WORKLOADS))
+    ap.add_argument("--mode", default="run-sharded", choices=["run-sharded", "data-sharded"])
+    ap.add_argument("--rows", type=float, default=6.4e7, help="rows of the data-sharded workload")
     ap.add_argument("--runs-per-gpu", type=int, default=1)
+    ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

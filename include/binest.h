@@ -207,8 +207,10 @@ int binest_crude_weights(int64_t M, const double *logL, const int64_t *pool, int
  * increment between them belongs to the later shard) and declares it a shard (collective).  From then on
  * binest_loglike / binest_run_* are collectives: all ranks must make the same calls with the same theta / options /
  * seed / first_run_id.  Every rank walks the same chains (same Philox counters); after each likelihood launch the
- * per-walker shard sums are all-gathered (NCCL, 8 P bytes per rank) and added in rank order, so every rank takes
- * bit-identical accept/reject decisions and returns the same samples.  The reference has no such mode (its only
+ * per-walker shard sums are exchanged — pushed by the reducing kernel itself into every peer's receive buffer over
+ * peer-mapped memory (CUDA IPC, NVLink), 8 P bytes to each peer, the whole S-step walk being one CUDA graph; or
+ * ncclAllGather on the fallback — and added in rank order, so every rank takes bit-identical accept/reject decisions
+ * and returns the same samples.  The reference has no such mode (its only
  * parallelism is independent runs, BS:1349-1357); logL values equal the unsharded ones up to summation order.
  * Not available for BINEST_OP_GP_SE (replicas only). */
 #define BINEST_COMM_ID_BYTES 128
@@ -218,6 +220,15 @@ int binest_comm_create(int rank, int world, const uint8_t *id, binest_comm **out
 int binest_comm_info(const binest_comm *c, int *rank, int *world);
 int binest_comm_free(binest_comm *c);
 int binest_problem_shard(binest_problem *p, binest_comm *c);
+/* Batch-sharded mode (BINEST_OP_GP_SE only): the data are replicated, every theta batch
+ * (binest_loglike, the proposals of a GP walk) is split into `world` contiguous slices, each rank fills and factors
+ * the covariance matrices of its slice (GP:130-141, 181-199), and the finished log-likelihoods are exchanged
+ * (8 * ceil(P / world) bytes to each peer).  Collective like the data-sharded mode: same calls on every rank. */
+int binest_problem_shard_batch(binest_problem *p, binest_comm *c);
+/* Exchange statistics: exchanges issued, payload bytes this rank stored into its peers' buffers, and peer_path = 1
+ * when the exchange runs inside our kernels over peer-mapped memory (CUDA IPC over NVLink; the default), 0 on the
+ * ncclAllGather fallback (BINEST_XCHG=nccl or no peer access). */
+int binest_comm_stats(const binest_comm *c, int64_t *exchanges, int64_t *bytes_pushed, int *peer_path);
 
 /* ---- measurement helper (bench.py): inputs resident in HBM, CUDA events on the launching stream ---- */
 /* Scores P prior draws `reps` times after `warmup`; flush_l2 != 0 writes 256 MiB between repetitions.

@@ -267,6 +267,14 @@ static int op_constraints_ok(const orc_problem *p, const double *th) {
     }
 }
 
+/* ORC_FAST (the second build of this file, libbinest_oracle_fast.so: -O3 -march=... -ffast-math, used ONLY by the
+ * timed CPU legs of bench.py): the sums may be vectorised and re-associated.  The parity build keeps the
+ * reference's sequential order (BS:492, 581). */
+#ifdef ORC_FAST
+#define ORC_SIMD _Pragma("omp simd reduction(+ : s)")
+#else
+#define ORC_SIMD
+#endif
 #define DEFINE_SUM_OPS(NAME, T, LOGF, EXPF, SQRTF)                                                   \
     static T NAME(const orc_problem *p, const double *th) {                                         \
         T s = 0;                                                                                    \
@@ -275,6 +283,7 @@ static int op_constraints_ok(const orc_problem *p, const double *th) {
         case OP_GAUSSIAN_IID: { /* -(x-mu)^2/(2 s^2) - log s - 1/2 log 2pi, summed as BS:492 */     \
             const T mu = th[0], sg = th[1];                                                         \
             const T c = -LOGF(sg) - (T)HALF_LOG_2PI, h = 1 / (2 * sg * sg);                         \
+            ORC_SIMD                                                                                \
             for (int64_t i = 0; i < n; ++i) { const T r = (T)p->in[i] - mu; s += c - r * r * h; }   \
             return s;                                                                               \
         }                                                                                           \
@@ -282,6 +291,7 @@ static int op_constraints_ok(const orc_problem *p, const double *th) {
             const int deg = p->iparam[0];                                                           \
             const T sg = th[deg + 1];                                                               \
             const T c = -LOGF(sg) - (T)HALF_LOG_2PI, h = 1 / (2 * sg * sg);                         \
+            ORC_SIMD                                                                                \
             for (int64_t i = 0; i < n; ++i) {                                                       \
                 const T x = p->in[i];                                                               \
                 T t = th[deg];                                                                      \
@@ -293,6 +303,7 @@ static int op_constraints_ok(const orc_problem *p, const double *th) {
         }                                                                                           \
         case OP_LOGISTIC: { /* categorical softmax, reference class K: z_K = 0 */       \
             const int F = p->n_in, K = p->iparam[1];                                                \
+            ORC_SIMD                                                                                \
             for (int64_t i = 0; i < n; ++i) {                                                       \
                 T z[ORC_MAXD];                                                                      \
                 T mx = 0;                                                                           \
@@ -314,6 +325,7 @@ static int op_constraints_ok(const orc_problem *p, const double *th) {
         case OP_GBM: { /* GeometricBrownianMotionProcess[mu, sigma, x0] on (t_i, x_i), SURVEY 8a */ \
             const T mu = th[0], sg = th[1];                                                         \
             const T m = mu - sg * sg / 2;                                                           \
+            ORC_SIMD                                                                                \
             for (int64_t i = 1; i < n; ++i) {                                                       \
                 const T dt = (T)p->in[i] - (T)p->in[i - 1];                                         \
                 const T r = LOGF((T)p->out[i] / (T)p->out[i - 1]);                                  \
@@ -1093,11 +1105,13 @@ ORC_API int64_t orc_bench_walks(const orc_problem *p, const orc_prior *pr, const
                     xn[a] = v;
                 }
                 orc_uniform2(seed, 0, (uint32_t)s, (uint32_t)rep, TAG_ACCEPT, (uint32_t)th, ua);
-                /* every proposal is scored (as the GPU batch does) so evals are comparable */
+                /* nsDensity (BS:602-617) is If[box && logL > L*, ...]: a proposal outside the box is rejected
+                 * without a likelihood evaluation, and is not counted as one */
+                if (!in_box(pr, xn)) continue;
                 const double nL = orc_loglike(p, NULL, xn);
                 ++total;
                 acc_sink += nL;
-                if (in_box(pr, xn) && nL > Lstar) {
+                if (nL > Lstar) {
                     const double nPr = orc_logprior(pr, xn);
                     if (nPr - xPr > log(ua[0])) { memcpy(x, xn, sizeof(double) * d); xPr = nPr; }
                 }

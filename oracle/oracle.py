@@ -348,11 +348,46 @@ def combine_runs(runs):
                 n_deleted=M - n_tot)
 
 
-def bench_walks(problem: Problem, prior: Prior, start_points, Lstar, reps_per_thread, S, seed, threads):
+_fast = None
+FAST_FLAGS = None
+
+
+def fast_lib():
+    """The timed CPU arm (bench.py only): the same source built -O3 with vectorised sums (oracle/Makefile).  Tries
+    -march=native on the machine being timed (into a private temp dir), else the prebuilt x86-64-v3 library."""
+    global _fast, FAST_FLAGS
+    if _fast is None:
+        import shutil
+        import tempfile
+        path, arch = os.path.join(_HERE, "_build", "libbinest_oracle_fast.so"), "x86-64-v3"
+        if shutil.which("gcc") or os.path.exists("/usr/bin/gcc"):
+            try:
+                tmp = os.path.join(tempfile.mkdtemp(prefix="binest_oracle_"), "libbinest_oracle_fast.so")
+                subprocess.check_call(["make", "-s", "-C", _HERE, tmp, f"FAST_OUT={tmp}", "FAST_ARCH=native"],
+                                      stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+                path, arch = tmp, "native"
+            except Exception:
+                pass
+        if not os.path.exists(path):
+            build(force=True)
+        _fast = C.CDLL(path)
+        dp = C.POINTER(C.c_double)
+        _fast.orc_bench_walks.restype = C.c_int64
+        _fast.orc_bench_walks.argtypes = [C.c_void_p, C.c_void_p, dp, C.c_int64, C.c_double, C.c_int64,
+                                          C.c_int64, C.c_uint64, C.c_int, dp]
+        FAST_FLAGS = f"gcc -O3 -march={arch} -ffast-math -fopenmp, omp simd sums"
+    return _fast
+
+
+def bench_walks(problem: Problem, prior: Prior, start_points, Lstar, reps_per_thread, S, seed, threads, fast=True):
+    """Timed CPU leg: returns the number of likelihood evaluations PERFORMED (proposals outside the box are rejected
+    without one, as nsDensity BS:602-617 does).  The handles come from the parity library; both builds share the
+    struct layout (same source)."""
     sp = _f64(start_points)
     sink = np.empty(max(threads, 1))
-    return int(lib().orc_bench_walks(problem.h, prior.h, _dp(sp), sp.shape[0], Lstar, reps_per_thread, S,
-                                     seed, threads, _dp(sink)))
+    L = fast_lib() if fast else lib()
+    return int(L.orc_bench_walks(problem.h, prior.h, _dp(sp), sp.shape[0], Lstar, reps_per_thread, S,
+                                 seed, threads, _dp(sink)))
 
 
 def max_threads():

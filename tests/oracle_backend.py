@@ -36,10 +36,11 @@ class Comm:
 
 
 class Problem:
-    def __init__(self, op, inputs, outputs, iparam, kinds, lo, hi, p0=None, p1=None, comm=None):
+    def __init__(self, op, inputs, outputs, iparam, kinds, lo, hi, p0=None, p1=None, comm=None, shard="rows"):
         self.d = len(kinds)
-        self.comm = comm
-        if comm is not None:
+        self.comm = comm if shard == "rows" else None
+        self.comm_batch = comm if shard == "batch" else None
+        if comm is not None and shard == "rows":
             from bayesianinference_b200 import configs as _cfg
             from bayesianinference_b200.engine import shard_rows
             inputs = np.asarray(inputs, float)
@@ -51,6 +52,16 @@ class Problem:
         self.prior = O.Prior(kinds, lo, hi, p0 or None, p1 or None)
 
     def loglike(self, theta):
+        if self.comm_batch is not None:
+            # batch-sharded (gp.cu: gp_loglike_device_strided): contiguous slices of cnt = ceil(P / world), one per rank
+            theta = np.atleast_2d(np.asarray(theta, float))
+            P, W, r = theta.shape[0], self.comm_batch.world, self.comm_batch.rank
+            cnt = -(-P // W)
+            lo, hi = min(P, r * cnt), min(P, r * cnt + cnt)
+            mine = np.zeros(cnt)
+            if hi > lo:
+                mine[:hi - lo] = self.prob.loglike(theta[lo:hi], self.prior)
+            return self.comm_batch.allgather(mine).reshape(-1)[:P]
         v = self.prob.loglike(theta, self.prior)
         if self.comm is None:
             return v

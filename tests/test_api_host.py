@@ -457,6 +457,47 @@ def _shard_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _batch_shard_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    c = cfg.c5_gp(N=24)
+    pars = [(nm, lo, hi) for nm, lo, hi in zip(c.names, c.lo, c.hi)]
+    obj = api.defineGaussianProcess((c.inputs[:, 0], c.outputs[:, 0]), api.SquaredExponentialGP(*c.names), pars,
+                                    ["ScaleParameter"] * 3, DataSharding="Automatic", _backend_override=OB)
+    th = obj["_problem"].sample_prior(7, 5)  # 7 vectors over 2 ranks: slices of 4 and 3
+    res = api.nestedSampling(obj, SamplePoolSize=12, BatchSize=5, MonteCarloSteps=6, MaxIterations=10, MinIterations=10,
+                             PostProcessSamplingRuns=None, Seed=2)
+    q.put((rank, obj["LogLikelihoodFunction"](th), res["Samples"]["LogLikelihood"]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_batch_sharding_gloo_matches_unsharded():
+    """Batch-sharded mode host logic, world_size 2 on CPU: the GP problem splits every theta batch
+    into contiguous slices, one per rank, and every rank ends with all values — likelihood batches (ragged: 7 over 2)
+    and a short nested-sampling run equal the unsharded ones exactly."""
+    import torch.multiprocessing as tmp
+    c = cfg.c5_gp(N=24)
+    pars = [(nm, lo, hi) for nm, lo, hi in zip(c.names, c.lo, c.hi)]
+    obj = api.defineGaussianProcess((c.inputs[:, 0], c.outputs[:, 0]), api.SquaredExponentialGP(*c.names), pars,
+                                    ["ScaleParameter"] * 3, _backend_override=OB)
+    th = obj["_problem"].sample_prior(7, 5)
+    want = obj["LogLikelihoodFunction"](th)
+    res = api.nestedSampling(obj, SamplePoolSize=12, BatchSize=5, MonteCarloSteps=6, MaxIterations=10, MinIterations=10,
+                             PostProcessSamplingRuns=None, Seed=2)
+    ctx = tmp.get_context("spawn")
+    q = ctx.Queue()
+    port = 30700 + os.getpid() % 2000
+    procs = [ctx.Process(target=_batch_shard_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    out = sorted((q.get(timeout=240) for _ in procs), key=lambda t: t[0])
+    [p.join(60) for p in procs]
+    for _, ll, L in out:
+        np.testing.assert_array_equal(ll, want)
+        np.testing.assert_array_equal(L, res["Samples"]["LogLikelihood"])
+
+
 def test_data_sharding_gloo_matches_unsharded():
     import torch.multiprocessing as tmp
     o2, th2, o4, th4 = _sharded_objs()  # no process group here: "Automatic" -> unsharded

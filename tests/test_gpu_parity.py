@@ -503,6 +503,66 @@ def test_gp_marginal_likelihood_matches_oracle(eng, O, N):
     np.testing.assert_allclose(out[[0, 1, 4]], got[[0, 1, 4]], rtol=1e-13)
 
 
+def _gp_logl_lapack(c, th):
+    """fp64 LAPACK Cholesky of the same covariance (scipy.linalg.cho_factor): -1/2 (N log 2pi + logdet + r.K^-1 r)."""
+    import scipy.linalg as sl
+    x, y = c.inputs[:, 0], c.outputs[:, 0]
+    N = x.size
+    d2 = (x[:, None] - x[None, :]) ** 2
+    out = []
+    for sf, ell, sn in th:
+        K = sf * sf * np.exp(-d2 / (2.0 * ell * ell))
+        K[np.diag_indices(N)] += sn * sn
+        L = sl.cholesky(K, lower=True, overwrite_a=True, check_finite=False)
+        z = sl.solve_triangular(L, y, lower=True, check_finite=False)
+        out.append(-0.5 * (N * np.log(2.0 * np.pi) + 2.0 * np.log(np.diag(L)).sum() + z @ z))
+    return np.array(out)
+
+
+def test_gp_c5_at_its_stated_size(eng, O):
+    """BASELINE config C5 as stated: N = 4096 (32 panels of 128, the two-level blocked sweep with its binary in-group
+    schedule and full-width K = 1024 updates).  Six hyper-parameter sets against LAPACK's fp64 Cholesky of the same
+    matrix, one of them also against the oracle's long-double Cholesky (GP:130-141 restated, ~30 s on the host);
+    tolerance 1e-10 relative (kappa(K) <~ 1e4 for these nuggets)."""
+    c = cfg.c5_gp()
+    assert c.inputs.shape[0] == 4096
+    gp, op, pr = _pair(eng, O, c)
+    th = np.vstack([[1.0, 0.8, 0.3], [0.7, 1.5, 0.1], [2.0, 0.4, 0.5], [0.3, 3.0, 0.05], pr.sample(2, 77)])
+    got = gp.loglike(th)
+    ref = _gp_logl_lapack(c, th)
+    np.testing.assert_allclose(got, ref, rtol=1e-10)
+    hi, _ = op.loglike_quad(th[:1])
+    assert abs(got[0] - hi[0]) <= 1e-10 * abs(hi[0]), (got[0], hi[0])
+    # a batch larger than one sub-batch split, with box violations inside it: values do not depend on the batch
+    big = np.vstack([th, th[::-1], th])
+    big[7, 2] = 0.0
+    out = gp.loglike(big)
+    assert out[7] == O.LOGZERO
+    np.testing.assert_array_equal(np.delete(out, 7), np.delete(np.concatenate([got, got[::-1], got]), 7))
+
+
+def test_gp_not_positive_definite_gives_logzero(eng, O):
+    """matrixInverseAndDet Throws for a singular matrix and the likelihood becomes logzero (GP:131-135, 190-197).  With
+    a nugget far below eps * sigma_f^2 and a long length scale the covariance has numerical rank ~15: a pivot of the
+    Cholesky sweep comes out <= 0 and the value must be exactly logzero — in the first panel (N = 100: diagonal-block
+    kernel only) and in a later one (N = 700)."""
+    for N in (100, 700):
+        c0 = cfg.c5_gp(N=N)
+        lo = list(c0.lo)
+        lo[2] = 1e-12
+        x = c0.inputs
+        if N == 700:
+            # first panel (128 inputs, spacing 7.9 >> ell) is well conditioned; the dense block behind it is not
+            x = np.concatenate([np.linspace(0.0, 1000.0, 128), 2000.0 + np.sort(c0.inputs[:572, 0])]).reshape(-1, 1)
+        c = cfg.Config(c0.name, c0.op, x, c0.outputs, c0.iparam, c0.names, c0.kinds, lo, c0.hi)
+        gp, op, pr = _pair(eng, O, c)
+        th = np.array([[1.0, 4.5, 1e-10], [1.0, 0.8, 0.3], [3.0, 4.9, 1e-11]])
+        got = gp.loglike(th)
+        assert got[0] == O.LOGZERO and got[2] == O.LOGZERO, got
+        hi, _ = op.loglike_quad(th[1:2])
+        assert abs(got[1] - hi[0]) <= 1e-10 * abs(hi[0])  # the healthy matrix of the same batch is unaffected
+
+
 def test_gp_nested_sampling_small(eng, O):
     """A short GP run end to end: engine trajectory equals the oracle's (same seed, frozen proposals)."""
     c = cfg.c5_gp(N=96)
