@@ -13,6 +13,7 @@
 #include "problem.cuh"
 #include "walk.cuh"
 #include "walk_grid.cuh"
+#include "walk_loop.cuh"
 #include "walk_resident.cuh"
 
 namespace binest {
@@ -37,6 +38,11 @@ struct binest_run {
     int res_cs = 1;             // cluster size of the resident kernel
     long long res_rpc = 0;      // data rows per CTA of the cluster
     size_t res_smem = 0;
+    bool loop = false;          // whole nested-sampling loop in one launch per advance (walk_loop.cuh)
+    int loop_nt = 256;
+    size_t loop_smem = 0;
+    LoopCtl *h_ctl = nullptr;   // pinned
+    DevBuf<LoopCtl> ctl;
     bool grid = false;          // whole walk in one persistent cooperative launch, data resident in all SMs' smem
     int grid_G = 0, grid_Gs = 0, grid_tw = 1, grid_passes = 0, grid_passesA = 0;
     long long grid_rpc = 0;
@@ -69,6 +75,7 @@ struct binest_run {
         if (h_state) cudaFreeHost(h_state);
         if (h_unfrozen) cudaFreeHost(h_unfrozen);
         if (h_abort) cudaFreeHost(h_abort);
+        if (h_ctl) cudaFreeHost(h_ctl);
     }
 };
 
@@ -117,6 +124,55 @@ void ensure_dead_capacity(binest_run &r, int64_t need) {
 inline bool G_own_too_many(int num_sms, int PA, int P) {
     const int a = std::min(PA, P), b = P - a;
     return (a + num_sms - 1) / num_sms > kGridMaxOwn || (b + num_sms - 1) / num_sms > kGridMaxOwn;
+}
+
+// Device-resident loop (walk_loop.cuh): data rows and the sort buffers fit one CTA's shared memory, at most 32 walkers
+// per iteration (a warp each), default acceptance range (the acceptance-retry protocol BS:730-736, 995-1004 needs the
+// host between blocks of steps).
+template <class OP>
+bool plan_loop(binest_run &r) {
+    binest_problem &p = *r.prob;
+    const RunParams &q = r.prm;
+    if (q.acc_min > 0.0 || q.acc_max < 1.0) return false;
+    if (q.K > 32 || p.rows * OP::NCOL > 4096 || r.n_pad > 4096) return false;
+    if (q.K > 8 && OP::D > 3) return false;  // the 1024-thread instantiation has 64 registers per thread
+    r.loop_nt = q.K <= 8 ? 256 : 1024;
+    r.loop_smem = loop_smem_bytes<OP>(p.rows, r.n_pad);
+    if (r.loop_nt == 256)
+        BN_CUDA(cudaFuncSetAttribute(ns_loop_kernel<OP, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r.loop_smem));
+    else
+        BN_CUDA(cudaFuncSetAttribute(ns_loop_kernel<OP, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r.loop_smem));
+    BN_CUDA(cudaHostAlloc((void **)&r.h_ctl, sizeof(LoopCtl), cudaHostAllocDefault));
+    r.ctl.alloc(1);
+    r.loop = true;
+    return true;
+}
+
+// One launch = iterations until every run of the group has terminated, `budget` iterations are done, or a dead list is
+// full.  Returns the number of iterations executed (max over the runs).
+template <class OP>
+long long launch_loop(binest_run &r, long long budget) {
+    binest_problem &p = *r.prob;
+    BN_CUDA(cudaMemsetAsync(r.ctl.p, 0, sizeof(LoopCtl), r.stream));
+    BN_CUDA(cudaMemsetAsync(r.n_unfrozen.p, 0, sizeof(int), r.stream));
+    const double *data = p.data.p;
+    const int mode = r.first ? 1 : 0;
+    BN_CUDA(cudaEventRecord(r.ev0, r.stream));
+    if (r.loop_nt == 256)
+        ns_loop_kernel<OP, 256><<<r.prm.R, 256, r.loop_smem, r.stream>>>(r.prm, r.A, p.prior, data, p.rows, p.cst, r.n_pad, mode, budget, r.ctl.p);
+    else
+        ns_loop_kernel<OP, 1024><<<r.prm.R, 1024, r.loop_smem, r.stream>>>(r.prm, r.A, p.prior, data, p.rows, p.cst, r.n_pad, mode, budget, r.ctl.p);
+    BN_LAUNCH_CHECK();
+    BN_CUDA(cudaEventRecord(r.ev1, r.stream));
+    r.first = false;
+    BN_CUDA(cudaMemcpyAsync(r.h_ctl, r.ctl.p, sizeof(LoopCtl), cudaMemcpyDeviceToHost, r.stream));
+    BN_CUDA(cudaMemcpyAsync(r.h_state, r.state.p, sizeof(RunState) * r.prm.R, cudaMemcpyDeviceToHost, r.stream));
+    BN_CUDA(cudaStreamSynchronize(r.stream));
+    float ms = 0;
+    BN_CUDA(cudaEventElapsedTime(&ms, r.ev0, r.ev1));
+    r.walk_ms += ms;
+    r.walk_graphs += 1;
+    return r.h_ctl->iters;
 }
 
 template <class OP>
@@ -274,6 +330,8 @@ void build_walk_graph(binest_run &r) {
             p.comm->exchanges = ex0; p.comm->bytes_pushed = by0; g_launches.store(l0);  // capture enqueued nothing
             return;
         }
+        // tiny, latency-bound problems: the whole nested-sampling loop stays on the device (walk_loop.cuh)
+        if (std::getenv("BINEST_NO_LOOP") == nullptr && plan_loop<OP>(r)) return;
         // small data: the resident cluster kernel replaces the per-step graph (walk_resident.cuh)
         if (std::getenv("BINEST_NO_RESIDENT") == nullptr) {
             const size_t budget = 200 * 1024;
@@ -501,7 +559,24 @@ int binest_run_advance(binest_run *r, int64_t max_batches, int32_t *finished) {
         const RunParams &q = r->prm;
         const bool acc_loop = q.acc_min > 0.0 || q.acc_max < 1.0;
         int64_t done_batches = 0;
-        while (!r->finished && (max_batches <= 0 || done_batches < max_batches)) {
+        // device-resident loop: no host round trip per iteration (walk_loop.cuh)
+        while (r->loop && !r->finished && (max_batches <= 0 || done_batches < max_batches)) {
+            ensure_dead_capacity(*r, r->dead_upper + q.K + 2);
+            const long long budget = max_batches > 0 ? (long long)(max_batches - done_batches) : (1LL << 60);
+            long long it0 = 0;
+            for (int i = 0; i < q.R; ++i) it0 += r->first ? 1 : r->h_state[i].iteration;
+            long long iters = 0;
+            dispatch_op(*r->prob, [&](auto op) { iters = launch_loop<decltype(op)>(*r, budget); });
+            long long it1 = 0, dmax = 0;
+            for (int i = 0; i < q.R; ++i) { it1 += r->h_state[i].iteration; dmax = std::max<long long>(dmax, r->h_state[i].n_dead); }
+            r->evals += (int64_t)q.S * (it1 - it0);
+            r->dead_upper = dmax;
+            done_batches += iters;
+            r->batches += iters;
+            if (all_done(*r)) { r->finished = true; break; }
+            if (r->h_ctl->need_grow) ensure_dead_capacity(*r, 2 * q.cap);
+        }
+        while (!r->loop && !r->finished && (max_batches <= 0 || done_batches < max_batches)) {
             ensure_dead_capacity(*r, r->dead_upper + q.K + 1);
             launch_update(*r);
             fetch_state(*r);
@@ -659,6 +734,7 @@ int binest_run_path(const binest_run *r, int *path) {
         BN_REQUIRE(r && path, BINEST_ERR_TYPE, "null run");
         if (r->prob->op == BINEST_OP_GP_SE) *path = BINEST_WALK_STEPPED_GP;
         else if (r->prob->comm) *path = BINEST_WALK_STEPPED_SHARDED;
+        else if (r->loop) *path = BINEST_WALK_DEVICE_LOOP;
         else if (r->resident) *path = BINEST_WALK_CLUSTER_RESIDENT;
         else if (r->grid) *path = BINEST_WALK_GRID_RESIDENT;
         else *path = BINEST_WALK_STEPPED_GRAPH;

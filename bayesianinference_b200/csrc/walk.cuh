@@ -108,21 +108,20 @@ __device__ inline int proposal_chol(const double *cov, int d, double *L) {
     return 1;
 }
 
-// one CTA (1024 threads) per run.  Dynamic smem: n_pad doubles + n_pad ints.
-__global__ void __launch_bounds__(1024) run_update_kernel(const __grid_constant__ RunParams prm, RunArrays A, int n_pad,
-                                                          int mode /* 0 normal, 1 first call, 2 insert only */) {
+// The per-iteration update of ONE run by one CTA (any multiple of 32 threads): shared by run_update_kernel (one launch
+// per iteration) and the device-resident loop (walk_loop.cuh).  s_key / s_idx: n_pad doubles / ints of shared memory.
+// Returns 1 when a new batch of walks has been set up, 0 when the run is finished / flushed (nothing to walk).
+__device__ __forceinline__ int run_update_body(const RunParams &prm, const RunArrays &A, int n_pad, int mode, int r,
+                                               double *s_key, int *s_idx) {
     const int first_call = (mode == 1);
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *s_key = reinterpret_cast<double *>(smem_raw);
-    int *s_idx = reinterpret_cast<int *>(s_key + n_pad);
     __shared__ double scratch[100];
     __shared__ double s_mean[BINEST_MAXD];
     __shared__ double s_cov[BINEST_MAXD * BINEST_MAXD];
 
-    const int r = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
-    const int d = prm.d, n = prm.n, K = prm.K, Ps = prm.Ps;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int d = prm.d, n = prm.n, K = prm.K;
     RunState &st = A.state[r];
-    if (st.done) return;
+    if (st.done) return 0;
     double *lth = A.live_theta + (size_t)r * n * d;
     double *lL = A.live_logL + (size_t)r * n, *lPr = A.live_logPr + (size_t)r * n, *lAcc = A.live_acc + (size_t)r * n;
     int *order = A.order + (size_t)r * n;
@@ -222,11 +221,11 @@ __global__ void __launch_bounds__(1024) run_update_kernel(const __grid_constant_
     }
     if (mode == 2) {  // flush for binest_run_fetch on an unfinished run: no kill, no new batch
         if (tid == 0) st.Kb = 0;
-        return;
+        return 0;
     }
     if (!go) {
         if (tid == 0) { st.done = 1; st.Kb = 0; }
-        return;
+        return 0;
     }
     long long Kb_ll = K;
     if (Kb_ll > prm.max_iter - it + 1) Kb_ll = prm.max_iter - it + 1;
@@ -322,6 +321,16 @@ __global__ void __launch_bounds__(1024) run_update_kernel(const __grid_constant_
         for (int a = 0; a < d * d; ++a) A.w_cov[(size_t)w * d * d + a] = st.covEst[a];
     }
     if (tid == 0) atomicAdd(A.n_unfrozen, Kb);
+    return 1;
+}
+
+// one CTA (1024 threads) per run.  Dynamic smem: n_pad doubles + n_pad ints.
+__global__ void __launch_bounds__(1024) run_update_kernel(const __grid_constant__ RunParams prm, RunArrays A, int n_pad,
+                                                          int mode /* 0 normal, 1 first call, 2 insert only */) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *s_key = reinterpret_cast<double *>(smem_raw);
+    int *s_idx = reinterpret_cast<int *>(s_key + n_pad);
+    run_update_body(prm, A, n_pad, mode, blockIdx.x, s_key, s_idx);
 }
 
 // ---------------------------------------------------------------------------------------------------

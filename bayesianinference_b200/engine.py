@@ -244,7 +244,7 @@ class RunGroup:
         check(_lib.load().binest_run_timing(self.h, C.byref(ms), C.byref(g), C.byref(b)))
         return dict(walk_ms=ms.value, walk_graphs=g.value, batches=b.value)
 
-    WALK_PATHS = ("stepped-graph", "cluster-resident", "grid-resident", "stepped-sharded", "stepped-gp")
+    WALK_PATHS = ("stepped-graph", "cluster-resident", "grid-resident", "stepped-sharded", "stepped-gp", "device-loop")
 
     def walk_path(self) -> str:
         v = C.c_int()

@@ -11,6 +11,8 @@ is advanced.  metric = log-likelihood evaluations per second (K*S evals per step
 
 Secondary objects in the same JSON line ("extras", each measured at the same N GPUs, each a STRONG-scaling point —
 total work fixed, so the driver's 1/2/4/8 sweep yields their curves; skipped with --no-extras):
+  "c1"            config C1 as the reference runs it: 100 live points, K = 1, 200 steps, to termination (latency-bound;
+                  the whole loop on the device, walk_loop.cuh).  Unit: live-point replacements/s.
   "c5"            config C5: GP marginal likelihood, N = 4096, ONE batched evaluation of 256 hyper-parameter sets
                   (fill + blocked Cholesky on FP64 DMMA); N > 1: batch-sharded, 256/N matrices per GPU, the finished
                   values exchanged in-kernel over peer-mapped memory.  Roofline: fp64 tensor pipe.
@@ -283,6 +285,34 @@ def measure_c5(ctx, steps, warmup, batch=256):
     }
     gp.close()
     return res
+
+
+def measure_c1(ctx, reps=5):
+    """Config C1 exactly as the reference runs it (BS:837-851 defaults): 100 live points, ONE replacement per iteration,
+    200 walk steps, to termination — a latency-bound chain of ~850 dependent iterations.  The whole loop stays on the
+    device (walk_loop.cuh); wall clock of binest_run_advance(0).  Every rank runs its own seeds (replicas)."""
+    eng = ctx.engine
+    c = cfg.c1_gaussian()
+    gp = eng.Problem.from_config(c)
+    best = None
+    for rep in range(reps + 1):
+        o = eng.default_options(pool_size=100, batch_k=1, mc_steps=MC_STEPS, max_iter=10**6, seed=500 + rep + 100 * ctx.rank)
+        run = eng.RunGroup(gp, o)
+        path = run.walk_path()
+        t0 = time.perf_counter()
+        run.advance(0)
+        dt = time.perf_counter() - t0
+        sz = run.sizes(0)
+        s = run.fetch(0)
+        run.close()
+        if rep > 0 and (best is None or sz["n_deleted"] / dt > best[0]):
+            best = (sz["n_deleted"] / dt, dt, sz["n_deleted"], s["crude_logZ"])
+    gp.close()
+    return {"metric": "live-point replacements/s", "unit": "replacements/s", "value": best[0], "s_per_run": best[1],
+            "replacements": int(best[2]), "crude_logZ": best[3], "logZ_quadrature": c.truth["logZ"], "walk_path": path,
+            "scaling": "replicas", "n_gpus": ctx.world,
+            "config": {"workload": "C1-gaussian: N=100 rows, 100 live points, K=1 (the reference scheme), 200 walk steps, "
+                                   "run to termination", "parallelism": "one sequential chain per GPU"}}
 
 
 def measure_c4_strong(ctx, reps=2):
@@ -561,7 +591,7 @@ def run_ours(args):
 
     if not args.no_extras:
         threading.Thread(target=watchdog, daemon=True).start()
-        plan = [("c5", lambda: measure_c5(ctx, 3, 1)), ("c4_strong", lambda: measure_c4_strong(ctx)),
+        plan = [("c1", lambda: measure_c1(ctx)), ("c5", lambda: measure_c5(ctx, 3, 1)), ("c4_strong", lambda: measure_c4_strong(ctx)),
                 ("data_sharded", lambda: measure_data_sharded(ctx, args.rows))]
         for name, fn in plan:
             # all ranks must agree to enter a collective measurement: a rank-local failure aborts the remaining extras

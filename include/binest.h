@@ -161,7 +161,8 @@ enum binest_walk_path {
     BINEST_WALK_CLUSTER_RESIDENT = 1,/* one launch per walk, data in the shared memories of a CTA cluster */
     BINEST_WALK_GRID_RESIDENT = 2,   /* one persistent cooperative launch per walk, data in all SMs' smem  */
     BINEST_WALK_STEPPED_SHARDED = 3, /* data-sharded: stepped with an all-gather per step                 */
-    BINEST_WALK_STEPPED_GP = 4       /* GP operator: stepped, hundreds of launches per likelihood          */
+    BINEST_WALK_STEPPED_GP = 4,      /* GP operator: stepped, hundreds of launches per likelihood          */
+    BINEST_WALK_DEVICE_LOOP = 5      /* tiny problems: the whole nested-sampling loop in one launch, warp per walker */
 };
 int binest_run_path(const binest_run *r, int *path);
 /* the CUDA stream (cudaStream_t) every kernel of this problem and of its runs is launched on, so that callers

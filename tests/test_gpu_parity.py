@@ -363,6 +363,75 @@ def test_every_walk_path_matches_oracle(eng, O, monkeypatch, path, case):
     run.close()
 
 
+@pytest.mark.parametrize("K,runs", [(1, 1), (8, 3), (32, 2)])
+def test_device_resident_loop_matches_oracle(eng, O, monkeypatch, K, runs):
+    """walk_loop.cuh: the whole nested-sampling loop in one launch (warp-per-walker walks, update by the same CTA) on
+    the C1-shaped problem it is meant for — whole trajectories against the oracle for the reference scheme (K = 1) and
+    for batches, several lock-step runs; the same run through the per-iteration kernels gives the same samples; an
+    advance in pieces (max_batches), a fetch in between and the dead-list growth inside the loop change nothing."""
+    monkeypatch.delenv("BINEST_NO_LOOP", raising=False)
+    c = cfg.c1_gaussian()
+    gp, op, pr = _pair(eng, O, c)
+    n, S, iters = 100, 40, 4800  # > the initial dead capacity of 4096: the loop stops, the host grows, relaunches
+    opts = eng.default_options(pool_size=n, batch_k=K, mc_steps=S, max_iter=iters, min_iter=iters, seed=21, n_runs=runs)
+    start = np.stack([pr.sample(n, 21, r) for r in range(runs)])
+    run = eng.RunGroup(gp, opts, start)
+    assert run.walk_path() == "device-loop"
+    assert not run.advance(3)
+    mid = run.fetch(0)
+    assert mid["n_deleted"] == min(3 * K, iters)
+    assert run.advance(0)
+    res = [run.fetch(r) for r in range(runs)]
+    run.close()
+    for r in range(runs):
+        ref = O.nested_sampling(op, pr, pool_size=n, batch_k=K, mc_steps=S, max_iter=iters, min_iter=iters, seed=21,
+                                adapt_in_walk=False, start_points=start[r], run_id=r)
+        got = res[r]
+        assert got["M"] == ref.logL.size and got["iterations"] == ref.iterations
+        np.testing.assert_allclose(got["logL"], ref.logL, rtol=1e-9)
+        np.testing.assert_allclose(got["points"], ref.points, rtol=1e-7, atol=1e-10)
+        np.testing.assert_allclose(got["acc"][~np.isnan(ref.acc)], ref.acc[~np.isnan(ref.acc)], rtol=1e-12)
+        assert abs(got["crude_logZ"] - ref.crude_logZ) < 1e-9 * abs(ref.crude_logZ)
+    monkeypatch.setenv("BINEST_NO_LOOP", "1")
+    run2 = eng.RunGroup(gp, opts, start)
+    assert run2.walk_path() == "cluster-resident"
+    assert run2.advance(0)
+    other = run2.fetch(runs - 1)
+    run2.close()
+    assert other["M"] == res[-1]["M"]
+    np.testing.assert_allclose(other["logL"], res[-1]["logL"], rtol=1e-10)
+
+
+def test_device_resident_loop_terminates_like_the_stepped_engine(eng, monkeypatch):
+    """Termination inside the device loop (BS:967-978 in the log domain): a full C1 run, reference scheme, stops at the
+    same iteration with the same evidence as the per-iteration engine; and it is the fast path (no host round trip
+    per iteration)."""
+    import time
+    c = cfg.c1_gaussian()
+    gp = eng.Problem.from_config(c)
+    out = {}
+    for mode in ("loop", "stepped"):
+        if mode == "stepped":
+            monkeypatch.setenv("BINEST_NO_LOOP", "1")
+        else:
+            monkeypatch.delenv("BINEST_NO_LOOP", raising=False)
+        opts = eng.default_options(pool_size=100, batch_k=1, mc_steps=200, max_iter=10**6, seed=5)
+        run = eng.RunGroup(gp, opts)
+        t0 = time.perf_counter()
+        assert run.advance(0)
+        dt = time.perf_counter() - t0
+        s = run.fetch(0)
+        out[mode] = (s, dt, run.sizes(0))
+        run.close()
+    a, b = out["loop"][0], out["stepped"][0]
+    assert a["M"] == b["M"] and abs(a["crude_logZ"] - b["crude_logZ"]) < 1e-8
+    assert abs(a["crude_logZ"] - c.truth["logZ"]) < 1.5  # ~ 5 sigma of sqrt(H/n) = 0.27
+    rate = {m: out[m][0]["n_deleted"] / out[m][1] for m in out}
+    print(f"C1 reference scheme (K = 1, S = 200): device loop {rate['loop']:.0f} replacements/s, "
+          f"per-iteration kernels {rate['stepped']:.0f} replacements/s")
+    assert rate["loop"] > 2.0 * rate["stepped"]
+
+
 @pytest.mark.parametrize("path", ["resident-cluster", "grid-2sets", "stepped-graph"])
 def test_acceptance_range_loops_match_oracle(eng, O, monkeypatch, path):
     """"MinMaxAcceptanceRate" (BS:848): the inner loop of nsMCMC (extra S-step blocks until the rate is in range or
