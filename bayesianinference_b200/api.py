@@ -765,8 +765,11 @@ def evidenceSampling(obj_or_assoc, paramNames=None, _backend_override=None, **op
 
 def _lex_order(pts, logL=None):
     """Stable order by (logL, point) — SortBy[{#LogLikelihood, #Point}&] (BS:814) — or by point alone.
-    One argsort on the leading key; only the (rare) runs of equal leading keys are refined with a lexsort."""
+    One stable argsort on the leading key (timsort: lists that arrive sorted, or as a concatenation of sorted runs,
+    cost O(M) / O(M log R)); only the (rare) runs of equal leading keys are refined with a lexsort."""
     lead = logL if logL is not None else pts[:, 0]
+    if lead.size > 1 and np.all(lead[1:] > lead[:-1]):
+        return np.arange(lead.size)  # strictly increasing already: the engine's fetch order
     o = np.argsort(lead, kind="stable")
     sl = lead[o]
     tie = sl[1:] == sl[:-1]
@@ -775,7 +778,8 @@ def _lex_order(pts, logL=None):
         m[1:] |= tie
         m[:-1] |= tie
         sub = o[m]
-        keys = tuple(pts[sub, j] for j in range(pts.shape[1] - 1, -1, -1)) + (lead[sub],)
+        # stable within fully equal rows: the original position is the last key
+        keys = (sub,) + tuple(pts[sub, j] for j in range(pts.shape[1] - 1, -1, -1)) + (lead[sub],)
         o[m] = sub[np.lexsort(keys)]
     return o
 
@@ -783,42 +787,72 @@ def _lex_order(pts, logL=None):
 def _merge_samples(tables, pool_sizes):
     """combineRuns BS:1293-1297: Join, DeleteDuplicatesBy Point (first kept), SortBy {logL, Point};
     per-sample pool size = sum over runs of that run's pool size at the sample's likelihood level.
-    O(M log M) for M samples in total, whatever the number of runs: every run's pool size is a step function of the
-    likelihood level that changes at its own samples, so the sum over runs is one cumulative sum over all samples
-    sorted by level (the reference recomputes X from scratch instead, calculateXValues BS:785-799)."""
-    pts = np.concatenate([t["Point"] for t in tables])
-    cols = {k: np.concatenate([t[k] for t in tables]) for k in ("LogLikelihood", "LogPriorPDF", "AcceptanceRate")}
-    rid = np.concatenate([np.full(t["LogLikelihood"].size, i) for i, t in enumerate(tables)])
-    # pool-size step functions: run r contributes tp_r[i] while i of its samples lie strictly below the level
-    base, ev_level, ev_delta = 0, [], []
+    O(M log R) for M samples in R runs: ONE stable sort of the joined list (a concatenation of sorted runs) serves
+    the merge, the duplicate removal and the pool sizes.  Duplicates are a walk's unmoved copies of a live point —
+    same point, same likelihood — so after the stable sort they are adjacent with the Join-order first in front
+    (DeleteDuplicatesBy keeps exactly that one).  Every run's pool size is a step function of the likelihood level
+    that changes at its own samples, so the sum over runs is one cumulative sum over the joined samples in level
+    order (the reference recomputes X from scratch instead, calculateXValues BS:785-799)."""
+    per = []
+    base = 0
     for t, n in zip(tables, pool_sizes):
         o = _lex_order(t["Point"], t["LogLikelihood"])
         tl = t["LogLikelihood"][o]
         tp = t.get("PoolSize")
-        tp = tp[o] if tp is not None else np.concatenate([np.full(tl.size - n, n), np.arange(n, 0, -1)])
+        tp = tp[o] if tp is not None else np.concatenate([np.full(max(tl.size - n, 0), n), np.arange(min(n, tl.size), 0, -1)])
         tp = np.asarray(tp, dtype=np.int64)
         if tl.size:
             base += int(tp[0])
-            ev_level.append(tl)
-            ev_delta.append(np.diff(np.concatenate([tp, [0]])))
-    ev_level, ev_delta = np.concatenate(ev_level), np.concatenate(ev_delta)
-    eo = np.argsort(ev_level, kind="stable")
-    ev_level, csum = ev_level[eo], np.concatenate([[0], np.cumsum(ev_delta[eo])])
-    # DeleteDuplicatesBy[Point]: the first of equal points in Join order survives
-    po = _lex_order(pts)
-    sp = pts[po]
-    dup_sorted = np.concatenate([[False], np.all(sp[1:] == sp[:-1], axis=1)])
-    keep = np.ones(pts.shape[0], dtype=bool)
-    keep[po[dup_sorted]] = False
-    pts, rid = pts[keep], rid[keep]
-    cols = {k: v[keep] for k, v in cols.items()}
+        per.append((o, tl, np.diff(np.concatenate([tp, [0]])) if tl.size else tp))
+    # Join in run order; every run's rows travel in that run's sorted order, `pos` remembers the Join position
+    pts = np.concatenate([t["Point"][o] for t, (o, _, _) in zip(tables, per)])
+    cols = {k: np.concatenate([t[k][o] for t, (o, _, _) in zip(tables, per)]) for k in ("LogLikelihood", "LogPriorPDF", "AcceptanceRate")}
+    rid = np.concatenate([np.full(o.size, i) for i, (o, _, _) in enumerate(per)])
+    offs = np.cumsum([0] + [o.size for o, _, _ in per[:-1]])
+    pos = np.concatenate([o + off for (o, _, _), off in zip(per, offs)])
+    delta = np.concatenate([d for _, _, d in per])
     order = _lex_order(pts, cols["LogLikelihood"])
-    pts, rid = pts[order], rid[order]
+    pts, rid, delta, pos = pts[order], rid[order], delta[order], pos[order]
     cols = {k: v[order] for k, v in cols.items()}
-    pool = base + csum[np.searchsorted(ev_level, cols["LogLikelihood"], side="left")]
+    L = cols["LogLikelihood"]
+    # pool size at a sample = base + sum of the deltas of all run samples STRICTLY below its level
+    csum = np.concatenate([[0], np.cumsum(delta)])
+    new_level = np.concatenate([[True], L[1:] != L[:-1]])
+    first_of_level = np.flatnonzero(new_level)
+    pool = base + csum[first_of_level[np.cumsum(new_level) - 1]]
+    # DeleteDuplicatesBy[Point] (first in Join order kept).  Duplicates are rare (a walk with no accepted move returns
+    # a copy of a live point): rows are hashed, the hashes sorted (integer sort), and only colliding rows are compared
+    # exactly.
+    keep = _first_occurrence_mask(pts, pos)
+    if not keep.all():
+        pts, rid, pool = pts[keep], rid[keep], pool[keep]
+        cols = {k: v[keep] for k, v in cols.items()}
     out = {"Point": pts, "PoolSize": pool.astype(np.int64), "RunIndex": rid}
     out.update(cols)
     return out
+
+
+def _first_occurrence_mask(pts, pos):
+    """True for the rows of `pts` that are the first (smallest `pos`) among rows with equal values."""
+    M, d = pts.shape
+    keep = np.ones(M, dtype=bool)
+    if M < 2:
+        return keep
+    bits = np.ascontiguousarray(pts + 0.0).view(np.uint64).reshape(M, d)  # + 0.0: -0.0 and 0.0 are the same point
+    mult = (np.arange(d, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15) + np.uint64(0xD6E8FEB86659FD93)) | np.uint64(1)
+    with np.errstate(over="ignore"):
+        h = np.bitwise_xor.reduce((bits ^ (bits >> np.uint64(29))) * mult, axis=1)
+    hs = np.sort(h)
+    coll = hs[1:][hs[1:] == hs[:-1]]
+    if coll.size == 0:
+        return keep
+    cand = np.flatnonzero(np.isin(h, np.unique(coll)))
+    sub = pts[cand]
+    o = np.lexsort((pos[cand],) + tuple(sub[:, j] for j in range(d - 1, -1, -1)))
+    so = sub[o]
+    dup = np.concatenate([[False], np.all(so[1:] == so[:-1], axis=1)])
+    keep[cand[o[dup]]] = False
+    return keep
 
 
 def _reference_pool_structure(t, n):

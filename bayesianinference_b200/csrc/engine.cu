@@ -36,6 +36,7 @@ struct binest_run {
     StreamGeom geom{};
     bool resident = false;      // whole walk in one launch, data in (distributed) shared memory
     int res_cs = 1;             // cluster size of the resident kernel
+    int res_tw = 1, res_ch = 16; // walkers per lane, pre-generated steps
     long long res_rpc = 0;      // data rows per CTA of the cluster
     size_t res_smem = 0;
     bool loop = false;          // whole nested-sampling loop in one launch per advance (walk_loop.cuh)
@@ -124,6 +125,47 @@ void ensure_dead_capacity(binest_run &r, int64_t need) {
 inline bool G_own_too_many(int num_sms, int PA, int P) {
     const int a = std::min(PA, P), b = P - a;
     return (a + num_sms - 1) / num_sms > kGridMaxOwn || (b + num_sms - 1) / num_sms > kGridMaxOwn;
+}
+
+// Geometry of the cluster-resident walk (walk_resident.cuh): TW walkers per lane (a cluster owns 32 TW walkers), CS CTAs
+// per cluster sharing the data rows, CH pre-generated steps of increments.  Wider tiles (TW) cut the shared-memory
+// traffic per DFMA but leave fewer clusters: the largest TW whose grid still covers >= 80 % of the SMs wins; if none
+// does (few walkers), the TW with the most CTAs.  BINEST_RES_TW forces a tile width (experiments).
+template <class OP>
+bool plan_resident(binest_run &r, int P) {
+    binest_problem &p = *r.prob;
+    const size_t budget = 200 * 1024;
+    static const int tw_force = [] { const char *e = std::getenv("BINEST_RES_TW"); return e ? std::atoi(e) : 0; }();
+    struct Plan { int tw = 0, cs = 0, ch = 0, ctas = 0; long long rpc = 0; size_t smem = 0; } best;
+    for (int tw = OP::TW_MAX; tw >= 1; tw >>= 1) {
+        if (tw_force > 0 && tw != tw_force && tw_force <= OP::TW_MAX) continue;
+        const int groups = (P + 32 * tw - 1) / (32 * tw);
+        if (tw > 1 && groups * 32 * tw >= 2 * P) continue;  // more than half of the tile would be padding
+        auto smem_of = [&](int c, int ch) {
+            const long long rpc = ((p.rows + c - 1) / c + 1) & ~1LL;
+            return resident_smem_doubles<OP>(rpc, c, tw, ch) * sizeof(double);
+        };
+        int cs = 1;
+        while (cs < 8 && smem_of(cs, 2) > budget) cs <<= 1;
+        if (smem_of(cs, 2) > budget) continue;
+        while (cs < 8 && groups * cs * 2 <= p.num_sms && p.rows / (cs * 2) >= 8 * kResWarps) cs <<= 1;
+        int ch = kResMaxChunk;
+        while (ch > 2 && smem_of(cs, ch) > budget) ch >>= 1;
+        Plan pl;
+        pl.tw = tw; pl.cs = cs; pl.ch = ch; pl.ctas = groups * cs;
+        pl.rpc = ((p.rows + cs - 1) / cs + 1) & ~1LL;
+        pl.smem = smem_of(cs, ch);
+        if (pl.ctas * 5 >= p.num_sms * 4) { best = pl; break; }  // the widest tile that still fills the GPU
+        if (pl.ctas > best.ctas) best = pl;
+    }
+    if (best.tw == 0) return false;
+    r.resident = true;
+    r.res_tw = best.tw; r.res_cs = best.cs; r.res_ch = best.ch; r.res_rpc = best.rpc; r.res_smem = best.smem;
+    dispatch_tw<OP>(best.tw, [&](auto twc) {
+        constexpr int TW = decltype(twc)::value;
+        BN_CUDA(cudaFuncSetAttribute(walk_resident_kernel<OP, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r.res_smem));
+    });
+    return true;
 }
 
 // Device-resident loop (walk_loop.cuh): data rows and the sort buffers fit one CTA's shared memory, at most 32 walkers
@@ -333,26 +375,7 @@ void build_walk_graph(binest_run &r) {
         // tiny, latency-bound problems: the whole nested-sampling loop stays on the device (walk_loop.cuh)
         if (std::getenv("BINEST_NO_LOOP") == nullptr && plan_loop<OP>(r)) return;
         // small data: the resident cluster kernel replaces the per-step graph (walk_resident.cuh)
-        if (std::getenv("BINEST_NO_RESIDENT") == nullptr) {
-            const size_t budget = 200 * 1024;
-            int cs = 1;
-            auto fits = [&](int c) {
-                long long rpc = ((p.rows + c - 1) / c + 1) & ~1LL;
-                return resident_smem_doubles<OP>(rpc, c) * sizeof(double) <= budget;
-            };
-            while (cs < 8 && !fits(cs)) cs <<= 1;
-            if (fits(cs)) {
-                const int groups = (P + 31) / 32;
-                while (cs < 8 && groups * cs * 2 <= p.num_sms && p.rows / (cs * 2) >= 8 * kResWarps) cs <<= 1;
-                r.resident = true;
-                r.res_cs = cs;
-                r.res_rpc = ((p.rows + cs - 1) / cs + 1) & ~1LL;
-                r.res_smem = resident_smem_doubles<OP>(r.res_rpc, cs) * sizeof(double);
-                BN_CUDA(cudaFuncSetAttribute(walk_resident_kernel<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)r.res_smem));
-                return;
-            }
-        }
+        if (std::getenv("BINEST_NO_RESIDENT") == nullptr && plan_resident<OP>(r, P)) return;
         // data that fits the shared memories of all SMs: one persistent launch per walk (walk_grid.cuh)
         if (std::getenv("BINEST_NO_GRID") == nullptr && plan_grid_walk<OP>(r, P)) return;
         const dim3 sgrid((P * 32 + 255) / 256), sblock(256);  // one warp per walker
@@ -386,7 +409,7 @@ void walk_block(binest_run &r, const RunParams &q) {
     if (r.resident) {
         dispatch_op(p, [&](auto op) {
             using OP = decltype(op);
-            const int groups = (q.R * q.K + 31) / 32;
+            const int groups = (q.R * q.K + 32 * r.res_tw - 1) / (32 * r.res_tw);
             cudaLaunchConfig_t cfg{};
             cudaLaunchAttribute attr[1];
             cfg.gridDim = dim3(groups * r.res_cs);
@@ -402,8 +425,11 @@ void walk_block(binest_run &r, const RunParams &q) {
             const double *data = p.data.p;
             long long rows = p.rows, rpc = r.res_rpc;
             OpCst cst = p.cst;
-            int cs = r.res_cs;
-            BN_CUDA(cudaLaunchKernelEx(&cfg, walk_resident_kernel<OP>, q, r.A, p.prior, data, rows, rpc, cst, cs));
+            int cs = r.res_cs, ch = r.res_ch;
+            dispatch_tw<OP>(r.res_tw, [&](auto twc) {
+                constexpr int TW = decltype(twc)::value;
+                BN_CUDA(cudaLaunchKernelEx(&cfg, walk_resident_kernel<OP, TW>, q, r.A, p.prior, data, rows, rpc, cst, cs, ch));
+            });
             BN_LAUNCH_CHECK();
         });
         return;

@@ -1,15 +1,21 @@
-// walk_resident.cuh — the whole S-step constrained walk in ONE launch for data sets that fit in shared memory.
+// walk_resident.cuh — the whole S-step constrained walk in ONE launch for data sets that fit in the shared memories
+// of a thread-block cluster (C4: 16 383 increments = 256 KB over 8 CTAs; small test problems in one CTA).
 //
-// For small data (C1: 800 B, C4: 256 KB) a likelihood launch per walk step is pure launch latency (~8 us fixed cost
-// for < 1 us of fp64 work).  Here a thread-block cluster of CS CTAs owns 32 walkers (lane = walker) for the whole
-// walk: the data rows are sharded over the CS shared memories once, every step each CTA reduces its shard for the
-// 32 proposals (8 warps split the rows; broadcast LDS feeds the operator's DFMA sequence exactly as in
-// loglike_stream_kernel), the CS partial sums are exchanged through distributed shared memory (one
-// barrier.cluster per step) and summed in a fixed order, and warp 0 of every CTA — redundantly and
-// deterministically — applies the accept rule of nsDensity (BS:602-617), the Haario recursion (BS:715-727) and
-// forms the next proposal.  Philox normals for the next 16 steps are produced by all 256 threads at once, off the
-// critical path.  Same Philox addressing and arithmetic as walk_step_kernel, so results are identical to the
-// stepped path and to the oracle.
+// For such data a likelihood launch per walk step is pure launch latency (~8 us fixed cost for ~1 us of fp64 work).
+// Here a cluster of CS CTAs owns WP = 32 TW walkers for the whole walk:
+//   * the data rows are sharded over the CS shared memories once per launch;
+//   * every step each CTA reduces ITS shard for all WP proposals: the 16 warps split the rows, lane = walker, TW walkers
+//     register-tiled per lane exactly as in loglike_stream_kernel (one broadcast LDS per row feeds TW DFMA chains — with
+//     TW = 1 the kernel was bound by the shared-memory return path: a GBM row is 2 DFMAs per walker against one LDS.128;
+//     r01: 0.33 of the fp64 peak on C4, profiles/r01b_resident_c4.md);
+//   * the first TW warps double as CHAIN warps, one per set of 32 walkers (lane = walker): they combine the 16 warp sums
+//     in a fixed order, exchange the CS per-CTA sums through distributed shared memory (st.async + mbarrier
+//     complete_tx: no cluster-wide barrier on the per-step path; two buffers alternate by step parity, a peer can be at
+//     most one step ahead), and — redundantly and deterministically in every CTA — apply the accept rule of nsDensity
+//     (BS:602-617), the Haario recursion (BS:715-727) and form the next proposal;
+//   * Philox normals / log u for the next CH steps are produced by all threads at once, off the per-step path.
+// Same Philox addressing and arithmetic as walk_step_kernel, so results are identical to the stepped path and to the
+// oracle.
 #pragma once
 #include <cooperative_groups.h>
 
@@ -19,34 +25,36 @@ namespace binest {
 
 namespace cg = cooperative_groups;
 
-constexpr int kResChunk = 16;  // walk steps of pre-generated increments held in shared memory
-constexpr int kResWarps = 16;  // warp 0: chain logic, warps 1..15: data (few resident warps per SM, so latency is hidden by ILP)
+constexpr int kResWarps = 16;     // all 16 sweep the data; warps 0..TW-1 also run the chains
+constexpr int kResMaxChunk = 16;  // walk steps of pre-generated increments held in shared memory (upper bound)
 
-// dynamic shared memory layout (doubles): tile | xch[2][CS][32] | red[kResWarps][32] | dz[kResChunk][D][32] |
-//                                          logu[kResChunk][32] | mean[D][32] | cov[D*D][32] | row[32] (OP::Row)
+// dynamic shared memory layout (doubles), WP = 32 TW:
+//   tile | xch[2][CS][WP] | red[kResWarps][WP] | dz[CH][D][WP] | logu[CH][WP] | mean[D][WP] | cov[D*D][WP] | row[WP] (OP::Row)
 template <class OP>
-__host__ __device__ inline size_t resident_smem_doubles(long long rows_per_cta, int CS) {
+__host__ __device__ inline size_t resident_smem_doubles(long long rows_per_cta, int CS, int TW, int CH) {
+    const size_t WP = 32 * (size_t)TW;
     const size_t tile = ((size_t)rows_per_cta * OP::NCOL + 1) & ~(size_t)1;
-    const size_t rowsz = (sizeof(typename OP::Row) * 32 + 7) / 8;
-    return tile + 2 * (size_t)CS * 32 + kResWarps * 32 + (size_t)kResChunk * OP::D * 32 + kResChunk * 32 + OP::D * 32 +
-           OP::D * OP::D * 32 + rowsz;
+    const size_t rowsz = (sizeof(typename OP::Row) * WP + 7) / 8;
+    return tile + 2 * (size_t)CS * WP + kResWarps * WP + (size_t)CH * OP::D * WP + (size_t)CH * WP + OP::D * WP +
+           OP::D * OP::D * WP + rowsz;
 }
 
-template <class OP>
+template <class OP, int TW>
 __global__ void __launch_bounds__(kResWarps * 32)
 walk_resident_kernel(const __grid_constant__ RunParams prm, RunArrays A, const __grid_constant__ PriorSpec prior,
-                     const double *__restrict__ data, long long rows, long long rows_per_cta, const OpCst cst, int CS) {
-    constexpr int D = OP::D, NCOL = OP::NCOL;
+                     const double *__restrict__ data, long long rows, long long rows_per_cta, const OpCst cst, int CS,
+                     int CH) {
+    constexpr int D = OP::D, NCOL = OP::NCOL, WP = 32 * TW;
     extern __shared__ __align__(16) double smem[];
     const size_t tile_sz = ((size_t)rows_per_cta * NCOL + 1) & ~(size_t)1;
     double *tile = smem;
-    double *xch = tile + tile_sz;                   // [2][CS][32]
-    double *red = xch + 2 * CS * 32;                // [kResWarps][32]
-    double *s_dz = red + kResWarps * 32;               // [kResChunk][D][32]
-    double *s_logu = s_dz + kResChunk * D * 32;     // [kResChunk][32]
-    double *s_mean = s_logu + kResChunk * 32;       // [D][32]
-    double *s_cov = s_mean + D * 32;                // [D*D][32]
-    typename OP::Row *s_row = reinterpret_cast<typename OP::Row *>(s_cov + D * D * 32);
+    double *xch = tile + tile_sz;                   // [2][CS][WP]
+    double *red = xch + 2 * CS * WP;                // [kResWarps][WP]
+    double *s_dz = red + kResWarps * WP;            // [CH][D][WP]
+    double *s_logu = s_dz + (size_t)CH * D * WP;    // [CH][WP]
+    double *s_mean = s_logu + (size_t)CH * WP;      // [D][WP]
+    double *s_cov = s_mean + D * WP;                // [D*D][WP]
+    typename OP::Row *s_row = reinterpret_cast<typename OP::Row *>(s_cov + D * D * WP);
 
     __shared__ uint64_t xbar[2];
     cg::cluster_group cluster = cg::this_cluster();
@@ -59,6 +67,7 @@ walk_resident_kernel(const __grid_constant__ RunParams prm, RunArrays A, const _
     const int group = blockIdx.x / CS;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, tid = threadIdx.x;
     const int K = prm.K, P = prm.R * K;
+    const bool chain = wid < TW;  // chain warp of walker set `wid`
 
     // ---- data shard of this CTA -> shared memory (once per launch)
     const long long r0 = (long long)rank * rows_per_cta;
@@ -66,29 +75,28 @@ walk_resident_kernel(const __grid_constant__ RunParams prm, RunArrays A, const _
     const int nr = r1 > r0 ? (int)(r1 - r0) : 0;
     for (int e = tid; e < nr * NCOL; e += blockDim.x) tile[e] = data[r0 * NCOL + e];
 
-    // ---- walker of this lane (the same in every warp and every CTA of the cluster)
-    const int w = group * 32 + lane;
-    const int run = (w < P) ? w / K : 0;
+    // ---- walker of this lane in a chain warp (the same in every CTA of the cluster)
+    const int wl = (chain ? wid : 0) * 32 + lane;  // walker slot inside the group (chain warps only)
+    const int w = group * WP + wl;
+    const int run = (chain && w < P) ? w / K : 0;
     const int j = w - run * K;
     const RunState &st = A.state[run];
-    bool active = (w < P) && !st.done && j < st.Kb && !(A.w_flags[w] & WF_FROZEN);
-    const uint32_t walk_id = (uint32_t)(st.walk_base + j), run_id = prm.first_run_id + run;
+    const bool active = chain && (w < P) && !st.done && j < st.Kb && !(A.w_flags[w < P ? w : 0] & WF_FROZEN);
     const double Lstar = st.Lstar;
-    const int chol_ok = st.chol_ok;
 
-    // chain state lives in the registers of warp 0 (lane = walker); every CTA keeps an identical copy
+    // chain state lives in the registers of the chain warps (lane = walker); every CTA keeps an identical copy
     double x[D], xPr = 0.0, xL = 0.0;
     int steps = 0, nacc = 0;
-    if (wid == 0) {
 #pragma unroll
-        for (int a = 0; a < D; ++a) x[a] = (w < P) ? A.w_theta[(size_t)w * D + a] : 1.0;
-        if (w < P) {
-            xPr = A.w_logPr[w]; xL = A.w_logL[w]; steps = A.w_steps[w]; nacc = A.w_nacc[w];
+    for (int a = 0; a < D; ++a) x[a] = 1.0;
+    if (chain && w < P) {
 #pragma unroll
-            for (int a = 0; a < D; ++a) s_mean[a * 32 + lane] = A.w_mean[(size_t)w * D + a];
+        for (int a = 0; a < D; ++a) x[a] = A.w_theta[(size_t)w * D + a];
+        xPr = A.w_logPr[w]; xL = A.w_logL[w]; steps = A.w_steps[w]; nacc = A.w_nacc[w];
 #pragma unroll
-            for (int a = 0; a < D * D; ++a) s_cov[a * 32 + lane] = A.w_cov[(size_t)w * D * D + a];
-        }
+        for (int a = 0; a < D; ++a) s_mean[a * WP + wl] = A.w_mean[(size_t)w * D + a];
+#pragma unroll
+        for (int a = 0; a < D * D; ++a) s_cov[a * WP + wl] = A.w_cov[(size_t)w * D * D + a];
     }
     if (CS > 1) cluster.sync();  // every CTA's mbarriers are initialised before a peer can signal them
     bool pre = false;
@@ -96,12 +104,12 @@ walk_resident_kernel(const __grid_constant__ RunParams prm, RunArrays A, const _
     const int S = (int)prm.S;
 
     for (int s = 0; s < S; ++s) {
-        // ---- (0) every kResChunk steps: all threads pre-generate the proposal increments L z and log u
-        if ((s % kResChunk) == 0) {
+        // ---- (0) every CH steps: all threads pre-generate the proposal increments L z and log u
+        if ((s % CH) == 0) {
             __syncthreads();
-            for (int e = tid; e < kResChunk * 32; e += blockDim.x) {
-                const int sc = e >> 5, wl = e & 31;
-                const int ww = group * 32 + wl;
+            for (int e = tid; e < CH * WP; e += blockDim.x) {
+                const int sc = e / WP, ws = e - sc * WP;
+                const int ww = group * WP + ws;
                 if (ww < P && s + sc < S) {
                     const int rr = ww / K, jj = ww - rr * K;
                     const RunState &sr = A.state[rr];
@@ -118,22 +126,24 @@ walk_resident_kernel(const __grid_constant__ RunParams prm, RunArrays A, const _
 #pragma unroll
                             for (int b = 0; b <= a; ++b) dz += sr.cholL[a * D + b] * z[b];
                         }
-                        s_dz[(sc * D + a) * 32 + wl] = dz;
+                        s_dz[((size_t)sc * D + a) * WP + ws] = dz;
                     }
                     double u0, u1;
                     rng_uniform2(prm.seed, (uint32_t)(16 * prm.attempt), stp, wid_, TAG_ACCEPT, rid_, u0, u1);
-                    s_logu[sc * 32 + wl] = log(u0);
+                    s_logu[(size_t)sc * WP + ws] = log(u0);
                 }
             }
             __syncthreads();
         }
-        // ---- (1) warp 0: proposal, box / prior pre-check, per-datum coefficients
-        if (wid == 0) {
-            const int sc = s % kResChunk;
+        // ---- (1) chain warps: proposal, box / prior pre-check, per-datum and epilogue coefficients
+        typename OP::Coef fin_c{};
+        bool fin_ok = false;
+        if (chain) {
+            const int sc = s % CH;
 #pragma unroll
             for (int a = 0; a < D; ++a) {
                 // same association as walk_step_kernel: x + (L z) accumulated term by term
-                xn[a] = x[a] + s_dz[(sc * D + a) * 32 + lane];
+                xn[a] = x[a] + ((w < P) ? s_dz[((size_t)sc * D + a) * WP + wl] : 0.0);
             }
             pre = false;
             if (active && in_box<D>(prior, xn)) {
@@ -141,60 +151,58 @@ walk_resident_kernel(const __grid_constant__ RunParams prm, RunArrays A, const _
 #pragma unroll
                 for (int a = 0; a < D; ++a) nPr += logprior_dim(prior, a, xn[a]);
                 if (!isfinite(nPr)) nPr = prm.logzero;
-                pre = (nPr - xPr > s_logu[sc * 32 + lane]);
+                pre = (nPr - xPr > s_logu[(size_t)sc * WP + wl]);
             }
-            s_row[lane] = OP::make_row(xn, cst);
+            s_row[wl] = OP::make_row(xn, cst);
+            fin_c = OP::prepare(xn, fin_ok, cst);  // log sigma, 1/(2 sigma^2), operator constraints
         }
         __syncthreads();
-        // ---- (2) warps 1..7: this CTA's shard of the reduction for the 32 proposals; warp 0 meanwhile evaluates the
-        //          epilogue coefficients of its proposal (log sigma, 1/(2 sigma^2), constraints) off the critical path
-        typename OP::Coef fin_c{};
-        bool fin_ok = false;
-        if (wid == 0) {
-            fin_c = OP::prepare(xn, fin_ok, cst);
-        } else {
-            typename OP::Row c[1];
-            c[0] = s_row[lane];
-            // four independent accumulators: with one walker per lane a single FMA-accumulate chain would be
-            // bound by the DFMA latency, not by its issue rate
-            typename OP::Acc a0[1] = {OP::acc_init()}, a1[1] = {OP::acc_init()}, a2[1] = {OP::acc_init()}, a3[1] = {OP::acc_init()};
-            constexpr int DW = kResWarps - 1;
-            int i = wid - 1;
+        // ---- (2) all warps: this CTA's shard of the reduction for the WP proposals, TW walkers per lane
+        {
+            typename OP::Row c[TW];
+#pragma unroll
+            for (int u = 0; u < TW; ++u) c[u] = s_row[u * 32 + lane];
+            typename OP::Acc acc[TW];
+#pragma unroll
+            for (int u = 0; u < TW; ++u) acc[u] = OP::acc_init();
+            if constexpr (TW == 1 && OP::RENORM == 0) {
+                // one walker per lane: four independent accumulators, or a single FMA-accumulate chain would be bound by
+                // the DFMA latency instead of its issue rate
+                typename OP::Acc a1[1] = {OP::acc_init()}, a2[1] = {OP::acc_init()}, a3[1] = {OP::acc_init()};
+                int i = wid;
 #pragma unroll 2
-            for (; i + 3 * DW < nr; i += 4 * DW) {
-                OP::template rows<1>(c, tile + (size_t)i * NCOL, a0);
-                OP::template rows<1>(c, tile + (size_t)(i + DW) * NCOL, a1);
-                OP::template rows<1>(c, tile + (size_t)(i + 2 * DW) * NCOL, a2);
-                OP::template rows<1>(c, tile + (size_t)(i + 3 * DW) * NCOL, a3);
-                if constexpr (OP::RENORM > 0) {  // one row per accumulator and iteration: small data, cost irrelevant
-                    OP::template renorm<1>(a0); OP::template renorm<1>(a1); OP::template renorm<1>(a2); OP::template renorm<1>(a3);
+                for (; i + 3 * kResWarps < nr; i += 4 * kResWarps) {
+                    OP::template rows<1>(c, tile + (size_t)i * NCOL, acc);
+                    OP::template rows<1>(c, tile + (size_t)(i + kResWarps) * NCOL, a1);
+                    OP::template rows<1>(c, tile + (size_t)(i + 2 * kResWarps) * NCOL, a2);
+                    OP::template rows<1>(c, tile + (size_t)(i + 3 * kResWarps) * NCOL, a3);
                 }
+                for (; i < nr; i += kResWarps) OP::template rows<1>(c, tile + (size_t)i * NCOL, acc);
+                red[wid * WP + lane] = (OP::acc_value(acc[0]) + OP::acc_value(a1[0])) + (OP::acc_value(a2[0]) + OP::acc_value(a3[0]));
+            } else {
+                sweep_rows<OP, TW>(c, tile, wid, kResWarps, nr, acc);
+#pragma unroll
+                for (int u = 0; u < TW; ++u) red[wid * WP + u * 32 + lane] = OP::acc_value(acc[u]);
             }
-            for (; i < nr; i += DW) {
-                OP::template rows<1>(c, tile + (size_t)i * NCOL, a0);
-                if constexpr (OP::RENORM > 0) OP::template renorm<1>(a0);
-            }
-            red[(wid - 1) * 32 + lane] = (OP::acc_value(a0[0]) + OP::acc_value(a1[0])) + (OP::acc_value(a2[0]) + OP::acc_value(a3[0]));
         }
         __syncthreads();
-        // ---- (3) warp 0: fixed-order combine inside the CTA, then all-to-all exchange of the CS partial sums through
-        //          distributed shared memory.  Each peer's value arrives with st.async and signals that CTA's
-        //          mbarrier (complete_tx), so no cluster-wide barrier sits on the per-step critical path; the two
+        // ---- (3) chain warps: fixed-order combine inside the CTA, then all-to-all exchange of the CS partial sums through
+        //          distributed shared memory.  Each peer's value arrives with st.async and signals that CTA's mbarrier
+        //          (complete_tx), so no cluster-wide barrier sits on the per-step critical path; the two
         //          buffers/mbarriers alternate by step parity (a peer can be at most one step ahead).
         const int par = s & 1;
-        if (wid == 0) {
+        if (chain) {
             double part = 0.0;
 #pragma unroll
-            for (int q = 0; q < kResWarps - 1; ++q) part += red[q * 32 + lane];
+            for (int q = 0; q < kResWarps; ++q) part += red[q * WP + wl];
             double sum = part;
             if (CS > 1) {
-                if (lane == 0) mbar_expect_tx(&xbar[par], (uint32_t)(CS * 32 * sizeof(double)));
-                __syncwarp();
-                const uint32_t slot = smem_u32(&xch[(par * CS + rank) * 32 + lane]), bar = smem_u32(&xbar[par]);
+                if (tid == 0) mbar_expect_tx(&xbar[par], (uint32_t)(CS * WP * sizeof(double)));
+                const uint32_t slot = smem_u32(&xch[(par * CS + rank) * WP + wl]), bar = smem_u32(&xbar[par]);
                 for (int dst = 0; dst < CS; ++dst) st_async_f64(mapa_u32(slot, dst), part, mapa_u32(bar, dst));
                 mbar_wait(&xbar[par], (uint32_t)((s >> 1) & 1));
                 sum = 0.0;
-                for (int q = 0; q < CS; ++q) sum += xch[(par * CS + q) * 32 + lane];
+                for (int q = 0; q < CS; ++q) sum += xch[(par * CS + q) * WP + wl];
             }
             // ---- (4) accept rule (nsDensity BS:602-617), Haario recursion (BS:715-727)
             bool acc = false;
@@ -214,31 +222,31 @@ walk_resident_kernel(const __grid_constant__ RunParams prm, RunArrays A, const _
                 double dm_o[D], dm_n[D];
 #pragma unroll
                 for (int a = 0; a < D; ++a) {
-                    const double mo = s_mean[a * 32 + lane];
+                    const double mo = s_mean[a * WP + wl];
                     const double mn = mo + (x[a] - mo) / (t + 1.0);
                     dm_o[a] = x[a] - mo;
                     dm_n[a] = x[a] - mn;
-                    s_mean[a * 32 + lane] = mn;
+                    s_mean[a * WP + wl] = mn;
                 }
                 const double f = (t - 1.0) / t;
 #pragma unroll
                 for (int a = 0; a < D; ++a)
 #pragma unroll
                     for (int b = 0; b < D; ++b)
-                        s_cov[(a * D + b) * 32 + lane] = f * s_cov[(a * D + b) * 32 + lane] + dm_o[a] * dm_n[b] / t;
+                        s_cov[(a * D + b) * WP + wl] = f * s_cov[(a * D + b) * WP + wl] + dm_o[a] * dm_n[b] / t;
                 ++steps;
             }
         }
     }
     // ---- write the chain state back (one CTA of the cluster); freeze per BS:730-736
-    if (wid == 0 && rank == 0 && active) {
+    if (chain && rank == 0 && active) {
 #pragma unroll
         for (int a = 0; a < D; ++a) {
             A.w_theta[(size_t)w * D + a] = x[a];
-            A.w_mean[(size_t)w * D + a] = s_mean[a * 32 + lane];
+            A.w_mean[(size_t)w * D + a] = s_mean[a * WP + wl];
         }
 #pragma unroll
-        for (int a = 0; a < D * D; ++a) A.w_cov[(size_t)w * D * D + a] = s_cov[a * 32 + lane];
+        for (int a = 0; a < D * D; ++a) A.w_cov[(size_t)w * D * D + a] = s_cov[a * WP + wl];
         A.w_logL[w] = xL;
         A.w_logPr[w] = xPr;
         A.w_nacc[w] = nacc;
