@@ -731,7 +731,10 @@ def evidenceSampling(obj_or_assoc, paramNames=None, _backend_override=None, **op
     M = S["LogLikelihood"].size
     if pool is None:
         pool = np.concatenate([np.full(M - n, n), np.arange(n, 0, -1)]).astype(np.int64)
+    import time as _time
+    _t0 = _time.perf_counter()
     cw = be.crude_weights(S["LogLikelihood"], pool, n)
+    _PHASES["crude_weights_s"] = _time.perf_counter() - _t0
     S["LogX"], S["X"], S["CrudeLogPosteriorWeight"] = cw["logX"], np.exp(cw["logX"]), cw["crude_logw"]
     out = dict(a)
     out.update({  # BS:1183-1194
@@ -742,7 +745,9 @@ def evidenceSampling(obj_or_assoc, paramNames=None, _backend_override=None, **op
     if not (isinstance(nruns, (int, np.integer)) and nruns > 0):  # BS:1195-1197
         out["Samples"] = S
         return inferenceObject(out) if wrap else out
+    _t0 = _time.perf_counter()
     ev = be.evidence_sampling(S["Point"], S["LogLikelihood"], pool, n, int(max(nruns, 2)), int(o["Seed"]))
+    _PHASES["evidence_sampling_s"] = _time.perf_counter() - _t0
     S["CrudeLogPosteriorWeight"] = S["CrudeLogPosteriorWeight"] - cw["crude_logZ"]          # BS:1236
     S["CrudePosteriorWeight"] = np.exp(S["CrudeLogPosteriorWeight"])                         # BS:1237
     S["SampledLogX"] = {"Mean": ev["slx_mean"], "StandardError": ev["slx_sd"]}                # BS:1244
@@ -867,6 +872,9 @@ def _reference_pool_structure(t, n):
     return bool(M >= n and np.all(tp[:M - n] == n) and np.array_equal(tp[M - n:], np.arange(n, 0, -1)))
 
 
+_PHASES = {}  # wall-clock seconds of the last combineRuns / evidenceSampling call, by phase (diagnostics for bench.py)
+
+
 def combineRuns(*results, _backend_override=None, **opts):
     """BS:1293-1315.  The merged list is re-weighted as ONE run (evidenceSampling -> calculateXValues BS:785-799).
     "MergeScheme" (not in the reference) selects the X sequence of the merged list:
@@ -886,7 +894,10 @@ def combineRuns(*results, _backend_override=None, **opts):
     pools = [int(a["SamplePoolSize"]) for a in assocs]
     if scheme == "Automatic":
         scheme = "Reference" if all(_reference_pool_structure(a["Samples"], n) for a, n in zip(assocs, pools)) else "PoolSizes"
+    import time as _time
+    _t0 = _time.perf_counter()
     merged = _merge_samples([a["Samples"] for a in assocs], pools)
+    _PHASES["merge_s"] = _time.perf_counter() - _t0
     n_tot = int(sum(pools))
     M = merged["LogLikelihood"].size
     a = dict(assocs[0])
@@ -976,6 +987,7 @@ def parallelNestedSampling(obj, _backend_override=None, **opts):
     res = combineRuns(*runs, _backend_override=be, PostProcessSamplingRuns=o["PostProcessSamplingRuns"],
                       EmpiricalPosteriorDistributionType=o["EmpiricalPosteriorDistributionType"], Seed=o["Seed"])
     tm["combine_and_evidence_s"] = _time.perf_counter() - t1
+    tm.update({"combine_" + k: v for k, v in _PHASES.items()})
     tm["total_s"] = _time.perf_counter() - t0
     if inferenceObjectQ(res):
         res._assoc["_Timing"] = tm  # wall-clock phases of this call on this rank (bench.py; keys() hides "_" entries)

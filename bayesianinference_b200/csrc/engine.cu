@@ -136,7 +136,7 @@ bool plan_resident(binest_run &r, int P) {
     binest_problem &p = *r.prob;
     const size_t budget = 200 * 1024;
     static const int tw_force = [] { const char *e = std::getenv("BINEST_RES_TW"); return e ? std::atoi(e) : 0; }();
-    struct Plan { int tw = 0, cs = 0, ch = 0, ctas = 0; long long rpc = 0; size_t smem = 0; } best;
+    struct Plan { int tw = 0, cs = 0, ch = 0, ctas = 0, waves = 1 << 20; bool fills = false; long long rpc = 0; size_t smem = 0; } best;
     for (int tw = OP::TW_MAX; tw >= 1; tw >>= 1) {
         if (tw_force > 0 && tw != tw_force && tw_force <= OP::TW_MAX) continue;
         const int groups = (P + 32 * tw - 1) / (32 * tw);
@@ -155,8 +155,33 @@ bool plan_resident(binest_run &r, int P) {
         pl.tw = tw; pl.cs = cs; pl.ch = ch; pl.ctas = groups * cs;
         pl.rpc = ((p.rows + cs - 1) / cs + 1) & ~1LL;
         pl.smem = smem_of(cs, ch);
-        if (pl.ctas * 5 >= p.num_sms * 4) { best = pl; break; }  // the widest tile that still fills the GPU
-        if (pl.ctas > best.ctas) best = pl;
+        // all clusters must be co-resident: a cluster of 8 only fits twice into a GPC and one GPC of a B200 is short of
+        // SMs — 15 clusters of 8, not 16 (ncu r2g: 16 clusters ran as two waves, 5.1 ms instead of 2.5 ms per walk)
+        int max_clusters = 0;
+        dispatch_tw<OP>(tw, [&](auto twc) {
+            constexpr int TW = decltype(twc)::value;
+            BN_CUDA(cudaFuncSetAttribute(walk_resident_kernel<OP, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+            cudaLaunchConfig_t cfg{};
+            cudaLaunchAttribute attr[1];
+            cfg.gridDim = dim3(pl.ctas);
+            cfg.blockDim = dim3(kResWarps * 32);
+            cfg.dynamicSmemBytes = pl.smem;
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            if (cudaOccupancyMaxActiveClusters(&max_clusters, walk_resident_kernel<OP, TW>, &cfg) != cudaSuccess) {
+                cudaGetLastError();
+                max_clusters = p.num_sms / cs;
+            }
+        });
+        const int waves = max_clusters > 0 ? (groups + max_clusters - 1) / max_clusters : 1 << 20;
+        pl.waves = waves;
+        // fewest waves first; among those the widest tile whose grid still covers >= 80 % of the SMs, else the most CTAs
+        const bool fills = pl.ctas * 5 >= p.num_sms * 4;
+        const bool better = best.tw == 0 || waves < best.waves ||
+                            (waves == best.waves && !best.fills && (fills || pl.ctas > best.ctas));
+        if (better) { best = pl; best.fills = fills; }
     }
     if (best.tw == 0) return false;
     r.resident = true;

@@ -8,10 +8,10 @@
 //   * one CTA per run; the data rows are loaded into shared memory once per launch;
 //   * the update (sort, evidence, termination test, kill, covariance blend, starts: run_update_body, walk.cuh) is
 //     executed by the whole CTA, exactly the code of run_update_kernel;
-//   * the walks are WARP-PER-WALKER: warp j walks walker j of the batch (K <= warps).  The 32 lanes split the data
-//     rows of every likelihood evaluation and combine with shuffles — no block barrier inside a walk.  Philox normals
-//     and log u are drawn 32 steps at a time (lane = step) and handed out by shuffle.  A proposal that fails the box
-//     or the prior-ratio test is rejected without touching the data (nsDensity's And short-circuits, BS:602-617).
+//   * the walks are WARP-PER-WALKER: warp j walks walker j of the batch (K <= warps), speculating over rejections
+//     (warp_walk below): the proposals of the next 8 steps are scored at once by 8 groups of 4 lanes and the first
+//     accepted one ends the round — no block barrier inside a walk.  Philox normals and log u are drawn 32 steps at a
+//     time (lane = step) and handed out by shuffle.
 //   * the host polls nothing inside the launch; it reads the run state once per launch.
 // Same Philox addressing, accept rule and Haario recursion as walk_step_walker, so trajectories coincide with the
 // other walk paths and with the oracle up to the summation order of the likelihood (pinned by
@@ -34,12 +34,23 @@ __host__ __device__ inline size_t loop_smem_bytes(long long rows, int n_pad) {
     return (tile + (size_t)n_pad) * sizeof(double) + (size_t)n_pad * sizeof(int);
 }
 
-// one walker, one warp, S steps
+// One walker, one warp, S steps — speculative over rejections.
+// A Metropolis chain only moves when a proposal is accepted; while proposals are rejected the base point stays put, so
+// the proposals of the next G = 8 steps can all be formed from the current point and scored AT ONCE (8 groups of 4
+// lanes, each group its own step: draws of that step, box / prior test, likelihood over the data rows split 4 ways).
+// The first accepted group g* ends the round: steps s .. s+g* are committed (g* rejections and one move), later groups
+// are discarded and their steps re-done from the new point in the next round — with the SAME Philox draws, because
+// draws are addressed by step.  The chain is therefore exactly the sequential one (same draws, same decisions, same
+// points); only the latency changes: ~1/acceptance steps per round instead of one.  The Haario recursion is applied
+// step by step for the committed steps (its divisors, which depend on the step count only, are precomputed by the
+// lanes in parallel and multiplied in: a last-ulp difference to x / t, far inside the trajectory tolerance).
+constexpr int kSpecGroups = 8, kSpecLanes = 4;
+
 template <class OP>
 __device__ __forceinline__ void warp_walk(const RunParams &prm, const RunArrays &A, const PriorSpec &prior,
                                           const double *__restrict__ tile, int nr, double rows, const OpCst &cst, int w,
                                           int lane) {
-    constexpr int D = OP::D, NZ = (D + 1) / 2, NCOL = OP::NCOL;
+    constexpr int D = OP::D, NZ = (D + 1) / 2, NCOL = OP::NCOL, G = kSpecGroups, GL = kSpecLanes;
     const int K = prm.K;
     const int r = w / K, j = w - r * K;
     const RunState &st = A.state[r];
@@ -61,14 +72,19 @@ __device__ __forceinline__ void warp_walk(const RunParams &prm, const RunArrays 
 #pragma unroll
     for (int e = 0; e < NC; ++e) cov[e] = (lane + 32 * e < D * D) ? A.w_cov[(size_t)w * D * D + lane + 32 * e] : 0.0;
     double xPr = A.w_logPr[w], xL = A.w_logL[w];
-    int steps = A.w_steps[w], nacc = A.w_nacc[w];
+    const int steps0 = A.w_steps[w];
+    int nacc = A.w_nacc[w];
     const int S = (int)prm.S;
+    const int g = lane / GL, sub = lane - g * GL;
+    const unsigned gmask = ((1u << GL) - 1u) << (g * GL);
 
-    double zl[2 * NZ], lul = 0.0;  // this lane's draws for step (chunk base + lane)
-    for (int s = 0; s < S; ++s) {
-        const int slot = s & 31;
-        if (slot == 0) {
-            const uint32_t c = (uint32_t)(steps + lane);
+    double zl[2 * NZ], lul = 0.0;  // this lane's draws for step (cb + lane)
+    int cb = -64;                  // first step of the current chunk of draws
+    int s = 0;
+    while (s < S) {
+        if (s + G > cb + 32) {  // the window [s, s + G) must lie inside the chunk
+            cb = s;
+            const uint32_t c = (uint32_t)(steps0 + cb + lane);
 #pragma unroll
             for (int b = 0; b < NZ; ++b)
                 rng_normal2(prm.seed, (uint32_t)(b + 16 * prm.attempt), c, walk_id, TAG_NORMAL, run_id, zl[2 * b], zl[2 * b + 1]);
@@ -76,85 +92,103 @@ __device__ __forceinline__ void warp_walk(const RunParams &prm, const RunArrays 
             rng_uniform2(prm.seed, (uint32_t)(16 * prm.attempt), c, walk_id, TAG_ACCEPT, run_id, u0, u1);
             lul = log(u0);
         }
+        // ---- group g scores the proposal of step s + g, formed from the current point
+        const int src = s + g - cb;  // < 32
         double z[D];
 #pragma unroll
-        for (int b = 0; b < D; ++b) z[b] = __shfl_sync(0xffffffffu, zl[b], slot);
-        const double logu = __shfl_sync(0xffffffffu, lul, slot);
-        // proposal x' = x + L z (same association as walk_step_walker)
+        for (int b = 0; b < D; ++b) z[b] = __shfl_sync(0xffffffffu, zl[b], src);
+        const double logu = __shfl_sync(0xffffffffu, lul, src);
         double xn[D];
 #pragma unroll
         for (int a = 0; a < D; ++a) {
-            double v = x[a];
+            double v = x[a];  // x' = x + L z (same association as walk_step_walker)
             if (chol_ok) {
 #pragma unroll
                 for (int b = 0; b <= a; ++b) v += L[a * (a + 1) / 2 + b] * z[b];
             }
             xn[a] = v;
         }
-        bool acc = false;
-        double nPr = 0.0, nL = 0.0;
-        if (in_box<D>(prior, xn)) {
+        double nPr = 0.0;
+        bool pre = false;
+        if (s + g < S && in_box<D>(prior, xn)) {
 #pragma unroll
             for (int a = 0; a < D; ++a) nPr += logprior_dim(prior, a, xn[a]);
             if (!isfinite(nPr)) nPr = prm.logzero;
-            if (nPr - xPr > logu) {  // Metropolis rule on the log density; only then is the likelihood needed
-                bool ok;
-                const typename OP::Coef cf = OP::prepare(xn, ok, cst);
-                typename OP::Row c[1] = {OP::make_row(xn, cst)};
-                typename OP::Acc a0[1] = {OP::acc_init()};
-                for (int i = lane; i < nr; i += 32) {
-                    OP::template rows<1>(c, tile + (size_t)i * NCOL, a0);
-                    if constexpr (OP::RENORM > 0) OP::template renorm<1>(a0);
+            pre = nPr - xPr > logu;  // Metropolis rule on the log density
+        }
+        // likelihood of every group's proposal (unconditionally: the warp runs the code once either way)
+        bool ok;
+        const typename OP::Coef cf = OP::prepare(xn, ok, cst);
+        typename OP::Row c[1] = {OP::make_row(xn, cst)};
+        typename OP::Acc a0[1] = {OP::acc_init()};
+        for (int i = sub; i < nr; i += GL) {
+            OP::template rows<1>(c, tile + (size_t)i * NCOL, a0);
+            if constexpr (OP::RENORM > 0) OP::template renorm<1>(a0);
+        }
+        double sum = OP::acc_value(a0[0]);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        double nL = op_finish<OP>(cf, sum, rows, cst);
+        if (!(ok && isfinite(nL))) nL = prm.logzero;  // RuntimeErrorHandler -> logzero, BS:500-503
+        const bool accg = pre && nL > Lstar;              // nsDensity: logL > threshold, strict (BS:605)
+        // ---- first accepted group ends the round
+        const unsigned votes = __ballot_sync(0xffffffffu, accg && sub == 0);
+        const int remaining = S - s;
+        int gstar = votes ? (__ffs(votes) - 1) / GL : -1;
+        const int n_adv = gstar >= 0 ? gstar + 1 : (remaining < G ? remaining : G);
+        double xa[D], aPr = 0.0, aL = 0.0;
+        if (gstar >= 0) {
+#pragma unroll
+            for (int a = 0; a < D; ++a) xa[a] = __shfl_sync(0xffffffffu, xn[a], gstar * GL);
+            aPr = __shfl_sync(0xffffffffu, nPr, gstar * GL);
+            aL = __shfl_sync(0xffffffffu, nL, gstar * GL);
+        }
+        // ---- Haario recursion for the committed steps, started at t = 10 (BS:715-727); divisors by lane k = step s + k
+        const double tk = 10.0 + (double)(steps0 + s + (lane < G ? lane : 0));
+        const double r1k = 1.0 / (tk + 1.0), fk = (tk - 1.0) / tk, r3k = 1.0 / tk;
+        for (int k = 0; k < n_adv; ++k) {
+            const double r1 = __shfl_sync(0xffffffffu, r1k, k), f = __shfl_sync(0xffffffffu, fk, k),
+                         r3 = __shfl_sync(0xffffffffu, r3k, k);
+            if (k == gstar) {
+#pragma unroll
+                for (int a = 0; a < D; ++a) x[a] = xa[a];
+                xPr = aPr;
+                xL = aL;
+                ++nacc;
+            }
+            double dm_o[D], dm_n[D];
+#pragma unroll
+            for (int a = 0; a < D; ++a) {
+                const double mn = fma(x[a] - mean[a], r1, mean[a]);
+                dm_o[a] = x[a] - mean[a];
+                dm_n[a] = x[a] - mn;
+                mean[a] = mn;
+            }
+#pragma unroll
+            for (int e = 0; e < NC; ++e) {
+                const int idx = lane + 32 * e;
+                if (idx < D * D) {
+                    const int a = idx / D, b = idx - a * D;
+                    double da = 0.0, db = 0.0;
+#pragma unroll
+                    for (int q = 0; q < D; ++q) { if (q == a) da = dm_o[q]; if (q == b) db = dm_n[q]; }
+                    cov[e] = fma(f, cov[e], da * db * r3);
                 }
-                double sum = OP::acc_value(a0[0]);
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-                nL = op_finish<OP>(cf, sum, rows, cst);
-                if (!(ok && isfinite(nL))) nL = prm.logzero;  // RuntimeErrorHandler -> logzero, BS:500-503
-                acc = nL > Lstar;                                // nsDensity: logL > threshold, strict (BS:605)
             }
         }
-        if (acc) {
-#pragma unroll
-            for (int a = 0; a < D; ++a) x[a] = xn[a];
-            xPr = nPr;
-            xL = nL;
-            ++nacc;
-        }
-        // Haario recursion on the chain state, started at t = 10 (BS:715-727)
-        const double t = 10.0 + (double)steps;
-        double dm_o[D], dm_n[D];
-#pragma unroll
-        for (int a = 0; a < D; ++a) {
-            const double mn = mean[a] + (x[a] - mean[a]) / (t + 1.0);
-            dm_o[a] = x[a] - mean[a];
-            dm_n[a] = x[a] - mn;
-            mean[a] = mn;
-        }
-        const double f = (t - 1.0) / t;
-#pragma unroll
-        for (int e = 0; e < NC; ++e) {
-            const int idx = lane + 32 * e;
-            if (idx < D * D) {
-                const int a = idx / D, b = idx - a * D;
-                double da = 0.0, db = 0.0;
-#pragma unroll
-                for (int k = 0; k < D; ++k) { if (k == a) da = dm_o[k]; if (k == b) db = dm_n[k]; }
-                cov[e] = f * cov[e] + da * db / t;
-            }
-        }
-        ++steps;
+        s += n_adv;
     }
     // chain state back (the update of the next iteration adopts it, BS:999, 1006-1016)
     if (lane == 0) {
 #pragma unroll
         for (int a = 0; a < D; ++a) { A.w_theta[(size_t)w * D + a] = x[a]; A.w_mean[(size_t)w * D + a] = mean[a]; }
-        A.w_logL[w] = xL; A.w_logPr[w] = xPr; A.w_nacc[w] = nacc; A.w_steps[w] = steps;
+        A.w_logL[w] = xL; A.w_logPr[w] = xPr; A.w_nacc[w] = nacc; A.w_steps[w] = steps0 + S;
         A.w_flags[w] = WF_FROZEN;
     }
 #pragma unroll
     for (int e = 0; e < NC; ++e)
         if (lane + 32 * e < D * D) A.w_cov[(size_t)w * D * D + lane + 32 * e] = cov[e];
+    (void)gmask;
 }
 
 // one CTA of NT threads per run: NT = 256 (K <= 8 walkers per iteration) or 1024 (K <= 32)

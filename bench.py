@@ -325,7 +325,7 @@ def measure_c4_strong(ctx, reps=2):
         Data=(c.inputs[:, 0], c.outputs[:, 0]), GeneratingDistribution=api.GeometricBrownianMotionProcess("mu", "sigma", 100.0),
         Parameters=[(nm, lo, hi) for nm, lo, hi in zip(c.names, c.lo, c.hi)],
         PriorDistribution=["LocationParameter", "ScaleParameter"])
-    best, info = None, None
+    best, info, allreps = None, None, []
     for rep in range(reps + 1):  # first pass warms the library up (kernel attributes, pools)
         ctx.barrier()
         t0 = time.perf_counter()
@@ -333,6 +333,7 @@ def measure_c4_strong(ctx, reps=2):
                                          Seed=2026 + rep, PostProcessSamplingRuns=100)
         ctx.torch.cuda.synchronize()
         dt = ctx.max_over_ranks(time.perf_counter() - t0)
+        allreps.append({"s": dt, "phases": res.get("_Timing")})
         if rep > 0 and (best is None or dt < best):
             best = dt
             info = (res["GeneratedNestedSamples"], res["LogEvidence"], res.get("_Timing"))
@@ -343,7 +344,7 @@ def measure_c4_strong(ctx, reps=2):
             "config": {"workload": "C4-gbm: 64 parallelNestedSampling runs x 512 live points, T=16384 increments, K=64 "
                                    "replaced per iteration per run, 200 walk steps", "parallelism": f"run-sharded x{ctx.world}: "
                                    f"{-(-64 // ctx.world)} runs per GPU, host merge (combineRuns)"},
-            "phases_s_rank0": timing, "log_evidence": logz, "pull_vs_quadrature": pull}
+            "phases_s_rank0": timing, "all_calls": allreps, "log_evidence": logz, "pull_vs_quadrature": pull}
 
 
 def measure_data_sharded(ctx, rows, iters=2, K=256):
