@@ -652,12 +652,14 @@ def _engine_options(be, o, n_runs=1, first_run_id=0):
 
 def _samples_table(s):
     """Columnar form of the per-sample records (BS:907-912, 1009-1015, 825-828)."""
-    return {
+    t = {
         "Point": s["points"], "LogLikelihood": s["logL"], "LogPriorPDF": s["logPrior"],
         "AcceptanceRate": s["acc"],  # NaN = Missing["InitialSample"] (BS:911)
-        "PoolSize": s["pool"], "LogX": s["logX"], "X": np.exp(s["logX"]),
-        "CrudeLogPosteriorWeight": s["crude_logw"],
+        "PoolSize": s["pool"],
     }
+    if s.get("logX") is not None:  # absent for runs fetched only to be merged (combineRuns re-weights, BS:1299)
+        t.update({"LogX": s["logX"], "X": np.exp(s["logX"]), "CrudeLogPosteriorWeight": s["crude_logw"]})
+    return t
 
 
 def _result_assoc(s, n):
@@ -929,6 +931,13 @@ def _shard(n_runs, rank, world):
     return lo, base + (1 if rank < rem else 0)
 
 
+def _fetch_for_merge(grp, i):
+    try:
+        return grp.fetch(i, weights=False)  # the merged list is re-weighted as one run: per-run weights are not needed
+    except TypeError:
+        return grp.fetch(i)
+
+
 def parallelNestedSampling(obj, _backend_override=None, **opts):
     """BS:1317-1371.  "ParallelRuns" independent runs, each drawing its own starting points, advanced in lock
     step on the GPU (one library call instead of ParallelTable over subkernels) and merged with combineRuns.
@@ -967,7 +976,7 @@ def parallelNestedSampling(obj, _backend_override=None, **opts):
         grp.advance(0)
         tm["device_loop_s"] = _time.perf_counter() - t0
         t1 = _time.perf_counter()
-        local = [(first + i, grp.fetch(i)) for i in range(count)]
+        local = [(first + i, _fetch_for_merge(grp, i)) for i in range(count)]
         grp.close()
         tm["fetch_s"] = _time.perf_counter() - t1
     t1 = _time.perf_counter()

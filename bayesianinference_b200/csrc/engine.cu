@@ -128,60 +128,64 @@ inline bool G_own_too_many(int num_sms, int PA, int P) {
 }
 
 // Geometry of the cluster-resident walk (walk_resident.cuh): TW walkers per lane (a cluster owns 32 TW walkers), CS CTAs
-// per cluster sharing the data rows, CH pre-generated steps of increments.  Wider tiles (TW) cut the shared-memory
-// traffic per DFMA but leave fewer clusters: the largest TW whose grid still covers >= 80 % of the SMs wins; if none
-// does (few walkers), the TW with the most CTAs.  BINEST_RES_TW forces a tile width (experiments).
+// per cluster sharing the data rows, CH pre-generated steps of increments.  Every (TW, CS) that fits is priced with a
+// small model of one walk step and the cheapest wins:
+//   data phase  rows_per_cta x max(4, TW SLOTS / 2) clocks per SM — one broadcast LDS.128 per row (512 B at 128 B/clk)
+//               against TW SLOTS warp-wide DFMAs at 64 lanes/clk; TW = 1 is bound by the shared-memory return path;
+//   per step    ~5000 clocks of chain logic, barriers and the DSMEM exchange (measured: C4, r2g);
+//   waves       all clusters must be co-resident or the walk runs in several waves: a cluster of 8 fits only twice into
+//               a GPC and one GPC of a B200 is short of SMs — 15 clusters of 8, not 16 (ncu r2g: 16 clusters of 8 ran
+//               as two waves, 5.1 ms instead of 2.5 ms per C4 walk) — cudaOccupancyMaxActiveClusters tells.
+// BINEST_RES_TW / BINEST_RES_CS force a tile width / cluster size (experiments).
 template <class OP>
 bool plan_resident(binest_run &r, int P) {
     binest_problem &p = *r.prob;
     const size_t budget = 200 * 1024;
     static const int tw_force = [] { const char *e = std::getenv("BINEST_RES_TW"); return e ? std::atoi(e) : 0; }();
-    struct Plan { int tw = 0, cs = 0, ch = 0, ctas = 0, waves = 1 << 20; bool fills = false; long long rpc = 0; size_t smem = 0; } best;
+    static const int cs_force = [] { const char *e = std::getenv("BINEST_RES_CS"); return e ? std::atoi(e) : 0; }();
+    struct Plan { int tw = 0, cs = 0, ch = 0, ctas = 0; double cost = 1e300; long long rpc = 0; size_t smem = 0; } best;
     for (int tw = OP::TW_MAX; tw >= 1; tw >>= 1) {
         if (tw_force > 0 && tw != tw_force && tw_force <= OP::TW_MAX) continue;
         const int groups = (P + 32 * tw - 1) / (32 * tw);
         if (tw > 1 && groups * 32 * tw >= 2 * P) continue;  // more than half of the tile would be padding
-        auto smem_of = [&](int c, int ch) {
-            const long long rpc = ((p.rows + c - 1) / c + 1) & ~1LL;
-            return resident_smem_doubles<OP>(rpc, c, tw, ch) * sizeof(double);
-        };
-        int cs = 1;
-        while (cs < 8 && smem_of(cs, 2) > budget) cs <<= 1;
-        if (smem_of(cs, 2) > budget) continue;
-        while (cs < 8 && groups * cs * 2 <= p.num_sms && p.rows / (cs * 2) >= 8 * kResWarps) cs <<= 1;
-        int ch = kResMaxChunk;
-        while (ch > 2 && smem_of(cs, ch) > budget) ch >>= 1;
-        Plan pl;
-        pl.tw = tw; pl.cs = cs; pl.ch = ch; pl.ctas = groups * cs;
-        pl.rpc = ((p.rows + cs - 1) / cs + 1) & ~1LL;
-        pl.smem = smem_of(cs, ch);
-        // all clusters must be co-resident: a cluster of 8 only fits twice into a GPC and one GPC of a B200 is short of
-        // SMs — 15 clusters of 8, not 16 (ncu r2g: 16 clusters ran as two waves, 5.1 ms instead of 2.5 ms per walk)
-        int max_clusters = 0;
-        dispatch_tw<OP>(tw, [&](auto twc) {
-            constexpr int TW = decltype(twc)::value;
-            BN_CUDA(cudaFuncSetAttribute(walk_resident_kernel<OP, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-            cudaLaunchConfig_t cfg{};
-            cudaLaunchAttribute attr[1];
-            cfg.gridDim = dim3(pl.ctas);
-            cfg.blockDim = dim3(kResWarps * 32);
-            cfg.dynamicSmemBytes = pl.smem;
-            attr[0].id = cudaLaunchAttributeClusterDimension;
-            attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-            cfg.attrs = attr;
-            cfg.numAttrs = 1;
-            if (cudaOccupancyMaxActiveClusters(&max_clusters, walk_resident_kernel<OP, TW>, &cfg) != cudaSuccess) {
-                cudaGetLastError();
-                max_clusters = p.num_sms / cs;
-            }
-        });
-        const int waves = max_clusters > 0 ? (groups + max_clusters - 1) / max_clusters : 1 << 20;
-        pl.waves = waves;
-        // fewest waves first; among those the widest tile whose grid still covers >= 80 % of the SMs, else the most CTAs
-        const bool fills = pl.ctas * 5 >= p.num_sms * 4;
-        const bool better = best.tw == 0 || waves < best.waves ||
-                            (waves == best.waves && !best.fills && (fills || pl.ctas > best.ctas));
-        if (better) { best = pl; best.fills = fills; }
+        for (int cs = 1; cs <= 8; cs <<= 1) {
+            if (cs_force > 0 && cs != cs_force) continue;
+            if (cs > 1 && p.rows / cs < 4 * kResWarps) break;  // shards thinner than a few rows per warp
+            auto smem_of = [&](int ch) {
+                const long long rpc = ((p.rows + cs - 1) / cs + 1) & ~1LL;
+                return resident_smem_doubles<OP>(rpc, cs, tw, ch) * sizeof(double);
+            };
+            if (smem_of(2) > budget) continue;
+            int ch = kResMaxChunk;
+            while (ch > 2 && smem_of(ch) > budget) ch >>= 1;
+            Plan pl;
+            pl.tw = tw; pl.cs = cs; pl.ch = ch; pl.ctas = groups * cs;
+            pl.rpc = ((p.rows + cs - 1) / cs + 1) & ~1LL;
+            pl.smem = smem_of(ch);
+            int max_clusters = 0;
+            dispatch_tw<OP>(tw, [&](auto twc) {
+                constexpr int TW = decltype(twc)::value;
+                BN_CUDA(cudaFuncSetAttribute(walk_resident_kernel<OP, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+                cudaLaunchConfig_t cfg{};
+                cudaLaunchAttribute attr[1];
+                cfg.gridDim = dim3(pl.ctas);
+                cfg.blockDim = dim3(kResWarps * 32);
+                cfg.dynamicSmemBytes = pl.smem;
+                attr[0].id = cudaLaunchAttributeClusterDimension;
+                attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+                cfg.attrs = attr;
+                cfg.numAttrs = 1;
+                if (cudaOccupancyMaxActiveClusters(&max_clusters, walk_resident_kernel<OP, TW>, &cfg) != cudaSuccess) {
+                    cudaGetLastError();
+                    max_clusters = p.num_sms / cs;
+                }
+            });
+            if (max_clusters < 1) continue;
+            const int waves = (groups + max_clusters - 1) / max_clusters;
+            const double data_clk = (double)pl.rpc * std::max(4.0, 0.5 * tw * OP::SLOTS);
+            pl.cost = waves * (data_clk + 5000.0 + 250.0 * cs);
+            if (pl.cost < best.cost * 0.999 || (pl.cost <= best.cost * 1.001 && pl.ctas > best.ctas)) best = pl;
+        }
     }
     if (best.tw == 0) return false;
     r.resident = true;
@@ -709,6 +713,7 @@ int binest_run_fetch(binest_run *r, int64_t run, double *points, double *logL, d
         BN_REQUIRE(!r->first, BINEST_ERR_FUNCTION, "binest_run_fetch: advance the run first");
         if (!r->finished) launch_update(*r, true);  // insert the batch in flight and re-sort; no new kill
         fetch_state(*r);
+        if (!points && !logL && !logPrior && !acc && !pool && !logX && !crude_logw && !summary) return;  // flush only
         const RunParams &q = r->prm;
         const RunState &s = r->h_state[run];
         const int64_t D = s.n_dead, n = q.n, M = D + n;
@@ -830,7 +835,11 @@ int binest_evidence_sampling(int64_t M, int64_t d, const double *points, const d
                    "bad sample list");
         BN_REQUIRE(post_runs >= 2 && post_runs <= 65535, BINEST_ERR_DIMENSION, "2 <= PostProcessSamplingRuns <= 65535");
         const int R = (int)post_runs;
-        DevBuf<double> dPts((size_t)M * d), dL(M), dSlx((size_t)R * M), dLw((size_t)R * M), dZ(R), dPm((size_t)R * d), dH(R);
+        // the two R x M work arrays (214 MB each for a merged C4 run) are kept between calls: returning them to the
+        // pool and mapping them again stalled one call in three by ~0.5 s (bench r2h)
+        static thread_local DevBuf<double> dSlx, dLw;
+        if (dSlx.n < (size_t)R * M) { dSlx.alloc((size_t)R * M); dLw.alloc((size_t)R * M); }
+        DevBuf<double> dPts((size_t)M * d), dL(M), dZ(R), dPm((size_t)R * d), dH(R);
         DevBuf<long long> dP(M);
         DevBuf<double> o1(M), o2(M), o3(M), o4(M);
         BN_CUDA(cudaMemcpy(dPts.p, points, sizeof(double) * M * d, cudaMemcpyHostToDevice));

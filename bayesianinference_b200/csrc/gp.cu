@@ -111,7 +111,16 @@ gp_fill_kernel(GpBatch g, const double *__restrict__ x, int dim, const double *_
         else {
             double d2 = 0.0;
             for (int k = 0; k < dim; ++k) { const double df = xi[r * dim + k] - xj[c * dim + k]; d2 = fma(df, df, d2); }
-            v = sf2 * exp(-d2 * il2);   // prediction rows: the cross-covariance k(x*, x_j), no nugget (GP:103-109)
+            // branch-free exp (operators.cuh: Cody-Waite + degree-10 polynomial, 3.4e-16 relative) instead of libdevice's
+            // (~50 integer instructions of constant set-up per call): the fill was 3.5 % of a B = 256 sweep
+            // (profiles/r02_gp_launches.md).  Below -700 the true value is < 1e-304 sigma_f^2: taken as 0.
+            const double arg = -d2 * il2;
+            double ev[1] = {0.0};
+            if (arg > -700.0) {
+                const double ax[1] = {arg};
+                exp_bounded<1>(ax, ev);
+            }
+            v = sf2 * ev[0];   // prediction rows: the cross-covariance k(x*, x_j), no nugget (GP:103-109)
             if (gi == gj) v += sn2;
         }
         A[(size_t)gj * g.ld + gi] = v;
@@ -518,7 +527,12 @@ __global__ void __launch_bounds__(512) gp_trsm_kernel(GpBatch g, int k0) {
     load_chunk_async(sB[0], linvT, NB);
     cp_async_commit();
     if (threadIdx.x < NB) sz[threadIdx.x] = g.z[(size_t)b * NB + threadIdx.x];
-    double acc[4][4][2];
+    // L11^-1 is lower triangular: column n of the product only needs k <= n.  Each warp owns two 16-column halves, h
+    // and 7 - h (h = wn), so that every warp skips the same number of all-zero K chunks: half h needs chunks
+    // 0 .. h / 2, i.e. 5 half-chunks per warp instead of 8 (the panel solves were 11 % of a B = 256 sweep,
+    // profiles/r02_gp_launches.md).
+    const int cb0 = wn * 16, cb1 = (7 - wn) * 16;
+    double acc[4][4][2];  // [i: 8-row block][j: 0,1 -> columns cb0 + 8 j; 2,3 -> columns cb1 + 8 (j - 2)]
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -534,7 +548,32 @@ __global__ void __launch_bounds__(512) gp_trsm_kernel(GpBatch g, int k0) {
             cp_async_wait<0>();
         }
         __syncthreads();
-        gemm_chunk<LDS_>(sAfull + c * KC * LDS_, sB[c & 1], wm, wn, lane, acc, false);
+        const bool use0 = c <= wn / 2, use1 = c <= (7 - wn) / 2;
+        const double *sAc = sAfull + c * KC * LDS_, *sBc = sB[c & 1];
+        if (use0 || use1) {
+#pragma unroll
+            for (int kk = 0; kk < KC; kk += 4) {
+                double a[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) a[i] = sAc[(kk + q) * LDS_ + wm * 32 + i * 8 + r];
+                if (use0) {
+                    const double b0 = sBc[(kk + q) * LDS_ + cb0 + r], b1 = sBc[(kk + q) * LDS_ + cb0 + 8 + r];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        dmma_8x8x4(acc[i][0][0], acc[i][0][1], a[i], b0);
+                        dmma_8x8x4(acc[i][1][0], acc[i][1][1], a[i], b1);
+                    }
+                }
+                if (use1) {
+                    const double b0 = sBc[(kk + q) * LDS_ + cb1 + r], b1 = sBc[(kk + q) * LDS_ + cb1 + 8 + r];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        dmma_8x8x4(acc[i][2][0], acc[i][2][1], a[i], b0);
+                        dmma_8x8x4(acc[i][3][0], acc[i][3][1], a[i], b1);
+                    }
+                }
+            }
+        }
         __syncthreads();
     }
     // results: write L21 in place and keep a copy in smem ([n][m] over the A tile buffer) for the y update
@@ -544,7 +583,7 @@ __global__ void __launch_bounds__(512) gp_trsm_kernel(GpBatch g, int k0) {
         for (int j = 0; j < 4; ++j)
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                const int m = wm * 32 + i * 8 + r, n = wn * 32 + j * 8 + 2 * q + h;
+                const int m = wm * 32 + i * 8 + r, n = (j < 2 ? cb0 + j * 8 : cb1 + (j - 2) * 8) + 2 * q + h;
                 A[(size_t)(k0 + n) * ld + i0 + m] = acc[i][j][h];
                 sAfull[n * LDS_ + m] = acc[i][j][h];
             }

@@ -45,7 +45,7 @@ __device__ __forceinline__ double op_finish(const typename OP::Coef &c, double a
 
 // ------------------------------------------------------------------ NormalDistribution[mu, sigma], i.i.d. data
 struct OpGaussian {
-    static constexpr int D = 2, NCOL = 1, TW_MAX = 8, RENORM = 0;
+    static constexpr int D = 2, NCOL = 1, TW_MAX = 8, RENORM = 0, SLOTS = 2;  // SLOTS: fp64 pipe instructions per datum
     struct Coef { double mu, h, lognorm; };
     struct Row { double mu; };
     using Acc = double;
@@ -117,7 +117,7 @@ __device__ __forceinline__ void polyreg_shift(const double *th, double xbar, dou
 
 template <int DEG>
 struct OpPolyReg {
-    static constexpr int D = DEG + 2, NCOL = 2, TW_MAX = 8, RENORM = 0;
+    static constexpr int D = DEG + 2, NCOL = 2, TW_MAX = 8, RENORM = 0, SLOTS = DEG + 1;
     struct Coef { double h, lognorm, c[DEG + 1]; };  // c[0] = delta, c[1..DEG] = shifted coefficients
     struct Row { double c[DEG + 1]; };               // c[0] unused per datum
     using Acc = double;
@@ -329,7 +329,7 @@ __device__ __forceinline__ void exp_bounded_tab(const double (&x)[N], double (&o
 
 template <int F, int K>
 struct OpLogistic {
-    static constexpr int D = (K - 1) * (F + 1), NCOL = (F + 2) & ~1, TW_MAX = 2;
+    static constexpr int D = (K - 1) * (F + 1), NCOL = (F + 2) & ~1, TW_MAX = 2, SLOTS = (K - 1) * (F + 12) + 6;
     struct Coef { int unused; };
     struct Row { double w[K - 1][F + 1]; };
     __device__ __forceinline__ static Row make_row(const double (&th)[D], const OpCst &) {
@@ -439,7 +439,7 @@ struct OpLogistic {
 // device row i = (a_i, b_i) = (r_i / sqrt(dt_i), sqrt(dt_i)), r_i = log(x_i / x_{i-1});
 // cst = Sum_i(-log x_i - 1/2 log dt_i) - rows * 1/2 log 2pi  (parameter independent, fixed at upload)
 struct OpGbm {
-    static constexpr int D = 2, NCOL = 2, TW_MAX = 8, RENORM = 0;
+    static constexpr int D = 2, NCOL = 2, TW_MAX = 8, RENORM = 0, SLOTS = 2;
     struct Coef { double h, lognorm; };
     struct Row { double negm; };
     using Acc = double;

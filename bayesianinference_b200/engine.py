@@ -251,22 +251,25 @@ class RunGroup:
         check(_lib.load().binest_run_path(self.h, C.byref(v)))
         return self.WALK_PATHS[v.value]
 
-    def fetch(self, run=0):
-        """Sorted sample list of one run + calculateWeightsCrude columns (BS:812-831)."""
+    def fetch(self, run=0, weights=True):
+        """Sorted sample list of one run + (weights=True) the calculateWeightsCrude columns (BS:812-831).
+        weights=False skips the per-run weight kernel: the caller is going to merge runs and re-weight anyway."""
         L = _lib.load()
-        # an unfinished run is flushed by the fetch itself, so sizes are read after a first NULL fetch
+        # an unfinished run is flushed by the fetch itself, so sizes are read after a first NULL fetch (flush only)
         check(L.binest_run_fetch(self.h, run, None, None, None, None, None, None, None, None))
         s = self.sizes(run)
         M, d = s["M"], self.problem.d
         pts = np.empty((M, d))
-        logL, logPr, acc, logX, lw = (np.empty(M) for _ in range(5))
+        logL, logPr, acc = (np.empty(M) for _ in range(3))
+        logX, lw, summ = (np.empty(M), np.empty(M), np.empty(4)) if weights else (None, None, None)
         pool = np.empty(M, dtype=np.int64)
-        summ = np.empty(4)
         check(L.binest_run_fetch(self.h, run, dptr(pts), dptr(logL), dptr(logPr), dptr(acc), iptr(pool), dptr(logX),
                                  dptr(lw), dptr(summ)))
-        return dict(points=pts, logL=logL, logPrior=logPr, acc=acc, pool=pool, logX=logX, crude_logw=lw,
-                    crude_logZ=float(summ[0]), entropy=float(summ[1]), logLmax=float(summ[2]),
-                    log_missing=float(summ[3]), n=int(self.options.pool_size), **s)
+        out = dict(points=pts, logL=logL, logPrior=logPr, acc=acc, pool=pool, n=int(self.options.pool_size), **s)
+        if weights:
+            out.update(logX=logX, crude_logw=lw, crude_logZ=float(summ[0]), entropy=float(summ[1]),
+                       logLmax=float(summ[2]), log_missing=float(summ[3]))
+        return out
 
     def estimates(self, run=0):
         d = self.problem.d

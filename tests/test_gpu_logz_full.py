@@ -6,7 +6,8 @@ quantities the reference itself defines in closed form:
   C2  exact evidence -31513.459131 (Appendix A) and its Laplace value (LA:22-30, tests/golden/laplace_pins.json)
   C3  Laplace evidence at N = 1e6 (error O(1/N), K5)
   C5  3-D quadrature of a C5-shaped GP problem at N = 256 (K7)
-C1 and C4 are covered by tests/test_gpu_api.py / test_gpu_parity.py.
+  C4  2-D quadrature (Appendix A), 64 parallel runs x 512 live points as stated
+C1 is covered by tests/test_gpu_api.py / test_gpu_calibration.py.
 """
 import json
 import os
@@ -67,17 +68,18 @@ def test_c2_full_size_log_evidence():
 
 
 def test_c3_full_size_log_evidence():
-    """C3: softmax classification, N = 1e6, 10 parameters, truncated-normal prior; 1024 live points here (half the
-    config's 2048 to bound the test time; scripts/full_runs.py runs the 2048 case)."""
+    """C3 as BASELINE.json states it: softmax classification, N = 1e6, 10 parameters, truncated-normal prior, 2048
+    live points (K = 512 replaced per iteration)."""
     c = cfg.c3_logistic()
     names = c.names
     obj = api.defineInferenceProblem(
         Data=(c.inputs, c.outputs[:, 0]), GeneratingDistribution=api.CategoricalSoftmax(tuple(names), 3),
         Parameters=[(nm, lo, hi) for nm, lo, hi in zip(names, c.lo, c.hi)],
         PriorDistribution=[api.NormalDistribution(0.0, 5.0)] * len(names))
-    res = api.nestedSampling(obj, SamplePoolSize=1024, BatchSize=256, MaxIterations=10**6, Seed=33)
-    # information ~ 68 nats -> sigma ~ sqrt(68/1024) = 0.26
-    z = _check(res, PINS["C3"]["logZ_laplace"], PINS["C3"]["mode"], names, 0.15, 0.42)
+    res = api.nestedSampling(obj, SamplePoolSize=2048, BatchSize=512, MaxIterations=10**6, Seed=33)
+    assert res["SamplePoolSize"] == 2048
+    # information ~ 68 nats -> sigma ~ sqrt(68/2048) = 0.18
+    z = _check(res, PINS["C3"]["logZ_laplace"], PINS["C3"]["mode"], names, 0.10, 0.32)
     # the best of ~60 000 samples of a 10-D posterior sits a little below the mode (chi^2_10 / 2 ~ 5 for a typical one)
     assert -4.0 < res["LogLikelihoodMaximum"] - PINS["C3"]["logL_mode"] <= 1e-6
     lap = api.approximateEvidence(res)
@@ -104,3 +106,22 @@ def test_c5_small_log_evidence_against_quadrature():
         got = np.array([res["ParameterExpectedValues"][nm]["Mean"] for nm in c.names])
         assert np.all(np.abs(got / mode - 1.0) < 0.25), (got, mode)  # posterior is skewed at N = 256: mean != mode
     print("C5 small runs:", zs, "quadrature", p["logZ_quadrature"])
+
+
+def test_c4_full_size_parallel_runs():
+    """C4 as BASELINE.json states it: 64 parallelNestedSampling runs x 512 live points (K = 64 per run and iteration)
+    on the 16 384-increment GBM path, merged with combineRuns (BS:1293-1315) — against the 2-D quadrature value."""
+    c = cfg.c4_gbm()
+    obj = api.defineInferenceProblem(
+        Data=(c.inputs[:, 0], c.outputs[:, 0]), GeneratingDistribution=api.GeometricBrownianMotionProcess("mu", "sigma", 100.0),
+        Parameters=[("mu", -1, 1), ("sigma", 0.01, 2)], PriorDistribution=["LocationParameter", "ScaleParameter"])
+    res = api.parallelNestedSampling(obj, ParallelRuns=64, SamplePoolSize=512, BatchSize=64, MaxIterations=10**6, Seed=77)
+    assert res["SamplePoolSize"] == 64 * 512 and res["MergeScheme"] == "PoolSizes"
+    z = res["LogEvidence"]
+    # H ~ 8.2 nats -> sigma ~ sqrt(H / (64 * 512)) = 0.016
+    assert 0.008 < z["StandardError"] < 0.04, z
+    assert abs(z["Mean"] - c.truth["logZ"]) < 3.0 * z["StandardError"], (z, c.truth["logZ"])
+    pe = res["ParameterExpectedValues"]
+    assert abs(pe["mu"]["Mean"] - 0.0970592) < 0.02 and abs(pe["sigma"]["Mean"] - 0.2498856) < 0.001
+    assert 7.0 < res["RelativeEntropy"]["Mean"] < 9.5
+    print("C4 full run:", z, "truth", c.truth["logZ"], "samples", res["TotalSamples"])
