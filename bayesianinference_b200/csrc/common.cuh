@@ -196,6 +196,30 @@ __device__ __forceinline__ double block_sum(double v, double *scratch) {
     __syncthreads();
     return scratch[32];
 }
+// block-wide sums of nv <= 16 values at once, broadcast to all threads (v[k] <- total); scratch: 33 * 16 doubles.
+// Per value the reduction tree is block_sum's (warp shuffles, then one warp over the warp sums): identical results.
+__device__ __forceinline__ void block_sum_multi(double (&v)[16], int nv, double *scratch) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+        if (k < nv) v[k] = warp_sum(v[k]);
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+            if (k < nv) scratch[k * 33 + w] = v[k];
+    }
+    __syncthreads();
+    for (int k = w; k < nv; k += nw) {
+        double t = lane < nw ? scratch[k * 33 + lane] : 0.0;
+        t = warp_sum(t);
+        if (lane == 0) scratch[k * 33 + 32] = t;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+        if (k < nv) v[k] = scratch[k * 33 + 32];
+}
 __device__ __forceinline__ double block_max(double v, double *scratch) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
     v = warp_max(v);

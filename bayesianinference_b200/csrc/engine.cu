@@ -184,6 +184,9 @@ bool plan_resident(binest_run &r, int P) {
             const int waves = (groups + max_clusters - 1) / max_clusters;
             const double data_clk = (double)pl.rpc * std::max(4.0, 0.5 * tw * OP::SLOTS);
             pl.cost = waves * (data_clk + 5000.0 + 250.0 * cs);
+            if (std::getenv("BINEST_PLAN_DEBUG"))
+                std::fprintf(stderr, "resident plan: tw %d cs %d ch %d groups %d ctas %d max_clusters %d waves %d smem %zu cost %.0f\n",
+                             tw, cs, ch, groups, pl.ctas, max_clusters, waves, pl.smem, pl.cost);
             if (pl.cost < best.cost * 0.999 || (pl.cost <= best.cost * 1.001 && pl.ctas > best.ctas)) best = pl;
         }
     }
@@ -521,7 +524,8 @@ extern "C" {
 int binest_run_create(binest_problem *p, const binest_options *o, const double *start_points, binest_run **out) {
     return guard([&] {
         BN_REQUIRE(p && o && out, BINEST_ERR_TYPE, "null argument");
-        BN_REQUIRE(o->pool_size >= 2 && o->pool_size <= 4096, BINEST_ERR_DIMENSION, "2 <= SamplePoolSize <= 4096");
+        // the live set is sorted in one CTA's shared memory (12 bytes per padded slot): 16384 slots = 192 KB
+        BN_REQUIRE(o->pool_size >= 2 && o->pool_size <= 16384, BINEST_ERR_DIMENSION, "2 <= SamplePoolSize <= 16384");
         BN_REQUIRE(o->batch_k >= 1 && o->batch_k < o->pool_size, BINEST_ERR_DIMENSION, "1 <= batch_k < SamplePoolSize");
         BN_REQUIRE(o->mc_steps >= 1 && o->mc_steps <= 100000, BINEST_ERR_DIMENSION, "MonteCarloSteps out of range");
         BN_REQUIRE(o->n_runs >= 1 && o->n_runs <= 4096, BINEST_ERR_DIMENSION, "n_runs out of range");
@@ -601,7 +605,12 @@ int binest_run_create(binest_problem *p, const binest_options *o, const double *
         }
         BN_CUDA(cudaMemcpyAsync(r->state.p, init.data(), sizeof(RunState) * q.R, cudaMemcpyHostToDevice, r->stream));
         BN_CUDA(cudaStreamSynchronize(r->stream));
-        BN_CUDA(cudaFuncSetAttribute(run_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        {   // the opt-in limit is per function, not per run: never lower it under a run that is still alive
+            static std::atomic<int> lim{0};
+            int want = std::max(64 * 1024, r->n_pad * 12), cur = lim.load();
+            while (want > cur && !lim.compare_exchange_weak(cur, want)) {}
+            BN_CUDA(cudaFuncSetAttribute(run_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lim.load()));
+        }
         build_walk_graph(*r);
         *out = r.release();
     });

@@ -115,6 +115,7 @@ __device__ __forceinline__ int run_update_body(const RunParams &prm, const RunAr
                                                double *s_key, int *s_idx) {
     const int first_call = (mode == 1);
     __shared__ double scratch[100];
+    __shared__ double scratch_m[33 * 16];
     __shared__ double s_mean[BINEST_MAXD];
     __shared__ double s_cov[BINEST_MAXD * BINEST_MAXD];
 
@@ -138,21 +139,38 @@ __device__ __forceinline__ int run_update_body(const RunParams &prm, const RunAr
             lPr[slot] = A.w_logPr[w];
             lAcc[slot] = (double)A.w_nacc[w] / (double)max(A.w_steps[w], 1);
         }
-        for (int a = 0; a < d; ++a) {
-            double v = 0.0;
-            for (int j = tid; j < Kprev; j += nt) v += A.w_mean[(size_t)(r * K + j) * d + a];
-            v = block_sum(v, scratch);
-            if (tid == 0) st.meanEst[a] = v / (double)Kprev;
-        }
-        for (int a = 0; a < d; ++a)
-            for (int b = 0; b <= a; ++b) {
+        if (Kprev <= 32) {
+            // few walkers: thread e owns one entry of the mean / covariance estimate and adds the walkers in order —
+            // no block reduction (with K = 1, the reference scheme, this is a copy)
+            for (int e = tid; e < d + d * d; e += nt) {
                 double v = 0.0;
-                for (int j = tid; j < Kprev; j += nt)
-                    v += 0.5 * (A.w_cov[(size_t)(r * K + j) * d * d + a * d + b] +
-                                A.w_cov[(size_t)(r * K + j) * d * d + b * d + a]);
-                v = block_sum(v, scratch);
-                if (tid == 0) st.covEst[a * d + b] = st.covEst[b * d + a] = v / (double)Kprev;
+                if (e < d) {
+                    for (int j = 0; j < Kprev; ++j) v += A.w_mean[(size_t)(r * K + j) * d + e];
+                    st.meanEst[e] = v / (double)Kprev;
+                } else {
+                    const int a = (e - d) / d, b = (e - d) - a * d;
+                    for (int j = 0; j < Kprev; ++j)
+                        v += 0.5 * (A.w_cov[(size_t)(r * K + j) * d * d + a * d + b] + A.w_cov[(size_t)(r * K + j) * d * d + b * d + a]);
+                    st.covEst[a * d + b] = v / (double)Kprev;
+                }
             }
+        } else {
+            for (int a = 0; a < d; ++a) {
+                double v = 0.0;
+                for (int j = tid; j < Kprev; j += nt) v += A.w_mean[(size_t)(r * K + j) * d + a];
+                v = block_sum(v, scratch);
+                if (tid == 0) st.meanEst[a] = v / (double)Kprev;
+            }
+            for (int a = 0; a < d; ++a)
+                for (int b = 0; b <= a; ++b) {
+                    double v = 0.0;
+                    for (int j = tid; j < Kprev; j += nt)
+                        v += 0.5 * (A.w_cov[(size_t)(r * K + j) * d * d + a * d + b] +
+                                    A.w_cov[(size_t)(r * K + j) * d * d + b * d + a]);
+                    v = block_sum(v, scratch);
+                    if (tid == 0) st.covEst[a * d + b] = st.covEst[b * d + a] = v / (double)Kprev;
+                }
+        }
         if (tid == 0) st.walk_base += Kprev;
     }
     __syncthreads();
@@ -232,22 +250,40 @@ __device__ __forceinline__ int run_update_body(const RunParams &prm, const RunAr
     if (Kb_ll > n - 1) Kb_ll = n - 1;
     const int Kb = (int)Kb_ll;
 
-    // ---- 5. covariance of the live set, blend with the running estimate (BS:989), proposal factor
-    for (int a = 0; a < d; ++a) {
-        double v = 0.0;
-        for (int i = tid; i < n; i += nt) v += lth[(size_t)i * d + a];
-        v = block_sum(v, scratch);
-        if (tid == 0) s_mean[a] = v / (double)n;
+    // ---- 5. covariance of the live set, blend with the running estimate (BS:989), proposal factor.  The d means, then
+    //         the d (d + 1) / 2 covariance entries, are reduced 16 at a time (block_sum_multi: three barriers per
+    //         round instead of per entry; same reduction tree per value as block_sum)
+    {
+        double v[16];
+        for (int a = 0; a < 16; ++a) v[a] = 0.0;
+        for (int i = tid; i < n; i += nt)
+            for (int a = 0; a < d; ++a) v[a] += lth[(size_t)i * d + a];
+        block_sum_multi(v, d, scratch_m);
+        if (tid < d) s_mean[tid] = v[tid] / (double)n;
     }
     __syncthreads();
-    for (int a = 0; a < d; ++a)
-        for (int b = 0; b <= a; ++b) {
-            double v = 0.0;
-            const double ma = s_mean[a], mb = s_mean[b];
-            for (int i = tid; i < n; i += nt) v += (lth[(size_t)i * d + a] - ma) * (lth[(size_t)i * d + b] - mb);
-            v = block_sum(v, scratch);
-            if (tid == 0) s_cov[a * d + b] = s_cov[b * d + a] = v / (double)(n - 1);
+    {
+        const int npair = d * (d + 1) / 2;
+        for (int p0 = 0; p0 < npair; p0 += 16) {
+            const int np = min(16, npair - p0);
+            double v[16];
+            for (int k = 0; k < 16; ++k) v[k] = 0.0;
+            for (int i = tid; i < n; i += nt) {
+                int a = 0, b = 0;
+                for (int k = 0; k < p0; ++k) { if (++b > a) { ++a; b = 0; } }  // pair index -> (a, b), b <= a
+                for (int k = 0; k < np; ++k) {
+                    v[k] += (lth[(size_t)i * d + a] - s_mean[a]) * (lth[(size_t)i * d + b] - s_mean[b]);
+                    if (++b > a) { ++a; b = 0; }
+                }
+            }
+            block_sum_multi(v, np, scratch_m);
+            if (tid < np) {
+                int a = 0, b = 0;
+                for (int k = 0; k < p0 + tid; ++k) { if (++b > a) { ++a; b = 0; } }
+                s_cov[a * d + b] = s_cov[b * d + a] = v[tid] / (double)(n - 1);
+            }
         }
+    }
     __syncthreads();
     if (tid == 0) {
         if (first_call) {  // BS:922-923

@@ -120,12 +120,25 @@ __device__ __forceinline__ void warp_walk(const RunParams &prm, const RunArrays 
         bool ok;
         const typename OP::Coef cf = OP::prepare(xn, ok, cst);
         typename OP::Row c[1] = {OP::make_row(xn, cst)};
-        typename OP::Acc a0[1] = {OP::acc_init()};
-        for (int i = sub; i < nr; i += GL) {
-            OP::template rows<1>(c, tile + (size_t)i * NCOL, a0);
-            if constexpr (OP::RENORM > 0) OP::template renorm<1>(a0);
+        // four independent accumulators: a single FMA-accumulate chain over ~25 rows would be DFMA-latency bound
+        typename OP::Acc a0[1] = {OP::acc_init()}, a1[1] = {OP::acc_init()}, a2[1] = {OP::acc_init()}, a3[1] = {OP::acc_init()};
+        {
+            int i = sub;
+            for (; i + 3 * GL < nr; i += 4 * GL) {
+                OP::template rows<1>(c, tile + (size_t)i * NCOL, a0);
+                OP::template rows<1>(c, tile + (size_t)(i + GL) * NCOL, a1);
+                OP::template rows<1>(c, tile + (size_t)(i + 2 * GL) * NCOL, a2);
+                OP::template rows<1>(c, tile + (size_t)(i + 3 * GL) * NCOL, a3);
+                if constexpr (OP::RENORM > 0) {
+                    OP::template renorm<1>(a0); OP::template renorm<1>(a1); OP::template renorm<1>(a2); OP::template renorm<1>(a3);
+                }
+            }
+            for (; i < nr; i += GL) {
+                OP::template rows<1>(c, tile + (size_t)i * NCOL, a0);
+                if constexpr (OP::RENORM > 0) OP::template renorm<1>(a0);
+            }
         }
-        double sum = OP::acc_value(a0[0]);
+        double sum = (OP::acc_value(a0[0]) + OP::acc_value(a1[0])) + (OP::acc_value(a2[0]) + OP::acc_value(a3[0]));
         sum += __shfl_xor_sync(0xffffffffu, sum, 1);
         sum += __shfl_xor_sync(0xffffffffu, sum, 2);
         double nL = op_finish<OP>(cf, sum, rows, cst);
@@ -146,33 +159,41 @@ __device__ __forceinline__ void warp_walk(const RunParams &prm, const RunArrays 
         // ---- Haario recursion for the committed steps, started at t = 10 (BS:715-727); divisors by lane k = step s + k
         const double tk = 10.0 + (double)(steps0 + s + (lane < G ? lane : 0));
         const double r1k = 1.0 / (tk + 1.0), fk = (tk - 1.0) / tk, r3k = 1.0 / tk;
-        for (int k = 0; k < n_adv; ++k) {
-            const double r1 = __shfl_sync(0xffffffffu, r1k, k), f = __shfl_sync(0xffffffffu, fk, k),
-                         r3 = __shfl_sync(0xffffffffu, r3k, k);
-            if (k == gstar) {
+        double r1[G], ff[G], r3[G];  // handed out before the recursion: no shuffle latency inside its dependent chain
 #pragma unroll
-                for (int a = 0; a < D; ++a) x[a] = xa[a];
-                xPr = aPr;
-                xL = aL;
-                ++nacc;
-            }
-            double dm_o[D], dm_n[D];
+        for (int k = 0; k < G; ++k) {
+            r1[k] = __shfl_sync(0xffffffffu, r1k, k);
+            ff[k] = __shfl_sync(0xffffffffu, fk, k);
+            r3[k] = __shfl_sync(0xffffffffu, r3k, k);
+        }
 #pragma unroll
-            for (int a = 0; a < D; ++a) {
-                const double mn = fma(x[a] - mean[a], r1, mean[a]);
-                dm_o[a] = x[a] - mean[a];
-                dm_n[a] = x[a] - mn;
-                mean[a] = mn;
-            }
+        for (int k = 0; k < G; ++k) {
+            if (k < n_adv) {
+                if (k == gstar) {
 #pragma unroll
-            for (int e = 0; e < NC; ++e) {
-                const int idx = lane + 32 * e;
-                if (idx < D * D) {
-                    const int a = idx / D, b = idx - a * D;
-                    double da = 0.0, db = 0.0;
+                    for (int a = 0; a < D; ++a) x[a] = xa[a];
+                    xPr = aPr;
+                    xL = aL;
+                    ++nacc;
+                }
+                double dm_o[D], dm_n[D];
 #pragma unroll
-                    for (int q = 0; q < D; ++q) { if (q == a) da = dm_o[q]; if (q == b) db = dm_n[q]; }
-                    cov[e] = fma(f, cov[e], da * db * r3);
+                for (int a = 0; a < D; ++a) {
+                    const double mn = fma(x[a] - mean[a], r1[k], mean[a]);
+                    dm_o[a] = x[a] - mean[a];
+                    dm_n[a] = x[a] - mn;
+                    mean[a] = mn;
+                }
+#pragma unroll
+                for (int e = 0; e < NC; ++e) {
+                    const int idx = lane + 32 * e;
+                    if (idx < D * D) {
+                        const int a = idx / D, b = idx - a * D;
+                        double da = 0.0, db = 0.0;
+#pragma unroll
+                        for (int q = 0; q < D; ++q) { if (q == a) da = dm_o[q]; if (q == b) db = dm_n[q]; }
+                        cov[e] = fma(ff[k], cov[e], da * db * r3[k]);
+                    }
                 }
             }
         }
