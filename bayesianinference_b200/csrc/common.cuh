@@ -234,6 +234,23 @@ __device__ __forceinline__ double block_max(double v, double *scratch) {
     __syncthreads();
     return scratch[32];
 }
+// block-wide LseAcc combine in two passes — block maximum of the partial maxima, ONE exp per thread to rescale its
+// partial sums, then two block sums — instead of a tree of pairwise merges with two exps each (10 dependent merge
+// levels: the evidence reductions were a third of the per-iteration update of a small run).  scratch: 33 doubles,
+// scratch_m: 33 * 16 doubles.
+__device__ __forceinline__ LseAcc block_lse2(const LseAcc &a, double *scratch, double *scratch_m) {
+    const double m = block_max(a.s0 == 0.0 ? -CUDART_INF : a.m, scratch);
+    if (!(m > -CUDART_INF)) return lse_empty();
+    const double sc = a.s0 == 0.0 ? 0.0 : exp(a.m - m);
+    double v[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = 0.0;
+    v[0] = a.s0 * sc;
+    v[1] = a.s1 * sc;
+    block_sum_multi(v, 2, scratch_m);
+    return LseAcc{m, v[0], v[1]};
+}
+
 // block-wide LseAcc merge broadcast to all threads; scratch: 3*33 doubles
 __device__ __forceinline__ LseAcc block_lse(LseAcc a, double *scratch) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;

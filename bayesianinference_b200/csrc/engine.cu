@@ -132,7 +132,9 @@ inline bool G_own_too_many(int num_sms, int PA, int P) {
 // small model of one walk step and the cheapest wins:
 //   data phase  rows_per_cta x max(4, TW SLOTS / 2) clocks per SM — one broadcast LDS.128 per row (512 B at 128 B/clk)
 //               against TW SLOTS warp-wide DFMAs at 64 lanes/clk; TW = 1 is bound by the shared-memory return path;
-//   per step    ~5000 clocks of chain logic, barriers and the DSMEM exchange (measured: C4, r2g);
+//   per step    ~5000 clocks of chain logic, barriers and the DSMEM exchange (measured: C4, r2g); CTAs that end up on
+//               the same SM multiply the data phase (r2k: TW = 2 / CS = 4 put 256 CTAs on 148 SMs, 3.5 ms per C4 walk
+//               against 2.5 ms for TW = 4 / CS = 4 with 128);
 //   waves       all clusters must be co-resident or the walk runs in several waves: a cluster of 8 fits only twice into
 //               a GPC and one GPC of a B200 is short of SMs — 15 clusters of 8, not 16 (ncu r2g: 16 clusters of 8 ran
 //               as two waves, 5.1 ms instead of 2.5 ms per C4 walk) — cudaOccupancyMaxActiveClusters tells.
@@ -182,8 +184,10 @@ bool plan_resident(binest_run &r, int P) {
             });
             if (max_clusters < 1) continue;
             const int waves = (groups + max_clusters - 1) / max_clusters;
-            const double data_clk = (double)pl.rpc * std::max(4.0, 0.5 * tw * OP::SLOTS);
-            pl.cost = waves * (data_clk + 5000.0 + 250.0 * cs);
+            // CTAs that share an SM share its fp64 pipe and its shared-memory port
+            const int per_sm = waves == 1 ? (pl.ctas + p.num_sms - 1) / p.num_sms : 1;
+            const double data_clk = (double)per_sm * pl.rpc * std::max(4.0, 0.5 * tw * OP::SLOTS);
+            pl.cost = waves * (data_clk + 5000.0 + 250.0 * cs) * (1.0 + 0.01 / tw);  // ties: the wider tile
             if (std::getenv("BINEST_PLAN_DEBUG"))
                 std::fprintf(stderr, "resident plan: tw %d cs %d ch %d groups %d ctas %d max_clusters %d waves %d smem %zu cost %.0f\n",
                              tw, cs, ch, groups, pl.ctas, max_clusters, waves, pl.smem, pl.cost);

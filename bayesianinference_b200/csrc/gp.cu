@@ -402,12 +402,12 @@ __global__ void __launch_bounds__(256, 1) gp_potf2_reg_kernel(GpBatch g, int k0)
 // shared GEMM core: acc[4][4][2] (32x32 per warp, 16 warps -> 128x128) += sign * A(128 x KC) B(128 x KC)^T
 // sA, sB: [KC][LDS_] (k-major).  Fragment maps of mma.m8n8k4.f64: a[row = lane/4][k = lane%4],
 // b[k = lane%4][col = lane/4], c[row = lane/4][col = 2*(lane%4) + {0,1}].
-template <int LDB>
+template <int LDB, int KCH = KC>
 __device__ __forceinline__ void gemm_chunk(const double *__restrict__ sA, const double *__restrict__ sB, int wm, int wn,
                                            int lane, double (&acc)[4][4][2], bool negate) {
     const int r = lane >> 2, q = lane & 3;
 #pragma unroll
-    for (int kk = 0; kk < KC; kk += 4) {
+    for (int kk = 0; kk < KCH; kk += 4) {
         double a[4], bb[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -496,6 +496,121 @@ __global__ void __launch_bounds__(256, 2) gp_syrk_kernel(GpBatch g, int k0, int 
         __syncthreads();
         gemm_chunk<LDSH_>(sA[c & 1], sB[c & 1], wm, wn, lane, acc, true);
         __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int gi = i0 + wm * 32 + i * 8 + r, gj = j0 + wn * 32 + j * 8 + 2 * q + h;
+                if (gi >= gj) A[(size_t)gj * ld + gi] = acc[i][j][h];
+            }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// trailing update, TMA-fed (the default; BINEST_GP_SYRK=0 selects gp_syrk_kernel above).  Same tiles, same DMMA core and
+// the same arithmetic order as gp_syrk_kernel; what changes is how the panel chunks reach shared memory and how the
+// warps synchronise:
+//   * every K-row of a chunk (128 resp. 64 consecutive doubles of a panel column) is ONE bulk copy of the TMA engine
+//     (cp.async.bulk -> SASS UBLKCP) into the padded row of the stage, issued by one thread, completion counted on the
+//     stage's `full` mbarrier — instead of 12 cp.async per thread and chunk;
+//   * a ring of 4 stages of 16 K-rows (same 100 KB as the two 32-row stages before, so still two CTAs per SM), filled
+//     three chunks ahead;
+//   * no CTA-wide barrier in the K loop: a warp waits on `full[s]`, multiplies, and arrives on `empty[s]`; only the
+//     issuing thread waits for `empty` — of the chunk BEFORE the one it has just finished — before it refills that
+//     stage.  (gp_syrk_kernel paid two __syncthreads per 32 rows of K: 64 lock-step points per tile.)
+// Every mbarrier wait is bounded (~2^30 polls -> trap): a protocol error ends the kernel with an error, not a hang.
+constexpr int WS_KC = 16, WS_NS = 4;
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    for (unsigned it = 0;; ++it) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(a), "r"(parity)
+            : "memory");
+        if (ok) return;
+        if (it > (1u << 30)) __trap();
+    }
+}
+
+__global__ void __launch_bounds__(256, 2) gp_syrk_ws_kernel(GpBatch g, int k0, int kw, int base, int ncol64) {
+    extern __shared__ __align__(128) double sm[];  // WS_NS stages x (A chunk [WS_KC][LDS_] + B chunk [WS_KC][LDSH_])
+    __shared__ uint64_t full[WS_NS], empty[WS_NS];
+    const int b = blockIdx.y;
+    if (g.fail[b]) return;
+    const int rest = (g.Np - base) / NB;
+    int t = blockIdx.x, ti = 0, tj;
+    if (ncol64 > 0) {
+        ti = t / ncol64;
+        tj = t - ti * ncol64;
+        if (tj * NBH > ti * NB + NB - 1) return;
+    } else if (t < rest * (rest + 1)) {
+        while ((ti + 1) * (ti + 2) <= t) ++ti;
+        tj = t - ti * (ti + 1);
+    } else {
+        t -= rest * (rest + 1);
+        ti = rest + t / (2 * rest);
+        tj = t % (2 * rest);
+    }
+    const int i0 = base + ti * NB, j0 = base + tj * NBH;
+    double *A = g.A + (size_t)b * g.mat();
+    const size_t ld = g.ld;
+    const double *PA = A + (size_t)k0 * ld + i0, *PB = A + (size_t)k0 * ld + j0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wm = warp >> 1, wn = warp & 1;
+    const int r = lane >> 2, q = lane & 3;
+    constexpr int STAGE = WS_KC * LDS_ + WS_KC * LDSH_;
+    constexpr uint32_t kStageBytes = WS_KC * (NB + NBH) * sizeof(double);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < WS_NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 8); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const int NCH = kw / WS_KC;
+    auto issue = [&](int c) {  // one thread: the WS_KC rows of chunk c of both panels -> stage c % WS_NS
+        const int s = c % WS_NS;
+        double *sA = sm + (size_t)s * STAGE, *sB = sA + WS_KC * LDS_;
+        mbar_expect_tx(&full[s], kStageBytes);
+#pragma unroll 4
+        for (int k = 0; k < WS_KC; ++k) {
+            bulk_g2s(sA + k * LDS_, PA + (size_t)(c * WS_KC + k) * ld, NB * sizeof(double), &full[s]);
+            bulk_g2s(sB + k * LDSH_, PB + (size_t)(c * WS_KC + k) * ld, NBH * sizeof(double), &full[s]);
+        }
+    };
+    if (threadIdx.x == 0)
+        for (int c = 0; c < WS_NS && c < NCH; ++c) issue(c);
+
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int gi = i0 + wm * 32 + i * 8 + r, gj = j0 + wn * 32 + j * 8 + 2 * q + h;
+                acc[i][j][h] = (gi >= gj) ? A[(size_t)gj * ld + gi] : 0.0;
+            }
+#pragma unroll 1
+    for (int c = 0; c < NCH; ++c) {
+        // refill the stage of the chunk before this one (every warp is done with it, or about to be)
+        if (threadIdx.x == 0 && c >= 1 && c - 1 + WS_NS < NCH) {
+            mbar_wait_bounded(&empty[(c - 1) % WS_NS], (uint32_t)(((c - 1) / WS_NS) & 1));
+            issue(c - 1 + WS_NS);
+        }
+        const int s = c % WS_NS;
+        mbar_wait_bounded(&full[s], (uint32_t)((c / WS_NS) & 1));
+        const double *sA = sm + (size_t)s * STAGE, *sB = sA + WS_KC * LDS_;
+        gemm_chunk<LDSH_, WS_KC>(sA, sB, wm, wn, lane, acc, true);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -690,6 +805,8 @@ void gp_sweep(const GpBatch &gc, int h0, int Bh, int nblk, cudaStream_t s, size_
     if (g.v2) g.v2 += (size_t)h0 * gc.ld;
     const int T = g.Np / NB, Tq = (g.ld - g.Np) / NB, rows_all = T + Tq, B = Bh;
     static const bool potf2_reg = [] { const char *e = getenv("BINEST_GP_POTF2"); return !(e && atoi(e) == 1); }();  // 1: column sweep
+    static const bool syrk_ws = [] { const char *e = getenv("BINEST_GP_SYRK"); return !(e && atoi(e) == 0); }();      // 0: cp.async kernel
+    const size_t smem_ws = (size_t)WS_NS * (WS_KC * LDS_ + WS_KC * LDSH_) * sizeof(double);
     const size_t smem_potf2_reg = (size_t)(NB * NB + 2 * NB + NB + NB * 17) * sizeof(double);
     for (int kb = 0; kb < T; kb += nblk) {
         const int kend = std::min(kb + nblk, T);  // panels [kb, kend) form one group
@@ -709,14 +826,17 @@ void gp_sweep(const GpBatch &gc, int h0, int Bh, int nblk, cudaStream_t s, size_
             const int o = k - kb + 1;
             if (o < kend - kb) {
                 const int w = o & -o, cols = std::min(w, kend - (k + 1));
-                gp_syrk_kernel<<<dim3(below * 2 * cols, B), 256, smem_syrk, s>>>(g, (k + 1 - w) * NB, w * NB, k0 + NB, 2 * cols);
+                if (syrk_ws) gp_syrk_ws_kernel<<<dim3(below * 2 * cols, B), 256, smem_ws, s>>>(g, (k + 1 - w) * NB, w * NB, k0 + NB, 2 * cols);
+                else gp_syrk_kernel<<<dim3(below * 2 * cols, B), 256, smem_syrk, s>>>(g, (k + 1 - w) * NB, w * NB, k0 + NB, 2 * cols);
                 BN_LAUNCH_CHECK();
             }
         }
         const int rest = T - kend;
         if (rest > 0) {
-            gp_syrk_kernel<<<dim3(rest * (rest + 1) + Tq * 2 * rest, B), 256, smem_syrk, s>>>(
-                g, kb * NB, (kend - kb) * NB, kend * NB, 0);
+            if (syrk_ws) gp_syrk_ws_kernel<<<dim3(rest * (rest + 1) + Tq * 2 * rest, B), 256, smem_ws, s>>>(
+                    g, kb * NB, (kend - kb) * NB, kend * NB, 0);
+            else gp_syrk_kernel<<<dim3(rest * (rest + 1) + Tq * 2 * rest, B), 256, smem_syrk, s>>>(
+                    g, kb * NB, (kend - kb) * NB, kend * NB, 0);
             BN_LAUNCH_CHECK();
         }
     }
@@ -735,6 +855,8 @@ void gp_factor_chunk(binest_problem &p, const GpBatch &g, const double *theta_de
     BN_CUDA(cudaFuncSetAttribute(gp_potf2_reg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)((NB * NB + 2 * NB + NB + NB * 17) * sizeof(double))));
     BN_CUDA(cudaFuncSetAttribute(gp_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_syrk));
+    BN_CUDA(cudaFuncSetAttribute(gp_syrk_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)((size_t)WS_NS * (WS_KC * LDS_ + WS_KC * LDSH_) * sizeof(double))));
     BN_CUDA(cudaFuncSetAttribute(gp_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_trsm));
     cudaStream_t s = p.stream;
     gp_fill_kernel<<<dim3(T * (T + 1) / 2 + Tq * T, B), 256, 2 * NB * p.gp_dim * sizeof(double), s>>>(

@@ -222,7 +222,7 @@ __device__ __forceinline__ int run_update_body(const RunParams &prm, const RunAr
         const double L = A.dead_logL[dbase + D - 1];
         acc = lse_merge(acc, lse_term(log_half + log_subtract(left, right) + L, L));
     }
-    acc = block_lse(acc, scratch);
+    acc = block_lse2(acc, scratch, scratch_m);
     const LseAcc tot = lse_merge(st.dead, acc);
     const double logZ = tot.m + log(tot.s0);
     const double entropy = tot.s1 / tot.s0 - logZ;  // BS:801-810
@@ -324,7 +324,7 @@ __device__ __forceinline__ int run_update_body(const RunParams &prm, const RunAr
             fin = lse_merge(fin, lse_term(log_half + log_subtract(left, right) + L, L));
         }
     }
-    fin = block_lse(fin, scratch);
+    fin = block_lse2(fin, scratch, scratch_m);
     if (tid == 0) {
         st.dead = lse_merge(st.dead, fin);
         st.n_dead = D + Kb;
