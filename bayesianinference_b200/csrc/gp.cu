@@ -509,9 +509,13 @@ __global__ void __launch_bounds__(256, 2) gp_syrk_kernel(GpBatch g, int k0, int 
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// trailing update, TMA-fed (the default; BINEST_GP_SYRK=0 selects gp_syrk_kernel above).  Same tiles, same DMMA core and
-// the same arithmetic order as gp_syrk_kernel; what changes is how the panel chunks reach shared memory and how the
-// warps synchronise:
+// trailing update, TMA-fed — an EXPERIMENT kept for the record (BINEST_GP_SYRK=1 selects it; gp_syrk_kernel above is the
+// default).  Measured on B200, N = 4096, B = 256 (r2l): 242.1 ms per batch against 222.2 ms with the cp.async kernel —
+// the panel chunks are rows of 1 KB / 512 B, so a chunk is 32 separate bulk copies whose fixed cost the TMA engine does
+// not amortise, while 256 threads issuing 16-byte cp.async spread the same traffic over all LSUs; and the tensor pipe
+// was never starved by the two barriers per chunk (83.6 % active, the rest is the C-tile prologue/epilogue).  Same
+// tiles, same DMMA core and the same arithmetic order as gp_syrk_kernel; what changes is how the panel chunks reach
+// shared memory and how the warps synchronise:
 //   * every K-row of a chunk (128 resp. 64 consecutive doubles of a panel column) is ONE bulk copy of the TMA engine
 //     (cp.async.bulk -> SASS UBLKCP) into the padded row of the stage, issued by one thread, completion counted on the
 //     stage's `full` mbarrier — instead of 12 cp.async per thread and chunk;
@@ -805,7 +809,7 @@ void gp_sweep(const GpBatch &gc, int h0, int Bh, int nblk, cudaStream_t s, size_
     if (g.v2) g.v2 += (size_t)h0 * gc.ld;
     const int T = g.Np / NB, Tq = (g.ld - g.Np) / NB, rows_all = T + Tq, B = Bh;
     static const bool potf2_reg = [] { const char *e = getenv("BINEST_GP_POTF2"); return !(e && atoi(e) == 1); }();  // 1: column sweep
-    static const bool syrk_ws = [] { const char *e = getenv("BINEST_GP_SYRK"); return !(e && atoi(e) == 0); }();      // 0: cp.async kernel
+    static const bool syrk_ws = [] { const char *e = getenv("BINEST_GP_SYRK"); return e && atoi(e) == 1; }();  // 1: TMA-fed variant
     const size_t smem_ws = (size_t)WS_NS * (WS_KC * LDS_ + WS_KC * LDSH_) * sizeof(double);
     const size_t smem_potf2_reg = (size_t)(NB * NB + 2 * NB + NB + NB * 17) * sizeof(double);
     for (int kb = 0; kb < T; kb += nblk) {
