@@ -57,6 +57,7 @@ struct binest_run {
     cudaStream_t stream = nullptr;
     cudaGraphExec_t walk_graph = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaEvent_t> chunk_ev;  // event pairs around the walks of a chunk of iterations
     int64_t graph_exchanges = 0, graph_bytes = 0, graph_launches = 0;  // per launch of the sharded walk graph
     double walk_ms = 0.0;   // device time spent in walk graphs (CUDA events on the run's stream)
     int64_t walk_graphs = 0;
@@ -73,6 +74,7 @@ struct binest_run {
         if (walk_graph) cudaGraphExecDestroy(walk_graph);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
+        for (cudaEvent_t e : chunk_ev) cudaEventDestroy(e);
         if (h_state) cudaFreeHost(h_state);
         if (h_unfrozen) cudaFreeHost(h_unfrozen);
         if (h_abort) cudaFreeHost(h_abort);
@@ -643,6 +645,46 @@ int binest_run_advance(binest_run *r, int64_t max_batches, int32_t *finished) {
             r->batches += iters;
             if (all_done(*r)) { r->finished = true; break; }
             if (r->h_ctl->need_grow) ensure_dead_capacity(*r, 2 * q.cap);
+        }
+        // resident / grid walk paths without the acceptance protocol: iterations are enqueued kChunk at a time and the
+        // run state is read once per chunk (the update and walk kernels of a terminated run return at once), instead
+        // of three host round trips per iteration
+        constexpr int kChunk = 8;
+        while (!r->loop && !acc_loop && (r->resident || r->grid) && !r->finished &&
+               (max_batches <= 0 ? true : max_batches - done_batches >= 2)) {
+            const int chunk = (int)std::min<int64_t>(kChunk, max_batches <= 0 ? kChunk : max_batches - done_batches);
+            ensure_dead_capacity(*r, r->dead_upper + (int64_t)chunk * q.K + 1);
+            long long it0 = 0;
+            for (int i = 0; i < q.R; ++i) it0 += r->first ? 1 : r->h_state[i].iteration;
+            while ((int)r->chunk_ev.size() < 2 * kChunk) {
+                cudaEvent_t e;
+                BN_CUDA(cudaEventCreate(&e));
+                r->chunk_ev.push_back(e);
+            }
+            for (int c = 0; c < chunk; ++c) {
+                launch_update(*r);
+                BN_CUDA(cudaEventRecord(r->chunk_ev[2 * c], r->stream));
+                walk_block(*r, q);
+                BN_CUDA(cudaEventRecord(r->chunk_ev[2 * c + 1], r->stream));
+            }
+            fetch_state(*r);
+            BN_REQUIRE(!(r->grid && *r->h_abort), BINEST_ERR_CUDA, "walk_grid_kernel: grid barrier timed out (walk aborted)");
+            long long it1 = 0, dmax = 0;
+            for (int i = 0; i < q.R; ++i) { it1 += r->h_state[i].iteration; dmax = std::max<long long>(dmax, r->h_state[i].n_dead); }
+            const long long reps = it1 - it0;                      // replacements of the chunk, all runs
+            const long long per_iter = (long long)q.R * q.K;
+            // walks after the last run terminated were no-ops: keep them out of the per-walk timing statistics
+            const int walked = (int)std::min<long long>(chunk, (reps + per_iter - 1) / std::max<long long>(per_iter, 1));
+            for (int c = 0; c < chunk; ++c) {
+                float ms = 0;
+                BN_CUDA(cudaEventElapsedTime(&ms, r->chunk_ev[2 * c], r->chunk_ev[2 * c + 1]));
+                if (c < std::max(walked, 1)) { r->walk_ms += ms; r->walk_graphs += 1; }
+            }
+            r->evals += (int64_t)q.S * reps;
+            r->dead_upper = dmax;
+            done_batches += chunk;
+            r->batches += chunk;
+            if (all_done(*r)) { r->finished = true; break; }
         }
         while (!r->loop && !r->finished && (max_batches <= 0 || done_batches < max_batches)) {
             ensure_dead_capacity(*r, r->dead_upper + q.K + 1);

@@ -316,6 +316,13 @@ walk_grid_kernel(const __grid_constant__ RunParams prm, RunArrays A, const __gri
     const long long r1 = (r0 + rows_per_cta < rows) ? r0 + rows_per_cta : rows;
     const int nr = r1 > r0 ? (int)(r1 - r0) : 0;
 
+    // nothing to walk (every run of the group has terminated: the host enqueues iterations ahead of reading the state):
+    // the run states are constant during the launch, so all CTAs take the same exit and no barrier is ever armed
+    {
+        int live = 0;
+        for (int rr = tid; rr < prm.R; rr += blockDim.x) live |= (!A.state[rr].done && A.state[rr].Kb > 0) ? 1 : 0;
+        if (!__syncthreads_or(live)) return;
+    }
     // ---- the row slice of this CTA -> shared memory, once (TMA bulk copies, one mbarrier phase)
     if (tid == 0) {
         mbar_init(&full, 1);

@@ -98,6 +98,9 @@ walk_resident_kernel(const __grid_constant__ RunParams prm, RunArrays A, const _
 #pragma unroll
         for (int a = 0; a < D * D; ++a) s_cov[a * WP + wl] = A.w_cov[(size_t)w * D * D + a];
     }
+    // nothing to walk for this group (its runs have terminated: the host enqueues iterations ahead of reading the
+    // state): every CTA of the cluster sees the same walkers and takes the same exit
+    if (!__syncthreads_or(active ? 1 : 0)) return;
     if (CS > 1) cluster.sync();  // every CTA's mbarriers are initialised before a peer can signal them
     bool pre = false;
     double xn[D], nPr = 0.0;

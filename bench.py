@@ -45,8 +45,8 @@ sys.path.insert(0, ROOT)
 from bayesianinference_b200 import configs as cfg  # noqa: E402
 
 MC_STEPS = 200  # "MonteCarloSteps" default, BS:844
-# profiles/r01g_ncu_walk_grid_c2.md: dram__bytes_read.sum + dram__bytes_write.sum of one walk_grid_kernel launch
-NCU_TRAFFIC_C2_GRID = 16.165e6 + 0.088e6
+# profiles/r02_ncu_walk_grid_c2.md: dram__bytes_read.sum + dram__bytes_write.sum of one walk_grid_kernel launch
+NCU_TRAFFIC_C2_GRID = 16.169e6 + 0.076e6
 GP_FLOP_PER_THETA = 2.31e10   # fill 2.1e8 + Cholesky N^3/3 = 2.29e10 + solve/logdet, N = 4096
 GP_BYTES_PER_THETA = 134.2e6  # lower triangle written once + read once (minimum traffic)
 WORKLOADS = {
@@ -501,7 +501,7 @@ def run_primary(ctx, args):
     roof = {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
             "frac": achieved_tf / peak_tf, "traffic": traffic,
             "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture "
-                              "profiles/r01g_ncu_walk_grid_c2.md (not re-measured in this run)" if traffic else None,
+                              "profiles/r02_ncu_walk_grid_c2.md (not re-measured in this run)" if traffic else None,
             "kernel": kernel, "walk_path": path, "walk_steps_per_launch": steps_per_launch,
             "ms_per_launch": ms_launch,
             "pipe_slots_note": "9 algorithmic flop per datum (SURVEY §8d) execute as 4 DFMA = 8 flop: hardware busy fraction = frac * 8/9",
