@@ -810,12 +810,24 @@ void gp_sweep(const GpBatch &gc, int h0, int Bh, int nblk, cudaStream_t s, size_
     const int T = g.Np / NB, Tq = (g.ld - g.Np) / NB, rows_all = T + Tq, B = Bh;
     static const bool potf2_reg = [] { const char *e = getenv("BINEST_GP_POTF2"); return !(e && atoi(e) == 1); }();  // 1: column sweep
     static const bool syrk_ws = [] { const char *e = getenv("BINEST_GP_SYRK"); return e && atoi(e) == 1; }();  // 1: TMA-fed variant
+    static const bool left_looking = [] { const char *e = getenv("BINEST_GP_LEFT"); return !(e && atoi(e) == 0); }();
     const size_t smem_ws = (size_t)WS_NS * (WS_KC * LDS_ + WS_KC * LDSH_) * sizeof(double);
+    auto launch_syrk = [&](dim3 grid, int k0, int kw, int base, int ncol64) {
+        if (syrk_ws) gp_syrk_ws_kernel<<<grid, 256, smem_ws, s>>>(g, k0, kw, base, ncol64);
+        else gp_syrk_kernel<<<grid, 256, smem_syrk, s>>>(g, k0, kw, base, ncol64);
+        BN_LAUNCH_CHECK();
+    };
     const size_t smem_potf2_reg = (size_t)(NB * NB + 2 * NB + NB + NB * 17) * sizeof(double);
     for (int kb = 0; kb < T; kb += nblk) {
         const int kend = std::min(kb + nblk, T);  // panels [kb, kend) form one group
         for (int k = kb; k < kend; ++k) {
             const int k0 = k * NB, below = rows_all - k - 1;
+            // in-group updates, left-looking (the default): right before panel k is factored, its column block receives
+            // ALL earlier panels of the group in ONE pass with K = 128 (k - kb) — every column block of a group is loaded
+            // once, flop-weighted mean K 640 (binary schedule below: up to three passes per block, mean K 384)
+            if (left_looking && k > kb) {
+                launch_syrk(dim3((rows_all - k) * 2, B), kb * NB, (k - kb) * NB, k0, 2);
+            }
             if (potf2_reg) gp_potf2_reg_kernel<<<B, 256, smem_potf2_reg, s>>>(g, k0);
             else gp_potf2_kernel<<<B, 256, smem_potf2, s>>>(g, k0);
             BN_LAUNCH_CHECK();
@@ -823,25 +835,19 @@ void gp_sweep(const GpBatch &gc, int h0, int Bh, int nblk, cudaStream_t s, size_
                 gp_trsm_kernel<<<dim3(below, B), 512, smem_trsm, s>>>(g, k0);
                 BN_LAUNCH_CHECK();
             }
-            // in-group updates, binary schedule: with o panels of the group done, the last w = lowbit(o) of them
-            // update the next w column blocks (all rows below) in one K = 128 w pass.  Every column block has then
-            // received all earlier panels of its group when its turn comes (the o's that reach it are the prefixes
-            // of its binary offset), in fewer and wider passes than panel-by-panel updates.
+            // in-group updates, binary schedule (BINEST_GP_LEFT=0): with o panels of the group done, the last
+            // w = lowbit(o) of them update the next w column blocks (all rows below) in one K = 128 w pass.  Every column
+            // block has then received all earlier panels of its group when its turn comes (the o's that reach it are the
+            // prefixes of its binary offset).
             const int o = k - kb + 1;
-            if (o < kend - kb) {
+            if (!left_looking && o < kend - kb) {
                 const int w = o & -o, cols = std::min(w, kend - (k + 1));
-                if (syrk_ws) gp_syrk_ws_kernel<<<dim3(below * 2 * cols, B), 256, smem_ws, s>>>(g, (k + 1 - w) * NB, w * NB, k0 + NB, 2 * cols);
-                else gp_syrk_kernel<<<dim3(below * 2 * cols, B), 256, smem_syrk, s>>>(g, (k + 1 - w) * NB, w * NB, k0 + NB, 2 * cols);
-                BN_LAUNCH_CHECK();
+                launch_syrk(dim3(below * 2 * cols, B), (k + 1 - w) * NB, w * NB, k0 + NB, 2 * cols);
             }
         }
         const int rest = T - kend;
         if (rest > 0) {
-            if (syrk_ws) gp_syrk_ws_kernel<<<dim3(rest * (rest + 1) + Tq * 2 * rest, B), 256, smem_ws, s>>>(
-                    g, kb * NB, (kend - kb) * NB, kend * NB, 0);
-            else gp_syrk_kernel<<<dim3(rest * (rest + 1) + Tq * 2 * rest, B), 256, smem_syrk, s>>>(
-                    g, kb * NB, (kend - kb) * NB, kend * NB, 0);
-            BN_LAUNCH_CHECK();
+            launch_syrk(dim3(rest * (rest + 1) + Tq * 2 * rest, B), kb * NB, (kend - kb) * NB, kend * NB, 0);
         }
     }
 }
@@ -868,7 +874,7 @@ void gp_factor_chunk(binest_problem &p, const GpBatch &g, const double *theta_de
     BN_LAUNCH_CHECK();
     static const int nblk_env = [] { const char *e = getenv("BINEST_GP_BLOCK"); return e ? atoi(e) : 0; }();
     static const int nsplit_env = [] { const char *e = getenv("BINEST_GP_STREAMS"); return e ? atoi(e) : 0; }();
-    const int nblk = std::max(1, std::min(nblk_env > 0 ? nblk_env : kGpBlockPanels, 8));
+    const int nblk = std::max(1, std::min(nblk_env > 0 ? nblk_env : kGpBlockPanels, 32));
     int nsplit = std::max(1, std::min(nsplit_env > 0 ? nsplit_env : kGpStreams, 8));
     nsplit = std::min(nsplit, std::max(1, B / 4));  // tiny batches stay whole
     if (nsplit == 1) {

@@ -519,24 +519,28 @@ def test_data_sharding_gloo_matches_unsharded():
 
 
 def test_gp_group_schedule_covers_every_panel_column_pair_once():
-    """The update schedule of the blocked Cholesky sweep (csrc/gp.cu, gp_sweep): panels in groups of nblk, binary
-    in-group updates (after o panels of the group the last lowbit(o) update the next lowbit(o) column blocks), one
-    full-width update per group.  Replayed here on block indices: when a column block is factored it has received every
-    earlier panel exactly once, and nothing is ever applied twice.  (Mirror of the C++ loop; the numerical result is
-    covered by the GPU parity tests for nblk = 1, 2, 3, 4, 8.)"""
-    for T in (1, 2, 5, 8, 13, 32):
-        for nblk in (1, 2, 3, 4, 8):
-            got = {c: [] for c in range(T)}  # column block -> panels applied so far
-            for kb in range(0, T, nblk):
-                kend = min(kb + nblk, T)
-                for k in range(kb, kend):
-                    assert sorted(got[k]) == list(range(k)), (T, nblk, k, got[k])  # complete when factored
-                    o = k - kb + 1
-                    if o < kend - kb:
-                        w = o & -o
-                        cols = min(w, kend - (k + 1))
-                        for c in range(k + 1, k + 1 + cols):
-                            got[c] += list(range(k + 1 - w, k + 1))
-                for c in range(kend, T):
-                    got[c] += list(range(kb, kend))
-            assert all(len(v) == len(set(v)) for v in got.values())
+    """The update schedules of the blocked Cholesky sweep (csrc/gp.cu, gp_sweep): panels in groups of nblk, one
+    full-width update per group, and inside a group either left-looking (the default: right before panel k is factored
+    its column block receives all earlier panels of the group in one pass) or the binary schedule (after o panels of the
+    group the last lowbit(o) update the next lowbit(o) column blocks).  Replayed here on block indices: when a column
+    block is factored it has received every earlier panel exactly once, and nothing is ever applied twice.  (Mirror of
+    the C++ loop; the numerical result is covered by the GPU parity tests.)"""
+    for left in (True, False):
+        for T in (1, 2, 5, 8, 13, 32):
+            for nblk in (1, 2, 3, 4, 8, 16):
+                got = {c: [] for c in range(T)}  # column block -> panels applied so far
+                for kb in range(0, T, nblk):
+                    kend = min(kb + nblk, T)
+                    for k in range(kb, kend):
+                        if left and k > kb:
+                            got[k] += list(range(kb, k))
+                        assert sorted(got[k]) == list(range(k)), (left, T, nblk, k, got[k])  # complete when factored
+                        o = k - kb + 1
+                        if not left and o < kend - kb:
+                            w = o & -o
+                            cols = min(w, kend - (k + 1))
+                            for c in range(k + 1, k + 1 + cols):
+                                got[c] += list(range(k + 1 - w, k + 1))
+                    for c in range(kend, T):
+                        got[c] += list(range(kb, kend))
+                assert all(len(v) == len(set(v)) for v in got.values())
