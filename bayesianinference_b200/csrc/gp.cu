@@ -34,7 +34,7 @@ namespace {
 constexpr int NB = 128;        // panel width / tile edge
 constexpr int KC = 32;         // K chunk of the GEMM kernels
 constexpr int LDS_ = NB + 4;   // smem leading dimension: half-warp fragment loads hit 16 distinct 8-byte banks
-constexpr int kGpBlockPanels = 8;
+constexpr int kGpBlockPanels = 16;
 constexpr int kGpStreams = 4;      // sub-batches of a chunk swept on separate streams (BINEST_GP_STREAMS overrides, 1..8)  // panels per group of the two-level blocking (BINEST_GP_BLOCK overrides, 1..8)
 
 struct GpBatch {
@@ -786,9 +786,19 @@ struct GpStreams {
     int device = -1;
     std::vector<cudaStream_t> aux;
     std::vector<cudaEvent_t> done;
+    std::vector<std::vector<cudaEvent_t>> panel;  // [sub-batch][panel]: diagonal block + panel solve finished
     cudaEvent_t fork = nullptr;
+    void ensure_panels(int nsub, int T) {
+        if ((int)panel.size() < nsub) panel.resize(nsub);
+        for (int h = 0; h < nsub; ++h)
+            while ((int)panel[h].size() < T) {
+                cudaEvent_t ev;
+                BN_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                panel[h].push_back(ev);
+            }
+    }
     void ensure(int dev, int n) {
-        if (device != dev) { aux.clear(); done.clear(); fork = nullptr; device = dev; }  // (a thread serves one device)
+        if (device != dev) { aux.clear(); done.clear(); panel.clear(); fork = nullptr; device = dev; }  // (a thread serves one device)
         if (!fork) BN_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
         while ((int)aux.size() < n) {
             cudaStream_t st; cudaEvent_t ev;
@@ -801,8 +811,12 @@ struct GpStreams {
 thread_local GpStreams g_streams;
 
 // blocked Cholesky sweep (with the fused forward solve) of matrices [h0, h0 + Bh) of the chunk on stream s
+// wait_ev / rec_ev (per panel, may be null): staggering of the sub-batches — this sweep starts panel k only after the
+// previous sub-batch has finished ITS diagonal block and panel solve of k (wait_ev[k]) and announces its own (rec_ev[k]),
+// so that the latency-bound small kernels of one sub-batch run under the trailing updates of the others instead of
+// all four sub-batches marching in phase.
 void gp_sweep(const GpBatch &gc, int h0, int Bh, int nblk, cudaStream_t s, size_t smem_potf2, size_t smem_trsm,
-              size_t smem_syrk) {
+              size_t smem_syrk, cudaEvent_t *wait_ev = nullptr, cudaEvent_t *rec_ev = nullptr) {
     GpBatch g = gc;
     g.A += (size_t)h0 * gc.mat(); g.y += (size_t)h0 * gc.ld; g.z += (size_t)h0 * NB; g.linvT += (size_t)h0 * NB * NB;
     g.logdet += h0; g.quad += h0; g.fail += h0; g.B = Bh;
@@ -828,6 +842,7 @@ void gp_sweep(const GpBatch &gc, int h0, int Bh, int nblk, cudaStream_t s, size_
             if (left_looking && k > kb) {
                 launch_syrk(dim3((rows_all - k) * 2, B), kb * NB, (k - kb) * NB, k0, 2);
             }
+            if (wait_ev) BN_CUDA(cudaStreamWaitEvent(s, wait_ev[k], 0));
             if (potf2_reg) gp_potf2_reg_kernel<<<B, 256, smem_potf2_reg, s>>>(g, k0);
             else gp_potf2_kernel<<<B, 256, smem_potf2, s>>>(g, k0);
             BN_LAUNCH_CHECK();
@@ -835,6 +850,7 @@ void gp_sweep(const GpBatch &gc, int h0, int Bh, int nblk, cudaStream_t s, size_
                 gp_trsm_kernel<<<dim3(below, B), 512, smem_trsm, s>>>(g, k0);
                 BN_LAUNCH_CHECK();
             }
+            if (rec_ev) BN_CUDA(cudaEventRecord(rec_ev[k], s));
             // in-group updates, binary schedule (BINEST_GP_LEFT=0): with o panels of the group done, the last
             // w = lowbit(o) of them update the next w column blocks (all rows below) in one K = 128 w pass.  Every column
             // block has then received all earlier panels of its group when its turn comes (the o's that reach it are the
@@ -883,12 +899,15 @@ void gp_factor_chunk(binest_problem &p, const GpBatch &g, const double *theta_de
     }
     GpStreams &st = g_streams;
     st.ensure(p.device, nsplit - 1);
+    static const bool stagger = [] { const char *e = getenv("BINEST_GP_STAGGER"); return !(e && atoi(e) == 0); }();
+    if (stagger) st.ensure_panels(nsplit, T);
     BN_CUDA(cudaEventRecord(st.fork, s));
     for (int h = 0; h < nsplit; ++h) {
         const int h0 = (int)((long long)B * h / nsplit), h1 = (int)((long long)B * (h + 1) / nsplit);
         cudaStream_t sh = h == 0 ? s : st.aux[h - 1];
         if (h > 0) BN_CUDA(cudaStreamWaitEvent(sh, st.fork, 0));
-        gp_sweep(g, h0, h1 - h0, nblk, sh, smem_potf2, smem_trsm, smem_syrk);
+        gp_sweep(g, h0, h1 - h0, nblk, sh, smem_potf2, smem_trsm, smem_syrk,
+                 (stagger && h > 0) ? st.panel[h - 1].data() : nullptr, (stagger && h + 1 < nsplit) ? st.panel[h].data() : nullptr);
         if (h > 0) {
             BN_CUDA(cudaEventRecord(st.done[h - 1], sh));
             BN_CUDA(cudaStreamWaitEvent(s, st.done[h - 1], 0));
