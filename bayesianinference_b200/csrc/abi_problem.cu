@@ -52,6 +52,25 @@ __global__ void pack_rows_kernel(const double *__restrict__ in, int n_in, const 
     }
 }
 
+// max_i |x_if| per input column of the packed rows (softmax operator: bound on the logits, operators.cuh OpLogistic::Row)
+__global__ void __launch_bounds__(256)
+colmax_kernel(const double *__restrict__ data, long long rows, int ncol, int n_in, double *__restrict__ out /* [gridDim.x][6] */) {
+    double mx[6] = {0, 0, 0, 0, 0, 0};
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += (long long)gridDim.x * blockDim.x)
+        for (int f = 0; f < n_in && f < 6; ++f) mx[f] = fmax(mx[f], fabs(data[i * ncol + f]));
+    __shared__ double sh[8][6];
+    for (int f = 0; f < 6; ++f) {
+        const double v = warp_max(mx[f]);
+        if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5][f] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        double v = 0.0;
+        for (int w = 0; w < 8; ++w) v = fmax(v, sh[w][threadIdx.x]);
+        out[(size_t)blockIdx.x * 6 + threadIdx.x] = v;
+    }
+}
+
 // Pivot selection for the polynomial operator (operators.cuh), plain fp64 block sums — the pivots only have to be
 // near the data, not exact.  With u = x - xbar:  out[b][k] = Sum u^k (k = 0..2 deg), out[b][11 + k] = Sum y u^k
 // (k = 0..deg): the normal equations of the least-squares polynomial in u.  Called first with xbar = 0, deg = 1
@@ -408,6 +427,15 @@ int binest_problem_create(int op_id, const int64_t *iparam, const double *inputs
                 pack_rows_kernel<<<grid, 256, 0, p->stream>>>(raw_in.p, (int)n_in, raw_out.p, p->rows, p->ncol, n_classes,
                                                             p->cst.xbar, p->cst.piv, p->data.p, bad.p);
                 BN_LAUNCH_CHECK();
+                // softmax: column maxima of |x| -> OpCst::m[f] (NaN / Inf inputs give an infinite bound: always checked)
+                const int cm_blocks = p->op == BINEST_OP_LOGISTIC ? 2 * p->num_sms : 0;
+                DevBuf<double> cm((size_t)cm_blocks * 6);
+                std::vector<double> h_cm((size_t)cm_blocks * 6);
+                if (cm_blocks) {
+                    colmax_kernel<<<cm_blocks, 256, 0, p->stream>>>(p->data.p, p->rows, p->ncol, (int)n_in, cm.p);
+                    BN_LAUNCH_CHECK();
+                    BN_CUDA(cudaMemcpyAsync(h_cm.data(), cm.p, h_cm.size() * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+                }
                 const int mom_blocks = poly ? 2 * p->num_sms : 0;
                 DevBuf<double> mom((size_t)mom_blocks * 12);
                 std::vector<double> h_mom((size_t)mom_blocks * 12);
@@ -420,6 +448,16 @@ int binest_problem_create(int op_id, const int64_t *iparam, const double *inputs
                 BN_CUDA(cudaMemcpyAsync(&h_bad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
                 BN_CUDA(cudaStreamSynchronize(p->stream));
                 BN_REQUIRE(!h_bad, BINEST_ERR_NUMERICAL, "logistic: class labels must be integers 0..K-1");
+                for (int f = 0; f < 6 && cm_blocks; ++f) {
+                    double m = 0.0;
+                    bool nan = false;
+                    for (int b = 0; b < cm_blocks; ++b) {
+                        const double v = h_cm[(size_t)b * 6 + f];
+                        nan = nan || !(v == v);
+                        m = std::max(m, v);
+                    }
+                    p->cst.m[f] = nan ? INFINITY : m;
+                }
                 for (int k = 0; k < 6 && mom_blocks; ++k) {
                     long double m = 0.0L;
                     for (int b = 0; b < mom_blocks; ++b)

@@ -331,13 +331,24 @@ template <int F, int K>
 struct OpLogistic {
     static constexpr int D = (K - 1) * (F + 1), NCOL = (F + 2) & ~1, TW_MAX = 2, SLOTS = (K - 1) * (F + 12) + 6;
     struct Coef { int unused; };
-    struct Row { double w[K - 1][F + 1]; };
-    __device__ __forceinline__ static Row make_row(const double (&th)[D], const OpCst &) {
+    // safe: every logit of this walker is bounded by 170 on ALL rows — |z_k| <= |b_k| + Sum_f |w_kf| max_i |x_if| with the
+    // column maxima fixed at upload (OpCst::m[f]) — so the per-row range checks of the fast exp path can be skipped
+    // (12 integer instructions per row and lane in a kernel that is bound by issue slots, not by the fp64 pipe)
+    struct Row { double w[K - 1][F + 1]; int safe; };
+    __device__ __forceinline__ static Row make_row(const double (&th)[D], const OpCst &cst) {
         Row c;
+        bool safe = true;
 #pragma unroll
-        for (int k = 0; k < K - 1; ++k)
+        for (int k = 0; k < K - 1; ++k) {
+            double bound = fabs(th[k * (F + 1) + F]);
 #pragma unroll
-            for (int f = 0; f <= F; ++f) c.w[k][f] = th[k * (F + 1) + f];
+            for (int f = 0; f <= F; ++f) {
+                c.w[k][f] = th[k * (F + 1) + f];
+                if (f < F) bound = fma(fabs(c.w[k][f]), cst.m[f], bound);
+            }
+            safe = safe && (bound < 169.0);  // NaN compares false
+        }
+        c.safe = safe ? 1 : 0;
         return c;
     }
     __device__ static Coef prepare(const double (&)[D], bool &ok, const OpCst &) {
@@ -387,11 +398,16 @@ struct OpLogistic {
 #pragma unroll
                 for (int u = 0; u < TW; ++u) z[u * E + k] = fma(c[u].w[k][f], x, z[u * E + k]);
         }
+        int safe = 1;
+#pragma unroll
+        for (int u = 0; u < TW; ++u) safe &= c[u].safe;
         bool fast = true;
+        if (!safe) {
 #pragma unroll
-        for (int u = 0; u < TW; ++u)
+            for (int u = 0; u < TW; ++u)
 #pragma unroll
-            for (int k = 0; k < E; ++k) fast = fast && exp_arg_bounded_170(z[u * E + k]);
+                for (int k = 0; k < E; ++k) fast = fast && exp_arg_bounded_170(z[u * E + k]);
+        }
         if (__builtin_expect(fast, 1)) {
 #if BINEST_EXP_TAB
             exp_bounded_tab<TW * E>(z, ex);
