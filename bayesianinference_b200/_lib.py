@@ -65,6 +65,12 @@ SIGNATURES = {
     "binest_evidence_sampling": (C.c_int, [C.c_int64, C.c_int64, _dp, _dp, _ip, C.c_int64, C.c_int64, C.c_uint64,
                                            _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
     "binest_crude_weights": (C.c_int, [C.c_int64, _dp, _ip, C.c_int64, _dp, _dp, _dp]),
+    "binest_merge_runs": (C.c_int, [C.c_int64, _ip, C.c_int64, _dp, _dp, _dp, _dp, _ip, _ip, _dp, _dp, _dp, _dp, _ip, _ip, _ip, _ip]),
+    "binest_combine_runs": (C.c_int, [C.c_int64, _ip, C.c_int64, _dp, _dp, _dp, _dp, _ip, _ip, C.c_int32, C.c_int64,
+                                      C.c_int64, C.c_uint64, _dp, _dp, _ip, _dp, _dp, _dp, _dp, _ip, _ip]),
+    "binest_run_merge_size": (C.c_int, [_vp, _ip]),
+    "binest_run_merge": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _ip, _ip, _ip, _ip]),
+    "binest_run_combine": (C.c_int, [_vp, C.c_int32, C.c_int64, C.c_uint64, _dp, _dp, _ip, _dp, _dp, _dp, _dp, _ip, _ip]),
     "binest_bench_loglike": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int64, C.c_int, _dp, _dp]),
     "binest_run_timing": (C.c_int, [_vp, _dp, _ip, _ip]),
     "binest_run_path": (C.c_int, [_vp, C.POINTER(C.c_int)]),

@@ -756,6 +756,12 @@ def evidenceSampling(obj_or_assoc, paramNames=None, _backend_override=None, **op
     S["LogPosteriorWeight"] = {"Mean": ev["logw_mean"], "StandardError": ev["logw_sd"]}       # BS:1245-1250
     srt = _stable_argsort(-S["CrudeLogPosteriorWeight"])                                      # BS:1241
     S = {k: ({kk: vv[srt] for kk, vv in v.items()} if isinstance(v, dict) else v[srt]) for k, v in S.items()}
+    _evidence_summary(out, S, ev, names, o)
+    return inferenceObject(out) if wrap else out
+
+
+def _evidence_summary(out, S, ev, names, o):
+    """the result keys evidenceSampling derives from the Monte-Carlo draws (BS:1252-1288)"""
     pme = _mean_and_error(ev["pmean"], 0)
     out.update({
         "Samples": S,
@@ -767,7 +773,6 @@ def evidenceSampling(obj_or_assoc, paramNames=None, _backend_override=None, **op
         "EmpiricalPosteriorDistribution": {"Type": o["EmpiricalPosteriorDistributionType"],  # BS:1269-1288
                                            "Weights": S["CrudePosteriorWeight"], "Points": S["Point"]},
     })
-    return inferenceObject(out) if wrap else out
 
 
 def _stable_argsort(key):
@@ -904,6 +909,30 @@ def _reference_pool_structure(t, n):
     return bool(M >= n and np.all(tp[:M - n] == n) and np.array_equal(tp[M - n:], np.arange(n, 0, -1)))
 
 
+def _merged_assoc(res, n_tot, scheme):
+    """result keys of a device combine (engine.combine_runs / RunGroup.combine): BS:1307-1309, BS:1183-1194"""
+    M = res["Samples"]["LogLikelihood"].size
+    out = {"SamplePoolSize": n_tot, "GeneratedNestedSamples": M - n_tot, "TotalSamples": M, "MergeScheme": scheme,
+           "CrudeLogEvidence": res["crude_logZ"], "LogLikelihoodMaximum": res["logLmax"],
+           "LogEstimatedMissingEvidence": res["log_missing"], "CrudeRelativeEntropy": res["entropy"]}
+    if scheme != "Reference":
+        out["_LiveBlock"] = int(res["n_live"])
+    return out
+
+
+def _sorted_run_table(t, n):
+    """one run's columns for the device merge: sorted by {logL, point} (the engine's fetch order: nothing moves) and
+    with the run's own pool sizes (the reference's structure BS:785-799 when the run does not carry them)"""
+    o = _lex_order(t["Point"], t["LogLikelihood"])
+    out = {k: _take(t[k], o) for k in ("Point", "LogLikelihood", "LogPriorPDF", "AcceptanceRate") if k in t}
+    tp = t.get("PoolSize")
+    M = out["LogLikelihood"].size
+    out["PoolSize"] = (_take(np.asarray(tp), o) if tp is not None
+                       else np.concatenate([np.full(max(M - n, 0), n), np.arange(min(n, M), 0, -1)]))
+    return out
+
+
+_HOST_MERGE = False  # tests: force the numpy merge on a backend that has the device one
 _PHASES = {}  # wall-clock seconds of the last combineRuns / evidenceSampling call, by phase (diagnostics for bench.py)
 
 
@@ -927,10 +956,29 @@ def combineRuns(*results, _backend_override=None, **opts):
     if scheme == "Automatic":
         scheme = "Reference" if all(_reference_pool_structure(a["Samples"], n) for a, n in zip(assocs, pools)) else "PoolSizes"
     import time as _time
+    _PHASES.clear()
+    n_tot = int(sum(pools))
+    be = _backend(_backend_override or assocs[0].get("_backend"))
+    ev_opts = {"PostProcessSamplingRuns": 100, "EmpiricalPosteriorDistributionType": "Simple", "Seed": 1}
+    bad = [k for k in opts if k not in ev_opts]
+    if bad:
+        raise TypeError(f"Unknown option(s) {bad}")
+    ev_opts.update(opts)
+    nruns = ev_opts["PostProcessSamplingRuns"]
+    if hasattr(be, "combine_runs") and isinstance(nruns, (int, np.integer)) and nruns > 0 and not _HOST_MERGE:
+        # the whole of combineRuns -> evidenceSampling on the device (csrc/merge.cu): one call, one table back
+        _t0 = _time.perf_counter()
+        res = be.combine_runs([_sorted_run_table(x["Samples"], n) for x, n in zip(assocs, pools)], scheme == "Reference",
+                              n_tot, int(max(nruns, 2)), int(ev_opts["Seed"]))
+        _PHASES["device_combine_s"] = _time.perf_counter() - _t0
+        a = dict(assocs[0])
+        a.pop("_LiveBlock", None)
+        a.update(_merged_assoc(res, n_tot, scheme))
+        _evidence_summary(a, res["Samples"], res, a.get("ParameterSymbols", []), ev_opts)
+        return inferenceObject(a)
     _t0 = _time.perf_counter()
     merged = _merge_samples([a["Samples"] for a in assocs], pools)
     _PHASES["merge_s"] = _time.perf_counter() - _t0
-    n_tot = int(sum(pools))
     M = merged["LogLikelihood"].size
     a = dict(assocs[0])
     a.pop("_LiveBlock", None)
@@ -1000,7 +1048,49 @@ def parallelNestedSampling(obj, _backend_override=None, **opts):
     tm = {}
     t0 = _time.perf_counter()
     first, count = _shard(R, rank, world)
+    n = int(o["SamplePoolSize"])
+    nruns = o["PostProcessSamplingRuns"]
+    ev_opts = {k: o[k] for k in ("PostProcessSamplingRuns", "EmpiricalPosteriorDistributionType", "Seed")}
+    # device merge (csrc/merge.cu): the runs never travel to the host one by one.  One GPU: the whole of combineRuns ->
+    # evidenceSampling runs on the group's device state; several GPUs: every rank merges its own runs on its GPU, the
+    # per-rank merges are gathered, and merging those equals merging all runs at once (summed pool sizes are additive).
+    on_device = (hasattr(be, "combine_runs") and hasattr(be.RunGroup, "combine") and isinstance(nruns, (int, np.integer))
+                 and nruns > 0 and not _HOST_MERGE)
+    reference_scheme = int(o.get("BatchSize", 1)) == 1  # K = 1 runs have the reference's pool structure (combineRuns "Automatic")
     local = []
+    if on_device:
+        _PHASES.clear()
+        res, part = None, None
+        if count > 0:
+            grp = be.RunGroup(a["_problem"], _engine_options(be, o, n_runs=count, first_run_id=first), None)
+            grp.advance(0)
+            tm["device_loop_s"] = _time.perf_counter() - t0
+            t1 = _time.perf_counter()
+            if world == 1:
+                res = grp.combine(reference_scheme, int(max(nruns, 2)), int(o["Seed"]))
+            else:
+                part = grp.merge()[0]
+            grp.close()
+            tm["device_merge_s"] = _time.perf_counter() - t1
+        if world > 1:
+            t1 = _time.perf_counter()
+            gathered = [None] * world
+            dist.all_gather_object(gathered, part)  # host gather of the per-GPU merges: no collective on the data path
+            tm["gather_s"] = _time.perf_counter() - t1
+            t1 = _time.perf_counter()
+            res = be.combine_runs([g for g in gathered if g is not None], reference_scheme, R * n, int(max(nruns, 2)),
+                                  int(o["Seed"]))
+            tm["device_combine_s"] = _time.perf_counter() - t1
+        t1 = _time.perf_counter()
+        out = dict(a)
+        out.update(_merged_assoc(res, R * n, "Reference" if reference_scheme else "PoolSizes"))
+        p0 = res["Samples"]["Point"][res["Samples"]["RunIndex"] == 0]  # combineRuns keeps First[results] (BS:1299-1305)
+        out["ParameterRanges"] = np.stack([p0.min(0), p0.max(0)], 1)
+        _evidence_summary(out, res["Samples"], res, out.get("ParameterSymbols", []), ev_opts)
+        tm["assemble_s"] = _time.perf_counter() - t1
+        tm["total_s"] = _time.perf_counter() - t0
+        out["_Timing"] = tm
+        return inferenceObject(out)
     if count > 0:
         grp = be.RunGroup(a["_problem"], _engine_options(be, o, n_runs=count, first_run_id=first), None)
         grp.advance(0)
@@ -1016,7 +1106,6 @@ def parallelNestedSampling(obj, _backend_override=None, **opts):
         local = [x for part in gathered for x in part]
     tm["gather_s"] = _time.perf_counter() - t1
     local.sort(key=lambda t: t[0])
-    n = int(o["SamplePoolSize"])
     t1 = _time.perf_counter()
     runs = []
     for _, s in local:

@@ -14,6 +14,7 @@
 #include "walk.cuh"
 #include "walk_grid.cuh"
 #include "walk_loop.cuh"
+#include "run_view.cuh"
 #include "walk_resident.cuh"
 
 namespace binest {
@@ -37,6 +38,7 @@ struct binest_run {
     bool resident = false;      // whole walk in one launch, data in (distributed) shared memory
     int res_cs = 1;             // cluster size of the resident kernel
     int res_tw = 1, res_ch = 16; // walkers per lane, pre-generated steps
+    int res_nw = 16;            // warps per CTA (8: two CTAs per SM)
     long long res_rpc = 0;      // data rows per CTA of the cluster
     size_t res_smem = 0;
     bool loop = false;          // whole nested-sampling loop in one launch per advance (walk_loop.cuh)
@@ -147,62 +149,98 @@ bool plan_resident(binest_run &r, int P) {
     const size_t budget = 200 * 1024;
     static const int tw_force = [] { const char *e = std::getenv("BINEST_RES_TW"); return e ? std::atoi(e) : 0; }();
     static const int cs_force = [] { const char *e = std::getenv("BINEST_RES_CS"); return e ? std::atoi(e) : 0; }();
-    struct Plan { int tw = 0, cs = 0, ch = 0, ctas = 0; double cost = 1e300; long long rpc = 0; size_t smem = 0; } best;
-    for (int tw = OP::TW_MAX; tw >= 1; tw >>= 1) {
-        if (tw_force > 0 && tw != tw_force && tw_force <= OP::TW_MAX) continue;
-        const int groups = (P + 32 * tw - 1) / (32 * tw);
-        if (tw > 1 && groups * 32 * tw >= 2 * P) continue;  // more than half of the tile would be padding
-        for (int cs = 1; cs <= 8; cs <<= 1) {
-            if (cs_force > 0 && cs != cs_force) continue;
-            if (cs > 1 && p.rows / cs < 4 * kResWarps) break;  // shards thinner than a few rows per warp
-            auto smem_of = [&](int ch) {
-                const long long rpc = ((p.rows + cs - 1) / cs + 1) & ~1LL;
-                return resident_smem_doubles<OP>(rpc, cs, tw, ch) * sizeof(double);
-            };
-            if (smem_of(2) > budget) continue;
-            int ch = kResMaxChunk;
-            while (ch > 2 && smem_of(ch) > budget) ch >>= 1;
-            Plan pl;
-            pl.tw = tw; pl.cs = cs; pl.ch = ch; pl.ctas = groups * cs;
-            pl.rpc = ((p.rows + cs - 1) / cs + 1) & ~1LL;
-            pl.smem = smem_of(ch);
-            int max_clusters = 0;
-            dispatch_tw<OP>(tw, [&](auto twc) {
-                constexpr int TW = decltype(twc)::value;
-                BN_CUDA(cudaFuncSetAttribute(walk_resident_kernel<OP, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-                cudaLaunchConfig_t cfg{};
-                cudaLaunchAttribute attr[1];
-                cfg.gridDim = dim3(pl.ctas);
-                cfg.blockDim = dim3(kResWarps * 32);
-                cfg.dynamicSmemBytes = pl.smem;
-                attr[0].id = cudaLaunchAttributeClusterDimension;
-                attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-                cfg.attrs = attr;
-                cfg.numAttrs = 1;
-                if (cudaOccupancyMaxActiveClusters(&max_clusters, walk_resident_kernel<OP, TW>, &cfg) != cudaSuccess) {
-                    cudaGetLastError();
-                    max_clusters = p.num_sms / cs;
-                }
-            });
-            if (max_clusters < 1) continue;
-            const int waves = (groups + max_clusters - 1) / max_clusters;
-            // CTAs that share an SM share its fp64 pipe and its shared-memory port
-            const int per_sm = waves == 1 ? (pl.ctas + p.num_sms - 1) / p.num_sms : 1;
-            const double data_clk = (double)per_sm * pl.rpc * std::max(4.0, 0.5 * tw * OP::SLOTS);
-            pl.cost = waves * (data_clk + 5000.0 + 250.0 * cs) * (1.0 + 0.01 / tw);  // ties: the wider tile
-            if (std::getenv("BINEST_PLAN_DEBUG"))
-                std::fprintf(stderr, "resident plan: tw %d cs %d ch %d groups %d ctas %d max_clusters %d waves %d smem %zu cost %.0f\n",
-                             tw, cs, ch, groups, pl.ctas, max_clusters, waves, pl.smem, pl.cost);
-            if (pl.cost < best.cost * 0.999 || (pl.cost <= best.cost * 1.001 && pl.ctas > best.ctas)) best = pl;
+    static const int nw_force = [] { const char *e = std::getenv("BINEST_RES_NW"); return e ? std::atoi(e) : 0; }();
+    struct Plan { int tw = 0, cs = 0, ch = 0, nw = 0, ctas = 0; double cost = 1e300; long long rpc = 0; size_t smem = 0; } best;
+    for (int nw = kResWarpsMax; nw >= 8; nw >>= 1) {
+        // 8 warps per CTA (two CTAs per SM) stay an experiment (BINEST_RES_NW=8): measured slower than 16 warps
+        // wherever the data phase matters (profiles/r02_resident_sweep.md)
+        if (nw_force > 0 ? nw != nw_force : nw != kResWarpsMax) continue;
+        for (int tw = OP::TW_MAX; tw >= 1; tw >>= 1) {
+            if (tw_force > 0 && tw != tw_force && tw_force <= OP::TW_MAX) continue;
+            const int groups = (P + 32 * tw - 1) / (32 * tw);
+            if (tw > 1 && groups * 32 * tw >= 2 * P) continue;  // more than half of the tile would be padding
+            for (int cs = 1; cs <= 16; cs <<= 1) {
+                if (cs_force > 0 && cs != cs_force) continue;
+                if (cs > 1 && p.rows / cs < 4 * nw) break;  // shards thinner than a few rows per warp
+                // two CTAs per SM need half the shared memory each (1 KB per CTA is reserved by the system)
+                const size_t lim = nw == 8 ? std::min<size_t>(budget, 112 * 1024) : budget;
+                auto smem_of = [&](int ch) {
+                    const long long rpc = ((p.rows + cs - 1) / cs + 1) & ~1LL;
+                    return resident_smem_doubles<OP>(rpc, cs, tw, ch, nw) * sizeof(double);
+                };
+                int ch = kResMaxChunk;
+                if (smem_of(2) > budget) continue;
+                while (ch > 2 && smem_of(ch) > lim) ch >>= 1;
+                if (nw == 8 && smem_of(ch) > lim) ch = kResMaxChunk;  // one CTA per SM after all: no reason to shorten the chunks
+                while (ch > 2 && smem_of(ch) > budget) ch >>= 1;
+                Plan pl;
+                pl.tw = tw; pl.cs = cs; pl.ch = ch; pl.nw = nw; pl.ctas = groups * cs;
+                pl.rpc = ((p.rows + cs - 1) / cs + 1) & ~1LL;
+                pl.smem = smem_of(ch);
+                int max_clusters = 0, per_sm_fit = 1;
+                dispatch_tw<OP>(tw, [&](auto twc) {
+                    constexpr int TW = decltype(twc)::value;
+                    auto query = [&](auto kern) {
+                        BN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+                        if (cs > 8 && cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+                            cudaGetLastError();
+                            return;
+                        }
+                        cudaLaunchConfig_t cfg{};
+                        cudaLaunchAttribute attr[1];
+                        cfg.gridDim = dim3(pl.ctas);
+                        cfg.blockDim = dim3(nw * 32);
+                        cfg.dynamicSmemBytes = pl.smem;
+                        attr[0].id = cudaLaunchAttributeClusterDimension;
+                        attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+                        cfg.attrs = attr;
+                        cfg.numAttrs = 1;
+                        if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg) != cudaSuccess) {
+                            cudaGetLastError();
+                            max_clusters = cs > 8 ? 0 : p.num_sms / cs;
+                        }
+                        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_fit, kern, nw * 32, pl.smem) != cudaSuccess) {
+                            cudaGetLastError();
+                            per_sm_fit = 1;
+                        }
+                    };
+                    if (nw == 8) query(walk_resident_kernel<OP, TW, 8>);
+                    else query(walk_resident_kernel<OP, TW, 16>);
+                });
+                if (max_clusters < 1) continue;
+                const int waves = (groups + max_clusters - 1) / max_clusters;
+                // Cost per walk step, fitted to a sweep of (NW, TW, CS) on C4 with 64 and 8 runs per GPU
+                // (profiles/r02_resident_sweep.md): a row costs 1.15 clocks of shared-memory traffic plus 0.435 clocks per
+                // DFMA slot of the TW walkers of a lane; the chain phase (barriers, DSMEM exchange, accept rule, Haario
+                // recursion, next proposal) ~3900 clocks, ~1500 more across a 16-CTA cluster.  Two CTAs on an SM (NW = 8)
+                // did NOT overlap one's chain phase with the other's data phase as hoped (16.6 vs 12.2 us per step on C4):
+                // they only pay when they save a second wave.
+                const int per_sm = waves == 1 ? std::min(std::max(per_sm_fit, 1), (pl.ctas + p.num_sms - 1) / p.num_sms) : std::max(per_sm_fit, 1);
+                const double data_clk = (double)pl.rpc * (1.15 + 0.435 * tw * OP::SLOTS);
+                const double chain_clk = 3900.0 + (cs > 8 ? 1500.0 : 0.0);
+                const double step_clk = (per_sm * data_clk + chain_clk) * (per_sm > 1 ? 1.4 : 1.0);
+                pl.cost = waves * step_clk * (1.0 + 0.01 / tw);  // ties: the wider tile
+                if (std::getenv("BINEST_PLAN_DEBUG"))
+                    std::fprintf(stderr, "resident plan: nw %d tw %d cs %d ch %d groups %d ctas %d max_clusters %d per_sm %d waves %d smem %zu cost %.0f\n",
+                                 nw, tw, cs, ch, groups, pl.ctas, max_clusters, per_sm, waves, pl.smem, pl.cost);
+                if (pl.cost < best.cost * 0.999 || (pl.cost <= best.cost * 1.001 && pl.ctas > best.ctas)) best = pl;
+            }
         }
     }
     if (best.tw == 0) return false;
     r.resident = true;
-    r.res_tw = best.tw; r.res_cs = best.cs; r.res_ch = best.ch; r.res_rpc = best.rpc; r.res_smem = best.smem;
+    r.res_tw = best.tw; r.res_cs = best.cs; r.res_ch = best.ch; r.res_rpc = best.rpc; r.res_smem = best.smem; r.res_nw = best.nw;
     dispatch_tw<OP>(best.tw, [&](auto twc) {
         constexpr int TW = decltype(twc)::value;
-        BN_CUDA(cudaFuncSetAttribute(walk_resident_kernel<OP, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r.res_smem));
+        auto prep = [&](auto kern) {
+            BN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r.res_smem));
+            if (best.cs > 8) BN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        };
+        if (best.nw == 8) prep(walk_resident_kernel<OP, TW, 8>);
+        else prep(walk_resident_kernel<OP, TW, 16>);
     });
+    if (std::getenv("BINEST_PLAN_DEBUG"))
+        std::fprintf(stderr, "resident plan chosen: nw %d tw %d cs %d ch %d ctas %d smem %zu\n", best.nw, best.tw, best.cs, best.ch, best.ctas, best.smem);
     return true;
 }
 
@@ -451,7 +489,7 @@ void walk_block(binest_run &r, const RunParams &q) {
             cudaLaunchConfig_t cfg{};
             cudaLaunchAttribute attr[1];
             cfg.gridDim = dim3(groups * r.res_cs);
-            cfg.blockDim = dim3(kResWarps * 32);
+            cfg.blockDim = dim3(r.res_nw * 32);
             cfg.dynamicSmemBytes = r.res_smem;
             cfg.stream = r.stream;
             attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -466,7 +504,10 @@ void walk_block(binest_run &r, const RunParams &q) {
             int cs = r.res_cs, ch = r.res_ch;
             dispatch_tw<OP>(r.res_tw, [&](auto twc) {
                 constexpr int TW = decltype(twc)::value;
-                BN_CUDA(cudaLaunchKernelEx(&cfg, walk_resident_kernel<OP, TW>, q, r.A, p.prior, data, rows, rpc, cst, cs, ch));
+                if (r.res_nw == 8)
+                    BN_CUDA(cudaLaunchKernelEx(&cfg, walk_resident_kernel<OP, TW, 8>, q, r.A, p.prior, data, rows, rpc, cst, cs, ch));
+                else
+                    BN_CUDA(cudaLaunchKernelEx(&cfg, walk_resident_kernel<OP, TW, 16>, q, r.A, p.prior, data, rows, rpc, cst, cs, ch));
             });
             BN_LAUNCH_CHECK();
         });
@@ -858,6 +899,27 @@ int binest_problem_stream(const binest_problem *p, void **stream) {
         *stream = (void *)p->stream;
     });
 }
+
+// device state of a run group for csrc/merge.cu (run_view.cuh)
+extern "C++" {
+namespace binest {
+void run_view(binest_run *r, RunView &v) {
+    BN_REQUIRE(r, BINEST_ERR_TYPE, "null run");
+    BN_CUDA(cudaSetDevice(r->prob->device));
+    BN_REQUIRE(!r->first, BINEST_ERR_FUNCTION, "advance the run first");
+    if (!r->finished) launch_update(*r, true);  // insert the batch in flight and re-sort; no new kill
+    fetch_state(*r);
+    BN_CUDA(cudaStreamSynchronize(r->stream));
+    const RunParams &q = r->prm;
+    v.device = r->prob->device;
+    v.dev = RunViewDev{q.R, q.n, q.d, q.cap, (long long)q.first_run_id,
+                       r->dead_theta.p, r->dead_logL.p, r->dead_logPr.p, r->dead_acc.p, r->dead_pool.p,
+                       r->live_theta.p, r->live_logL.p, r->live_logPr.p, r->live_acc.p, r->order.p};
+    v.n_dead.resize(q.R);
+    for (int c = 0; c < q.R; ++c) v.n_dead[c] = r->h_state[c].n_dead;
+}
+}  // namespace binest
+}  // extern "C++"
 
 int binest_run_free(binest_run *r) {
     return guard([&] {

@@ -25,22 +25,24 @@ namespace binest {
 
 namespace cg = cooperative_groups;
 
-constexpr int kResWarps = 16;     // all 16 sweep the data; warps 0..TW-1 also run the chains
+constexpr int kResWarpsMax = 16;  // NW = 16 or 8 warps per CTA: all sweep the data; warps 0..TW-1 also run the chains.  With 8
+                                  // warps two CTAs (of different clusters) share an SM: one's chain phase runs under the
+                                  // other's data phase
 constexpr int kResMaxChunk = 16;  // walk steps of pre-generated increments held in shared memory (upper bound)
 
 // dynamic shared memory layout (doubles), WP = 32 TW:
-//   tile | xch[2][CS][WP] | red[kResWarps][WP] | dz[CH][D][WP] | logu[CH][WP] | mean[D][WP] | cov[D*D][WP] | row[WP] (OP::Row)
+//   tile | xch[2][CS][WP] | red[NW][WP] | dz[CH][D][WP] | logu[CH][WP] | mean[D][WP] | cov[D*D][WP] | row[WP] (OP::Row)
 template <class OP>
-__host__ __device__ inline size_t resident_smem_doubles(long long rows_per_cta, int CS, int TW, int CH) {
+__host__ __device__ inline size_t resident_smem_doubles(long long rows_per_cta, int CS, int TW, int CH, int NW) {
     const size_t WP = 32 * (size_t)TW;
     const size_t tile = ((size_t)rows_per_cta * OP::NCOL + 1) & ~(size_t)1;
     const size_t rowsz = (sizeof(typename OP::Row) * WP + 7) / 8;
-    return tile + 2 * (size_t)CS * WP + kResWarps * WP + (size_t)CH * OP::D * WP + (size_t)CH * WP + OP::D * WP +
+    return tile + 2 * (size_t)CS * WP + (size_t)NW * WP + (size_t)CH * OP::D * WP + (size_t)CH * WP + OP::D * WP +
            OP::D * OP::D * WP + rowsz;
 }
 
-template <class OP, int TW>
-__global__ void __launch_bounds__(kResWarps * 32)
+template <class OP, int TW, int NW>
+__global__ void __launch_bounds__(NW * 32, NW <= 8 ? 2 : 1)
 walk_resident_kernel(const __grid_constant__ RunParams prm, RunArrays A, const __grid_constant__ PriorSpec prior,
                      const double *__restrict__ data, long long rows, long long rows_per_cta, const OpCst cst, int CS,
                      int CH) {
@@ -49,8 +51,8 @@ walk_resident_kernel(const __grid_constant__ RunParams prm, RunArrays A, const _
     const size_t tile_sz = ((size_t)rows_per_cta * NCOL + 1) & ~(size_t)1;
     double *tile = smem;
     double *xch = tile + tile_sz;                   // [2][CS][WP]
-    double *red = xch + 2 * CS * WP;                // [kResWarps][WP]
-    double *s_dz = red + kResWarps * WP;            // [CH][D][WP]
+    double *red = xch + 2 * CS * WP;                // [NW][WP]
+    double *s_dz = red + NW * WP;                   // [CH][D][WP]
     double *s_logu = s_dz + (size_t)CH * D * WP;    // [CH][WP]
     double *s_mean = s_logu + (size_t)CH * WP;      // [D][WP]
     double *s_cov = s_mean + D * WP;                // [D*D][WP]
@@ -174,16 +176,16 @@ walk_resident_kernel(const __grid_constant__ RunParams prm, RunArrays A, const _
                 typename OP::Acc a1[1] = {OP::acc_init()}, a2[1] = {OP::acc_init()}, a3[1] = {OP::acc_init()};
                 int i = wid;
 #pragma unroll 2
-                for (; i + 3 * kResWarps < nr; i += 4 * kResWarps) {
+                for (; i + 3 * NW < nr; i += 4 * NW) {
                     OP::template rows<1>(c, tile + (size_t)i * NCOL, acc);
-                    OP::template rows<1>(c, tile + (size_t)(i + kResWarps) * NCOL, a1);
-                    OP::template rows<1>(c, tile + (size_t)(i + 2 * kResWarps) * NCOL, a2);
-                    OP::template rows<1>(c, tile + (size_t)(i + 3 * kResWarps) * NCOL, a3);
+                    OP::template rows<1>(c, tile + (size_t)(i + NW) * NCOL, a1);
+                    OP::template rows<1>(c, tile + (size_t)(i + 2 * NW) * NCOL, a2);
+                    OP::template rows<1>(c, tile + (size_t)(i + 3 * NW) * NCOL, a3);
                 }
-                for (; i < nr; i += kResWarps) OP::template rows<1>(c, tile + (size_t)i * NCOL, acc);
+                for (; i < nr; i += NW) OP::template rows<1>(c, tile + (size_t)i * NCOL, acc);
                 red[wid * WP + lane] = (OP::acc_value(acc[0]) + OP::acc_value(a1[0])) + (OP::acc_value(a2[0]) + OP::acc_value(a3[0]));
             } else {
-                sweep_rows<OP, TW>(c, tile, wid, kResWarps, nr, acc);
+                sweep_rows<OP, TW>(c, tile, wid, NW, nr, acc);
 #pragma unroll
                 for (int u = 0; u < TW; ++u) red[wid * WP + u * 32 + lane] = OP::acc_value(acc[u]);
             }
@@ -197,7 +199,7 @@ walk_resident_kernel(const __grid_constant__ RunParams prm, RunArrays A, const _
         if (chain) {
             double part = 0.0;
 #pragma unroll
-            for (int q = 0; q < kResWarps; ++q) part += red[q * WP + wl];
+            for (int q = 0; q < NW; ++q) part += red[q * WP + wl];
             double sum = part;
             if (CS > 1) {
                 if (tid == 0) mbar_expect_tx(&xbar[par], (uint32_t)(CS * WP * sizeof(double)));

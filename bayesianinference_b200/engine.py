@@ -271,6 +271,35 @@ class RunGroup:
                        logLmax=float(summ[2]), log_missing=float(summ[3]))
         return out
 
+    def merge(self):
+        """combineRuns BS:1293-1297 of the group's runs on the device (binest_run_merge): merged table (summed PoolSize,
+        RunIndex = global run ids) and the live-block length.  No per-run fetch."""
+        L = _lib.load()
+        Mt = C.c_int64()
+        check(L.binest_run_merge_size(self.h, C.byref(Mt)))
+        Mt, d = Mt.value, self.problem.d
+        pts, cols = np.empty((Mt, d)), [np.empty(Mt) for _ in range(3)]
+        pool, rid = np.empty(Mt, dtype=np.int64), np.empty(Mt, dtype=np.int64)
+        M, live = C.c_int64(), C.c_int64()
+        check(L.binest_run_merge(self.h, dptr(pts), dptr(cols[0]), dptr(cols[1]), dptr(cols[2]), iptr(pool), iptr(rid),
+                                 C.byref(M), C.byref(live)))
+        m = M.value
+        return ({"Point": pts[:m], "LogLikelihood": cols[0][:m], "LogPriorPDF": cols[1][:m], "AcceptanceRate": cols[2][:m],
+                 "PoolSize": pool[:m], "RunIndex": rid[:m]}, live.value)
+
+    def combine(self, reference_scheme, post_runs=100, seed=1):
+        """combineRuns -> evidenceSampling of the group's runs in one device call (binest_run_combine)."""
+        L = _lib.load()
+        Mt = C.c_int64()
+        check(L.binest_run_merge_size(self.h, C.byref(Mt)))
+        Mt, d = Mt.value, self.problem.d
+        o_pts, tab, itab = np.empty((Mt, d)), np.empty((len(COLS), Mt)), np.empty((2, Mt), dtype=np.int64)
+        z, H, pm, summ = np.empty(post_runs), np.empty(post_runs), np.empty((post_runs, d)), np.empty(4)
+        M, n_live = C.c_int64(), C.c_int64()
+        check(L.binest_run_combine(self.h, 0 if reference_scheme else 1, int(post_runs), int(seed), dptr(o_pts), dptr(tab),
+                                   iptr(itab), dptr(z), dptr(pm), dptr(H), dptr(summ), C.byref(M), C.byref(n_live)))
+        return _combined(M.value, o_pts, tab, itab, z, H, pm, summ, n_live.value, True, True)
+
     def estimates(self, run=0):
         d = self.problem.d
         m, c = np.empty(d), np.empty((d, d))
@@ -352,6 +381,73 @@ def crude_weights(logL, pool, n_live):
     check(_lib.load().binest_crude_weights(M, dptr(logL), iptr(pool), n_live, dptr(lx), dptr(lw), dptr(s)))
     return dict(logX=lx, crude_logw=lw, crude_logZ=float(s[0]), entropy=float(s[1]), logLmax=float(s[2]),
                 log_missing=float(s[3]))
+
+
+def _join_runs(tables):
+    """the runs' columns concatenated in Join order (BS:1293) for the device merge"""
+    sizes = np.array([t["LogLikelihood"].size for t in tables], dtype=np.int64)
+    pts = _f64(np.concatenate([np.asarray(t["Point"], float).reshape(t["LogLikelihood"].size, -1) for t in tables]))
+    col = lambda k: _f64(np.concatenate([t[k] for t in tables])) if all(k in t for t in tables) else None  # noqa: E731
+    pool = np.ascontiguousarray(np.concatenate([t["PoolSize"] for t in tables]), dtype=np.int64)
+    rid = (np.ascontiguousarray(np.concatenate([t["RunIndex"] for t in tables]), dtype=np.int64)
+           if all("RunIndex" in t for t in tables) else None)
+    return sizes, pts, col("LogLikelihood"), col("LogPriorPDF"), col("AcceptanceRate"), pool, rid
+
+
+def merge_runs(tables):
+    """combineRuns BS:1293-1297 on the device (binest_merge_runs): tables = the runs' sample tables, each sorted by
+    {logL, point} and carrying its own "PoolSize" column.  Returns the merged table and the live-block length."""
+    _ensure_init()
+    sizes, pts, L, lp, acc, pool, rid = _join_runs(tables)
+    Mt, d = pts.shape
+    o_pts, o_L, o_lp, o_acc = np.empty((Mt, d)), np.empty(Mt), np.empty(Mt), np.empty(Mt)
+    o_pool, o_rid = np.empty(Mt, dtype=np.int64), np.empty(Mt, dtype=np.int64)
+    M, live = C.c_int64(), C.c_int64()
+    check(_lib.load().binest_merge_runs(len(tables), iptr(sizes), d, dptr(pts), dptr(L), dptr(lp), dptr(acc), iptr(pool),
+                                        iptr(rid), dptr(o_pts), dptr(o_L), dptr(o_lp), dptr(o_acc), iptr(o_pool),
+                                        iptr(o_rid), C.byref(M), C.byref(live)))
+    m = M.value
+    out = {"Point": o_pts[:m], "PoolSize": o_pool[:m], "RunIndex": o_rid[:m], "LogLikelihood": o_L[:m]}
+    if lp is not None:
+        out["LogPriorPDF"] = o_lp[:m]
+    if acc is not None:
+        out["AcceptanceRate"] = o_acc[:m]
+    return out, live.value
+
+
+COLS = ("LogLikelihood", "LogPriorPDF", "AcceptanceRate", "LogX", "X", "CrudeLogPosteriorWeight", "CrudePosteriorWeight",
+        "SampledLogX.Mean", "SampledLogX.StandardError", "LogPosteriorWeight.Mean", "LogPosteriorWeight.StandardError")
+
+
+def combine_runs(tables, reference_scheme, n_tot, post_runs=100, seed=1):
+    """combineRuns -> evidenceSampling (BS:1293-1315, 1158-1291) in one device call (binest_combine_runs): merge, X
+    sequence, crude weights, Monte-Carlo evidence error, final sort by posterior weight.  Returns the finished sample
+    table (columns as api.evidenceSampling builds them) and the per-draw / summary outputs."""
+    _ensure_init()
+    sizes, pts, L, lp, acc, pool, rid = _join_runs(tables)
+    Mt, d = pts.shape
+    o_pts, tab, itab = np.empty((Mt, d)), np.empty((len(COLS), Mt)), np.empty((2, Mt), dtype=np.int64)
+    z, H, pm, summ = np.empty(post_runs), np.empty(post_runs), np.empty((post_runs, d)), np.empty(4)
+    M, n_live = C.c_int64(), C.c_int64()
+    check(_lib.load().binest_combine_runs(len(tables), iptr(sizes), d, dptr(pts), dptr(L), dptr(lp), dptr(acc), iptr(pool),
+                                          iptr(rid), 0 if reference_scheme else 1, int(n_tot), int(post_runs), int(seed),
+                                          dptr(o_pts), dptr(tab), iptr(itab), dptr(z), dptr(pm), dptr(H), dptr(summ),
+                                          C.byref(M), C.byref(n_live)))
+    return _combined(M.value, o_pts, tab, itab, z, H, pm, summ, n_live.value, lp is not None, acc is not None)
+
+
+def _combined(m, o_pts, tab, itab, z, H, pm, summ, n_live, has_lp, has_acc):
+    S = {"Point": o_pts[:m], "PoolSize": itab[0, :m], "RunIndex": itab[1, :m]}
+    for c, name in enumerate(COLS):
+        if name == "LogPriorPDF" and not has_lp or name == "AcceptanceRate" and not has_acc:
+            continue
+        if "." in name:
+            k, sub = name.split(".")
+            S.setdefault(k, {})[sub] = tab[c, :m]
+        else:
+            S[name] = tab[c, :m]
+    return dict(Samples=S, z=z, H=H, pmean=pm, crude_logZ=float(summ[0]), entropy=float(summ[1]), logLmax=float(summ[2]),
+                log_missing=float(summ[3]), n_live=n_live)
 
 
 def fp64_peak():

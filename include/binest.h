@@ -202,6 +202,50 @@ int binest_evidence_sampling(int64_t M, int64_t d, const double *points, const d
 int binest_crude_weights(int64_t M, const double *logL, const int64_t *pool, int64_t n_live,
                          double *logX, double *crude_logw, double *summary /*[4]*/);
 
+/* ---- combineRuns (BS:1293-1315) on the device ------------------------------------------------ */
+/* Join of R runs' sample lists, DeleteDuplicatesBy Point (the first in Join order kept), SortBy {logL, point}
+ * (BS:1293-1297), plus what the re-weighting of the merged list needs: the summed pool size at every sample's
+ * likelihood level (the runs' pool sizes are step functions of the level) and the index of the run a sample came from.
+ * Inputs: the runs concatenated in Join order — sizes[R]; points Mtot x d; logL, logPrior (may be NULL), acc (may be
+ * NULL) [Mtot]; pool [Mtot] = each run's own pool size at its samples; run_id [Mtot] or NULL (= position in the Join).
+ * Every run must be sorted by {logL, point}, the order binest_run_fetch returns (BINEST_ERR_DIMENSION otherwise).
+ * Outputs (caller allocates Mtot entries, *M_out <= Mtot are written; any may be NULL).  *live_block = length of the
+ * tail whose summed pool sizes are M, M-1, .., 1 counted from its start — the part that acts as a final live set. */
+int binest_merge_runs(int64_t R, const int64_t *sizes, int64_t d, const double *points, const double *logL,
+                      const double *logPrior, const double *acc, const int64_t *pool, const int64_t *run_id,
+                      double *points_out, double *logL_out, double *logPrior_out, double *acc_out, int64_t *pool_out,
+                      int64_t *run_out, int64_t *M_out, int64_t *live_block);
+/* The whole of combineRuns -> evidenceSampling (BS:1293-1315, 1158-1291) in one call: the merge above, the X sequence
+ * of the merged list (scheme), calculateWeightsCrude, the Monte-Carlo evidence error, and the final
+ * SortBy[-CrudePosteriorWeight] (BS:1241, stable) applied to every column.
+ *   BINEST_MERGE_REFERENCE: pool size n_tot = Total[SamplePoolSize] for the first M - n_tot samples, then n_tot..1
+ *                           (BS:1307-1309 feeding BS:785-799);
+ *   BINEST_MERGE_POOLSIZES: the summed pool sizes to the end, live block as returned by binest_merge_runs.
+ * table_out: BINEST_NCOL_F columns of stride Mtot (column c at table_out + c*Mtot), itable_out: PoolSize, RunIndex
+ * (stride Mtot); points_out M x d; z, H [post_runs]; pmean [post_runs x d]; summary[4] as binest_crude_weights. */
+enum { BINEST_MERGE_REFERENCE = 0, BINEST_MERGE_POOLSIZES = 1 };
+enum {
+    BINEST_COL_LOGL = 0, BINEST_COL_LOGPRIOR, BINEST_COL_ACC, BINEST_COL_LOGX, BINEST_COL_X, BINEST_COL_CRUDE_LOGW,
+    BINEST_COL_CRUDE_W, BINEST_COL_SLX_MEAN, BINEST_COL_SLX_SD, BINEST_COL_LOGW_MEAN, BINEST_COL_LOGW_SD, BINEST_NCOL_F
+};
+int binest_combine_runs(int64_t R, const int64_t *sizes, int64_t d, const double *points, const double *logL,
+                        const double *logPrior, const double *acc, const int64_t *pool, const int64_t *run_id,
+                        int32_t scheme, int64_t n_tot, int64_t post_runs, uint64_t seed, double *points_out,
+                        double *table_out, int64_t *itable_out, double *z, double *pmean, double *H, double *summary,
+                        int64_t *M_out, int64_t *n_live_out);
+
+/* The same two operations on a run group's own device state (no per-run fetch, no host round trip of the inputs):
+ * the Join is the runs of the group in order, each as binest_run_fetch would return it, run_id = first_run_id + index.
+ * binest_run_merge_size gives the allocation bound (total samples before duplicate removal).  binest_run_combine uses
+ * n_tot = n_runs * pool_size.  A pre-merged list (its summed PoolSize and RunIndex columns) can itself be an input
+ * of binest_merge_runs / binest_combine_runs: merging per-GPU merges equals merging all runs at once. */
+int binest_run_merge_size(binest_run *r, int64_t *M_total);
+int binest_run_merge(binest_run *r, double *points_out, double *logL_out, double *logPrior_out, double *acc_out,
+                     int64_t *pool_out, int64_t *run_out, int64_t *M_out, int64_t *live_block);
+int binest_run_combine(binest_run *r, int32_t scheme, int64_t post_runs, uint64_t seed, double *points_out,
+                       double *table_out, int64_t *itable_out, double *z, double *pmean, double *H, double *summary,
+                       int64_t *M_out, int64_t *n_live_out);
+
 /* ---- data-sharded mode ("very large N"): rows split across the GPUs of one box ------------
  * One process per GPU.  Rank 0 makes an id, the host passes it to every rank (any channel), every rank creates
  * its communicator (collective), defines its problem from ITS rows only (GBM: shards overlap by one point, the
