@@ -386,7 +386,8 @@ def crude_weights(logL, pool, n_live):
 def _join_runs(tables):
     """the runs' columns concatenated in Join order (BS:1293) for the device merge"""
     sizes = np.array([t["LogLikelihood"].size for t in tables], dtype=np.int64)
-    pts = _f64(np.concatenate([np.asarray(t["Point"], float).reshape(t["LogLikelihood"].size, -1) for t in tables]))
+    d = max(np.asarray(t["Point"]).shape[1] for t in tables if np.asarray(t["Point"]).ndim == 2)
+    pts = _f64(np.concatenate([np.asarray(t["Point"], float).reshape(t["LogLikelihood"].size, d) for t in tables]))
     col = lambda k: _f64(np.concatenate([t[k] for t in tables])) if all(k in t for t in tables) else None  # noqa: E731
     pool = np.ascontiguousarray(np.concatenate([t["PoolSize"] for t in tables]), dtype=np.int64)
     rid = (np.ascontiguousarray(np.concatenate([t["RunIndex"] for t in tables]), dtype=np.int64)

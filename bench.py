@@ -17,8 +17,9 @@ total work fixed, so the driver's 1/2/4/8 sweep yields their curves; skipped wit
                   (fill + blocked Cholesky on FP64 DMMA); N > 1: batch-sharded, 256/N matrices per GPU, the finished
                   values exchanged in-kernel over peer-mapped memory.  Roofline: fp64 tensor pipe.
   "c4_strong"     config C4 as BASELINE states it: 64 parallelNestedSampling runs x 512 live points through
-                  api.parallelNestedSampling, the WHOLE call timed (device loop + gather + combineRuns +
-                  evidenceSampling); N > 1: 64/N runs per GPU.  Unit: live-point replacements/s.
+                  api.parallelNestedSampling, the WHOLE call timed (device loop + merge of the runs + evidenceSampling,
+                  both on the device); N > 1: 64/N runs per GPU.  Unit: live-point replacements/s.
+  "c4_strong_T262144"  the same job on 16x the data (262 144 increments): a walk step is fp64 work instead of latency.
   "data_sharded"  the data-sharded mode: C2-shaped data with --rows rows (default 6.4e7) split N ways, K = 256
                   walkers x 200 steps per iteration, per-step exchange of 8 P bytes to every peer.
 A watchdog bounds the extras: if they do not finish in time the line is printed without the missing ones.
@@ -315,12 +316,15 @@ def measure_c1(ctx, reps=5):
                                    "run to termination", "parallelism": "one sequential chain per GPU"}}
 
 
-def measure_c4_strong(ctx, reps=2):
+def measure_c4_strong(ctx, reps=2, T=16384):
     """Config C4 as BASELINE states it, through the reference-facing call: parallelNestedSampling with 64 runs x 512 live
-    points (BS:1317-1371), whole call timed on every rank (max over ranks): device loops of this rank's runs, gather of
-    the sample lists, combineRuns (BS:1293-1315), evidenceSampling (BS:1158-1291)."""
+    points (BS:1317-1371), whole call timed on every rank (max over ranks): device loops of this rank's runs, the merge of
+    the runs (combineRuns BS:1293-1315) and evidenceSampling (BS:1158-1291) — on the device (csrc/merge.cu): one GPU merges
+    its run group in place; several GPUs merge their own runs, gather the per-GPU merges and merge those.
+    T = 262144 (BASELINE.md §4 lists it beside 16384) is the same job on 16x the data: there a walk step is fp64 work, not
+    latency, and the job scales."""
     from bayesianinference_b200 import api
-    c = cfg.c4_gbm()
+    c = cfg.c4_gbm(T=T)
     obj = api.defineInferenceProblem(
         Data=(c.inputs[:, 0], c.outputs[:, 0]), GeneratingDistribution=api.GeometricBrownianMotionProcess("mu", "sigma", 100.0),
         Parameters=[(nm, lo, hi) for nm, lo, hi in zip(c.names, c.lo, c.hi)],
@@ -338,13 +342,18 @@ def measure_c4_strong(ctx, reps=2):
             best = dt
             info = (res["GeneratedNestedSamples"], res["LogEvidence"], res.get("_Timing"))
     gen, logz, timing = info
-    pull = (logz["Mean"] - c.truth["logZ"]) / max(logz["StandardError"], 1e-12)
+    truth = c.truth.get("logZ")
+    pull = (logz["Mean"] - truth) / max(logz["StandardError"], 1e-12) if truth is not None else None
+    iters = gen / (64 * 64)
+    walk_flop = 4.0 * T * 64 * 64 * MC_STEPS * iters  # 4 flop per increment and proposal
     return {"metric": "live-point replacements/s", "unit": "replacements/s", "value": gen / best, "s_per_call": best,
             "scaling": "strong", "n_gpus": ctx.world, "replacements": int(gen),
-            "config": {"workload": "C4-gbm: 64 parallelNestedSampling runs x 512 live points, T=16384 increments, K=64 "
+            "config": {"workload": f"C4-gbm: 64 parallelNestedSampling runs x 512 live points, T={T} increments, K=64 "
                                    "replaced per iteration per run, 200 walk steps", "parallelism": f"run-sharded x{ctx.world}: "
-                                   f"{-(-64 // ctx.world)} runs per GPU, host merge (combineRuns)"},
-            "phases_s_rank0": timing, "all_calls": allreps, "log_evidence": logz, "pull_vs_quadrature": pull}
+                                   f"{-(-64 // ctx.world)} runs per GPU, runs merged on the device (combineRuns + "
+                                   "evidenceSampling in csrc/merge.cu)"},
+            "phases_s_rank0": timing, "all_calls": allreps, "log_evidence": logz, "pull_vs_quadrature": pull,
+            "device_loop_tflops_aggregate": walk_flop / max(timing.get("device_loop_s", float("nan")), 1e-9) / 1e12 if timing else None}
 
 
 def measure_data_sharded(ctx, rows, iters=2, K=256):
@@ -593,6 +602,7 @@ def run_ours(args):
     if not args.no_extras:
         threading.Thread(target=watchdog, daemon=True).start()
         plan = [("c1", lambda: measure_c1(ctx)), ("c5", lambda: measure_c5(ctx, 3, 1)), ("c4_strong", lambda: measure_c4_strong(ctx)),
+                ("c4_strong_T262144", lambda: measure_c4_strong(ctx, reps=1, T=262144)),
                 ("data_sharded", lambda: measure_data_sharded(ctx, args.rows))]
         for name, fn in plan:
             # all ranks must agree to enter a collective measurement: a rank-local failure aborts the remaining extras

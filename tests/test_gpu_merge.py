@@ -57,6 +57,22 @@ def test_device_merge_equals_host_merge(R, n, K, iters):
     assert live == want
 
 
+def test_device_merge_edge_cases():
+    """an empty run, a run that is an exact copy of another (every sample a duplicate), a single-sample run"""
+    from bayesianinference_b200 import engine
+    runs = _synthetic_runs(3, 24, 2, 12, seed=31)
+    empty = {k: v[:0] for k, v in runs[0].items()}
+    copy = {k: v.copy() for k, v in runs[1].items()}
+    one = {k: v[-1:].copy() for k, v in runs[2].items()}
+    one["PoolSize"] = np.array([1], dtype=np.int64)
+    for tabs, pools in (([runs[0], empty, runs[1]], [24, 24, 24]), ([runs[0], runs[1], copy], [24, 24, 24]),
+                        ([one, runs[0]], [1, 24]), ([empty, runs[2], empty], [24, 24, 24])):
+        host = api._merge_samples(tabs, pools)
+        dev, _ = engine.merge_runs(tabs)
+        for k in ("Point", "LogLikelihood", "LogPriorPDF", "AcceptanceRate", "PoolSize", "RunIndex"):
+            assert np.array_equal(dev[k], host[k]), k
+
+
 def test_device_merge_rejects_unsorted_runs():
     from bayesianinference_b200 import _lib, engine
     runs = _synthetic_runs(2, 16, 1, 10, seed=5, dup_frac=0, tie_frac=0)
