@@ -143,6 +143,8 @@ inline bool G_own_too_many(int num_sms, int PA, int P) {
 //               a GPC and one GPC of a B200 is short of SMs — 15 clusters of 8, not 16 (ncu r2g: 16 clusters of 8 ran
 //               as two waves, 5.1 ms instead of 2.5 ms per C4 walk) — cudaOccupancyMaxActiveClusters tells.
 // BINEST_RES_TW / BINEST_RES_CS force a tile width / cluster size (experiments).
+constexpr double kResChainClocks = 2000.0;
+
 template <class OP>
 bool plan_resident(binest_run &r, int P) {
     binest_problem &p = *r.prob;
@@ -150,33 +152,24 @@ bool plan_resident(binest_run &r, int P) {
     static const int tw_force = [] { const char *e = std::getenv("BINEST_RES_TW"); return e ? std::atoi(e) : 0; }();
     static const int cs_force = [] { const char *e = std::getenv("BINEST_RES_CS"); return e ? std::atoi(e) : 0; }();
     static const int nw_force = [] { const char *e = std::getenv("BINEST_RES_NW"); return e ? std::atoi(e) : 0; }();
-    struct Plan { int tw = 0, cs = 0, ch = 0, nw = 0, ctas = 0; double cost = 1e300; long long rpc = 0; size_t smem = 0; } best;
+    struct Plan { int tw = 0, cs = 0, nw = 0, ctas = 0; double cost = 1e300; long long rpc = 0; size_t smem = 0; } best;
     for (int nw = kResWarpsMax; nw >= 8; nw >>= 1) {
-        // 8 warps per CTA (two CTAs per SM) stay an experiment (BINEST_RES_NW=8): measured slower than 16 warps
-        // wherever the data phase matters (profiles/r02_resident_sweep.md)
+        // 8 data warps per CTA (two CTAs per SM) stay an experiment (BINEST_RES_NW=8): measured slower than 16 wherever
+        // the data phase matters (profiles/r02_resident_sweep.md)
         if (nw_force > 0 ? nw != nw_force : nw != kResWarpsMax) continue;
         for (int tw = OP::TW_MAX; tw >= 1; tw >>= 1) {
             if (tw_force > 0 && tw != tw_force && tw_force <= OP::TW_MAX) continue;
+            if ((nw + tw) * 32 > 640) continue;  // 65536 registers / ~100 per thread
             const int groups = (P + 32 * tw - 1) / (32 * tw);
             if (tw > 1 && groups * 32 * tw >= 2 * P) continue;  // more than half of the tile would be padding
             for (int cs = 1; cs <= 16; cs <<= 1) {
                 if (cs_force > 0 && cs != cs_force) continue;
                 if (cs > 1 && p.rows / cs < 4 * nw) break;  // shards thinner than a few rows per warp
-                // two CTAs per SM need half the shared memory each (1 KB per CTA is reserved by the system)
-                const size_t lim = nw == 8 ? std::min<size_t>(budget, 112 * 1024) : budget;
-                auto smem_of = [&](int ch) {
-                    const long long rpc = ((p.rows + cs - 1) / cs + 1) & ~1LL;
-                    return resident_smem_doubles<OP>(rpc, cs, tw, ch, nw) * sizeof(double);
-                };
-                int ch = kResMaxChunk;
-                if (smem_of(2) > budget) continue;
-                while (ch > 2 && smem_of(ch) > lim) ch >>= 1;
-                if (nw == 8 && smem_of(ch) > lim) ch = kResMaxChunk;  // one CTA per SM after all: no reason to shorten the chunks
-                while (ch > 2 && smem_of(ch) > budget) ch >>= 1;
                 Plan pl;
-                pl.tw = tw; pl.cs = cs; pl.ch = ch; pl.nw = nw; pl.ctas = groups * cs;
+                pl.tw = tw; pl.cs = cs; pl.nw = nw; pl.ctas = groups * cs;
                 pl.rpc = ((p.rows + cs - 1) / cs + 1) & ~1LL;
-                pl.smem = smem_of(ch);
+                pl.smem = resident_smem_doubles<OP>(pl.rpc, cs, tw, nw) * sizeof(double);
+                if (pl.smem > budget) continue;
                 int max_clusters = 0, per_sm_fit = 1;
                 dispatch_tw<OP>(tw, [&](auto twc) {
                     constexpr int TW = decltype(twc)::value;
@@ -189,7 +182,7 @@ bool plan_resident(binest_run &r, int P) {
                         cudaLaunchConfig_t cfg{};
                         cudaLaunchAttribute attr[1];
                         cfg.gridDim = dim3(pl.ctas);
-                        cfg.blockDim = dim3(nw * 32);
+                        cfg.blockDim = dim3((nw + tw) * 32);
                         cfg.dynamicSmemBytes = pl.smem;
                         attr[0].id = cudaLaunchAttributeClusterDimension;
                         attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
@@ -199,7 +192,7 @@ bool plan_resident(binest_run &r, int P) {
                             cudaGetLastError();
                             max_clusters = cs > 8 ? 0 : p.num_sms / cs;
                         }
-                        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_fit, kern, nw * 32, pl.smem) != cudaSuccess) {
+                        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_fit, kern, (nw + tw) * 32, pl.smem) != cudaSuccess) {
                             cudaGetLastError();
                             per_sm_fit = 1;
                         }
@@ -211,25 +204,24 @@ bool plan_resident(binest_run &r, int P) {
                 const int waves = (groups + max_clusters - 1) / max_clusters;
                 // Cost per walk step, fitted to a sweep of (NW, TW, CS) on C4 with 64 and 8 runs per GPU
                 // (profiles/r02_resident_sweep.md): a row costs 1.15 clocks of shared-memory traffic plus 0.435 clocks per
-                // DFMA slot of the TW walkers of a lane; the chain phase (barriers, DSMEM exchange, accept rule, Haario
-                // recursion, next proposal) ~3900 clocks, ~1500 more across a 16-CTA cluster.  Two CTAs on an SM (NW = 8)
-                // did NOT overlap one's chain phase with the other's data phase as hoped (16.6 vs 12.2 us per step on C4):
-                // they only pay when they save a second wave.
+                // DFMA slot of the TW walkers of a lane; what stays between two data phases (barriers, combine, DSMEM
+                // exchange, accept rule) ~2000 clocks, ~1500 more across a 16-CTA cluster.  CTAs sharing an SM share its
+                // fp64 pipe; they did not overlap one's chain phase with the other's data phase as hoped.
                 const int per_sm = waves == 1 ? std::min(std::max(per_sm_fit, 1), (pl.ctas + p.num_sms - 1) / p.num_sms) : std::max(per_sm_fit, 1);
                 const double data_clk = (double)pl.rpc * (1.15 + 0.435 * tw * OP::SLOTS);
-                const double chain_clk = 3900.0 + (cs > 8 ? 1500.0 : 0.0);
+                const double chain_clk = kResChainClocks + (cs > 8 ? 1500.0 : 0.0);
                 const double step_clk = (per_sm * data_clk + chain_clk) * (per_sm > 1 ? 1.4 : 1.0);
                 pl.cost = waves * step_clk * (1.0 + 0.01 / tw);  // ties: the wider tile
                 if (std::getenv("BINEST_PLAN_DEBUG"))
-                    std::fprintf(stderr, "resident plan: nw %d tw %d cs %d ch %d groups %d ctas %d max_clusters %d per_sm %d waves %d smem %zu cost %.0f\n",
-                                 nw, tw, cs, ch, groups, pl.ctas, max_clusters, per_sm, waves, pl.smem, pl.cost);
+                    std::fprintf(stderr, "resident plan: nw %d tw %d cs %d groups %d ctas %d max_clusters %d per_sm %d waves %d smem %zu cost %.0f\n",
+                                 nw, tw, cs, groups, pl.ctas, max_clusters, per_sm, waves, pl.smem, pl.cost);
                 if (pl.cost < best.cost * 0.999 || (pl.cost <= best.cost * 1.001 && pl.ctas > best.ctas)) best = pl;
             }
         }
     }
     if (best.tw == 0) return false;
     r.resident = true;
-    r.res_tw = best.tw; r.res_cs = best.cs; r.res_ch = best.ch; r.res_rpc = best.rpc; r.res_smem = best.smem; r.res_nw = best.nw;
+    r.res_tw = best.tw; r.res_cs = best.cs; r.res_rpc = best.rpc; r.res_smem = best.smem; r.res_nw = best.nw;
     dispatch_tw<OP>(best.tw, [&](auto twc) {
         constexpr int TW = decltype(twc)::value;
         auto prep = [&](auto kern) {
@@ -240,7 +232,7 @@ bool plan_resident(binest_run &r, int P) {
         else prep(walk_resident_kernel<OP, TW, 16>);
     });
     if (std::getenv("BINEST_PLAN_DEBUG"))
-        std::fprintf(stderr, "resident plan chosen: nw %d tw %d cs %d ch %d ctas %d smem %zu\n", best.nw, best.tw, best.cs, best.ch, best.ctas, best.smem);
+        std::fprintf(stderr, "resident plan chosen: nw %d tw %d cs %d ctas %d smem %zu\n", best.nw, best.tw, best.cs, best.ctas, best.smem);
     return true;
 }
 
@@ -489,7 +481,7 @@ void walk_block(binest_run &r, const RunParams &q) {
             cudaLaunchConfig_t cfg{};
             cudaLaunchAttribute attr[1];
             cfg.gridDim = dim3(groups * r.res_cs);
-            cfg.blockDim = dim3(r.res_nw * 32);
+            cfg.blockDim = dim3((r.res_nw + r.res_tw) * 32);
             cfg.dynamicSmemBytes = r.res_smem;
             cfg.stream = r.stream;
             attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -501,13 +493,13 @@ void walk_block(binest_run &r, const RunParams &q) {
             const double *data = p.data.p;
             long long rows = p.rows, rpc = r.res_rpc;
             OpCst cst = p.cst;
-            int cs = r.res_cs, ch = r.res_ch;
+            int cs = r.res_cs;
             dispatch_tw<OP>(r.res_tw, [&](auto twc) {
                 constexpr int TW = decltype(twc)::value;
                 if (r.res_nw == 8)
-                    BN_CUDA(cudaLaunchKernelEx(&cfg, walk_resident_kernel<OP, TW, 8>, q, r.A, p.prior, data, rows, rpc, cst, cs, ch));
+                    BN_CUDA(cudaLaunchKernelEx(&cfg, walk_resident_kernel<OP, TW, 8>, q, r.A, p.prior, data, rows, rpc, cst, cs));
                 else
-                    BN_CUDA(cudaLaunchKernelEx(&cfg, walk_resident_kernel<OP, TW, 16>, q, r.A, p.prior, data, rows, rpc, cst, cs, ch));
+                    BN_CUDA(cudaLaunchKernelEx(&cfg, walk_resident_kernel<OP, TW, 16>, q, r.A, p.prior, data, rows, rpc, cst, cs));
             });
             BN_LAUNCH_CHECK();
         });
