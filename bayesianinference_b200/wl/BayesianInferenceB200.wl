@@ -66,6 +66,7 @@ binestRunCreate := ll["binestRunCreate", {Integer, {Integer, 1}, {Real, 1}, {Rea
 binestRunAdvance := ll["binestRunAdvance", {Integer, Integer}, Integer];
 binestRunFetch := ll["binestRunFetch", {Integer, Integer, Integer}, {Real, 2}];
 binestRunFree := ll["binestRunFree", {Integer}, Integer];
+binestRunCombine := ll["binestRunCombine", {Integer, Integer, Integer, Integer, Integer}, {Real, 2}];
 binestEvidenceSampling := ll["binestEvidenceSampling", {{Real, 2, "Constant"}, {Real, 1, "Constant"}, {Integer, 1, "Constant"}, Integer, Integer, Integer}, {Real, 1}];
 binestCrudeWeights := ll["binestCrudeWeights", {{Real, 1, "Constant"}, {Integer, 1, "Constant"}, Integer}, {Real, 1}];
 
@@ -270,15 +271,17 @@ Options[nestedSampling] = Join[{
 Options[parallelNestedSampling] = Join[DeleteCases[Options[nestedSampling], "StartingPoints" -> _], {"ParallelRuns" :> 4}];
 Options[combineRuns] = Join[Options[evidenceSampling], {"MergeScheme" -> Automatic}];
 
+createRunGroup[handle_, opts_, nRuns_, firstRun_, start_] := check @ binestRunCreate[handle,
+    {opts["SamplePoolSize"], opts["BatchSize"], opts["MonteCarloSteps"], opts["MaxIterations"], opts["MinIterations"],
+        opts["Seed"], firstRun, nRuns},
+    N @ {opts["TerminationFraction"], opts["MinMaxAcceptanceRate"][[1]], opts["MinMaxAcceptanceRate"][[2]],
+        (* "LogLikelihoodMaximum" -> number replaces the running maximum in the termination estimate (BS:925-932);
+           Automatic travels as 1.*^308 (a packed real vector cannot carry NaN portably) *)
+        If[NumericQ[opts["LogLikelihoodMaximum"]], opts["LogLikelihoodMaximum"], 1.*^308]},
+    start];
+
 runGroup[handle_, d_, opts_, nRuns_, firstRun_, start_] := Module[{run, fin, tables},
-    run = check @ binestRunCreate[handle,
-        {opts["SamplePoolSize"], opts["BatchSize"], opts["MonteCarloSteps"], opts["MaxIterations"], opts["MinIterations"],
-            opts["Seed"], firstRun, nRuns},
-        N @ {opts["TerminationFraction"], opts["MinMaxAcceptanceRate"][[1]], opts["MinMaxAcceptanceRate"][[2]],
-            (* "LogLikelihoodMaximum" -> number replaces the running maximum in the termination estimate (BS:925-932);
-               Automatic travels as 1.*^308 (a packed real vector cannot carry NaN portably) *)
-            If[NumericQ[opts["LogLikelihoodMaximum"]], opts["LogLikelihoodMaximum"], 1.*^308]},
-        start];
+    run = createRunGroup[handle, opts, nRuns, firstRun, start];
     If[run === $Failed, Return[$Failed, Module]];
     fin = binestRunAdvance[run, 0];
     tables = Table[binestRunFetch[run, i, d], {i, 0, nRuns - 1}];
@@ -415,12 +418,48 @@ parallelNestedSampling[inferenceObject[assoc_?AssociationQ], opts : OptionsPatte
 (* One library call advances all runs in lock step on the GPU (instead of ParallelTable over subkernels, BS:1349-1357:
    eight subkernels would mean eight CUDA contexts fighting for the device). *)
 parallelNestedSampling[inferenceObject[assoc_?AssociationQ], opts : OptionsPattern[]] := Module[{
-    o = Association[Options[parallelNestedSampling], opts], d = Length[assoc["Parameters"]], tables},
-    tables = runGroup[assoc["binestHandle"], d, o, o["ParallelRuns"], 0, {}];
-    If[tables === $Failed, Return["Bad likelihood function", Module]];
-    combineRuns[
-        Sequence @@ (inferenceObject[Join[assoc, resultAssociation[#, d, o["SamplePoolSize"]]]] & /@ tables),
-        Sequence @@ FilterRules[Normal[o], Options[combineRuns]]]
+    o = Association[Options[parallelNestedSampling], opts], d = Length[assoc["Parameters"]], tables, run, fin, r, tab, m, nTot,
+    rows, draws, last, s, scheme, run0},
+    r = o["PostProcessSamplingRuns"];
+    If[!TrueQ[IntegerQ[r] && r > 0],
+        (* no Monte-Carlo post-processing asked for (BS:1195-1197): per-run fetch and the host merge *)
+        tables = runGroup[assoc["binestHandle"], d, o, o["ParallelRuns"], 0, {}];
+        If[tables === $Failed, Return["Bad likelihood function", Module]];
+        Return[combineRuns[
+            Sequence @@ (inferenceObject[Join[assoc, resultAssociation[#, d, o["SamplePoolSize"]]]] & /@ tables),
+            Sequence @@ FilterRules[Normal[o], Options[combineRuns]]], Module]];
+    (* combineRuns -> evidenceSampling of the group's runs in ONE library call on the device (binest_run_combine,
+       csrc/merge.cu): same result as combineRuns[runs...] above, the runs never travel to the host one by one *)
+    run = createRunGroup[assoc["binestHandle"], o, o["ParallelRuns"], 0, {}];
+    If[run === $Failed, Return["Bad likelihood function", Module]];
+    fin = binestRunAdvance[run, 0];
+    scheme = If[o["BatchSize"] == 1, "Reference", "PoolSizes"]; (* combineRuns' Automatic: K = 1 runs have the reference's pool structure *)
+    tab = binestRunCombine[run, d, If[scheme === "Reference", 0, 1], Max[r, 2], o["Seed"]];
+    binestRunFree[run];
+    If[!MatrixQ[tab], Return[$Failed, Module]];
+    last = Last[tab]; m = Round[last[[6]]]; nTot = o["ParallelRuns"] o["SamplePoolSize"];
+    rows = tab[[;; m]]; draws = tab[[m + 1 ;; m + Max[r, 2]]];
+    s = <|
+        "Point" -> rows[[All, ;; d]], "LogLikelihood" -> rows[[All, d + 1]], "LogPriorPDF" -> rows[[All, d + 2]],
+        "AcceptanceRate" -> Replace[rows[[All, d + 3]], x_ /; !NumericQ[x] || x != x :> Missing["InitialSample"], {1}], (* BS:911 *)
+        "LogX" -> rows[[All, d + 4]], "X" -> rows[[All, d + 5]],
+        "CrudeLogPosteriorWeight" -> rows[[All, d + 6]], "CrudePosteriorWeight" -> rows[[All, d + 7]],
+        "SampledLogX" -> <|"Mean" -> rows[[All, d + 8]], "StandardError" -> rows[[All, d + 9]]|>,
+        "LogPosteriorWeight" -> <|"Mean" -> rows[[All, d + 10]], "StandardError" -> rows[[All, d + 11]]|>,
+        "PoolSize" -> Round @ rows[[All, d + 12]], "RunIndex" -> Round @ rows[[All, d + 13]]|>;
+    run0 = Pick[s["Point"], s["RunIndex"], 0]; (* combineRuns keeps First[results] for the other keys (BS:1299-1305) *)
+    inferenceObject @ Join[assoc, <|
+        "Samples" -> s,
+        "ParameterRanges" -> CoordinateBounds[run0],
+        "SamplePoolSize" -> nTot, "GeneratedNestedSamples" -> m - nTot, "TotalSamples" -> m, "MergeScheme" -> scheme, (* BS:1307-1309 *)
+        "CrudeLogEvidence" -> last[[1]], "CrudeRelativeEntropy" -> last[[2]], "LogLikelihoodMaximum" -> last[[3]],
+        "LogEstimatedMissingEvidence" -> last[[4]],                                                  (* BS:1183-1194 *)
+        "LogEvidence" -> meanAndError[draws[[All, 1]]],                                             (* BS:1254 *)
+        "RelativeEntropy" -> meanAndError[draws[[All, 2]]],                                          (* BS:1263 *)
+        "ParameterExpectedValues" -> AssociationThread[
+            Lookup[assoc, "ParameterSymbols", Range[d]], meanAndError /@ Transpose[draws[[All, 3 ;; d + 2]]]], (* BS:1255-1262 *)
+        "EmpiricalPosteriorDistribution" -> EmpiricalDistribution[s["CrudePosteriorWeight"] -> s["Point"]]|>, (* BS:1272-1277 *)
+        If[scheme === "Reference", <||>, <|"binestLiveBlock" -> Round[last[[5]]]|>]]
 ];
 
 End[];

@@ -352,3 +352,66 @@ DLLEXPORT int binestCrudeWeights(WolframLibraryData libData, mint Argc, MArgumen
     MArgument_setMTensor(Res, out);
     return LIBRARY_NO_ERROR;
 }
+
+/* binestRunCombine[run, d, scheme, postRuns, seed] -> {Real,2}: combineRuns -> evidenceSampling of the group's runs on
+ * the device (binest_run_combine).  (M + R + 1) x (d + 13) rows:
+ *   rows 1..M      point (d), the BINEST_NCOL_F double columns in the order of binest.h, PoolSize, RunIndex
+ *   rows M+1..M+R  per Monte-Carlo draw: z, H, parameter means (d)
+ *   last row       summary (4), live block, M */
+DLLEXPORT int binestRunCombine(WolframLibraryData libData, mint Argc, MArgument *Args, MArgument Res) {
+    binest_run *r = (binest_run *)(intptr_t)MArgument_getInteger(Args[0]);
+    const mint d = MArgument_getInteger(Args[1]), R = MArgument_getInteger(Args[3]);
+    const mint W = d + BINEST_NCOL_F + 2;
+    int64_t Mt = 0, M = 0, nlive = 0;
+    MTensor out, tab, itab, pts, zz;
+    mint dims[2], len, k, j;
+    double *o, *T, *P, *Z, summary[4];
+    int64_t *I;
+    int rc = binest_run_merge_size(r, &Mt);
+    if (rc) return st(rc);
+    len = (mint)Mt * BINEST_NCOL_F;
+    rc = libData->MTensor_new(MType_Real, 1, &len, &tab);
+    if (rc) return rc;
+    len = (mint)Mt * 2;
+    rc = libData->MTensor_new(MType_Integer, 1, &len, &itab);
+    if (rc) return rc;
+    len = (mint)Mt * d;
+    rc = libData->MTensor_new(MType_Real, 1, &len, &pts);
+    if (rc) return rc;
+    len = R * (d + 2);
+    rc = libData->MTensor_new(MType_Real, 1, &len, &zz);
+    if (rc) return rc;
+    T = libData->MTensor_getRealData(tab); P = libData->MTensor_getRealData(pts); Z = libData->MTensor_getRealData(zz);
+    I = (int64_t *)libData->MTensor_getIntegerData(itab);
+    rc = binest_run_combine(r, (int32_t)MArgument_getInteger(Args[2]), R, (uint64_t)MArgument_getInteger(Args[4]), P, T, I,
+                            Z, Z + 2 * R, Z + R, summary, &M, &nlive);
+    if (!rc) {
+        dims[0] = (mint)M + R + 1; dims[1] = W;
+        rc = libData->MTensor_new(MType_Real, 2, dims, &out);
+    }
+    if (!rc) {
+        o = libData->MTensor_getRealData(out);
+        memset(o, 0, sizeof(double) * (size_t)(dims[0] * dims[1]));
+        for (k = 0; k < (mint)M; ++k) { /* column blocks interleaved row-wise; no arithmetic */
+            double *row = o + k * W;
+            for (j = 0; j < d; ++j) row[j] = P[k * d + j];
+            for (j = 0; j < BINEST_NCOL_F; ++j) row[d + j] = T[j * (mint)Mt + k];
+            row[d + BINEST_NCOL_F] = (double)I[k];
+            row[d + BINEST_NCOL_F + 1] = (double)I[(mint)Mt + k];
+        }
+        for (k = 0; k < R; ++k) {
+            double *row = o + ((mint)M + k) * W;
+            row[0] = Z[k]; row[1] = Z[R + k];
+            for (j = 0; j < d; ++j) row[2 + j] = Z[2 * R + k * d + j];
+        }
+        {
+            double *row = o + ((mint)M + R) * W;
+            row[0] = summary[0]; row[1] = summary[1]; row[2] = summary[2]; row[3] = summary[3];
+            row[4] = (double)nlive; row[5] = (double)M;
+        }
+    }
+    libData->MTensor_free(tab); libData->MTensor_free(itab); libData->MTensor_free(pts); libData->MTensor_free(zz);
+    if (rc) return st(rc);
+    MArgument_setMTensor(Res, out);
+    return LIBRARY_NO_ERROR;
+}

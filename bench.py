@@ -334,7 +334,7 @@ def measure_c4_strong(ctx, reps=2, T=16384):
         ctx.barrier()
         t0 = time.perf_counter()
         res = api.parallelNestedSampling(obj, ParallelRuns=64, SamplePoolSize=512, BatchSize=64, MaxIterations=10**6,
-                                         Seed=2026 + rep, PostProcessSamplingRuns=100)
+                                         Seed=2026, PostProcessSamplingRuns=100)  # same job every repetition and GPU count
         ctx.torch.cuda.synchronize()
         dt = ctx.max_over_ranks(time.perf_counter() - t0)
         allreps.append({"s": dt, "phases": res.get("_Timing")})
