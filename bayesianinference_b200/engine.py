@@ -278,8 +278,8 @@ class RunGroup:
         Mt = C.c_int64()
         check(L.binest_run_merge_size(self.h, C.byref(Mt)))
         Mt, d = Mt.value, self.problem.d
-        pts, cols = np.empty((Mt, d)), [np.empty(Mt) for _ in range(3)]
-        pool, rid = np.empty(Mt, dtype=np.int64), np.empty(Mt, dtype=np.int64)
+        pts, cols = _host_out((Mt, d)), [_host_out(Mt) for _ in range(3)]
+        pool, rid = _host_out(Mt, np.int64), _host_out(Mt, np.int64)
         M, live = C.c_int64(), C.c_int64()
         check(L.binest_run_merge(self.h, dptr(pts), dptr(cols[0]), dptr(cols[1]), dptr(cols[2]), iptr(pool), iptr(rid),
                                  C.byref(M), C.byref(live)))
@@ -293,7 +293,7 @@ class RunGroup:
         Mt = C.c_int64()
         check(L.binest_run_merge_size(self.h, C.byref(Mt)))
         Mt, d = Mt.value, self.problem.d
-        o_pts, tab, itab = np.empty((Mt, d)), np.empty((len(COLS), Mt)), np.empty((2, Mt), dtype=np.int64)
+        o_pts, tab, itab = _host_out((Mt, d)), _host_out((len(COLS), Mt)), _host_out((2, Mt), np.int64)
         z, H, pm, summ = np.empty(post_runs), np.empty(post_runs), np.empty((post_runs, d)), np.empty(4)
         M, n_live = C.c_int64(), C.c_int64()
         check(L.binest_run_combine(self.h, 0 if reference_scheme else 1, int(post_runs), int(seed), dptr(o_pts), dptr(tab),
@@ -383,6 +383,20 @@ def crude_weights(logL, pool, n_live):
                 log_missing=float(s[3]))
 
 
+def _host_out(shape, dtype=np.float64):
+    """Output buffer of a device merge: page-locked when torch is there to provide it (its caching host allocator reuses
+    the blocks, so repeated calls neither pin nor page-fault 30 MB of fresh memory: the D2H copy of a merged C4 table
+    went from ~9 ms to ~2 ms), plain numpy otherwise.  The array owns (a reference to) its memory either way."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            tdt = {np.dtype(np.float64): torch.float64, np.dtype(np.int64): torch.int64}[np.dtype(dtype)]
+            return torch.empty(shape, dtype=tdt, pin_memory=True).numpy()
+    except Exception:  # no torch / no pinned memory: pageable buffers work the same, only slower
+        pass
+    return np.empty(shape, dtype=dtype)
+
+
 def _join_runs(tables):
     """the runs' columns concatenated in Join order (BS:1293) for the device merge"""
     sizes = np.array([t["LogLikelihood"].size for t in tables], dtype=np.int64)
@@ -427,7 +441,7 @@ def combine_runs(tables, reference_scheme, n_tot, post_runs=100, seed=1):
     _ensure_init()
     sizes, pts, L, lp, acc, pool, rid = _join_runs(tables)
     Mt, d = pts.shape
-    o_pts, tab, itab = np.empty((Mt, d)), np.empty((len(COLS), Mt)), np.empty((2, Mt), dtype=np.int64)
+    o_pts, tab, itab = _host_out((Mt, d)), _host_out((len(COLS), Mt)), _host_out((2, Mt), np.int64)
     z, H, pm, summ = np.empty(post_runs), np.empty(post_runs), np.empty((post_runs, d)), np.empty(4)
     M, n_live = C.c_int64(), C.c_int64()
     check(_lib.load().binest_combine_runs(len(tables), iptr(sizes), d, dptr(pts), dptr(L), dptr(lp), dptr(acc), iptr(pool),

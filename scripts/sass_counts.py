@@ -12,10 +12,12 @@ HOT = ["walk_grid_kernel", "walk_resident_kernel", "ns_loop_kernel", "loglike_st
        "run_update_kernel", "gp_syrk_kernel", "gp_trsm_kernel", "gp_potf2_reg_kernel", "gp_fill_kernel",
        "shard_reduce_push_kernel", "xchg_push_kernel", "xchg_gather_kernel", "evidence_sampling_kernel"]
 PICK = {"C2 walk": "walk_grid_kernelINS_9OpPolyRegILi3EEELi4", "C2 stream": "loglike_stream_kernelINS_9OpPolyRegILi3EEELi8",
-        "C3 stream": "loglike_stream_kernelINS_10OpLogisticILi4ELi3EEELi2", "C4 resident": "walk_resident_kernelINS_5OpGbmELi4",
+        "C3 stream": "loglike_stream_kernelINS_10OpLogisticILi4ELi3EEELi2", "C4 resident": "walk_resident_kernelINS_5OpGbmELi4ELi16",
         "C1 loop": "ns_loop_kernelINS_10OpGaussianELi256", "GP syrk": "gp_syrk_kernel", "GP trsm": "gp_trsm_kernel",
         "GP potf2": "gp_potf2_reg_kernel", "GP fill": "gp_fill_kernel", "shard push (C2)": "shard_reduce_push_kernelINS_9OpPolyRegILi3",
-        "xchg push": "xchg_push_kernel", "xchg gather": "xchg_gather_kernel", "update": "run_update_kernel"}
+        "xchg push": "xchg_push_kernel", "xchg gather": "xchg_gather_kernel", "update": "run_update_kernel",
+        "merge rank (samples)": "rank_kernelINS_9CmpSample", "merge rank (keys)": "rank_kernelINS_6CmpKey",
+        "merge scan": "merge_scan_kernel", "merge chunk sort": "chunk_sort_desc_kernel", "merge join": "join_runs_kernel"}
 COLS = ["DFMA", "DMUL", "DADD", "DMMA", "UBLKCP", "LDGSTS", "SYNCS", "BAR", "LDS", "STS", "LDG", "STG", "ST.E", "ATOM", "RED", "MUFU", "SHFL", "total"]
 
 sass = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True, check=True).stdout
