@@ -2,13 +2,14 @@
   compute-sanitizer --tool racecheck python scripts/sanitize_cases.py [case ...]
 Cases: loop (ns_loop_kernel), resident (walk_resident_kernel: DSMEM exchange, clusters), grid (walk_grid_kernel: grid
 barriers), stepped (graph of walk_step + loglike_stream with PDL), gp (fill / potf2 / trsm / syrk / finish, predict),
-evidence (crude weights, evidence sampling), mcmc (posterior sampler).  Sizes are small: the tools slow kernels 10-100x."""
+evidence (crude weights, evidence sampling), mcmc (posterior sampler), merge (combineRuns on the device: host-array and
+run-group variants).  Sizes are small: the tools slow kernels 10-100x."""
 import os, sys
 sys.path.insert(0, '.')
 import numpy as np
 from bayesianinference_b200 import engine, configs as cfg
 
-cases = sys.argv[1:] or ["loop", "resident", "grid", "stepped", "gp", "evidence", "mcmc"]
+cases = sys.argv[1:] or ["loop", "resident", "grid", "stepped", "gp", "evidence", "mcmc", "merge"]
 engine.init()
 
 
@@ -63,4 +64,22 @@ for case in cases:
         gp = engine.Problem.from_config(c)
         ch = engine.Chain(gp, [[0.5, -1.2, 0.8, 0.3, 0.25]] * 4, np.diag([1e-4] * 5), learn_delay=5, seed=2)
         print("  mcmc", ch.iterate(20)[-1, 0])
+    elif case == "merge":
+        c = cfg.c4_gbm(T=512)
+        gp = engine.Problem.from_config(c)
+        o = engine.default_options(pool_size=48, batch_k=6, mc_steps=20, seed=5, n_runs=5, first_run_id=3)
+        grp = engine.RunGroup(gp, o)
+        grp.advance(0)
+        tabs = []
+        for i in range(5):
+            f = grp.fetch(i, weights=False)
+            tabs.append({"Point": f["points"], "LogLikelihood": f["logL"], "LogPriorPDF": f["logPrior"], "AcceptanceRate": f["acc"],
+                         "PoolSize": f["pool"]})
+        m, live = grp.merge()
+        print("  run merge", m["LogLikelihood"].size, live)
+        res = grp.combine(False, 20, 3)
+        print("  run combine", res["z"][:2], res["n_live"])
+        m2, _ = engine.merge_runs(tabs)
+        res2 = engine.combine_runs(tabs, True, 5 * 48, 20, 3)
+        print("  host-array merge / combine", m2["LogLikelihood"].size, res2["z"][:2])
 print("done")
