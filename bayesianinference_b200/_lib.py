@@ -71,6 +71,9 @@ SIGNATURES = {
     "binest_run_merge_size": (C.c_int, [_vp, _ip]),
     "binest_run_merge": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _ip, _ip, _ip, _ip]),
     "binest_run_combine": (C.c_int, [_vp, C.c_int32, C.c_int64, C.c_uint64, _dp, _dp, _ip, _dp, _dp, _dp, _dp, _ip, _ip]),
+    "binest_run_merge_dev": (C.c_int, [_vp, _vp, _ip, _ip]),
+    "binest_combine_runs_dev": (C.c_int, [C.c_int64, _ip, C.c_int64, _vp, C.c_int32, C.c_int64, C.c_int64, C.c_uint64,
+                                          _dp, _dp, _ip, _dp, _dp, _dp, _dp, _ip, _ip]),
     "binest_bench_loglike": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int64, C.c_int, _dp, _dp]),
     "binest_run_timing": (C.c_int, [_vp, _dp, _ip, _ip]),
     "binest_run_path": (C.c_int, [_vp, C.POINTER(C.c_int)]),

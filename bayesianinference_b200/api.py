@@ -933,6 +933,7 @@ def _sorted_run_table(t, n):
 
 
 _HOST_MERGE = False  # tests: force the numpy merge on a backend that has the device one
+_HOST_GATHER = False  # tests: gather the per-GPU merges through the host (all_gather_object) under an NCCL process group
 _PHASES = {}  # wall-clock seconds of the last combineRuns / evidenceSampling call, by phase (diagnostics for bench.py)
 
 
@@ -1056,6 +1057,8 @@ def parallelNestedSampling(obj, _backend_override=None, **opts):
     # per-rank merges are gathered, and merging those equals merging all runs at once (summed pool sizes are additive).
     on_device = (hasattr(be, "combine_runs") and hasattr(be.RunGroup, "combine") and isinstance(nruns, (int, np.integer))
                  and nruns > 0 and not _HOST_MERGE)
+    nccl_gather = (on_device and world > 1 and hasattr(be, "combine_runs_dev") and dist.get_backend() == "nccl"
+                   and not _HOST_GATHER)
     reference_scheme = int(o.get("BatchSize", 1)) == 1  # K = 1 runs have the reference's pool structure (combineRuns "Automatic")
     local = []
     if on_device:
@@ -1068,14 +1071,36 @@ def parallelNestedSampling(obj, _backend_override=None, **opts):
             t1 = _time.perf_counter()
             if world == 1:
                 res = grp.combine(reference_scheme, int(max(nruns, 2)), int(o["Seed"]))
+            elif nccl_gather:
+                part = grp.merge_dev()[0]
             else:
                 part = grp.merge()[0]
             grp.close()
             tm["device_merge_s"] = _time.perf_counter() - t1
-        if world > 1:
+        if world > 1 and nccl_gather:
+            # the per-GPU merges stay in device memory and are all-gathered over NCCL (the one exchange step of the
+            # call); every rank then merges the gathered lists on its GPU
+            import torch
+            t1 = _time.perf_counter()
+            width = len(a["Parameters"]) + 5 if part is None else part.shape[1]
+            mine = part if part is not None else torch.empty((0, width), dtype=torch.float64, device="cuda")
+            cnt = torch.tensor([mine.shape[0]], dtype=torch.int64, device="cuda")
+            cnts = torch.empty(world, dtype=torch.int64, device="cuda")
+            dist.all_gather_into_tensor(cnts, cnt)
+            cnts = cnts.tolist()
+            padded = torch.zeros((max(cnts), width), dtype=torch.float64, device="cuda")
+            padded[:mine.shape[0]] = mine
+            allt = torch.empty((world, max(cnts), width), dtype=torch.float64, device="cuda")
+            dist.all_gather_into_tensor(allt.view(-1), padded.view(-1))
+            tm["gather_s"] = _time.perf_counter() - t1
+            t1 = _time.perf_counter()
+            res = be.combine_runs_dev([allt[r, :cnts[r]] for r in range(world)], reference_scheme, R * n, int(max(nruns, 2)),
+                                      int(o["Seed"]))
+            tm["device_combine_s"] = _time.perf_counter() - t1
+        elif world > 1:
             t1 = _time.perf_counter()
             gathered = [None] * world
-            dist.all_gather_object(gathered, part)  # host gather of the per-GPU merges: no collective on the data path
+            dist.all_gather_object(gathered, part)  # host gather of the per-GPU merges (no NCCL process group)
             tm["gather_s"] = _time.perf_counter() - t1
             t1 = _time.perf_counter()
             res = be.combine_runs([g for g in gathered if g is not None], reference_scheme, R * n, int(max(nruns, 2)),

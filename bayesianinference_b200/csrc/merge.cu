@@ -368,6 +368,51 @@ __global__ void join_runs_kernel(RunViewDev v, long long Mt, const long long *__
     rid[i] = v.first_run_id + c;
 }
 
+// packed device tables of the *_dev entry points: row k = (point[d], logL, logPrior, acc, pool, run id), all as doubles
+__global__ void pack_merged_kernel(long long M, int d, const double *__restrict__ pts, const double *__restrict__ L,
+                                   const double *__restrict__ lp, const double *__restrict__ acc,
+                                   const long long *__restrict__ pool, const long long *__restrict__ rid,
+                                   double *__restrict__ out) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= M) return;
+    double *row = out + (size_t)k * (d + 5);
+    for (int a = 0; a < d; ++a) row[a] = pts[k * d + a];
+    row[d] = L[k]; row[d + 1] = lp[k]; row[d + 2] = acc[k]; row[d + 3] = (double)pool[k]; row[d + 4] = (double)rid[k];
+}
+__global__ void unpack_joined_kernel(long long M, int d, const double *__restrict__ in, double *__restrict__ pts,
+                                     double *__restrict__ L, double *__restrict__ lp, double *__restrict__ acc,
+                                     long long *__restrict__ pool, long long *__restrict__ rid) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= M) return;
+    const double *row = in + (size_t)k * (d + 5);
+    for (int a = 0; a < d; ++a) pts[k * d + a] = row[a];
+    L[k] = row[d]; lp[k] = row[d + 1]; acc[k] = row[d + 2]; pool[k] = (long long)row[d + 3]; rid[k] = (long long)row[d + 4];
+}
+
+void join_from_dev(int64_t R, const int64_t *sizes, int64_t d, const double *table_dev, Joined &j) {
+    BN_REQUIRE(R >= 1 && sizes && d >= 1 && d <= BINEST_MAXD && table_dev, BINEST_ERR_DIMENSION, "bad run lists");
+    std::vector<long long> offs((size_t)R + 1, 0);
+    for (int64_t c = 0; c < R; ++c) {
+        BN_REQUIRE(sizes[c] >= 0, BINEST_ERR_DIMENSION, "negative run size");
+        offs[c + 1] = offs[c] + sizes[c];
+    }
+    const long long Mt = offs[R];
+    BN_REQUIRE(Mt >= 1 && Mt < (1LL << 31), BINEST_ERR_DIMENSION, "1 <= total samples < 2^31");
+    for (int64_t c = 0; c < R; ++c)
+        if (sizes[c] > 0) {  // pool size at the first sample of every list
+            double v = 0.0;
+            BN_CUDA(cudaMemcpy(&v, table_dev + (size_t)offs[c] * (d + 5) + d + 3, sizeof(double), cudaMemcpyDeviceToHost));
+            j.base += (long long)v;
+        }
+    j.Mt = Mt; j.R = (int)R; j.d = (int)d;
+    j.has_lp = j.has_acc = j.has_rid = true;
+    j.pts.alloc((size_t)Mt * d); j.L.alloc(Mt); j.lp.alloc(Mt); j.acc.alloc(Mt); j.pool.alloc(Mt); j.rid.alloc(Mt);
+    j.offs.alloc(R + 1);
+    BN_CUDA(cudaMemcpy(j.offs.p, offs.data(), sizeof(long long) * (R + 1), cudaMemcpyHostToDevice));
+    unpack_joined_kernel<<<nblk(Mt), 256>>>(Mt, (int)d, table_dev, j.pts.p, j.L.p, j.lp.p, j.acc.p, j.pool.p, j.rid.p);
+    BN_LAUNCH_CHECK();
+}
+
 void join_from_run(binest_run *r, Joined &j) {
     RunView v;
     run_view(r, v);  // flushes the batch in flight, reads the run states
@@ -595,6 +640,35 @@ int binest_run_combine(binest_run *r, int32_t scheme, int64_t post_runs, uint64_
         join_from_run(r, j);
         device_merge(j, m);
         device_post(j, m, scheme, j.base, post_runs, seed, points_out, table_out, itable_out, z, pmean, H, summary, M_out,
+                    n_live_out);
+    });
+}
+
+int binest_run_merge_dev(binest_run *r, double *table_dev, int64_t *M_out, int64_t *live_block) {
+    return guard([&] {
+        BN_REQUIRE(r && table_dev, BINEST_ERR_TYPE, "null argument");
+        Joined j;
+        Merged m;
+        join_from_run(r, j);
+        device_merge(j, m);
+        pack_merged_kernel<<<nblk(m.M), 256>>>(m.M, j.d, m.pts.p, m.L.p, m.lp.p, m.acc.p, m.pool.p, m.rid.p, table_dev);
+        BN_LAUNCH_CHECK();
+        BN_CUDA(cudaDeviceSynchronize());
+        if (M_out) *M_out = m.M;
+        if (live_block) *live_block = m.M - (m.last_bad + 1);
+    });
+}
+
+int binest_combine_runs_dev(int64_t R, const int64_t *sizes, int64_t d, const double *table_dev, int32_t scheme,
+                            int64_t n_tot, int64_t post_runs, uint64_t seed, double *points_out, double *table_out,
+                            int64_t *itable_out, double *z, double *pmean, double *H, double *summary, int64_t *M_out,
+                            int64_t *n_live_out) {
+    return guard([&] {
+        Joined j;
+        Merged m;
+        join_from_dev(R, sizes, d, table_dev, j);
+        device_merge(j, m);
+        device_post(j, m, scheme, n_tot, post_runs, seed, points_out, table_out, itable_out, z, pmean, H, summary, M_out,
                     n_live_out);
     });
 }

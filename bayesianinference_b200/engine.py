@@ -300,6 +300,18 @@ class RunGroup:
                                    iptr(itab), dptr(z), dptr(pm), dptr(H), dptr(summ), C.byref(M), C.byref(n_live)))
         return _combined(M.value, o_pts, tab, itab, z, H, pm, summ, n_live.value, True, True)
 
+    def merge_dev(self):
+        """binest_run_merge_dev: the merge of the group's runs as a packed table IN DEVICE MEMORY (a torch tensor
+        [M, d + 5] on this GPU: point, logL, logPrior, acc, pool size, run id) for an NCCL gather across ranks."""
+        import torch
+        L = _lib.load()
+        Mt = C.c_int64()
+        check(L.binest_run_merge_size(self.h, C.byref(Mt)))
+        t = torch.empty((Mt.value, self.problem.d + 5), dtype=torch.float64, device="cuda")
+        M, live = C.c_int64(), C.c_int64()
+        check(L.binest_run_merge_dev(self.h, C.c_void_p(t.data_ptr()), C.byref(M), C.byref(live)))
+        return t[:M.value], live.value
+
     def estimates(self, run=0):
         d = self.problem.d
         m, c = np.empty(d), np.empty((d, d))
@@ -449,6 +461,26 @@ def combine_runs(tables, reference_scheme, n_tot, post_runs=100, seed=1):
                                           dptr(o_pts), dptr(tab), iptr(itab), dptr(z), dptr(pm), dptr(H), dptr(summ),
                                           C.byref(M), C.byref(n_live)))
     return _combined(M.value, o_pts, tab, itab, z, H, pm, summ, n_live.value, lp is not None, acc is not None)
+
+
+def combine_runs_dev(tables, reference_scheme, n_tot, post_runs=100, seed=1):
+    """binest_combine_runs_dev: as combine_runs, the inputs being packed device tables (torch tensors [M_r, d + 5] on this
+    GPU, e.g. the NCCL-gathered RunGroup.merge_dev() of every rank, in rank order)."""
+    import torch
+    _ensure_init()
+    tables = [t for t in tables if t.shape[0] > 0]
+    sizes = np.array([t.shape[0] for t in tables], dtype=np.int64)
+    packed = torch.cat(tables).contiguous()
+    Mt, d = int(sizes.sum()), packed.shape[1] - 5
+    o_pts, tab, itab = _host_out((Mt, d)), _host_out((len(COLS), Mt)), _host_out((2, Mt), np.int64)
+    z, H, pm, summ = np.empty(post_runs), np.empty(post_runs), np.empty((post_runs, d)), np.empty(4)
+    M, n_live = C.c_int64(), C.c_int64()
+    torch.cuda.current_stream().synchronize()  # the gathered tensor is complete before the library's streams read it
+    check(_lib.load().binest_combine_runs_dev(len(tables), iptr(sizes), d, C.c_void_p(packed.data_ptr()),
+                                              0 if reference_scheme else 1, int(n_tot), int(post_runs), int(seed), dptr(o_pts),
+                                              dptr(tab), iptr(itab), dptr(z), dptr(pm), dptr(H), dptr(summ), C.byref(M),
+                                              C.byref(n_live)))
+    return _combined(M.value, o_pts, tab, itab, z, H, pm, summ, n_live.value, True, True)
 
 
 def _combined(m, o_pts, tab, itab, z, H, pm, summ, n_live, has_lp, has_acc):

@@ -246,6 +246,18 @@ int binest_run_combine(binest_run *r, int32_t scheme, int64_t post_runs, uint64_
                        double *table_out, int64_t *itable_out, double *z, double *pmean, double *H, double *summary,
                        int64_t *M_out, int64_t *n_live_out);
 
+/* Device-resident variants for multi-GPU jobs (one process per GPU): the per-GPU merge stays in device memory, the
+ * host language gathers the merges with its collective library (NCCL all-gather over NVLink: the one exchange step of
+ * parallelNestedSampling, BS:1349-1363) and hands the gathered lists back without a host round trip.
+ * A packed table has one row per sample, d + 5 doubles: point[d], logL, logPrior, acc, pool size, run id.
+ * binest_run_merge_dev writes the merge of the group's runs to table_dev (caller-allocated, binest_run_merge_size
+ * rows); binest_combine_runs_dev takes R such lists concatenated in rank order (sizes[R] rows each). */
+int binest_run_merge_dev(binest_run *r, double *table_dev, int64_t *M_out, int64_t *live_block);
+int binest_combine_runs_dev(int64_t R, const int64_t *sizes, int64_t d, const double *table_dev, int32_t scheme,
+                            int64_t n_tot, int64_t post_runs, uint64_t seed, double *points_out, double *table_out,
+                            int64_t *itable_out, double *z, double *pmean, double *H, double *summary, int64_t *M_out,
+                            int64_t *n_live_out);
+
 /* ---- data-sharded mode ("very large N"): rows split across the GPUs of one box ------------
  * One process per GPU.  Rank 0 makes an id, the host passes it to every rank (any channel), every rank creates
  * its communicator (collective), defines its problem from ITS rows only (GBM: shards overlap by one point, the

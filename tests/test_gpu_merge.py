@@ -1,6 +1,8 @@
 """combineRuns (BS:1293-1315) on the device (csrc/merge.cu) against the host merge of bayesianinference_b200.api
 (numpy; itself pinned to a literal evaluation of the reference formula in tests/test_api_host.py).  Index work is exact:
 the merged lists must be equal sample for sample."""
+import os
+
 import numpy as np
 import pytest
 
@@ -175,3 +177,56 @@ def test_run_group_merge_equals_merge_of_fetched_runs():
     for k in ("Point", "LogLikelihood", "LogPriorPDF", "PoolSize"):
         assert np.array_equal(two[k], host[k]), k
     assert np.array_equal(two["RunIndex"], host["RunIndex"]) and live2 == live
+
+
+def _two_gpu_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world)
+    from bayesianinference_b200 import engine
+    engine.init(device=rank)
+    out = {}
+    for mode in ("nccl", "host"):
+        api._HOST_GATHER = mode == "host"
+        res = _c4_small_parallel(5)  # 5 runs over 2 ranks: 3 + 2
+        out[mode] = (res["Samples"]["Point"], res["Samples"]["LogLikelihood"], res["Samples"]["PoolSize"],
+                     res["Samples"]["RunIndex"], res["LogEvidence"], sorted(res.Normal()["_Timing"]))
+    q.put((rank, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _c4_small_parallel(runs):
+    c = cfg.c4_gbm(T=1024)
+    obj = api.defineInferenceProblem(
+        Data=(c.inputs[:, 0], c.outputs[:, 0]), GeneratingDistribution=api.GeometricBrownianMotionProcess("mu", "sigma", 100.0),
+        Parameters=[("mu", -1, 1), ("sigma", 0.01, 2)], PriorDistribution=["LocationParameter", "ScaleParameter"])
+    return api.parallelNestedSampling(obj, ParallelRuns=runs, SamplePoolSize=64, BatchSize=8, MaxIterations=100000, Seed=33,
+                                      PostProcessSamplingRuns=30)
+
+
+def test_two_gpu_parallel_runs_nccl_gather_equals_single_gpu():
+    """run-sharded parallelNestedSampling on 2 GPUs: per-GPU merges gathered over NCCL in device memory (and, second
+    mode, through the host) and merged again — the same object as all runs on one GPU, on every rank."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as tmp
+    ctx = tmp.get_context("spawn")
+    q = ctx.Queue()
+    port = 34500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_two_gpu_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    allres = dict(q.get(timeout=600) for _ in procs)
+    [p.join(120) for p in procs]
+    one = _c4_small_parallel(5)
+    want = (one["Samples"]["Point"], one["Samples"]["LogLikelihood"], one["Samples"]["PoolSize"], one["Samples"]["RunIndex"])
+    for rank in (0, 1):
+        for mode in ("nccl", "host"):
+            got = allres[rank][mode]
+            for a, b in zip(got[:4], want):
+                assert np.array_equal(a, b), (rank, mode)
+            assert got[4] == one["LogEvidence"], (rank, mode)
+            assert "gather_s" in got[5] and "device_combine_s" in got[5]
