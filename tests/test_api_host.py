@@ -544,3 +544,40 @@ def test_gp_group_schedule_covers_every_panel_column_pair_once():
                     for c in range(kend, T):
                         got[c] += list(range(kb, kend))
                 assert all(len(v) == len(set(v)) for v in got.values())
+
+
+def test_merging_partial_merges_equals_merging_all_runs():
+    """The multi-GPU path of parallelNestedSampling merges per-GPU merges (BS:1293-1297 applied twice).  Summed pool sizes
+    are step functions of the likelihood level and add up, so the two-level merge must equal the flat one — here with the
+    numpy merge (the device merge is checked against it in tests/test_gpu_merge.py), and both against the oracle's
+    independent formulation (np.unique + one searchsorted per run)."""
+    from types import SimpleNamespace
+
+    from oracle import oracle as O
+    rng = np.random.default_rng(12)
+    runs = []
+    for r in range(5):
+        n, K, iters = 24, 3, 10
+        M = iters * K + n
+        L = np.sort(rng.normal(size=M)) * 10 - 50
+        pts = rng.normal(size=(M, 2))
+        if r:  # a few copies of earlier runs' samples (same point => same likelihood) and ties with different points
+            src = runs[r - 1]
+            pick = rng.choice(src["LogLikelihood"].size, 4, replace=False)
+            where = rng.choice(M, 4, replace=False)
+            L[where], pts[where] = src["LogLikelihood"][pick], src["Point"][pick]
+        L[5] = L[4]
+        o = np.lexsort((pts[:, 1], pts[:, 0], L))
+        pool = np.concatenate([np.tile(np.arange(n, n - K, -1), iters), np.arange(n, 0, -1)]).astype(np.int64)
+        runs.append({"Point": pts[o], "LogLikelihood": L[o], "LogPriorPDF": rng.normal(size=M), "AcceptanceRate": rng.random(M),
+                     "PoolSize": pool})
+    flat = api._merge_samples(runs, [24] * 5)
+    a = api._merge_samples(runs[:3], [24] * 3)
+    b = api._merge_samples(runs[3:], [24] * 2)
+    two = api._merge_samples([a, b], [72, 48])
+    for k in ("Point", "LogLikelihood", "LogPriorPDF", "AcceptanceRate", "PoolSize"):
+        assert np.array_equal(two[k], flat[k]), k
+    want = O.combine_runs([SimpleNamespace(points=t["Point"], logL=t["LogLikelihood"], logPrior=t["LogPriorPDF"],
+                                           acc=t["AcceptanceRate"], pool=t["PoolSize"], n=24) for t in runs])
+    assert np.array_equal(flat["Point"], want["points"]) and np.array_equal(flat["PoolSize"], want["pool"])
+    assert np.array_equal(flat["RunIndex"], want["run_id"])

@@ -59,6 +59,22 @@ def test_device_merge_equals_host_merge(R, n, K, iters):
     assert live == want
 
 
+def test_device_merge_equals_oracle_restatement():
+    """against oracle.combine_runs: an independent formulation (np.unique for the duplicates, one searchsorted per run for
+    the summed pool sizes) of BS:1293-1297"""
+    from types import SimpleNamespace
+
+    from bayesianinference_b200 import engine
+    from oracle import oracle as O
+    runs = _synthetic_runs(7, 48, 6, 15, seed=404)
+    dev, _ = engine.merge_runs(runs)
+    want = O.combine_runs([SimpleNamespace(points=t["Point"], logL=t["LogLikelihood"], logPrior=t["LogPriorPDF"],
+                                           acc=t["AcceptanceRate"], pool=t["PoolSize"], n=48) for t in runs])
+    for k, kk in (("Point", "points"), ("LogLikelihood", "logL"), ("LogPriorPDF", "logPrior"), ("AcceptanceRate", "acc"),
+                  ("PoolSize", "pool"), ("RunIndex", "run_id")):
+        assert np.array_equal(dev[k], want[kk]), k
+
+
 def test_device_merge_edge_cases():
     """an empty run, a run that is an exact copy of another (every sample a duplicate), a single-sample run"""
     from bayesianinference_b200 import engine
