@@ -43,6 +43,7 @@ struct binest_run {
     size_t res_smem = 0;
     bool loop = false;          // whole nested-sampling loop in one launch per advance (walk_loop.cuh)
     int loop_nt = 256;
+    bool loop_k1 = false;       // K = 1: CTA-wide two-level speculative walk
     size_t loop_smem = 0;
     LoopCtl *h_ctl = nullptr;   // pinned
     DevBuf<LoopCtl> ctl;
@@ -248,6 +249,11 @@ bool plan_loop(binest_run &r) {
     if (q.K > 8 && OP::D > 3) return false;  // the 1024-thread instantiation has 64 registers per thread
     r.loop_nt = q.K <= 8 ? 256 : 1024;
     r.loop_smem = loop_smem_bytes<OP>(p.rows, r.n_pad);
+    // K = 1 (the reference scheme): the whole CTA walks the run's single walker, two speculation levels deep
+    // (cta_walk_k1); its draw / divisor tables follow the sort buffers in shared memory
+    r.loop_k1 = q.K == 1 && r.loop_nt == 256 && std::getenv("BINEST_NO_K1") == nullptr &&
+                k1_table_doubles<OP>(q.S) * sizeof(double) <= (size_t)kK1MaxTableBytes;
+    if (r.loop_k1) r.loop_smem = ((r.loop_smem + 15) & ~(size_t)15) + k1_table_doubles<OP>(q.S) * sizeof(double);
     if (r.loop_nt == 256)
         BN_CUDA(cudaFuncSetAttribute(ns_loop_kernel<OP, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r.loop_smem));
     else
@@ -269,9 +275,9 @@ long long launch_loop(binest_run &r, long long budget) {
     const int mode = r.first ? 1 : 0;
     BN_CUDA(cudaEventRecord(r.ev0, r.stream));
     if (r.loop_nt == 256)
-        ns_loop_kernel<OP, 256><<<r.prm.R, 256, r.loop_smem, r.stream>>>(r.prm, r.A, p.prior, data, p.rows, p.cst, r.n_pad, mode, budget, r.ctl.p);
+        ns_loop_kernel<OP, 256><<<r.prm.R, 256, r.loop_smem, r.stream>>>(r.prm, r.A, p.prior, data, p.rows, p.cst, r.n_pad, mode, budget, r.ctl.p, r.loop_k1 ? 1 : 0);
     else
-        ns_loop_kernel<OP, 1024><<<r.prm.R, 1024, r.loop_smem, r.stream>>>(r.prm, r.A, p.prior, data, p.rows, p.cst, r.n_pad, mode, budget, r.ctl.p);
+        ns_loop_kernel<OP, 1024><<<r.prm.R, 1024, r.loop_smem, r.stream>>>(r.prm, r.A, p.prior, data, p.rows, p.cst, r.n_pad, mode, budget, r.ctl.p, 0);
     BN_LAUNCH_CHECK();
     BN_CUDA(cudaEventRecord(r.ev1, r.stream));
     r.first = false;
